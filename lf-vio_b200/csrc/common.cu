@@ -1,0 +1,48 @@
+// Error reporting, device probing and launch accounting for the lfvio C-ABI.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace lfvio {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void clear_error() { g_err[0] = 0; }
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int sm_count(int device) {
+    static int cached[64] = {0};
+    if (device < 0 || device >= 64) return 148;
+    if (cached[device] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+        cached[device] = v;
+    }
+    return cached[device];
+}
+
+}  // namespace lfvio
+
+extern "C" const char *lfvio_last_error(void) { return lfvio::g_err; }
+
+extern "C" int lfvio_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();  // clear sticky "no device" state
+        return 0;
+    }
+    return n;
+}
+
+extern "C" const char *lfvio_version(void) { return "lfvio-b200 0.1 (sm_100a)"; }
+
+extern "C" uint64_t lfvio_launch_count(void) { return lfvio::g_launches.load(); }

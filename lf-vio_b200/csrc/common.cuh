@@ -1,0 +1,96 @@
+// Shared host/device helpers for the lfvio CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/lfvio.h"
+
+namespace lfvio {
+
+// thread-local last error text (lfvio_last_error)
+void set_error(const char *fmt, ...);
+void clear_error();
+// process-wide kernel launch counter (lfvio_launch_count)
+void count_launch(int n = 1);
+
+#define LFVIO_CUDA_TRY(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            ::lfvio::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,              \
+                               cudaGetErrorString(_e));                                   \
+            return LFVIO_ERR_CUDA;                                                        \
+        }                                                                                 \
+    } while (0)
+
+#define LFVIO_TRY(expr)                 \
+    do {                                \
+        int _s = (expr);                \
+        if (_s != LFVIO_OK) return _s;  \
+    } while (0)
+
+#define LFVIO_REQUIRE(cond, msg)                                        \
+    do {                                                                \
+        if (!(cond)) {                                                  \
+            ::lfvio::set_error("%s:%d: %s", __FILE__, __LINE__, msg);   \
+            return LFVIO_ERR_ARG;                                       \
+        }                                                               \
+    } while (0)
+
+// Check the launch itself (configuration errors); execution errors surface at the next sync.
+#define LFVIO_LAUNCH_CHECK()                      \
+    do {                                          \
+        ::lfvio::count_launch();                  \
+        LFVIO_CUDA_TRY(cudaPeekAtLastError());    \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// B200: 148 SMs.  Queried once per device and cached.
+int sm_count(int device);
+
+}  // namespace lfvio
+
+#ifdef __CUDACC__
+namespace lfvio {
+
+// OpenCV cvRound(float/double) == lrint == round-half-to-even.
+__device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
+__device__ __forceinline__ int cv_round(double v) { return __double2int_rn(v); }
+__device__ __forceinline__ int cv_floor(float v) { return __float2int_rd(v); }
+
+// cv::borderInterpolate(p, len, BORDER_REFLECT_101) for |overshoot| < len-1 repeated.
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) {
+        if (p < 0) p = -p;
+        else p = 2 * (len - 1) - p;
+    }
+    return p;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace lfvio
+#endif

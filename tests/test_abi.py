@@ -1,0 +1,48 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/lfvio.h declares."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lfvio.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lfvio_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_entry_points():
+    syms = declared_symbols()
+    assert "lfvio_lift_projective" in syms and "lfvio_last_error" in syms
+
+
+def test_library_exports_every_declared_symbol(lfvio_mod):
+    lib = ctypes.CDLL(lfvio_mod.LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, f"declared in include/lfvio.h but not exported: {missing}"
+
+
+def test_version_and_error_strings(lfvio_mod):
+    assert b"sm_100a" in lfvio_mod.lib.lfvio_version()
+    assert lfvio_mod.lib.lfvio_device_count() >= 0
+
+
+def test_bad_arguments_fail_loudly(lfvio_mod):
+    st = lfvio_mod.lib.lfvio_lift_projective(None, None, None, 4, 0, 0)
+    assert st == -2
+    assert b"bad arguments" in lfvio_mod.lib.lfvio_last_error()
+
+
+def test_product_never_imports_oracle():
+    """The product tree must not reference the oracle (no CPU fallback)."""
+    bad = []
+    for dp, _, fns in os.walk(os.path.join(ROOT, "lf-vio_b200")):
+        if "build" in dp:
+            continue
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dp, fn), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\".*oracle/", src, flags=re.M):
+                    bad.append(os.path.join(dp, fn))
+    assert not bad, bad
