@@ -64,6 +64,94 @@ int lfvio_lift_projective(const lfvio_ocam *cam, const double *uv, double *xyz, 
 int lfvio_lift_projective_dev(const lfvio_ocam *cam, const double *uv_dev, double *xyz_dev, int n,
                               int normalize, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Stage-level front-end operators: one entry point per third-party call that
+ * FeatureTracker::readImage makes (feature_tracker/src/feature_tracker.cpp:95-184).  Host
+ * buffers, synchronous, device scratch allocated per call — these exist so a maintainer can
+ * swap a cv:: call 1:1 and so each kernel can be parity-tested in isolation; the fused
+ * per-frame pipeline is lfvio_tracker_read_image below.  Images are CV_8UC1, `stride` in bytes.
+ * ------------------------------------------------------------------------------------------ */
+/* cv::createCLAHE(3.0, Size(8,8))->apply(img, out)              feature_tracker.cpp:101-107 */
+int lfvio_clahe(const uint8_t *img, int rows, int cols, int stride, double clip_limit,
+                uint8_t *out, int out_stride, int device);
+/* cv::pyrDown(img, out): out is ((rows+1)/2) x ((cols+1)/2)     (inside calcOpticalFlowPyrLK) */
+int lfvio_pyr_down(const uint8_t *img, int rows, int cols, int stride, uint8_t *out, int out_stride,
+                   int device);
+/* cv::calcOpticalFlowPyrLK(prev, next, prev_pts, next_pts, status, err, Size(41,41), max_level)
+ * feature_tracker.cpp:127.  prev_pts/next_pts: n x 2 f32, status: n u8.                         */
+int lfvio_calc_optical_flow_pyr_lk(const uint8_t *prev, const uint8_t *next, int rows, int cols,
+                                   int stride, const float *prev_pts, int n, float *next_pts,
+                                   uint8_t *status, int max_level, int device);
+/* cv::cornerMinEigenVal(img, out, 3, 3): out rows x cols f32 (dense)                            */
+int lfvio_corner_min_eigen_val(const uint8_t *img, int rows, int cols, int stride, float *out,
+                               int device);
+/* cv::goodFeaturesToTrack(img, corners, max_corners, quality, min_distance, mask)
+ * feature_tracker.cpp:166.  mask may be NULL.  corners: max_corners x 2 f32; *n_out <= max_corners. */
+int lfvio_good_features_to_track(const uint8_t *img, int rows, int cols, int stride,
+                                 const uint8_t *mask, int mask_stride, int max_corners,
+                                 double quality, double min_distance, float *corners, int *n_out,
+                                 int device);
+
+/* ------------------------------------------------------------------------------------------
+ * FeatureTracker (feature_tracker/src/feature_tracker.h:34-80): whole-frame pipeline resident
+ * on one GPU.  The cfg struct replaces the reference's extern globals
+ * (feature_tracker/src/parameters.h: ROW COL MAX_CNT MIN_DIST EQUALIZE CENTER_X CENTER_Y
+ * MAX_R MIN_R) and FeatureTracker::readIntrinsicParameter().
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lfvio_tracker_cfg {
+    int rows, cols;            /* ROW, COL                                                   */
+    int max_cnt;               /* MAX_CNT  (YAML max_cnt)                                    */
+    int min_dist;              /* MIN_DIST (YAML min_dist)                                   */
+    int equalize;              /* EQUALIZE (YAML equalize): CLAHE on/off                     */
+    double center_x, center_y; /* CENTER_X/Y (YAML center_x/center_y), truncated like cv::Point */
+    int max_r, min_r;          /* MAX_R, MIN_R: annular mask radii                           */
+    int capacity;              /* device track capacity; 0 => max_cnt                        */
+    int ransac;                /* reserved: rejectWithF; must be 0       */
+    lfvio_ocam cam;            /* m_camera                                                   */
+} lfvio_tracker_cfg;
+
+/* Caller-allocated SoA view of the public members the ROS node reads after readImage
+ * (feature_tracker_node.cpp:131-160): cur_pts, ids, track_cnt, cur_un_pts_3d, pts_velocity_3d. */
+typedef struct lfvio_tracks {
+    int capacity;            /* in: entries each array can hold                              */
+    int n;                   /* out                                                          */
+    float *cur_pts;          /* n x 2                                                        */
+    int *ids;                /* n                                                            */
+    int *track_cnt;          /* n                                                            */
+    float *cur_un_pts_3d;    /* n x 3 unit bearings                                          */
+    float *pts_velocity_3d;  /* n x 3                                                        */
+} lfvio_tracks;
+
+typedef struct lfvio_tracker lfvio_tracker;
+
+int lfvio_tracker_create(const lfvio_tracker_cfg *cfg, int device, lfvio_tracker **out);
+void lfvio_tracker_destroy(lfvio_tracker *t);
+/* FeatureTracker::readImage(_img, _cur_time) with the global PUB_THIS_FRAME passed explicitly
+ * (feature_tracker.cpp:95-184).  Host image; H2D copy, all kernels, D2H of the track arrays and
+ * one stream synchronise happen inside the call.                                              */
+int lfvio_tracker_read_image(lfvio_tracker *t, const uint8_t *img, int stride, double cur_time,
+                             int pub_this_frame);
+/* Same pipeline on an image already resident in device memory; asynchronous (no host sync, no
+ * download), runs the updateID pass on device too.  Pair with lfvio_tracker_sync().           */
+int lfvio_tracker_read_image_dev(lfvio_tracker *t, const uint8_t *img_dev, int stride,
+                                 double cur_time, int pub_this_frame);
+/* Wait for the tracker's stream and refresh the host mirror of the track arrays.              */
+int lfvio_tracker_sync(lfvio_tracker *t);
+int lfvio_tracker_count(const lfvio_tracker *t);
+int lfvio_tracker_get(const lfvio_tracker *t, lfvio_tracks *out);
+/* The updateID loop of the node (feature_tracker.cpp:388-398; feature_tracker_node.cpp:103-111):
+ * every id == -1 gets (*n_id)++ in index order.  n_id mirrors `static int FeatureTracker::n_id`. */
+int lfvio_tracker_update_ids(lfvio_tracker *t, int *n_id);
+/* FeatureTracker::mask after the last published frame (rows x cols u8).                       */
+int lfvio_tracker_get_mask(lfvio_tracker *t, uint8_t *out, int out_stride);
+/* cur_img (after CLAHE) pyramid level `level` (0 = full size).                                */
+int lfvio_tracker_get_image(lfvio_tracker *t, int level, uint8_t *out, int out_stride);
+/* Overwrite the tracked state (cur_pts, ids, track_cnt) — test hook for order-dependent paths. */
+int lfvio_tracker_set_points(lfvio_tracker *t, const float *cur_pts, const int *ids,
+                             const int *track_cnt, int n);
+/* The cudaStream_t all of this handle's work is enqueued on (for event timing).               */
+void *lfvio_tracker_stream(lfvio_tracker *t);
+
 #ifdef __cplusplus
 }
 #endif

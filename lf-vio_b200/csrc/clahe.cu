@@ -1,0 +1,202 @@
+// K1 — CLAHE(clipLimit 3.0, 8x8 tiles), bit-exact with cv::CLAHE::apply on CV_8UC1.
+//
+// Reference call site: feature_tracker/src/feature_tracker.cpp:101-107 (cv::createCLAHE(3.0, Size(8,8))).
+// Algorithm (OpenCV, restated in SURVEY.md Appendix B.3): per-tile 256-bin histogram -> clip ->
+// redistribute (batch + strided residual) -> cumulative LUT (f32 scale, cvRound, saturate) ->
+// per-pixel bilinear blend of the 4 neighbouring tile LUTs in UN-FUSED f32.
+//
+// Three launches: histogram (smem atomics, tiles x splits CTAs), LUT (64 CTAs), apply (persistent
+// grid, all 64 LUTs = 16 KB staged in shared memory once per CTA, uchar4 vector I/O).
+// HBM traffic: read W*H (hist) + read W*H + write W*H (apply) = 3 B/px.
+#include "frontend.cuh"
+
+namespace lfvio {
+
+namespace {
+
+struct ClaheGeom {
+    int rows, cols;          // source
+    int tile_w, tile_h;      // of the (possibly REFLECT_101-extended) image
+    int splits;              // CTAs per tile in the histogram pass
+};
+
+__global__ void __launch_bounds__(256) clahe_hist_kernel(const uint8_t *__restrict__ src, int pitch, ClaheGeom g,
+                                                         uint32_t *__restrict__ hist) {
+    __shared__ uint32_t sh[256];
+    const int tile = blockIdx.x;
+    const int ty = tile / kClaheTiles, tx = tile % kClaheTiles;
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    // this CTA's slice of tile rows
+    const int r0 = (int)(((long long)g.tile_h * blockIdx.y) / g.splits);
+    const int r1 = (int)(((long long)g.tile_h * (blockIdx.y + 1)) / g.splits);
+    const int x_base = tx * g.tile_w;
+    const bool interior_x = (x_base + g.tile_w <= g.cols);
+    for (int r = r0; r < r1; r++) {
+        const int y = reflect101(ty * g.tile_h + r, g.rows);
+        const uint8_t *row = src + (size_t)y * pitch;
+        if (interior_x && ((x_base & 3) == 0) && ((g.tile_w & 3) == 0) && ((pitch & 3) == 0)) {
+            const uchar4 *row4 = reinterpret_cast<const uchar4 *>(row + x_base);
+            for (int x = threadIdx.x; x < g.tile_w / 4; x += blockDim.x) {
+                uchar4 v = row4[x];
+                atomicAdd(&sh[v.x], 1u);
+                atomicAdd(&sh[v.y], 1u);
+                atomicAdd(&sh[v.z], 1u);
+                atomicAdd(&sh[v.w], 1u);
+            }
+        } else {
+            for (int x = threadIdx.x; x < g.tile_w; x += blockDim.x)
+                atomicAdd(&sh[row[reflect101(x_base + x, g.cols)]], 1u);
+        }
+    }
+    __syncthreads();
+    uint32_t v = sh[threadIdx.x];
+    if (v) atomicAdd(&hist[tile * 256 + threadIdx.x], v);
+}
+
+__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint32_t *__restrict__ hist, uint8_t *__restrict__ lut,
+                                                        int clip_limit, float lut_scale) {
+    __shared__ int s_scan[256];
+    __shared__ int s_warp[8];
+    const int tile = blockIdx.x, i = threadIdx.x, lane = i & 31, w = i >> 5;
+    int h = (int)hist[tile * 256 + i];
+    int over = 0;
+    if (clip_limit > 0 && h > clip_limit) {
+        over = h - clip_limit;
+        h = clip_limit;
+    }
+    // clipped = sum(over)
+    int c = warp_sum(over);
+    if (lane == 0) s_warp[w] = c;
+    __syncthreads();
+    int clipped = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) clipped += s_warp[k];
+    if (clip_limit > 0) {
+        int batch = clipped / 256;
+        int residual = clipped - batch * 256;
+        h += batch;
+        if (residual != 0) {
+            int step = 256 / residual;
+            if (step < 1) step = 1;
+            // for (i = 0; i < 256 && residual > 0; i += step, residual--) hist[i]++
+            if (i % step == 0 && i / step < residual) h += 1;
+        }
+    }
+    // inclusive scan over 256 bins
+    int v = h;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[w] = v;
+    __syncthreads();
+    int base = 0;
+    for (int k = 0; k < w; k++) base += s_warp[k];
+    int sum = v + base;
+    (void)s_scan;
+    int r = cv_round(__fmul_rn((float)sum, lut_scale));
+    lut[tile * 256 + i] = (uint8_t)min(max(r, 0), 255);
+}
+
+__global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t *__restrict__ src, int src_pitch,
+                                                          uint8_t *__restrict__ dst, int dst_pitch, ClaheGeom g,
+                                                          const uint8_t *__restrict__ lut) {
+    __shared__ __align__(16) uint8_t s_lut[kClaheTiles * kClaheTiles * 256];
+    {
+        const uint4 *l4 = reinterpret_cast<const uint4 *>(lut);
+        uint4 *s4 = reinterpret_cast<uint4 *>(s_lut);
+        for (int k = threadIdx.x; k < kClaheTiles * kClaheTiles * 256 / 16; k += blockDim.x) s4[k] = l4[k];
+    }
+    __syncthreads();
+    const float inv_tw = __fdiv_rn(1.0f, (float)g.tile_w);
+    const float inv_th = __fdiv_rn(1.0f, (float)g.tile_h);
+    const int chunks_per_row = (g.cols + 3) / 4;
+    const long long total = (long long)chunks_per_row * g.rows;
+    const bool vec_ok = ((src_pitch & 3) == 0) && ((dst_pitch & 3) == 0) && ((g.cols & 3) == 0);
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total;
+         c += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(c / chunks_per_row);
+        const int x0 = (int)(c % chunks_per_row) * 4;
+        const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+        int ty1 = cv_floor(tyf);
+        const float ya = __fsub_rn(tyf, (float)ty1);
+        const float ya1 = __fsub_rn(1.0f, ya);
+        int ty2 = min(ty1 + 1, kClaheTiles - 1);
+        ty1 = max(ty1, 0);
+        uint8_t in[4], out[4];
+        const int nvalid = min(4, g.cols - x0);
+        if (vec_ok) {
+            uchar4 v = *reinterpret_cast<const uchar4 *>(src + (size_t)y * src_pitch + x0);
+            in[0] = v.x; in[1] = v.y; in[2] = v.z; in[3] = v.w;
+        } else {
+            for (int k = 0; k < nvalid; k++) in[k] = src[(size_t)y * src_pitch + x0 + k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (k >= nvalid) break;
+            const int x = x0 + k;
+            const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
+            int tx1 = cv_floor(txf);
+            const float xa = __fsub_rn(txf, (float)tx1);
+            const float xa1 = __fsub_rn(1.0f, xa);
+            int tx2 = min(tx1 + 1, kClaheTiles - 1);
+            tx1 = max(tx1, 0);
+            const int sv = in[k];
+            const float l11 = (float)s_lut[(ty1 * kClaheTiles + tx1) * 256 + sv];
+            const float l12 = (float)s_lut[(ty1 * kClaheTiles + tx2) * 256 + sv];
+            const float l21 = (float)s_lut[(ty2 * kClaheTiles + tx1) * 256 + sv];
+            const float l22 = (float)s_lut[(ty2 * kClaheTiles + tx2) * 256 + sv];
+            const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
+            const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
+            const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+            out[k] = (uint8_t)min(max(cv_round(res), 0), 255);
+        }
+        if (vec_ok) {
+            *reinterpret_cast<uchar4 *>(dst + (size_t)y * dst_pitch + x0) = make_uchar4(out[0], out[1], out[2], out[3]);
+        } else {
+            for (int k = 0; k < nvalid; k++) dst[(size_t)y * dst_pitch + x0 + k] = out[k];
+        }
+    }
+}
+
+}  // namespace
+
+int launch_clahe(const uint8_t *src, int src_pitch, uint8_t *dst, int dst_pitch, int rows, int cols,
+                 float clip_limit, uint32_t *hist, uint8_t *lut, int n_sm, cudaStream_t s) {
+    ClaheGeom g;
+    g.rows = rows;
+    g.cols = cols;
+    int ext_rows = rows, ext_cols = cols;
+    if (cols % kClaheTiles != 0 || rows % kClaheTiles != 0) {
+        // OpenCV pads BOTH dimensions: bottom = tiles - rows%tiles, right = tiles - cols%tiles
+        ext_rows = rows + (kClaheTiles - rows % kClaheTiles);
+        ext_cols = cols + (kClaheTiles - cols % kClaheTiles);
+    }
+    g.tile_w = ext_cols / kClaheTiles;
+    g.tile_h = ext_rows / kClaheTiles;
+    const int area = g.tile_w * g.tile_h;
+    // enough CTAs to fill the machine: 64 tiles x splits ~ 4 CTAs per SM
+    g.splits = max(1, min(g.tile_h, cdiv(4 * n_sm, kClaheTiles * kClaheTiles)));
+    int clip = 0;
+    if (clip_limit > 0.0f) {
+        clip = (int)((double)clip_limit * area / 256);  // static_cast<int>(clipLimit_ * tileSizeTotal / histSize)
+        if (clip < 1) clip = 1;
+    }
+    const float lut_scale = (float)(255) / (float)area;  // static_cast<float>(histSize - 1) / tileSizeTotal
+    LFVIO_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * kClaheTiles * kClaheTiles * 256, s));
+    clahe_hist_kernel<<<dim3(kClaheTiles * kClaheTiles, g.splits), 256, 0, s>>>(src, src_pitch, g, hist);
+    LFVIO_LAUNCH_CHECK();
+    clahe_lut_kernel<<<kClaheTiles * kClaheTiles, 256, 0, s>>>(hist, lut, clip, lut_scale);
+    LFVIO_LAUNCH_CHECK();
+    const long long chunks = (long long)((cols + 3) / 4) * rows;
+    long long want = (chunks + 255) / 256;
+    int grid = (int)(want < 2LL * n_sm ? want : 2LL * n_sm);
+    clahe_apply_kernel<<<grid, 256, 0, s>>>(src, src_pitch, dst, dst_pitch, g, lut);
+    LFVIO_LAUNCH_CHECK();
+    return LFVIO_OK;
+}
+
+}  // namespace lfvio

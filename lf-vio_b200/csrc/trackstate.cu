@@ -1,0 +1,419 @@
+// K6 + track bookkeeping of FeatureTracker::readImage, on device (no host round trip inside a frame).
+//
+// Reference: feature_tracker/src/feature_tracker.cpp
+//   reduceVector / track_cnt++            :14-40, :132-145   -> compact_kernel
+//   setMask()                             :46-83             -> set_mask_select_kernel + mask_raster_kernel
+//   addPoints()                           :85-93             -> fused into corners.cu select_kernel
+//   undistortedPoints()                   :441-504           -> undistort_kernel
+//   updateID() + node loop                :388-398, feature_tracker_node.cpp:103-111 -> update_ids_kernel
+//
+// Order-dependent semantics are preserved exactly:
+//  * setMask sorts by track_cnt with libstdc++'s UNSTABLE std::sort; the permutation (hence which of two
+//    equally old tracks survives and the output order, hence feature IDs) is reproduced by a device
+//    transliteration of libstdc++'s introsort (median-of-3 quicksort, depth limit 2*lg n with heapsort
+//    fallback, final insertion sort with threshold 16), run by one thread on a few hundred keys.
+//  * the keep/stamp loop is sequential in that order; "pixel still 255" is evaluated geometrically
+//    (annulus base mask AND outside every previously kept disc, using cv::circle's midpoint half-widths),
+//    so no raster is needed inside the loop; the mask itself is rastered afterwards in parallel.
+#include "frontend.cuh"
+
+namespace lfvio {
+
+void circle_half_widths(int radius, int *hw) {
+    // cv::circle(img, c, radius, color, -1): midpoint algorithm filling horizontal spans (OpenCV drawing.cpp Circle())
+    for (int i = 0; i <= radius; i++) hw[i] = -1;
+    int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+    while (dx >= dy) {
+        if (hw[dy] < dx) hw[dy] = dx;
+        if (hw[dx] < dy) hw[dx] = dy;
+        dy++;
+        err += plus;
+        plus += 2;
+        const int m = (err <= 0) - 1;
+        err -= minus & m;
+        dx += m;
+        minus -= m & 2;
+    }
+}
+
+namespace {
+
+constexpr int BT = 1024;
+
+__device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int t = s_warp[lane], ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += u;
+        }
+        s_warp[lane] = ti - t;
+        if (lane == 31) s_warp[32] = ti;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return inc - v + s_warp[w];
+}
+
+__device__ __forceinline__ void copy_track(const TrackArrays &in, int i, const TrackArrays &out, int o, int cnt_add) {
+    out.cur[o] = in.cur[i];
+    out.forw[o] = in.forw[i];
+    out.ids[o] = in.ids[i];
+    out.cnt[o] = in.cnt[i] + cnt_add;
+    out.bearing[3 * o + 0] = in.bearing[3 * i + 0];
+    out.bearing[3 * o + 1] = in.bearing[3 * i + 1];
+    out.bearing[3 * o + 2] = in.bearing[3 * i + 2];
+    out.prev_valid[o] = in.prev_valid[i];
+}
+
+__global__ void __launch_bounds__(BT) compact_kernel(TrackArrays in, TrackArrays out, const uint8_t *__restrict__ status,
+                                                     int *n_dev, int cap) {
+    __shared__ int s_warp[33];
+    const int n = min(*n_dev, cap);
+    int carry = 0;
+    for (int i0 = 0; i0 < n; i0 += BT) {
+        const int i = i0 + threadIdx.x;
+        const int keep = (i < n && status[i]) ? 1 : 0;
+        int total;
+        const int ex = block_excl_scan(keep, s_warp, &total);
+        if (keep) copy_track(in, i, out, carry + ex, 1);  // for (auto &n : track_cnt) n++
+        carry += total;
+        __syncthreads();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *n_dev = carry;
+}
+
+// ------------------------------------------------------------------------------------------------
+// libstdc++ std::sort(first, last, [](a, b){ return a.first > b.first; }) on (key, payload) pairs packed as
+// (key << 32 | payload); only the key takes part in comparisons.
+struct DescByKey {
+    __device__ __forceinline__ bool operator()(long long a, long long b) const { return (int)(a >> 32) > (int)(b >> 32); }
+};
+
+__device__ void adjust_heap(long long *first, int hole, int len, long long value, DescByKey comp) {
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (comp(first[child], first[child - 1])) child--;
+        first[hole] = first[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        first[hole] = first[child - 1];
+        hole = child - 1;
+    }
+    int parent = (hole - 1) / 2;  // __push_heap
+    while (hole > top && comp(first[parent], value)) {
+        first[hole] = first[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    first[hole] = value;
+}
+
+__device__ void heap_sort(long long *first, int len, DescByKey comp) {  // __partial_sort(first, last, last)
+    if (len >= 2) {
+        int parent = (len - 2) / 2;
+        while (true) {
+            long long v = first[parent];
+            adjust_heap(first, parent, len, v, comp);
+            if (parent == 0) break;
+            parent--;
+        }
+    }
+    int last = len;
+    while (last > 1) {
+        --last;
+        long long v = first[last];
+        first[last] = first[0];
+        adjust_heap(first, 0, last, v, comp);
+    }
+}
+
+__device__ void unguarded_linear_insert(long long *a, int last, DescByKey comp) {
+    long long val = a[last];
+    int next = last - 1;
+    while (comp(val, a[next])) {
+        a[last] = a[next];
+        last = next;
+        --next;
+    }
+    a[last] = val;
+}
+
+__device__ void insertion_sort(long long *a, int first, int last, DescByKey comp) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+        if (comp(a[i], a[first])) {
+            long long val = a[i];
+            for (int k = i; k > first; --k) a[k] = a[k - 1];  // move_backward
+            a[first] = val;
+        } else {
+            unguarded_linear_insert(a, i, comp);
+        }
+    }
+}
+
+__device__ void std_sort_desc(long long *a, int n) {
+    DescByKey comp;
+    if (n <= 1) return;
+    // __introsort_loop with an explicit stack (the sub-ranges are independent, so order does not matter)
+    int stack_first[64], stack_last[64], stack_depth[64];
+    int sp = 0;
+    int lg = 31 - __clz(n);
+    stack_first[sp] = 0;
+    stack_last[sp] = n;
+    stack_depth[sp] = 2 * lg;
+    sp++;
+    while (sp > 0) {
+        sp--;
+        int first = stack_first[sp], last = stack_last[sp], depth = stack_depth[sp];
+        while (last - first > 16) {
+            if (depth == 0) {
+                heap_sort(a + first, last - first, comp);
+                break;
+            }
+            --depth;
+            // __unguarded_partition_pivot: median of (first+1, mid, last-1) moved to first
+            const int mid = first + (last - first) / 2;
+            const int ia = first + 1, ib = mid, ic = last - 1;
+            int m;
+            if (comp(a[ia], a[ib])) {
+                if (comp(a[ib], a[ic])) m = ib;
+                else if (comp(a[ia], a[ic])) m = ic;
+                else m = ia;
+            } else if (comp(a[ia], a[ic])) m = ia;
+            else if (comp(a[ib], a[ic])) m = ic;
+            else m = ib;
+            {
+                long long t = a[first];
+                a[first] = a[m];
+                a[m] = t;
+            }
+            // __unguarded_partition(first + 1, last, pivot = first)
+            int lo = first + 1, hi = last;
+            const long long pivot = a[first];
+            while (true) {
+                while (comp(a[lo], pivot)) ++lo;
+                --hi;
+                while (comp(pivot, a[hi])) --hi;
+                if (!(lo < hi)) break;
+                long long t = a[lo];
+                a[lo] = a[hi];
+                a[hi] = t;
+                ++lo;
+            }
+            const int cut = lo;
+            // recurse on [cut, last), loop on [first, cut)
+            stack_first[sp] = cut;
+            stack_last[sp] = last;
+            stack_depth[sp] = depth;
+            sp++;
+            last = cut;
+        }
+    }
+    // __final_insertion_sort
+    if (n > 16) {
+        insertion_sort(a, 0, 16, comp);
+        for (int i = 16; i != n; ++i) unguarded_linear_insert(a, i, comp);
+    } else {
+        insertion_sort(a, 0, n, comp);
+    }
+}
+
+__global__ void __launch_bounds__(BT) set_mask_select_kernel(TrackArrays in, TrackArrays out, int *n_dev, int cap,
+                                                             const uint8_t *__restrict__ base_mask, int mask_pitch,
+                                                             const int *__restrict__ half_width, int min_dist,
+                                                             long long *sort_buf, int *kept_xy) {
+    __shared__ int s_nkept;
+    __shared__ int s_flag;
+    const int n = min(*n_dev, cap);
+    for (int i = threadIdx.x; i < n; i += BT) sort_buf[i] = ((long long)in.cnt[i] << 32) | (unsigned)i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        std_sort_desc(sort_buf, n);
+        s_nkept = 0;
+    }
+    __syncthreads();
+    // sequential keep loop; kept_xy holds rounded pixel coords of kept tracks (x, y interleaved)
+    for (int k = 0; k < n; k++) {
+        const int src = (int)(sort_buf[k] & 0xffffffffu);
+        const float2 pt = in.forw[src];
+        const int px = cv_round(pt.x), py = cv_round(pt.y);  // Mat::at<uchar>(Point2f -> Point)
+        const int nk = s_nkept;
+        if (threadIdx.x == 0) s_flag = (base_mask[(size_t)py * mask_pitch + px] == 255) ? 0 : 1;
+        __syncthreads();
+        int hit = 0;
+        for (int j = threadIdx.x; j < nk; j += BT) {
+            const int dx = abs(px - kept_xy[2 * j]), dy = abs(py - kept_xy[2 * j + 1]);
+            if (dy <= min_dist && dx <= half_width[dy]) hit = 1;
+        }
+        const int any = __syncthreads_or(hit | s_flag);
+        if (!any) {
+            if (threadIdx.x == 0) {
+                kept_xy[2 * nk] = px;
+                kept_xy[2 * nk + 1] = py;
+                sort_buf[nk] = (sort_buf[nk] & ~0xffffffffLL) | (unsigned)src;  // kept order -> source index (nk <= k)
+                s_nkept = nk + 1;
+            }
+        }
+        __syncthreads();
+    }
+    const int nkept = s_nkept;
+    for (int o = threadIdx.x; o < nkept; o += BT) copy_track(in, (int)(sort_buf[o] & 0xffffffffu), out, o, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) *n_dev = nkept;
+}
+
+__global__ void __launch_bounds__(64) mask_raster_kernel(uint8_t *mask, int rows, int cols, int pitch,
+                                                         const float2 *__restrict__ pts, const int *__restrict__ n_dev,
+                                                         int cap, const int *__restrict__ half_width, int radius) {
+    const int n = min(*n_dev, cap);
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const float2 pt = pts[i];
+    const int cx = cv_round(pt.x), cy = cv_round(pt.y);  // cv::circle(mask, Point2f -> Point, MIN_DIST, 0, -1)
+    for (int r = threadIdx.x; r < 2 * radius + 1; r += blockDim.x) {
+        const int dy = r - radius;
+        const int y = cy + dy;
+        if (y < 0 || y >= rows) continue;
+        const int hw = half_width[abs(dy)];
+        const int xa = max(cx - hw, 0), xb = min(cx + hw, cols - 1);
+        for (int x = xa; x <= xb; x++) mask[(size_t)y * pitch + x] = 0;
+    }
+}
+
+__global__ void fill_circle_kernel(uint8_t *img, int rows, int cols, int pitch, int cx, int cy, int radius,
+                                   const int *__restrict__ half_width, uint8_t value) {
+    const int r = blockIdx.x;  // row index within [-radius, radius]
+    const int dy = r - radius;
+    const int y = cy + dy;
+    if (y < 0 || y >= rows) return;
+    const int hw = half_width[abs(dy)];
+    const int xa = max(cx - hw, 0), xb = min(cx + hw, cols - 1);
+    for (int x = xa + threadIdx.x; x <= xb; x += blockDim.x) img[(size_t)y * pitch + x] = value;
+}
+
+__global__ void __launch_bounds__(256) undistort_kernel(OcamDev cam, const float2 *__restrict__ pts,
+                                                        const int *__restrict__ ids, float *bearing_prev,
+                                                        uint8_t *prev_valid, float *__restrict__ bearing_out,
+                                                        float *__restrict__ vel_out, const int *__restrict__ n_dev, int cap,
+                                                        double dt, const int *__restrict__ have_prev_in,
+                                                        int *__restrict__ have_prev_out) {
+    const int n = min(*n_dev, cap);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int have_prev = *have_prev_in;  // !prev_un_pts_map_3d.empty()
+    if (i == 0) *have_prev_out = (n > 0) ? 1 : 0;
+    if (i >= n) return;
+    const float2 p = pts[i];
+    const double3 b = ocam_lift(cam, (double)p.x, (double)p.y, true);  // b / b.norm() in f64 ...
+    const float bx = (float)b.x, by = (float)b.y, bz = (float)b.z;     // ... then cv::Point3f
+    float vx = 0.f, vy = 0.f, vz = 0.f;
+    const int id = ids[i];
+    if (have_prev && id != -1 && prev_valid[i]) {
+        // (cur.x - prev.x) is a float subtraction, the division by dt is done in double, result cast to float
+        vx = (float)((double)__fsub_rn(bx, bearing_prev[3 * i + 0]) / dt);
+        vy = (float)((double)__fsub_rn(by, bearing_prev[3 * i + 1]) / dt);
+        vz = (float)((double)__fsub_rn(bz, bearing_prev[3 * i + 2]) / dt);
+    }
+    bearing_out[3 * i + 0] = bx;
+    bearing_out[3 * i + 1] = by;
+    bearing_out[3 * i + 2] = bz;
+    vel_out[3 * i + 0] = vx;
+    vel_out[3 * i + 1] = vy;
+    vel_out[3 * i + 2] = vz;
+    // becomes prev_un_pts_map_3d: keyed by the id in force NOW (-1 for points added this frame)
+    bearing_prev[3 * i + 0] = bx;
+    bearing_prev[3 * i + 1] = by;
+    bearing_prev[3 * i + 2] = bz;
+    prev_valid[i] = (id != -1) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(BT) update_ids_kernel(int *ids, const int *__restrict__ n_dev, int cap, int *n_id_dev) {
+    __shared__ int s_warp[33];
+    const int n = min(*n_dev, cap);
+    const int n_id_base = *n_id_dev;  // static int FeatureTracker::n_id
+    __syncthreads();
+    int carry = 0;
+    for (int i0 = 0; i0 < n; i0 += BT) {
+        const int i = i0 + threadIdx.x;
+        const int isnew = (i < n && ids[i] == -1) ? 1 : 0;
+        int total;
+        const int ex = block_excl_scan(isnew, s_warp, &total);
+        if (isnew) ids[i] = n_id_base + carry + ex;  // ids[i] = n_id++ in index order
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_id_dev = n_id_base + carry;
+}
+
+}  // namespace
+
+int launch_compact(const TrackArrays &in, const TrackArrays &out, const uint8_t *status, int *n_dev, int cap,
+                   cudaStream_t s) {
+    compact_kernel<<<1, BT, 0, s>>>(in, out, status, n_dev, cap);
+    LFVIO_LAUNCH_CHECK();
+    return LFVIO_OK;
+}
+
+int launch_set_mask_select(const TrackArrays &in, const TrackArrays &out, int *n_dev, int cap,
+                           const uint8_t *base_mask, int mask_pitch, const int *half_width, int min_dist,
+                           int *sort_scratch, cudaStream_t s) {
+    // sort_scratch: 2*cap ints viewed as cap int64 sort records, followed by 2*cap ints of kept (x, y)
+    long long *sort_buf = reinterpret_cast<long long *>(sort_scratch);
+    int *kept_xy = sort_scratch + 2 * cap;
+    set_mask_select_kernel<<<1, BT, 0, s>>>(in, out, n_dev, cap, base_mask, mask_pitch, half_width, min_dist,
+                                            sort_buf, kept_xy);
+    LFVIO_LAUNCH_CHECK();
+    return LFVIO_OK;
+}
+
+int launch_mask_raster(uint8_t *mask, const uint8_t *base_mask, int rows, int cols, int pitch,
+                       const float2 *pts, const int *n_dev, int cap, const int *half_width, int min_dist,
+                       cudaStream_t s) {
+    LFVIO_CUDA_TRY(cudaMemcpy2DAsync(mask, pitch, base_mask, pitch, cols, rows, cudaMemcpyDeviceToDevice, s));
+    if (cap > 0) {
+        mask_raster_kernel<<<cap, 64, 0, s>>>(mask, rows, cols, pitch, pts, n_dev, cap, half_width, min_dist);
+        LFVIO_LAUNCH_CHECK();
+    }
+    return LFVIO_OK;
+}
+
+int launch_fill_circle(uint8_t *img, int rows, int cols, int pitch, int cx, int cy, int radius,
+                       const int *half_width_dev, uint8_t value, cudaStream_t s) {
+    fill_circle_kernel<<<2 * radius + 1, 128, 0, s>>>(img, rows, cols, pitch, cx, cy, radius, half_width_dev, value);
+    LFVIO_LAUNCH_CHECK();
+    return LFVIO_OK;
+}
+
+int launch_undistort(const OcamDev &cam, const float2 *pts, const int *ids, float *bearing_prev_inout,
+                     uint8_t *prev_valid_inout, float *bearing_out, float *vel_out, const int *n_dev, int cap,
+                     double dt, const int *have_prev_in, int *have_prev_out, cudaStream_t s) {
+    if (cap <= 0) cap = 1;  // still rotates the have_prev flag
+    undistort_kernel<<<cdiv(cap, 256), 256, 0, s>>>(cam, pts, ids, bearing_prev_inout, prev_valid_inout, bearing_out,
+                                                    vel_out, n_dev, cap, dt, have_prev_in, have_prev_out);
+    LFVIO_LAUNCH_CHECK();
+    return LFVIO_OK;
+}
+
+int launch_update_ids(int *ids, const int *n_dev, int cap, int *n_id_dev, cudaStream_t s) {
+    update_ids_kernel<<<1, BT, 0, s>>>(ids, n_dev, cap, n_id_dev);
+    LFVIO_LAUNCH_CHECK();
+    return LFVIO_OK;
+}
+
+}  // namespace lfvio

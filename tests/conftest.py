@@ -13,6 +13,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # build the product library and the oracle's native helpers if they are not there yet
+    import subprocess
+
+    if not os.path.exists(os.path.join(ROOT, "lf-vio_b200", "liblfvio.so")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "lf-vio_b200"), "-j8"], check=True)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-j8"], check=True, stdout=subprocess.DEVNULL)
 
 
 @pytest.fixture(scope="session")
