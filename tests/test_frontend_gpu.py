@@ -213,12 +213,12 @@ def test_set_mask_unstable_sort_order(lfvio_mod, gpu, frames):
         # survivors of the LK pass on identical images (same kernel, stage-level entry point) + inBorder
         flat = frames[0]
         nxt, st = lfvio_mod.calc_optical_flow_pyr_lk(flat, flat, pts, device=gpu)
-        assert np.array_equal(nxt[st.astype(bool)], pts[st.astype(bool)])  # b == 0 => delta == 0 exactly
+        assert np.abs(nxt - pts)[st.astype(bool)].max() < 1e-4  # b == 0 => delta == 0; (x - 20) + 20 may move 1 ulp
         x, y = np.rint(nxt[:, 0]), np.rint(nxt[:, 1])
         ok = st.astype(bool) & (1 <= x) & (x < COLS - 1) & (1 <= y) & (y < ROWS - 1)
         # oracle: setMask on the surviving state
         o = fe.FeatureTrackerOracle(PAL_UP, cfg, "restated")
-        o.forw_pts, o.ids, o.track_cnt = pts[ok].copy(), ids[ok].astype(np.int64), cnt[ok].astype(np.int64)
+        o.forw_pts, o.ids, o.track_cnt = nxt[ok].copy(), ids[ok].astype(np.int64), cnt[ok].astype(np.int64)
         o.set_mask()
         tr = lfvio_mod.FeatureTracker(PAL_UP, dict(cfg, equalize=0), device=gpu)
         tr.read_image(flat, 0.0, False)          # first frame, no detection
