@@ -152,6 +152,130 @@ int lfvio_tracker_set_points(lfvio_tracker *t, const float *cur_pts, const int *
 /* The cudaStream_t all of this handle's work is enqueued on (for event timing).               */
 void *lfvio_tracker_stream(lfvio_tracker *t);
 
+/* ==========================================================================================
+ * Sliding-window back end: Estimator::optimization() (vins_estimator/src/estimator.cpp:676-1009).
+ *
+ * The Ceres problem the reference builds (:678-772) is passed as flat arrays.  Parameter blocks keep the
+ * reference's layout (estimator.h:107-113): para_Pose[F][7] = x y z qx qy qz qw, para_SpeedBias[F][9] =
+ * v ba bg, para_Ex_Pose[7], para_Feature[L] (inverse depth), para_Td.  Parameter-block ids used by the
+ * prior: pose f -> 2f, speed-bias f -> 2f+1, extrinsic -> 2F, td -> 2F+1 (F = n_frames).
+ * ========================================================================================== */
+typedef struct lfvio_proj_factor { /* ProjectionTdFactor / ProjectionFactor ctor arguments        */
+    int frame_i, frame_j;          /* imu_i (host frame), imu_j            estimator.cpp:735-744  */
+    int landmark;                  /* feature_index into para_Feature       estimator.cpp:733      */
+    int reserved;
+    double pts_i[3], pts_j[3];     /* unit bearings (feature_per_frame.point)                      */
+    double vel_i[3], vel_j[3];     /* bearing velocities (.velocity); unused when estimate_td = 0  */
+    double td_i, td_j;             /* .cur_td                                                      */
+    double row_i, row_j;           /* .uv.y()  (rolling-shutter term)                              */
+} lfvio_proj_factor;
+
+typedef struct lfvio_imu_factor { /* IMUFactor(pre_integrations[j]) == IntegrationBase members      */
+    int frame_i;                  /* connects frame_i and frame_i + 1       estimator.cpp:717-724 */
+    int reserved;
+    double sum_dt;
+    double delta_p[3];
+    double delta_q[4];            /* w x y z                                                       */
+    double delta_v[3];
+    double linearized_ba[3], linearized_bg[3];
+    double jacobian[225];         /* 15 x 15 row-major, order O_P O_R O_V O_BA O_BG (parameters.h:50-57) */
+    double covariance[225];       /* 15 x 15 row-major                                             */
+} lfvio_imu_factor;
+
+typedef struct lfvio_prior { /* MarginalizationInfo after marginalize() (marginalization_factor.h:43-73) */
+    int n;              /* residuals == total LOCAL size of the kept blocks (pose blocks count 6)  */
+    int n_blocks;       /* keep_block_size.size()                                                  */
+    int *block_id;      /* n_blocks parameter-block ids (see above)                                */
+    int *block_idx;     /* n_blocks: keep_block_idx - m  (column offset in J0)                     */
+    double *x0;         /* keep_block_data concatenated in block order, GLOBAL sizes (7/9/7/1)     */
+    double *J0;         /* linearized_jacobians, n x n row-major                                   */
+    double *r0;         /* linearized_residuals, n                                                 */
+    int cap_n, cap_blocks; /* capacities of the arrays when used as an output                     */
+} lfvio_prior;
+
+typedef struct lfvio_window_state {
+    int n_frames;            /* F = WINDOW_SIZE + 1                                                */
+    int n_landmarks;         /* L                                                                  */
+    double *para_Pose;       /* F x 7                                                              */
+    double *para_SpeedBias;  /* F x 9                                                              */
+    double *para_Ex_Pose;    /* 7                                                                  */
+    double *para_Feature;    /* L                                                                  */
+    double *para_Td;         /* 1                                                                  */
+} lfvio_window_state;
+
+typedef struct lfvio_factor_list {
+    int n_proj;
+    const lfvio_proj_factor *proj; /* in the reference's insertion order (estimator.cpp:725-772)    */
+    int n_imu;
+    const lfvio_imu_factor *imu;
+    const lfvio_prior *prior;      /* last_marginalization_info, may be NULL                        */
+} lfvio_factor_list;
+
+typedef struct lfvio_solver_opts {
+    int max_num_iterations;   /* NUM_ITERATIONS (YAML max_num_iterations, 8)                        */
+    int fixed_iterations;     /* 1: ignore the function/parameter/gradient tolerances (timing runs) */
+    int estimate_td;          /* ESTIMATE_TD: ProjectionTdFactor vs ProjectionFactor                */
+    int estimate_extrinsic;   /* 0 => para_Ex_Pose is SetParameterBlockConstant                     */
+    int row;                  /* ROW (image height) for the rolling-shutter term                    */
+    int reserved;
+    double focal_length;      /* FOCAL_LENGTH; sqrt_info = focal_length / 1.5 * I2 (estimator.cpp:18) */
+    double tr;                /* TR, rolling shutter read-out time                                  */
+    double g[3];              /* gravity vector G                                                   */
+    double cauchy_a;          /* ceres::CauchyLoss(1.0)                                             */
+    /* ceres::Solver::Options defaults of release 1.12.0 that the reference relies on               */
+    double initial_trust_region_radius, max_trust_region_radius, min_trust_region_radius;
+    double min_relative_decrease, function_tolerance, gradient_tolerance, parameter_tolerance;
+} lfvio_solver_opts;
+
+#define LFVIO_MAX_ITER_LOG 64
+typedef struct lfvio_solve_summary {
+    int iterations;            /* trust-region iterations performed (successful + unsuccessful)     */
+    int num_successful_steps;
+    int termination;           /* 0 max iterations, 1 converged, -1 numerical failure               */
+    int reserved;
+    double initial_cost, final_cost;
+    double cost[LFVIO_MAX_ITER_LOG];    /* cost after each iteration (index 0 = initial)            */
+    double radius[LFVIO_MAX_ITER_LOG];  /* trust-region radius after each iteration                 */
+    int accepted[LFVIO_MAX_ITER_LOG];
+} lfvio_solve_summary;
+
+/* Fills *o with the Ceres 1.12 defaults + the reference's settings (estimator.cpp:810-822, parameters.h). */
+void lfvio_solver_default_opts(lfvio_solver_opts *o);
+
+#define LFVIO_MARGIN_OLD 0        /* estimator.h MarginalizationFlag */
+#define LFVIO_MARGIN_SECOND_NEW 1
+
+typedef struct lfvio_window lfvio_window;
+/* window_size = WINDOW_SIZE (10 in the reference, compile-time there; runtime here), max_landmarks
+ * replaces NUM_OF_F, max_proj bounds the projection-factor count.                                   */
+int lfvio_window_create(int window_size, int max_landmarks, int max_proj, int device, lfvio_window **out);
+void lfvio_window_destroy(lfvio_window *w);
+/* ceres::Solve() of estimator.cpp:825 on the problem of :678-772 (DENSE_SCHUR + traditional DOGLEG +
+ * CauchyLoss on projection factors), entirely on device; state is updated in place.                 */
+int lfvio_window_optimize(lfvio_window *w, lfvio_window_state *state, const lfvio_factor_list *factors,
+                          const lfvio_solver_opts *opts, lfvio_solve_summary *summary);
+/* Construction of the next prior (estimator.cpp:833-1005 + MarginalizationInfo::preMarginalize /
+ * marginalize / getParameterBlocks, marginalization_factor.cpp:110-319) at the given state.  The factors
+ * to drop are selected from `factors` as the reference does; block ids in `out` are already shifted
+ * (addr_shift).  out->n == 0 if nothing is to be marginalised (SECOND_NEW without a matching prior).  */
+int lfvio_window_marginalize(lfvio_window *w, const lfvio_window_state *state, const lfvio_factor_list *factors,
+                             const lfvio_solver_opts *opts, int margin_flag, lfvio_prior *out);
+/* ceres::CostFunction::Evaluate of every factor at `state` (debug / parity hook): residuals are
+ * written factor by factor (2 per projection factor incl. the Cauchy correction when robust != 0,
+ * 15 per IMU factor, prior.n for the prior); jacobians likewise in LOCAL parameterisation, row-major:
+ * projection 2 x 20 [pose_i 6 | pose_j 6 | ex 6 | lambda 1 | td 1], IMU 15 x 30 [pose_i 6 | sb_i 9 |
+ * pose_j 6 | sb_j 9], prior n x n.  Any output pointer may be NULL.                                   */
+int lfvio_window_evaluate(lfvio_window *w, const lfvio_window_state *state, const lfvio_factor_list *factors,
+                          const lfvio_solver_opts *opts, int robust, double *res_proj, double *jac_proj,
+                          double *res_imu, double *jac_imu, double *res_prior, double *cost);
+void *lfvio_window_stream(lfvio_window *w);
+/* Device-resident variant for throughput runs: upload once, then solve repeatedly from the uploaded
+ * initial state without host traffic (each call restores the initial state on device first).        */
+int lfvio_window_upload(lfvio_window *w, const lfvio_window_state *state, const lfvio_factor_list *factors,
+                        const lfvio_solver_opts *opts);
+int lfvio_window_optimize_dev(lfvio_window *w, int with_marginalize, int margin_flag);
+int lfvio_window_download(lfvio_window *w, lfvio_window_state *state, lfvio_solve_summary *summary);
+
 #ifdef __cplusplus
 }
 #endif

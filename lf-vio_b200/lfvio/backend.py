@@ -1,0 +1,238 @@
+"""ctypes view of the back-end half of include/lfvio.h (structs + lfvio_window_* prototypes).
+
+The struct classes are also used by the oracle's ctypes wrapper (oracle/backend.py): the oracle consumes
+the same interface structs as the product so that one problem description feeds both.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+MAX_ITER_LOG = 64
+MARGIN_OLD, MARGIN_SECOND_NEW = 0, 1
+
+
+class ProjFactor(C.Structure):
+    _fields_ = [("frame_i", C.c_int), ("frame_j", C.c_int), ("landmark", C.c_int), ("reserved", C.c_int),
+                ("pts_i", C.c_double * 3), ("pts_j", C.c_double * 3), ("vel_i", C.c_double * 3), ("vel_j", C.c_double * 3),
+                ("td_i", C.c_double), ("td_j", C.c_double), ("row_i", C.c_double), ("row_j", C.c_double)]
+
+
+class ImuFactor(C.Structure):
+    _fields_ = [("frame_i", C.c_int), ("reserved", C.c_int), ("sum_dt", C.c_double), ("delta_p", C.c_double * 3),
+                ("delta_q", C.c_double * 4), ("delta_v", C.c_double * 3), ("linearized_ba", C.c_double * 3),
+                ("linearized_bg", C.c_double * 3), ("jacobian", C.c_double * 225), ("covariance", C.c_double * 225)]
+
+
+class Prior(C.Structure):
+    _fields_ = [("n", C.c_int), ("n_blocks", C.c_int), ("block_id", _ip), ("block_idx", _ip), ("x0", _dp), ("J0", _dp),
+                ("r0", _dp), ("cap_n", C.c_int), ("cap_blocks", C.c_int)]
+
+
+class WindowState(C.Structure):
+    _fields_ = [("n_frames", C.c_int), ("n_landmarks", C.c_int), ("para_Pose", _dp), ("para_SpeedBias", _dp),
+                ("para_Ex_Pose", _dp), ("para_Feature", _dp), ("para_Td", _dp)]
+
+
+class FactorList(C.Structure):
+    _fields_ = [("n_proj", C.c_int), ("proj", C.POINTER(ProjFactor)), ("n_imu", C.c_int), ("imu", C.POINTER(ImuFactor)),
+                ("prior", C.POINTER(Prior))]
+
+
+class SolverOpts(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int), ("fixed_iterations", C.c_int), ("estimate_td", C.c_int),
+                ("estimate_extrinsic", C.c_int), ("row", C.c_int), ("reserved", C.c_int), ("focal_length", C.c_double),
+                ("tr", C.c_double), ("g", C.c_double * 3), ("cauchy_a", C.c_double),
+                ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
+                ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double),
+                ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double)]
+
+
+class SolveSummary(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("num_successful_steps", C.c_int), ("termination", C.c_int), ("reserved", C.c_int),
+                ("initial_cost", C.c_double), ("final_cost", C.c_double), ("cost", C.c_double * MAX_ITER_LOG),
+                ("radius", C.c_double * MAX_ITER_LOG), ("accepted", C.c_int * MAX_ITER_LOG)]
+
+
+def _p(a: np.ndarray, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class PriorData:
+    """numpy-owned storage behind a lfvio_prior."""
+
+    def __init__(self, cap_n: int = 512, cap_blocks: int = 64):
+        self.block_id = np.zeros(cap_blocks, np.int32)
+        self.block_idx = np.zeros(cap_blocks, np.int32)
+        self.x0 = np.zeros(cap_blocks * 9, np.float64)
+        self.J0 = np.zeros(cap_n * cap_n, np.float64)
+        self.r0 = np.zeros(cap_n, np.float64)
+        self.c = Prior(0, 0, _p(self.block_id, C.c_int), _p(self.block_idx, C.c_int), _p(self.x0), _p(self.J0), _p(self.r0),
+                       cap_n, cap_blocks)
+
+    @property
+    def n(self):
+        return self.c.n
+
+    @property
+    def n_blocks(self):
+        return self.c.n_blocks
+
+    def jacobian(self) -> np.ndarray:
+        return self.J0[: self.n * self.n].reshape(self.n, self.n)
+
+    def residual(self) -> np.ndarray:
+        return self.r0[: self.n]
+
+    def information(self):
+        """(J0^T J0, J0^T r0): the invariants of the prior (marginalization_factor.cpp:295-296)."""
+        J, r = self.jacobian(), self.residual()
+        return J.T @ J, J.T @ r
+
+
+class WindowProblem:
+    """One Estimator::optimization() problem in the flat layout of include/lfvio.h (numpy-owned)."""
+
+    def __init__(self, n_frames: int, pose, speed_bias, ex_pose, feature, td, proj: list, imu: list, prior: PriorData | None,
+                 opts: SolverOpts):
+        self.F = n_frames
+        self.pose = np.ascontiguousarray(pose, np.float64).reshape(n_frames, 7).copy()
+        self.sb = np.ascontiguousarray(speed_bias, np.float64).reshape(n_frames, 9).copy()
+        self.ex = np.ascontiguousarray(ex_pose, np.float64).reshape(7).copy()
+        self.feat = np.ascontiguousarray(feature, np.float64).reshape(-1).copy()
+        self.td = np.array([td], np.float64)
+        self.L = self.feat.shape[0]
+        self.proj = (ProjFactor * max(len(proj), 1))(*proj)
+        self.n_proj = len(proj)
+        self.imu = (ImuFactor * max(len(imu), 1))(*imu)
+        self.n_imu = len(imu)
+        self.prior = prior
+        self.opts = opts
+        self._feat_buf = self.feat if self.L > 0 else np.zeros(1)
+
+    def state(self) -> WindowState:
+        return WindowState(self.F, self.L, _p(self.pose), _p(self.sb), _p(self.ex), _p(self._feat_buf), _p(self.td))
+
+    def factors(self) -> FactorList:
+        pr = C.pointer(self.prior.c) if (self.prior is not None and self.prior.n > 0) else None
+        return FactorList(self.n_proj, self.proj, self.n_imu, self.imu, pr)
+
+    def clone(self) -> "WindowProblem":
+        w = WindowProblem.__new__(WindowProblem)
+        w.__dict__.update(self.__dict__)
+        w.pose, w.sb, w.ex, w.feat, w.td = self.pose.copy(), self.sb.copy(), self.ex.copy(), self.feat.copy(), self.td.copy()
+        w._feat_buf = w.feat if w.L > 0 else np.zeros(1)
+        return w
+
+    def state_vector(self) -> np.ndarray:
+        return np.concatenate([self.pose.ravel(), self.sb.ravel(), self.ex, self.feat, self.td])
+
+
+def bind(lib):
+    """Declare the lfvio_window_* prototypes on a loaded liblfvio.so."""
+    lib.lfvio_solver_default_opts.argtypes = [C.POINTER(SolverOpts)]
+    lib.lfvio_solver_default_opts.restype = None
+    lib.lfvio_window_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.lfvio_window_destroy.argtypes = [C.c_void_p]
+    lib.lfvio_window_destroy.restype = None
+    lib.lfvio_window_optimize.argtypes = [C.c_void_p, C.POINTER(WindowState), C.POINTER(FactorList), C.POINTER(SolverOpts),
+                                          C.POINTER(SolveSummary)]
+    lib.lfvio_window_marginalize.argtypes = [C.c_void_p, C.POINTER(WindowState), C.POINTER(FactorList), C.POINTER(SolverOpts),
+                                             C.c_int, C.POINTER(Prior)]
+    lib.lfvio_window_evaluate.argtypes = [C.c_void_p, C.POINTER(WindowState), C.POINTER(FactorList), C.POINTER(SolverOpts),
+                                          C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
+    lib.lfvio_window_stream.argtypes = [C.c_void_p]
+    lib.lfvio_window_stream.restype = C.c_void_p
+    lib.lfvio_window_upload.argtypes = [C.c_void_p, C.POINTER(WindowState), C.POINTER(FactorList), C.POINTER(SolverOpts)]
+    lib.lfvio_window_optimize_dev.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.lfvio_window_download.argtypes = [C.c_void_p, C.POINTER(WindowState), C.POINTER(SolveSummary)]
+
+
+def default_opts(lib) -> SolverOpts:
+    o = SolverOpts()
+    lib.lfvio_solver_default_opts(C.byref(o))
+    return o
+
+
+class EvalResult:
+    def __init__(self, w: WindowProblem):
+        n = w.prior.n if (w.prior is not None) else 0
+        self.res_proj = np.zeros(2 * max(w.n_proj, 1))
+        self.jac_proj = np.zeros(40 * max(w.n_proj, 1))
+        self.res_imu = np.zeros(15 * max(w.n_imu, 1))
+        self.jac_imu = np.zeros(450 * max(w.n_imu, 1))
+        self.res_prior = np.zeros(max(n, 1))
+        self.cost = C.c_double(0)
+        self.n_proj, self.n_imu, self.n_prior = w.n_proj, w.n_imu, n
+
+    def args(self):
+        return (_p(self.res_proj), _p(self.jac_proj), _p(self.res_imu), _p(self.jac_imu), _p(self.res_prior), C.byref(self.cost))
+
+    def trim(self):
+        self.res_proj = self.res_proj[: 2 * self.n_proj]
+        self.jac_proj = self.jac_proj[: 40 * self.n_proj].reshape(-1, 2, 20)
+        self.res_imu = self.res_imu[: 15 * self.n_imu]
+        self.jac_imu = self.jac_imu[: 450 * self.n_imu].reshape(-1, 15, 30)
+        self.res_prior = self.res_prior[: self.n_prior]
+        return self
+
+
+class Window:
+    """lfvio_window handle: Estimator::optimization() on device."""
+
+    def __init__(self, lib, check, window_size: int = 10, max_landmarks: int = 1000, max_proj: int = 16384, device: int = 0):
+        self._lib, self._check = lib, check
+        self._h = C.c_void_p()
+        check(lib.lfvio_window_create(window_size, max_landmarks, max_proj, device, C.byref(self._h)), "lfvio_window_create")
+
+    def close(self):
+        if self._h:
+            self._lib.lfvio_window_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def optimize(self, w: WindowProblem) -> SolveSummary:
+        s = SolveSummary()
+        st, fl = w.state(), w.factors()
+        self._check(self._lib.lfvio_window_optimize(self._h, C.byref(st), C.byref(fl), C.byref(w.opts), C.byref(s)),
+                    "lfvio_window_optimize")
+        return s
+
+    def marginalize(self, w: WindowProblem, flag: int, out: PriorData | None = None) -> PriorData:
+        out = out or PriorData()
+        st, fl = w.state(), w.factors()
+        self._check(self._lib.lfvio_window_marginalize(self._h, C.byref(st), C.byref(fl), C.byref(w.opts), flag, C.byref(out.c)),
+                    "lfvio_window_marginalize")
+        return out
+
+    def evaluate(self, w: WindowProblem, robust: bool = True) -> EvalResult:
+        e = EvalResult(w)
+        st, fl = w.state(), w.factors()
+        self._check(self._lib.lfvio_window_evaluate(self._h, C.byref(st), C.byref(fl), C.byref(w.opts), int(robust), *e.args()),
+                    "lfvio_window_evaluate")
+        return e.trim()
+
+    def upload(self, w: WindowProblem):
+        st, fl = w.state(), w.factors()
+        self._check(self._lib.lfvio_window_upload(self._h, C.byref(st), C.byref(fl), C.byref(w.opts)), "lfvio_window_upload")
+
+    def optimize_dev(self, with_marginalize: bool = True, flag: int = MARGIN_OLD):
+        self._check(self._lib.lfvio_window_optimize_dev(self._h, int(with_marginalize), flag), "lfvio_window_optimize_dev")
+
+    def download(self, w: WindowProblem) -> SolveSummary:
+        s = SolveSummary()
+        st = w.state()
+        self._check(self._lib.lfvio_window_download(self._h, C.byref(st), C.byref(s)), "lfvio_window_download")
+        return s
+
+    @property
+    def stream(self) -> int:
+        return self._lib.lfvio_window_stream(self._h) or 0

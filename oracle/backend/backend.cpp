@@ -1,0 +1,1122 @@
+// ORACLE (test infrastructure only; never linked into liblfvio.so, never called by the product path).
+//
+// Self-contained fp64 restatement of the reference's sliding-window back end, Estimator::optimization()
+// (vins_estimator/src/estimator.cpp:676-1009), for parity checks and as the timed CPU baseline:
+//   eval_projection      <- ProjectionTdFactor::Evaluate  factor/projection_td_factor.cpp:8-151
+//                           ProjectionFactor::Evaluate    factor/projection_factor.cpp:6-121
+//   eval_imu             <- IMUFactor::Evaluate           factor/imu_factor.h:19-200
+//                           IntegrationBase::evaluate     factor/integration_base.h:160-186
+//   eval_prior           <- MarginalizationFactor::Evaluate factor/marginalization_factor.cpp:333-381
+//   pose_plus            <- PoseLocalParameterization::Plus factor/pose_local_parameterization.cpp:3-19
+//   solve()              <- ceres::Solve as configured at estimator.cpp:810-825.  Ceres 1.12.0 (pinned by
+//                           docker/Dockerfile:3) is NOT in the reference tree: its published algorithm is
+//                           restated here — TrustRegionMinimizer + DoglegStrategy(TRADITIONAL_DOGLEG) +
+//                           DENSE_SCHUR with Jacobi scaling, Corrector for CauchyLoss — SURVEY.md App. B.4.
+//   marginalize()        <- estimator.cpp:833-1005 + MarginalizationInfo (marginalization_factor.cpp:89-319)
+//
+// Parity status: the reference has no tests for this path and neither Eigen nor Ceres exist in the build
+// container => "parity unpinned" against the reference binary; pinned by finite-difference Jacobian checks
+// (the reference's own check() convention, projection_td_factor.cpp:153-268), by the identities
+// J0^T J0 = A', J0^T r0 = b' (marginalization_factor.cpp:295-296) and by synthetic windows with known truth.
+// Canonical choices where the reference is non-deterministic: blocks are ordered by id
+// instead of by heap address, iteration count instead of wall-clock budget.
+#include <chrono>
+#include <cstdio>
+#include <map>
+#include <thread>
+
+#include "../../include/lfvio.h"
+#include "smallmat.h"
+
+using namespace ob;
+
+namespace {
+
+constexpr int O_P = 0, O_R = 3, O_V = 6, O_BA = 9, O_BG = 12;
+
+struct Pose {
+    V3 p;
+    Q q;
+};
+inline Pose load_pose(const double *x) { return {V3(x[0], x[1], x[2]), Q(x[6], x[3], x[4], x[5])}; }
+
+// ---------------------------------------------------------------------------------------------
+// projection factors: r[2], J[2][20] = [pose_i 6 | pose_j 6 | ex 6 | lambda | td]
+// ---------------------------------------------------------------------------------------------
+void eval_projection(const lfvio_proj_factor &f, const double *pose_i, const double *pose_j, const double *ex,
+                     double inv_dep_i, double td, const lfvio_solver_opts &o, double *r, double (*J)[20]) {
+    const Pose Pi = load_pose(pose_i), Pj = load_pose(pose_j), Pe = load_pose(ex);
+    const V3 pts_i(f.pts_i[0], f.pts_i[1], f.pts_i[2]), pts_j(f.pts_j[0], f.pts_j[1], f.pts_j[2]);
+    const V3 vel_i(f.vel_i[0], f.vel_i[1], f.vel_i[2]), vel_j(f.vel_j[0], f.vel_j[1], f.vel_j[2]);
+    // tangent basis from the un-shifted pts_j (ctor, projection_td_factor.cpp:23-33)
+    const V3 a = normalized(pts_j);
+    V3 tmp(0, 0, 1);
+    if (a.x == tmp.x && a.y == tmp.y && a.z == tmp.z) tmp = V3(1, 0, 0);
+    const V3 b1 = normalized(tmp - a * dot(a, tmp));
+    const V3 b2 = cross(a, b1);
+    V3 pts_i_td = pts_i, pts_j_td = pts_j;
+    if (o.estimate_td) {
+        const double row_i = f.row_i - o.row / 2, row_j = f.row_j - o.row / 2;  // integer ROW / 2
+        pts_i_td = pts_i - (td - f.td_i + o.tr / o.row * row_i) * vel_i;
+        pts_j_td = pts_j - (td - f.td_j + o.tr / o.row * row_j) * vel_j;
+    }
+    const V3 pts_camera_i = pts_i_td / inv_dep_i;
+    const V3 pts_imu_i = rot(Pe.q, pts_camera_i) + Pe.p;
+    const V3 pts_w = rot(Pi.q, pts_imu_i) + Pi.p;
+    const V3 pts_imu_j = rot(inverse(Pj.q), pts_w - Pj.p);
+    const V3 pts_camera_j = rot(inverse(Pe.q), pts_imu_j - Pe.p);
+    const double sq = o.focal_length / 1.5;  // sqrt_info = FOCAL_LENGTH / 1.5 * Identity (estimator.cpp:18-19)
+    const V3 d = normalized(pts_camera_j) - normalized(pts_j_td);
+    r[0] = sq * dot(b1, d);
+    r[1] = sq * dot(b2, d);
+    if (!J) return;
+    const M3 Ri = to_rot(Pi.q), Rj = to_rot(Pj.q), ric = to_rot(Pe.q);
+    const double n = norm(pts_camera_j);
+    const double x1 = pts_camera_j.x, x2 = pts_camera_j.y, x3 = pts_camera_j.z;
+    const double n3 = std::pow(n, 3);
+    M3 nj;
+    nj(0, 0) = 1.0 / n - x1 * x1 / n3; nj(0, 1) = -x1 * x2 / n3;          nj(0, 2) = -x1 * x3 / n3;
+    nj(1, 0) = -x1 * x2 / n3;          nj(1, 1) = 1.0 / n - x2 * x2 / n3; nj(1, 2) = -x2 * x3 / n3;
+    nj(2, 0) = -x1 * x3 / n3;          nj(2, 1) = -x2 * x3 / n3;          nj(2, 2) = 1.0 / n - x3 * x3 / n3;
+    double reduce[2][3];
+    for (int c = 0; c < 3; c++) {
+        reduce[0][c] = sq * (b1.x * nj(0, c) + b1.y * nj(1, c) + b1.z * nj(2, c));
+        reduce[1][c] = sq * (b2.x * nj(0, c) + b2.y * nj(1, c) + b2.z * nj(2, c));
+    }
+    auto put = [&](int col0, const M3 &A) {  // J[:, col0:col0+3] = reduce * A
+        for (int rr = 0; rr < 2; rr++)
+            for (int c = 0; c < 3; c++)
+                J[rr][col0 + c] = reduce[rr][0] * A(0, c) + reduce[rr][1] * A(1, c) + reduce[rr][2] * A(2, c);
+    };
+    const M3 ricT = transpose(ric), RjT = transpose(Rj);
+    const M3 A = ricT * RjT;
+    put(0, A);                                        // d/dPi
+    put(3, A * Ri * (-skew(pts_imu_i)));              // d/dtheta_i
+    put(6, ricT * (-RjT));                            // d/dPj
+    put(9, ricT * skew(pts_imu_j));                   // d/dtheta_j
+    put(12, ricT * (RjT * Ri - M3::identity()));      // d/dtic
+    const M3 tmp_r = A * Ri * ric;
+    put(15, (-tmp_r) * skew(pts_camera_i) + skew(tmp_r * pts_camera_i) +
+                skew(ricT * (RjT * (Ri * Pe.p + Pi.p - Pj.p) - Pe.p)));  // d/dtheta_ic
+    const V3 dl = (tmp_r * pts_i_td) * (-1.0 / (inv_dep_i * inv_dep_i));
+    const V3 dt = (tmp_r * vel_i) * (-1.0 / inv_dep_i);
+    for (int rr = 0; rr < 2; rr++) {
+        J[rr][18] = reduce[rr][0] * dl.x + reduce[rr][1] * dl.y + reduce[rr][2] * dl.z;
+        J[rr][19] = 0.0;
+        if (o.estimate_td)  // reduce * R * vel_i / lambda * -1 + sqrt_info * velocity_j.head(2)  (:140-146, as is)
+            J[rr][19] = reduce[rr][0] * dt.x + reduce[rr][1] * dt.y + reduce[rr][2] * dt.z + sq * (rr == 0 ? vel_j.x : vel_j.y);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// IMU factors: r[15], J[15][30] = [pose_i 6 | sb_i 9 | pose_j 6 | sb_j 9]
+// ---------------------------------------------------------------------------------------------
+bool imu_sqrt_info(const lfvio_imu_factor &f, Mat &sqrt_info) {
+    // Eigen::LLT<..>(covariance.inverse()).matrixL().transpose()   (imu_factor.h:64)
+    Mat cov(15, 15), inv;
+    for (int i = 0; i < 225; i++) cov.a[i] = f.covariance[i];
+    if (!invert(cov, inv)) return false;
+    if (!cholesky_lower(inv)) return false;
+    sqrt_info = Mat(15, 15);
+    for (int i = 0; i < 15; i++)
+        for (int j = 0; j < 15; j++) sqrt_info(i, j) = inv(j, i);
+    return true;
+}
+
+inline M3 jac_block(const lfvio_imu_factor &f, int r0, int c0) {
+    M3 m;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) m(i, j) = f.jacobian[(r0 + i) * 15 + c0 + j];
+    return m;
+}
+
+void eval_imu(const lfvio_imu_factor &f, const Mat &sqrt_info, const double *pose_i, const double *sb_i,
+              const double *pose_j, const double *sb_j, const lfvio_solver_opts &o, double *r, double (*J)[30]) {
+    const Pose Pi = load_pose(pose_i), Pj = load_pose(pose_j);
+    const V3 Vi(sb_i[0], sb_i[1], sb_i[2]), Bai(sb_i[3], sb_i[4], sb_i[5]), Bgi(sb_i[6], sb_i[7], sb_i[8]);
+    const V3 Vj(sb_j[0], sb_j[1], sb_j[2]), Baj(sb_j[3], sb_j[4], sb_j[5]), Bgj(sb_j[6], sb_j[7], sb_j[8]);
+    const V3 G(o.g[0], o.g[1], o.g[2]);
+    const double sum_dt = f.sum_dt;
+    const M3 dp_dba = jac_block(f, O_P, O_BA), dp_dbg = jac_block(f, O_P, O_BG), dq_dbg = jac_block(f, O_R, O_BG);
+    const M3 dv_dba = jac_block(f, O_V, O_BA), dv_dbg = jac_block(f, O_V, O_BG);
+    const V3 dba = Bai - V3(f.linearized_ba[0], f.linearized_ba[1], f.linearized_ba[2]);
+    const V3 dbg = Bgi - V3(f.linearized_bg[0], f.linearized_bg[1], f.linearized_bg[2]);
+    const Q delta_q(f.delta_q[0], f.delta_q[1], f.delta_q[2], f.delta_q[3]);
+    const V3 delta_p(f.delta_p[0], f.delta_p[1], f.delta_p[2]), delta_v(f.delta_v[0], f.delta_v[1], f.delta_v[2]);
+    const Q corrected_delta_q = delta_q * ::delta_q(dq_dbg * dbg);
+    const V3 corrected_delta_v = delta_v + dv_dba * dba + dv_dbg * dbg;
+    const V3 corrected_delta_p = delta_p + dp_dba * dba + dp_dbg * dbg;
+    const Q Qi_inv = inverse(Pi.q);
+    double raw[15];
+    const V3 rp = rot(Qi_inv, 0.5 * G * sum_dt * sum_dt + Pj.p - Pi.p - Vi * sum_dt) - corrected_delta_p;
+    const V3 rq = 2.0 * (inverse(corrected_delta_q) * (Qi_inv * Pj.q)).vec();
+    const V3 rv = rot(Qi_inv, G * sum_dt + Vj - Vi) - corrected_delta_v;
+    const V3 rba = Baj - Bai, rbg = Bgj - Bgi;
+    for (int k = 0; k < 3; k++) {
+        raw[O_P + k] = rp[k];
+        raw[O_R + k] = rq[k];
+        raw[O_V + k] = rv[k];
+        raw[O_BA + k] = rba[k];
+        raw[O_BG + k] = rbg[k];
+    }
+    for (int i = 0; i < 15; i++) {
+        double s = 0;
+        for (int k = 0; k < 15; k++) s += sqrt_info(i, k) * raw[k];
+        r[i] = s;
+    }
+    if (!J) return;
+    double Jr[15][30];
+    std::memset(Jr, 0, sizeof(Jr));
+    auto put = [&](int r0, int c0, const M3 &A) {
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) Jr[r0 + i][c0 + j] = A(i, j);
+    };
+    const M3 RiT = to_rot(Qi_inv);
+    auto br_of_product = [&](const Q &ql, const Q &qr) {  // (Qleft(ql) * Qright(qr)).bottomRightCorner<3,3>()
+        double L[4][4], R[4][4];
+        qleft4(ql, L);
+        qright4(qr, R);
+        M3 out;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                double s = 0;
+                for (int k = 0; k < 4; k++) s += L[i + 1][k] * R[k][j + 1];
+                out(i, j) = s;
+            }
+        return out;
+    };
+    // pose_i (cols 0..5)
+    put(O_P, 0, -RiT);
+    put(O_P, 3, skew(rot(Qi_inv, 0.5 * G * sum_dt * sum_dt + Pj.p - Pi.p - Vi * sum_dt)));
+    put(O_R, 3, -br_of_product(inverse(Pj.q) * Pi.q, corrected_delta_q));
+    put(O_V, 3, skew(rot(Qi_inv, G * sum_dt + Vj - Vi)));
+    // speed-bias_i (cols 6..14)
+    put(O_P, 6, (-sum_dt) * RiT);
+    put(O_P, 9, -dp_dba);
+    put(O_P, 12, -dp_dbg);
+    put(O_R, 12, -(qleft_br(inverse(Pj.q) * Pi.q * delta_q) * dq_dbg));
+    put(O_V, 6, -RiT);
+    put(O_V, 9, -dv_dba);
+    put(O_V, 12, -dv_dbg);
+    put(O_BA, 9, -M3::identity());
+    put(O_BG, 12, -M3::identity());
+    // pose_j (cols 15..20)
+    put(O_P, 15, RiT);
+    put(O_R, 18, qleft_br(inverse(corrected_delta_q) * Qi_inv * Pj.q));
+    // speed-bias_j (cols 21..29)
+    put(O_V, 21, RiT);
+    put(O_BA, 24, M3::identity());
+    put(O_BG, 27, M3::identity());
+    for (int i = 0; i < 15; i++)
+        for (int c = 0; c < 30; c++) {
+            double s = 0;
+            for (int k = 0; k < 15; k++) s += sqrt_info(i, k) * Jr[k][c];
+            J[i][c] = s;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// parameter-block bookkeeping
+// ---------------------------------------------------------------------------------------------
+struct Layout {
+    int F, L;
+    int D;  // reduced (non-landmark) local dimension: 15 F + 6 + 1
+    int col_pose(int f) const { return 15 * f; }
+    int col_sb(int f) const { return 15 * f + 6; }
+    int col_ex() const { return 15 * F; }
+    int col_td() const { return 15 * F + 6; }
+    int block_col(int id) const {  // parameter-block id -> first local column
+        if (id < 2 * F) return (id & 1) ? col_sb(id >> 1) : col_pose(id >> 1);
+        return id == 2 * F ? col_ex() : col_td();
+    }
+    int block_gsize(int id) const { return id < 2 * F ? ((id & 1) ? 9 : 7) : (id == 2 * F ? 7 : 1); }
+    int block_lsize(int id) const { return id < 2 * F ? ((id & 1) ? 9 : 6) : (id == 2 * F ? 6 : 1); }
+};
+
+struct State {
+    std::vector<double> pose, sb, ex, feat;
+    double td;
+    const double *block(const Layout &lay, int id) const {
+        if (id < 2 * lay.F) return (id & 1) ? &sb[9 * (id >> 1)] : &pose[7 * (id >> 1)];
+        return id == 2 * lay.F ? ex.data() : &td;
+    }
+};
+
+State load_state(const lfvio_window_state &s) {
+    State st;
+    st.pose.assign(s.para_Pose, s.para_Pose + 7 * s.n_frames);
+    st.sb.assign(s.para_SpeedBias, s.para_SpeedBias + 9 * s.n_frames);
+    st.ex.assign(s.para_Ex_Pose, s.para_Ex_Pose + 7);
+    st.feat.assign(s.para_Feature, s.para_Feature + s.n_landmarks);
+    st.td = s.para_Td[0];
+    return st;
+}
+void store_state(const State &st, lfvio_window_state &s) {
+    std::copy(st.pose.begin(), st.pose.end(), s.para_Pose);
+    std::copy(st.sb.begin(), st.sb.end(), s.para_SpeedBias);
+    std::copy(st.ex.begin(), st.ex.end(), s.para_Ex_Pose);
+    std::copy(st.feat.begin(), st.feat.end(), s.para_Feature);
+    s.para_Td[0] = st.td;
+}
+
+// PoseLocalParameterization::Plus
+void pose_plus(const double *x, const double *d, double *out) {
+    out[0] = x[0] + d[0];
+    out[1] = x[1] + d[1];
+    out[2] = x[2] + d[2];
+    const Q q(x[6], x[3], x[4], x[5]);
+    const Q nq = normalized(q * delta_q(V3(d[3], d[4], d[5])));
+    out[3] = nq.x;
+    out[4] = nq.y;
+    out[5] = nq.z;
+    out[6] = nq.w;
+}
+
+// MarginalizationFactor::Evaluate residual part: r = r0 + J0 * dx
+void prior_dx(const lfvio_prior &p, const Layout &lay, const State &st, std::vector<double> &dx) {
+    dx.assign(p.n, 0.0);
+    int off = 0;
+    for (int b = 0; b < p.n_blocks; b++) {
+        const int id = p.block_id[b], size = lay.block_gsize(id), idx = p.block_idx[b];
+        const double *x = st.block(lay, id), *x0 = p.x0 + off;
+        if (size != 7) {
+            for (int k = 0; k < size; k++) dx[idx + k] = x[k] - x0[k];
+        } else {
+            for (int k = 0; k < 3; k++) dx[idx + k] = x[k] - x0[k];
+            const Q dq = inverse(Q(x0[6], x0[3], x0[4], x0[5])) * Q(x[6], x[3], x[4], x[5]);
+            const double s = (dq.w >= 0) ? 2.0 : -2.0;
+            dx[idx + 3] = s * dq.x;
+            dx[idx + 4] = s * dq.y;
+            dx[idx + 5] = s * dq.z;
+        }
+        off += size;
+    }
+}
+void eval_prior(const lfvio_prior &p, const Layout &lay, const State &st, double *r) {
+    std::vector<double> dx;
+    prior_dx(p, lay, st, dx);
+    for (int i = 0; i < p.n; i++) {
+        double s = p.r0[i];
+        for (int k = 0; k < p.n; k++) s += p.J0[(size_t)i * p.n + k] * dx[k];
+        r[i] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// whole-problem evaluation (Ceres evaluator + Corrector)
+// ---------------------------------------------------------------------------------------------
+struct Eval {
+    std::vector<double> rp;    // 2 R
+    std::vector<double> Jp;    // 2 x 20 per factor
+    std::vector<double> ri;    // 15 NI
+    std::vector<double> Ji;    // 15 x 30 per factor
+    std::vector<double> rm;    // prior n
+    double cost = 0;
+};
+
+struct Problem {
+    Layout lay;
+    lfvio_solver_opts o;
+    const lfvio_factor_list *fl;
+    std::vector<Mat> sqrt_info;  // per IMU factor, hoisted (covariance is constant during a solve)
+    std::vector<char> imu_active;
+    bool ok = true;
+};
+
+Problem make_problem(const lfvio_window_state &s, const lfvio_factor_list &fl, const lfvio_solver_opts &o) {
+    Problem P;
+    P.lay.F = s.n_frames;
+    P.lay.L = s.n_landmarks;
+    P.lay.D = 15 * s.n_frames + 7;
+    P.o = o;
+    P.fl = &fl;
+    P.sqrt_info.resize(fl.n_imu);
+    P.imu_active.assign(fl.n_imu, 1);
+    for (int k = 0; k < fl.n_imu; k++) {
+        if (fl.imu[k].sum_dt > 10.0) {  // estimator.cpp:720-721
+            P.imu_active[k] = 0;
+            continue;
+        }
+        if (!imu_sqrt_info(fl.imu[k], P.sqrt_info[k])) P.ok = false;
+    }
+    return P;
+}
+
+void evaluate(const Problem &P, const State &st, bool want_jac, bool robust, Eval &E) {
+    const lfvio_factor_list &fl = *P.fl;
+    E.rp.assign(2 * (size_t)fl.n_proj, 0.0);
+    E.ri.assign(15 * (size_t)fl.n_imu, 0.0);
+    if (want_jac) {
+        E.Jp.assign(40 * (size_t)fl.n_proj, 0.0);
+        E.Ji.assign(450 * (size_t)fl.n_imu, 0.0);
+    }
+    double cost = 0;
+    if (fl.prior && fl.prior->n > 0) {
+        E.rm.assign(fl.prior->n, 0.0);
+        eval_prior(*fl.prior, P.lay, st, E.rm.data());
+        for (double v : E.rm) cost += 0.5 * v * v;
+    } else {
+        E.rm.clear();
+    }
+    for (int k = 0; k < fl.n_imu; k++) {
+        if (!P.imu_active[k]) continue;
+        const int i = fl.imu[k].frame_i, j = i + 1;
+        eval_imu(fl.imu[k], P.sqrt_info[k], &st.pose[7 * i], &st.sb[9 * i], &st.pose[7 * j], &st.sb[9 * j], P.o,
+                 &E.ri[15 * k], want_jac ? reinterpret_cast<double(*)[30]>(&E.Ji[450 * (size_t)k]) : nullptr);
+        for (int q = 0; q < 15; q++) cost += 0.5 * E.ri[15 * k + q] * E.ri[15 * k + q];
+    }
+    const double b = P.o.cauchy_a * P.o.cauchy_a, c = 1.0 / b;
+    for (int k = 0; k < fl.n_proj; k++) {
+        const lfvio_proj_factor &f = fl.proj[k];
+        double *r = &E.rp[2 * (size_t)k];
+        double(*J)[20] = want_jac ? reinterpret_cast<double(*)[20]>(&E.Jp[40 * (size_t)k]) : nullptr;
+        eval_projection(f, &st.pose[7 * f.frame_i], &st.pose[7 * f.frame_j], st.ex.data(), st.feat[f.landmark], st.td, P.o, r, J);
+        const double sq_norm = r[0] * r[0] + r[1] * r[1];
+        if (robust) {
+            // ceres::CauchyLoss: rho = b log(1 + s c), rho' = 1 / (1 + s c), rho'' = -c rho'^2 <= 0
+            // => Corrector takes the (rho[2] <= 0) branch: residual and Jacobian scaled by sqrt(rho')
+            const double sum = 1.0 + sq_norm * c, inv = 1.0 / sum;
+            cost += 0.5 * b * std::log(sum);
+            const double sr = std::sqrt(inv);
+            r[0] *= sr;
+            r[1] *= sr;
+            if (J)
+                for (int q = 0; q < 20; q++) {
+                    J[0][q] *= sr;
+                    J[1][q] *= sr;
+                }
+        } else {
+            cost += 0.5 * sq_norm;
+        }
+    }
+    E.cost = cost;
+}
+
+// Apply a local step (size D + L, ordering [reduced params | landmarks]) : x_plus_delta = Plus(x, delta)
+void apply_step(const Problem &P, const State &x, const std::vector<double> &delta, State &out) {
+    const Layout &lay = P.lay;
+    out = x;
+    for (int f = 0; f < lay.F; f++) {
+        pose_plus(&x.pose[7 * f], &delta[lay.col_pose(f)], &out.pose[7 * f]);
+        for (int k = 0; k < 9; k++) out.sb[9 * f + k] = x.sb[9 * f + k] + delta[lay.col_sb(f) + k];
+    }
+    if (P.o.estimate_extrinsic) pose_plus(x.ex.data(), &delta[lay.col_ex()], out.ex.data());
+    if (P.o.estimate_td) out.td = x.td + delta[lay.col_td()];
+    for (int l = 0; l < lay.L; l++) out.feat[l] = x.feat[l] + delta[lay.D + l];
+}
+
+double global_norm_diff(const Problem &P, const State &a, const State *b) {
+    double s = 0;
+    auto acc = [&](const std::vector<double> &u, const std::vector<double> *v) {
+        for (size_t i = 0; i < u.size(); i++) {
+            const double d = v ? u[i] - (*v)[i] : u[i];
+            s += d * d;
+        }
+    };
+    acc(a.pose, b ? &b->pose : nullptr);
+    acc(a.sb, b ? &b->sb : nullptr);
+    if (P.o.estimate_extrinsic) acc(a.ex, b ? &b->ex : nullptr);
+    acc(a.feat, b ? &b->feat : nullptr);
+    if (P.o.estimate_td) {
+        const double d = b ? a.td - b->td : a.td;
+        s += d * d;
+    }
+    return std::sqrt(s);
+}
+
+// Visit every (residual row, local column, value) of the (un-scaled) Jacobian.
+template <class Fn>
+void for_each_jacobian_entry(const Problem &P, const Eval &E, Fn fn) {
+    const Layout &lay = P.lay;
+    const lfvio_factor_list &fl = *P.fl;
+    int row = 0;
+    if (fl.prior && fl.prior->n > 0) {
+        const lfvio_prior &p = *fl.prior;
+        for (int i = 0; i < p.n; i++)
+            for (int b = 0; b < p.n_blocks; b++) {
+                const int id = p.block_id[b], ls = lay.block_lsize(id), c0 = lay.block_col(id), idx = p.block_idx[b];
+                for (int k = 0; k < ls; k++) fn(row + i, c0 + k, p.J0[(size_t)i * p.n + idx + k]);
+            }
+        row += p.n;
+    }
+    for (int k = 0; k < fl.n_imu; k++) {
+        if (P.imu_active[k]) {
+            const int i = fl.imu[k].frame_i, j = i + 1;
+            const int cols[4] = {lay.col_pose(i), lay.col_sb(i), lay.col_pose(j), lay.col_sb(j)};
+            const int off[4] = {0, 6, 15, 21}, sz[4] = {6, 9, 6, 9};
+            for (int r = 0; r < 15; r++)
+                for (int b = 0; b < 4; b++)
+                    for (int q = 0; q < sz[b]; q++) fn(row + r, cols[b] + q, E.Ji[450 * (size_t)k + 30 * r + off[b] + q]);
+        }
+        row += 15;
+    }
+    for (int k = 0; k < fl.n_proj; k++) {
+        const lfvio_proj_factor &f = fl.proj[k];
+        for (int r = 0; r < 2; r++) {
+            const double *J = &E.Jp[40 * (size_t)k + 20 * r];
+            for (int q = 0; q < 6; q++) fn(row + r, lay.col_pose(f.frame_i) + q, J[q]);
+            for (int q = 0; q < 6; q++) fn(row + r, lay.col_pose(f.frame_j) + q, J[6 + q]);
+            if (P.o.estimate_extrinsic)
+                for (int q = 0; q < 6; q++) fn(row + r, lay.col_ex() + q, J[12 + q]);
+            fn(row + r, lay.D + f.landmark, J[18]);
+            if (P.o.estimate_td) fn(row + r, lay.col_td(), J[19]);
+        }
+        row += 2;
+    }
+}
+
+void residual_vector(const Problem &P, const Eval &E, std::vector<double> &r) {
+    r.clear();
+    r.insert(r.end(), E.rm.begin(), E.rm.end());
+    r.insert(r.end(), E.ri.begin(), E.ri.end());
+    r.insert(r.end(), E.rp.begin(), E.rp.end());
+}
+
+struct Summary {
+    std::vector<double> cost, radius;
+    std::vector<int> accepted;
+    int termination = 0, successful = 0;
+};
+
+// ceres::Solve: TrustRegionMinimizer + DoglegStrategy(TRADITIONAL) + DENSE_SCHUR
+void solve(const Problem &P, State &x, Summary &sum) {
+    const Layout &lay = P.lay;
+    const lfvio_solver_opts &o = P.o;
+    const int D = lay.D, L = lay.L, N = D + L;
+    Eval E;
+    evaluate(P, x, true, true, E);
+    double cost = E.cost;
+    sum.cost.push_back(cost);
+    sum.radius.push_back(o.initial_trust_region_radius);
+    sum.accepted.push_back(1);
+    std::vector<double> r;
+    // Jacobi scaling, computed once at the initial point: scale = 1 / (1 + sqrt(sum J_ij^2))
+    std::vector<double> scale(N, 0.0);
+    for_each_jacobian_entry(P, E, [&](int, int c, double v) { scale[c] += v * v; });
+    for (int c = 0; c < N; c++) scale[c] = 1.0 / (1.0 + std::sqrt(scale[c]));
+    double x_norm = global_norm_diff(P, x, nullptr);
+    // DoglegStrategy state
+    double radius = o.initial_trust_region_radius, mu = 1e-8;
+    const double min_mu = 1e-8, max_mu = 1.0, mu_increase = 10.0;
+    bool reuse = false;
+    double dogleg_step_norm = 0, alpha = 0;
+    std::vector<double> diagonal(N), gradient(N), gn(N), step(N), delta(N);
+    int invalid_in_a_row = 0;
+    // gradient max-norm convergence at the start
+    {
+        residual_vector(P, E, r);
+        std::vector<double> g(N, 0.0);
+        for_each_jacobian_entry(P, E, [&](int row, int c, double v) { g[c] += v * r[row]; });
+        double gmax = 0;
+        for (double v : g) gmax = std::max(gmax, std::fabs(v));
+        if (!o.fixed_iterations && gmax <= o.gradient_tolerance) {
+            sum.termination = 1;
+            return;
+        }
+    }
+    for (int iter = 1; iter <= o.max_num_iterations; iter++) {
+        bool step_valid = true;
+        residual_vector(P, E, r);
+        if (!reuse) {
+            reuse = true;
+            // diagonal_ = sqrt(clamp(column norms^2 of the SCALED Jacobian, 1e-6, 1e32))
+            std::fill(diagonal.begin(), diagonal.end(), 0.0);
+            std::fill(gradient.begin(), gradient.end(), 0.0);
+            for_each_jacobian_entry(P, E, [&](int row, int c, double v) {
+                const double vs = v * scale[c];
+                diagonal[c] += vs * vs;
+                gradient[c] += vs * r[row];
+            });
+            for (int c = 0; c < N; c++) diagonal[c] = std::sqrt(std::min(std::max(diagonal[c], 1e-6), 1e32));
+            for (int c = 0; c < N; c++) gradient[c] /= diagonal[c];
+            // Cauchy point: alpha = |g|^2 / |J (g / diag)|^2
+            {
+                std::vector<double> Jg(r.size(), 0.0);
+                for_each_jacobian_entry(P, E, [&](int row, int c, double v) { Jg[row] += v * scale[c] * (gradient[c] / diagonal[c]); });
+                double gg = 0, jj = 0;
+                for (double v : gradient) gg += v * v;
+                for (double v : Jg) jj += v * v;
+                alpha = gg / jj;
+            }
+            // Gauss-Newton step through the Schur complement, with the LM regulariser diag * sqrt(mu)
+            bool solved = false;
+            while (mu < max_mu) {
+                Mat S(D, D);
+                std::vector<double> rhs(D, 0.0), c_l(L, 0.0), g_l(L, 0.0);
+                Mat W(L, D);  // row l: J_p^T j_lambda for landmark l
+                // normal equations of [J; D]: accumulate factor by factor
+                {
+                    // dense accumulation through per-row sparse lists keeps the restatement simple
+                    std::vector<std::vector<std::pair<int, double>>> rows(r.size());
+                    for_each_jacobian_entry(P, E, [&](int row, int c, double v) {
+                        if (v != 0.0) rows[row].push_back({c, v * scale[c]});
+                    });
+                    for (size_t row = 0; row < rows.size(); row++) {
+                        const auto &e = rows[row];
+                        for (size_t a = 0; a < e.size(); a++) {
+                            const int ca = e[a].first;
+                            const double va = e[a].second;
+                            if (ca >= D) {
+                                c_l[ca - D] += va * va;
+                                g_l[ca - D] += va * r[row];
+                                for (size_t b2 = 0; b2 < e.size(); b2++)
+                                    if (e[b2].first < D) W(ca - D, e[b2].first) += va * e[b2].second;
+                            } else {
+                                rhs[ca] += va * r[row];
+                                for (size_t b2 = 0; b2 < e.size(); b2++)
+                                    if (e[b2].first < D) S(ca, e[b2].first) += va * e[b2].second;
+                            }
+                        }
+                    }
+                }
+                for (int c = 0; c < D; c++) S(c, c) += diagonal[c] * diagonal[c] * mu;
+                for (int l = 0; l < L; l++) c_l[l] += diagonal[D + l] * diagonal[D + l] * mu;
+                for (int l = 0; l < L; l++) {
+                    const double inv = 1.0 / c_l[l];
+                    for (int a = 0; a < D; a++) {
+                        const double wa = W(l, a);
+                        if (wa == 0.0) continue;
+                        rhs[a] -= wa * g_l[l] * inv;
+                        for (int b2 = 0; b2 < D; b2++) S(a, b2) -= wa * W(l, b2) * inv;
+                    }
+                }
+                Mat Lc = S;
+                if (!cholesky_lower(Lc)) {
+                    mu *= mu_increase;
+                    continue;
+                }
+                std::vector<double> y = rhs;
+                chol_solve(Lc, y);
+                bool finite = true;
+                for (int c = 0; c < D; c++) {
+                    gn[c] = y[c];
+                    finite &= std::isfinite(y[c]);
+                }
+                for (int l = 0; l < L; l++) {
+                    double s = g_l[l];
+                    for (int a = 0; a < D; a++) s -= W(l, a) * y[a];
+                    gn[D + l] = s / c_l[l];
+                    finite &= std::isfinite(gn[D + l]);
+                }
+                if (!finite) {
+                    mu *= mu_increase;
+                    continue;
+                }
+                solved = true;
+                break;
+            }
+            if (!solved) {
+                step_valid = false;
+            } else {
+                for (int c = 0; c < N; c++) gn[c] *= -diagonal[c];  // scaled GN step: D * (-(J^T J)^-1 g)
+            }
+        }
+        if (step_valid) {
+            // traditional dogleg interpolation
+            double gnorm = 0, gnn = 0, gdot = 0;
+            for (int c = 0; c < N; c++) {
+                gnorm += gradient[c] * gradient[c];
+                gnn += gn[c] * gn[c];
+                gdot += gradient[c] * gn[c];
+            }
+            gnorm = std::sqrt(gnorm);
+            gnn = std::sqrt(gnn);
+            if (gnn <= radius) {
+                for (int c = 0; c < N; c++) step[c] = gn[c];
+                dogleg_step_norm = gnn;
+            } else if (gnorm * alpha >= radius) {
+                for (int c = 0; c < N; c++) step[c] = -(radius / gnorm) * gradient[c];
+                dogleg_step_norm = radius;
+            } else {
+                const double b_dot_a = -alpha * gdot;
+                const double a_sq = std::pow(alpha * gnorm, 2.0);
+                const double bma_sq = a_sq - 2 * b_dot_a + std::pow(gnn, 2);
+                const double cc = b_dot_a - a_sq;
+                const double dd = std::sqrt(cc * cc + bma_sq * (std::pow(radius, 2.0) - a_sq));
+                const double beta = (cc <= 0) ? (dd - cc) / bma_sq : (radius * radius - a_sq) / (dd + cc);
+                double sn = 0;
+                for (int c = 0; c < N; c++) {
+                    step[c] = (-alpha * (1.0 - beta)) * gradient[c] + beta * gn[c];
+                    sn += step[c] * step[c];
+                }
+                dogleg_step_norm = std::sqrt(sn);
+            }
+            for (int c = 0; c < N; c++) step[c] /= diagonal[c];
+            // model_cost_change = -(J step) . (r + J step / 2)
+            std::vector<double> Js(r.size(), 0.0);
+            for_each_jacobian_entry(P, E, [&](int row, int c, double v) { Js[row] += v * scale[c] * step[c]; });
+            double model_cost_change = 0;
+            for (size_t q = 0; q < r.size(); q++) model_cost_change -= Js[q] * (r[q] + Js[q] / 2.0);
+            if (!(model_cost_change > 0.0)) step_valid = false;
+            bool successful = false;
+            double relative_decrease = 0;
+            State xp;
+            Eval En;
+            if (step_valid) {
+                invalid_in_a_row = 0;
+                for (int c = 0; c < N; c++) delta[c] = step[c] * scale[c];
+                apply_step(P, x, delta, xp);
+                evaluate(P, xp, false, true, En);
+                if (!std::isfinite(En.cost)) {
+                    step_valid = false;
+                } else {
+                    const double step_norm = global_norm_diff(P, x, &xp);
+                    if (!o.fixed_iterations && step_norm <= o.parameter_tolerance * (x_norm + o.parameter_tolerance)) {
+                        sum.termination = 1;
+                        return;
+                    }
+                    const double cost_change = cost - En.cost;
+                    if (!o.fixed_iterations && std::fabs(cost_change) <= o.function_tolerance * cost) {
+                        // Ceres 1.12 takes the step into account only if it is successful; the termination
+                        // itself does not move x (TrustRegionMinimizer returns before accepting)
+                        sum.termination = 1;
+                        return;
+                    }
+                    relative_decrease = cost_change / model_cost_change;
+                    successful = relative_decrease > o.min_relative_decrease;
+                }
+            }
+            if (successful) {
+                // StepAccepted
+                if (relative_decrease < 0.25) radius *= 0.5;
+                if (relative_decrease > 0.75) radius = std::max(radius, 3.0 * dogleg_step_norm);
+                radius = std::min(radius, o.max_trust_region_radius);
+                mu = std::max(min_mu, 2.0 * mu / mu_increase);
+                reuse = false;
+                x = xp;
+                x_norm = global_norm_diff(P, x, nullptr);
+                evaluate(P, x, true, true, E);
+                cost = E.cost;
+                sum.successful++;
+                sum.cost.push_back(cost);
+                sum.radius.push_back(radius);
+                sum.accepted.push_back(1);
+                // gradient tolerance
+                residual_vector(P, E, r);
+                std::vector<double> g(N, 0.0);
+                for_each_jacobian_entry(P, E, [&](int row, int c, double v) { g[c] += v * r[row]; });
+                double gmax = 0;
+                for (double v : g) gmax = std::max(gmax, std::fabs(v));
+                if (!o.fixed_iterations && gmax <= o.gradient_tolerance) {
+                    sum.termination = 1;
+                    return;
+                }
+                continue;
+            }
+            if (step_valid) {  // StepRejected
+                radius *= 0.5;
+                reuse = true;
+            }
+        }
+        if (!step_valid) {  // StepIsInvalid
+            mu *= mu_increase;
+            reuse = false;
+            if (++invalid_in_a_row >= 5) {
+                sum.termination = -1;
+                return;
+            }
+        }
+        sum.cost.push_back(cost);
+        sum.radius.push_back(radius);
+        sum.accepted.push_back(0);
+        if (radius < o.min_trust_region_radius) {
+            sum.termination = 1;
+            return;
+        }
+    }
+    sum.termination = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// marginalisation
+// ---------------------------------------------------------------------------------------------
+struct MargBlock {
+    int id, gsize, lsize, idx;
+};
+
+// Returns false when there is nothing to marginalise.
+bool marginalize(const Problem &P, const State &st, int flag, int n_threads, std::vector<MargBlock> &kept, Mat &J0,
+                 std::vector<double> &r0, std::vector<double> &x0, int &m_out) {
+    const Layout &lay = P.lay;
+    const lfvio_factor_list &fl = *P.fl;
+    const int F = lay.F;
+    const bool have_prior = fl.prior && fl.prior->n > 0;
+    // ---- which factors, which blocks are dropped (estimator.cpp:833-1005) ----
+    std::map<int, int> is_drop;  // id -> 1 if marginalised (ordered map: canonical order by id)
+    auto touch = [&](int id, bool drop) {
+        auto it = is_drop.find(id);
+        if (it == is_drop.end()) is_drop[id] = drop ? 1 : 0;
+        else if (drop) it->second = 1;
+    };
+    const int LM0 = 2 * F + 2;  // landmark ids
+    std::vector<int> proj_sel, imu_sel;
+    bool use_prior = false;
+    if (flag == LFVIO_MARGIN_OLD) {
+        if (have_prior) {
+            use_prior = true;
+            for (int b = 0; b < fl.prior->n_blocks; b++) touch(fl.prior->block_id[b], fl.prior->block_id[b] == 0 || fl.prior->block_id[b] == 1);
+        }
+        for (int k = 0; k < fl.n_imu; k++)
+            if (fl.imu[k].frame_i == 0 && fl.imu[k].sum_dt < 10.0) {
+                imu_sel.push_back(k);
+                touch(0, true);
+                touch(1, true);
+                touch(2, false);
+                touch(3, false);
+            }
+        for (int k = 0; k < fl.n_proj; k++)
+            if (fl.proj[k].frame_i == 0) {
+                proj_sel.push_back(k);
+                touch(0, true);
+                touch(2 * fl.proj[k].frame_j, false);
+                touch(2 * F, false);
+                touch(LM0 + fl.proj[k].landmark, true);
+                if (P.o.estimate_td) touch(2 * F + 1, false);
+            }
+    } else {
+        const int drop_id = 2 * (F - 2);  // para_Pose[WINDOW_SIZE - 1]
+        bool found = false;
+        if (have_prior)
+            for (int b = 0; b < fl.prior->n_blocks; b++) found |= (fl.prior->block_id[b] == drop_id);
+        if (!found) return false;
+        use_prior = true;
+        for (int b = 0; b < fl.prior->n_blocks; b++) touch(fl.prior->block_id[b], fl.prior->block_id[b] == drop_id);
+    }
+    if (is_drop.empty()) return false;
+    auto gsz = [&](int id) { return id >= LM0 ? 1 : lay.block_gsize(id); };
+    auto lsz = [&](int id) { return id >= LM0 ? 1 : lay.block_lsize(id); };
+    std::map<int, int> idx;  // id -> local offset; marginalised blocks first, each group in id order
+    int pos = 0;
+    for (auto &kv : is_drop)
+        if (kv.second) {
+            idx[kv.first] = pos;
+            pos += lsz(kv.first);
+        }
+    const int m = pos;
+    for (auto &kv : is_drop)
+        if (!kv.second) {
+            idx[kv.first] = pos;
+            pos += lsz(kv.first);
+        }
+    const int n = pos - m;
+    // ---- A = sum J^T J, b = sum J^T r over the selected factors (ResidualBlockInfo::Evaluate + ThreadsConstructA)
+    struct Entry {
+        std::vector<double> r;                 // residuals
+        std::vector<int> col;                  // global column of each local jacobian column
+        std::vector<double> J;                 // rows x cols row-major
+    };
+    std::vector<Entry> entries;
+    if (use_prior) {
+        const lfvio_prior &p = *fl.prior;
+        Entry e;
+        e.r.assign(p.n, 0.0);
+        eval_prior(p, lay, st, e.r.data());
+        for (int b = 0; b < p.n_blocks; b++)
+            for (int k = 0; k < lay.block_lsize(p.block_id[b]); k++) e.col.push_back(idx[p.block_id[b]] + k);
+        e.J.assign((size_t)p.n * e.col.size(), 0.0);
+        for (int i = 0; i < p.n; i++) {
+            int cc = 0;
+            for (int b = 0; b < p.n_blocks; b++)
+                for (int k = 0; k < lay.block_lsize(p.block_id[b]); k++, cc++)
+                    e.J[(size_t)i * e.col.size() + cc] = p.J0[(size_t)i * p.n + p.block_idx[b] + k];
+        }
+        entries.push_back(std::move(e));
+    }
+    for (int k : imu_sel) {
+        Entry e;
+        e.r.assign(15, 0.0);
+        double J[15][30];
+        eval_imu(fl.imu[k], P.sqrt_info[k], &st.pose[0], &st.sb[0], &st.pose[7], &st.sb[9], P.o, e.r.data(), J);
+        const int ids[4] = {0, 1, 2, 3};
+        for (int b = 0; b < 4; b++)
+            for (int q = 0; q < lsz(ids[b]); q++) e.col.push_back(idx[ids[b]] + q);
+        e.J.assign(15 * 30, 0.0);
+        for (int r = 0; r < 15; r++)
+            for (int c = 0; c < 30; c++) e.J[r * 30 + c] = J[r][c];
+        entries.push_back(std::move(e));
+    }
+    const double cb = P.o.cauchy_a * P.o.cauchy_a, cc_ = 1.0 / cb;
+    for (int k : proj_sel) {
+        const lfvio_proj_factor &f = fl.proj[k];
+        Entry e;
+        e.r.assign(2, 0.0);
+        double J[2][20];
+        eval_projection(f, &st.pose[7 * f.frame_i], &st.pose[7 * f.frame_j], st.ex.data(), st.feat[f.landmark], st.td, P.o, e.r.data(), J);
+        // loss correction exactly as ResidualBlockInfo::Evaluate (marginalization_factor.cpp:37-68)
+        const double sq_norm = e.r[0] * e.r[0] + e.r[1] * e.r[1];
+        const double rho1 = 1.0 / (1.0 + sq_norm * cc_), rho2 = -cc_ * rho1 * rho1;
+        const double sqrt_rho1 = std::sqrt(rho1);
+        double residual_scaling, alpha_sq_norm;
+        if (sq_norm == 0.0 || rho2 <= 0.0) {
+            residual_scaling = sqrt_rho1;
+            alpha_sq_norm = 0.0;
+        } else {
+            const double Dd = 1.0 + 2.0 * sq_norm * rho2 / rho1;
+            const double al = 1.0 - std::sqrt(Dd);
+            residual_scaling = sqrt_rho1 / (1 - al);
+            alpha_sq_norm = al / sq_norm;
+        }
+        std::vector<int> cols;
+        std::vector<int> src;
+        auto add = [&](int id, int off, int cnt) {
+            for (int q = 0; q < cnt; q++) {
+                cols.push_back(idx[id] + q);
+                src.push_back(off + q);
+            }
+        };
+        add(2 * f.frame_i, 0, 6);
+        add(2 * f.frame_j, 6, 6);
+        add(2 * F, 12, 6);
+        add(LM0 + f.landmark, 18, 1);
+        if (P.o.estimate_td) add(2 * F + 1, 19, 1);
+        e.col = cols;
+        e.J.assign(2 * cols.size(), 0.0);
+        for (size_t q = 0; q < cols.size(); q++) {
+            const double rTj = e.r[0] * J[0][src[q]] + e.r[1] * J[1][src[q]];
+            for (int rr = 0; rr < 2; rr++)
+                e.J[rr * cols.size() + q] = sqrt_rho1 * (J[rr][src[q]] - alpha_sq_norm * e.r[rr] * rTj);
+        }
+        e.r[0] *= residual_scaling;
+        e.r[1] *= residual_scaling;
+        entries.push_back(std::move(e));
+    }
+    Mat A(pos, pos);
+    std::vector<double> b(pos, 0.0);
+    auto accumulate = [&](size_t lo, size_t hi, Mat &Aa, std::vector<double> &bb) {
+        for (size_t q = lo; q < hi; q++) {
+            const Entry &e = entries[q];
+            const int nr = (int)e.r.size(), nc = (int)e.col.size();
+            for (int a = 0; a < nc; a++) {
+                double gb = 0;
+                for (int r = 0; r < nr; r++) gb += e.J[(size_t)r * nc + a] * e.r[r];
+                bb[e.col[a]] += gb;
+                for (int c = 0; c < nc; c++) {
+                    double s = 0;
+                    for (int r = 0; r < nr; r++) s += e.J[(size_t)r * nc + a] * e.J[(size_t)r * nc + c];
+                    Aa(e.col[a], e.col[c]) += s;
+                }
+            }
+        }
+    };
+    if (n_threads <= 1 || entries.size() < 8) {
+        accumulate(0, entries.size(), A, b);
+    } else {  // NUM_THREADS partial sums (marginalization_factor.h:13, .cpp:232-261)
+        std::vector<Mat> As(n_threads, Mat(pos, pos));
+        std::vector<std::vector<double>> bs(n_threads, std::vector<double>(pos, 0.0));
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++)
+            th.emplace_back([&, t]() {
+                const size_t lo = entries.size() * t / n_threads, hi = entries.size() * (t + 1) / n_threads;
+                accumulate(lo, hi, As[t], bs[t]);
+            });
+        for (auto &t : th) t.join();
+        for (int t = 0; t < n_threads; t++) {
+            for (size_t q = 0; q < A.a.size(); q++) A.a[q] += As[t].a[q];
+            for (int q = 0; q < pos; q++) b[q] += bs[t][q];
+        }
+    }
+    // ---- Schur complement with eigen-decomposition pseudo-inverse (eps = 1e-8) ----
+    const double eps = 1e-8;
+    Mat Amm(m, m);
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < m; j++) Amm(i, j) = 0.5 * (A(i, j) + A(j, i));
+    std::vector<double> w;
+    Mat V;
+    sym_eig(Amm, w, V);
+    Mat Amm_inv(m, m);
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < m; j++) {
+            double s = 0;
+            for (int k = 0; k < m; k++)
+                if (w[k] > eps) s += V(i, k) * V(j, k) / w[k];
+            Amm_inv(i, j) = s;
+        }
+    Mat T(n, m);  // Arm * Amm_inv
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < m; j++) {
+            double s = 0;
+            for (int k = 0; k < m; k++) s += A(m + i, k) * Amm_inv(k, j);
+            T(i, j) = s;
+        }
+    Mat Ar(n, n);
+    std::vector<double> br(n);
+    for (int i = 0; i < n; i++) {
+        double sb = b[m + i];
+        for (int k = 0; k < m; k++) sb -= T(i, k) * b[k];
+        br[i] = sb;
+        for (int j = 0; j < n; j++) {
+            double s = A(m + i, m + j);
+            for (int k = 0; k < m; k++) s -= T(i, k) * A(k, m + j);
+            Ar(i, j) = s;
+        }
+    }
+    std::vector<double> w2;
+    Mat V2;
+    sym_eig(Ar, w2, V2);
+    J0 = Mat(n, n);
+    r0.assign(n, 0.0);
+    for (int k = 0; k < n; k++) {
+        const double S = w2[k] > eps ? w2[k] : 0.0, Sinv = w2[k] > eps ? 1.0 / w2[k] : 0.0;
+        const double ss = std::sqrt(S), si = std::sqrt(Sinv);
+        double vb = 0;
+        for (int i = 0; i < n; i++) {
+            J0(k, i) = ss * V2(i, k);
+            vb += V2(i, k) * br[i];
+        }
+        r0[k] = si * vb;
+    }
+    // ---- kept blocks, data copies and the addr_shift renaming ----
+    kept.clear();
+    x0.clear();
+    for (auto &kv : is_drop) {
+        if (kv.second) continue;
+        const int id = kv.first;
+        int new_id = id;
+        if (id < 2 * F) {
+            const int f = id >> 1;
+            if (flag == LFVIO_MARGIN_OLD) new_id = id - 2;            // pose/sb i -> i - 1
+            else if (f == F - 1) new_id = id - 2;                     // newest -> second newest
+        }
+        kept.push_back({new_id, gsz(id), lsz(id), idx[id] - m});
+        const double *src = st.block(lay, id);
+        x0.insert(x0.end(), src, src + gsz(id));
+    }
+    m_out = m;
+    return true;
+}
+
+Summary g_last;
+
+}  // namespace
+
+// ================================================================================================
+// C entry points for ctypes (tests, bench.py cpu_baseline)
+// ================================================================================================
+extern "C" {
+
+void oracle_default_opts(lfvio_solver_opts *o) {
+    std::memset(o, 0, sizeof(*o));
+    o->max_num_iterations = 8;
+    o->fixed_iterations = 0;
+    o->estimate_td = 1;
+    o->estimate_extrinsic = 1;
+    o->row = 960;
+    o->focal_length = 160.0;
+    o->tr = 0.0;
+    o->g[0] = 0;
+    o->g[1] = 0;
+    o->g[2] = 9.81007;
+    o->cauchy_a = 1.0;
+    o->initial_trust_region_radius = 1e4;
+    o->max_trust_region_radius = 1e16;
+    o->min_trust_region_radius = 1e-32;
+    o->min_relative_decrease = 1e-3;
+    o->function_tolerance = 1e-6;
+    o->gradient_tolerance = 1e-10;
+    o->parameter_tolerance = 1e-8;
+}
+
+int oracle_evaluate(const lfvio_window_state *s, const lfvio_factor_list *fl, const lfvio_solver_opts *o, int robust,
+                    double *res_proj, double *jac_proj, double *res_imu, double *jac_imu, double *res_prior, double *cost) {
+    Problem P = make_problem(*s, *fl, *o);
+    if (!P.ok) return -4;
+    State st = load_state(*s);
+    Eval E;
+    evaluate(P, st, true, robust != 0, E);
+    if (res_proj) std::copy(E.rp.begin(), E.rp.end(), res_proj);
+    if (jac_proj) std::copy(E.Jp.begin(), E.Jp.end(), jac_proj);
+    if (res_imu) std::copy(E.ri.begin(), E.ri.end(), res_imu);
+    if (jac_imu) std::copy(E.Ji.begin(), E.Ji.end(), jac_imu);
+    if (res_prior) std::copy(E.rm.begin(), E.rm.end(), res_prior);
+    if (cost) *cost = E.cost;
+    return 0;
+}
+
+int oracle_imu_sqrt_info(const lfvio_imu_factor *f, double *out225) {
+    Mat s;
+    if (!imu_sqrt_info(*f, s)) return -4;
+    std::copy(s.a.begin(), s.a.end(), out225);
+    return 0;
+}
+
+void oracle_pose_plus(const double *x, const double *delta, double *out) { pose_plus(x, delta, out); }
+
+int oracle_optimize(lfvio_window_state *s, const lfvio_factor_list *fl, const lfvio_solver_opts *o, lfvio_solve_summary *out) {
+    Problem P = make_problem(*s, *fl, *o);
+    if (!P.ok) return -4;
+    State st = load_state(*s);
+    Summary sum;
+    solve(P, st, sum);
+    store_state(st, *s);
+    if (out) {
+        std::memset(out, 0, sizeof(*out));
+        out->iterations = (int)sum.cost.size() - 1;
+        out->num_successful_steps = sum.successful;
+        out->termination = sum.termination;
+        out->initial_cost = sum.cost.front();
+        out->final_cost = sum.cost.back();
+        for (size_t i = 0; i < sum.cost.size() && i < LFVIO_MAX_ITER_LOG; i++) {
+            out->cost[i] = sum.cost[i];
+            out->radius[i] = sum.radius[i];
+            out->accepted[i] = sum.accepted[i];
+        }
+    }
+    return sum.termination < 0 ? -4 : 0;
+}
+
+int oracle_marginalize(const lfvio_window_state *s, const lfvio_factor_list *fl, const lfvio_solver_opts *o, int flag,
+                       int n_threads, lfvio_prior *out) {
+    Problem P = make_problem(*s, *fl, *o);
+    if (!P.ok) return -4;
+    State st = load_state(*s);
+    std::vector<MargBlock> kept;
+    Mat J0;
+    std::vector<double> r0, x0;
+    int m = 0;
+    if (!marginalize(P, st, flag, n_threads, kept, J0, r0, x0, m)) {
+        out->n = 0;
+        out->n_blocks = 0;
+        return 0;
+    }
+    const int n = (int)r0.size();
+    if (n > out->cap_n || (int)kept.size() > out->cap_blocks) return -3;
+    out->n = n;
+    out->n_blocks = (int)kept.size();
+    for (size_t b = 0; b < kept.size(); b++) {
+        out->block_id[b] = kept[b].id;
+        out->block_idx[b] = kept[b].idx;
+    }
+    std::copy(x0.begin(), x0.end(), out->x0);
+    std::copy(J0.a.begin(), J0.a.end(), out->J0);
+    std::copy(r0.begin(), r0.end(), out->r0);
+    return 0;
+}
+
+// Timed CPU baseline: `reps` x (optimize from the same initial state [+ marginalize]); returns seconds per rep.
+double oracle_time_backend(const lfvio_window_state *s, const lfvio_factor_list *fl, const lfvio_solver_opts *o,
+                           int with_marginalize, int flag, int marg_threads, int reps) {
+    Problem P = make_problem(*s, *fl, *o);
+    const State st0 = load_state(*s);
+    const auto t0 = std::chrono::steady_clock::now();
+    volatile double sink = 0;
+    for (int k = 0; k < reps; k++) {
+        Problem Pk = make_problem(*s, *fl, *o);  // includes the per-solve sqrt-information factorisations
+        State st = st0;
+        Summary sum;
+        solve(Pk, st, sum);
+        sink += sum.cost.back();
+        if (with_marginalize) {
+            std::vector<MargBlock> kept;
+            Mat J0;
+            std::vector<double> r0, x0;
+            int m = 0;
+            marginalize(Pk, st, flag, marg_threads, kept, J0, r0, x0, m);
+            sink += r0.empty() ? 0.0 : r0[0];
+        }
+    }
+    const auto t1 = std::chrono::steady_clock::now();
+    (void)P;
+    return std::chrono::duration<double>(t1 - t0).count() / reps;
+}
+
+}  // extern "C"
