@@ -1,0 +1,428 @@
+// Estimator::optimization() handle: device residency, upload/download, launch sequence and the back-end
+// C-ABI entry points of include/lfvio.h.
+//
+// Reference: vins_estimator/src/estimator.cpp:676-1009.  Layout in HBM: one contiguous "problem blob"
+// (projection factor records | IMU factor records | landmark->factor index | prior x0, J0, r0 | initial state)
+// uploaded with a single H2D copy from pinned memory; two state buffers and two evaluation buffers
+// (current / candidate) so an accepted step is a flag flip; the reduced system and dogleg vectors in one
+// scratch allocation.  The trust-region loop runs as a fixed launch sequence with a device-side control block
+// (no host synchronisation until the result is read back).
+#include <cstring>
+#include <vector>
+
+#include "backend.cuh"
+
+namespace lfvio {
+int launch_solver_init(SolverCtl *ctl, const lfvio_solver_opts &o, cudaStream_t s);
+int launch_marginalize(const DevProblem &P, const EvalBuf &e, const double *x, int flag, struct MargScratch &m, cudaStream_t s);
+}  // namespace lfvio
+
+using namespace lfvio;
+
+namespace {
+
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    int alloc(size_t n) {
+        if (n == 0) n = 1;
+        LFVIO_CUDA_TRY(cudaMalloc(&p, sizeof(T) * n));
+        LFVIO_CUDA_TRY(cudaMemset(p, 0, sizeof(T) * n));
+        return LFVIO_OK;
+    }
+    ~DBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+size_t align8(size_t v) { return (v + 7) & ~size_t(7); }
+
+}  // namespace
+
+struct lfvio_window {
+    int device = 0, F = 0, Lmax = 0, Rmax = 0, nmax = 0;
+    cudaStream_t stream = nullptr;
+    // blob offsets (bytes)
+    size_t off_proj = 0, off_imu = 0, off_lm = 0, off_px0 = 0, off_pJ0 = 0, off_pr0 = 0, off_x = 0, blob_bytes = 0;
+    DBuf<uint8_t> blob;
+    uint8_t *h_blob = nullptr;  // pinned
+    DBuf<double> x[2], x_out, imu_sqrt_info, H0;
+    DBuf<double> rp[2], Jp[2], ri[2], Ji[2], rm[2];
+    DBuf<double> scratch;
+    SolverScratch w;
+    DBuf<SolverCtl> ctl;
+    SolverCtl *h_ctl = nullptr;  // pinned
+    double *h_x = nullptr;       // pinned
+    DBuf<int> status;
+    DevProblem P;
+    EvalBuf e[2];
+    bool uploaded = false;
+
+    ~lfvio_window() {
+        if (h_blob) cudaFreeHost(h_blob);
+        if (h_ctl) cudaFreeHost(h_ctl);
+        if (h_x) cudaFreeHost(h_x);
+    }
+};
+
+namespace {
+
+int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_proj, int device) {
+    w->device = device;
+    LFVIO_CUDA_TRY(cudaSetDevice(device));
+    LFVIO_CUDA_TRY(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    const int F = window_size + 1;
+    w->F = F;
+    w->Lmax = max_landmarks;
+    w->Rmax = max_proj;
+    w->nmax = 15 * F + 7;
+    const int NI = F - 1;
+    StateLayout lay{F, max_landmarks};
+    size_t o = 0;
+    w->off_proj = o;
+    o = align8(o + sizeof(lfvio_proj_factor) * (size_t)max_proj);
+    w->off_imu = o;
+    o = align8(o + sizeof(lfvio_imu_factor) * (size_t)NI);
+    w->off_lm = o;
+    o = align8(o + sizeof(int) * (size_t)(max_landmarks + 1));
+    w->off_px0 = o;
+    o = align8(o + sizeof(double) * 9 * (size_t)kMaxPriorBlocks);
+    w->off_pJ0 = o;
+    o = align8(o + sizeof(double) * (size_t)w->nmax * w->nmax);
+    w->off_pr0 = o;
+    o = align8(o + sizeof(double) * (size_t)w->nmax);
+    w->off_x = o;
+    o = align8(o + sizeof(double) * (size_t)lay.size());
+    w->blob_bytes = o;
+    LFVIO_TRY(w->blob.alloc(o));
+    LFVIO_CUDA_TRY(cudaMallocHost(&w->h_blob, o));
+    memset(w->h_blob, 0, o);
+    for (int k = 0; k < 2; k++) {
+        LFVIO_TRY(w->x[k].alloc(lay.size()));
+        LFVIO_TRY(w->rp[k].alloc(2 * (size_t)max_proj));
+        LFVIO_TRY(w->Jp[k].alloc(40 * (size_t)max_proj));
+        LFVIO_TRY(w->ri[k].alloc(15 * (size_t)NI));
+        LFVIO_TRY(w->Ji[k].alloc(450 * (size_t)NI));
+        LFVIO_TRY(w->rm[k].alloc(w->nmax));
+        w->e[k] = EvalBuf{w->rp[k].p, w->Jp[k].p, w->ri[k].p, w->Ji[k].p, w->rm[k].p};
+    }
+    LFVIO_TRY(w->x_out.alloc(lay.size()));
+    LFVIO_TRY(w->imu_sqrt_info.alloc(225 * (size_t)NI));
+    LFVIO_TRY(w->H0.alloc((size_t)w->nmax * w->nmax));
+    // scratch: [S D*D | rhs D | diag2 D | grad D | lm_c L | lm_g L] (zeroed per iteration) | lm_ws | proj_wj | scale | ...
+    const size_t D = lay.D(), L = max_landmarks, N = D + L;
+    const size_t n_scr = D * D + 3 * D + 2 * L + 13 * L + 6 * (size_t)max_proj + 5 * N + D;
+    LFVIO_TRY(w->scratch.alloc(n_scr));
+    double *p = w->scratch.p;
+    SolverScratch &s = w->w;
+    s.S = p;          p += D * D;
+    s.rhs = p;        p += D;
+    s.diag2 = p;      p += D;
+    s.grad = p;       p += D;
+    s.lm_c = p;       p += L;
+    s.lm_g = p;       p += L;
+    s.zero_bytes = sizeof(double) * (size_t)(p - s.S);
+    s.lm_ws = p;      p += 13 * L;
+    s.proj_wj = p;    p += 6 * (size_t)max_proj;
+    s.scale = p;      p += N;
+    s.diagonal = p;   p += N;
+    s.gradient = p;   p += N;
+    s.gn = p;         p += N;
+    s.step = p;       p += N;
+    s.y = p;          p += D;
+    LFVIO_TRY(w->ctl.alloc(1));
+    LFVIO_CUDA_TRY(cudaMallocHost(&w->h_ctl, sizeof(SolverCtl)));
+    LFVIO_CUDA_TRY(cudaMallocHost(&w->h_x, sizeof(double) * lay.size()));
+    LFVIO_TRY(w->status.alloc(4));
+    return LFVIO_OK;
+}
+
+// Pack the problem into the pinned blob, enqueue the single H2D copy and fill the device-side descriptor.
+int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_list *fl, const lfvio_solver_opts *o) {
+    LFVIO_REQUIRE(st && fl && o, "window: null argument");
+    LFVIO_REQUIRE(st->n_frames == w->F, "window: n_frames != window_size + 1 of the handle");
+    LFVIO_REQUIRE(st->n_landmarks >= 0 && st->n_landmarks <= w->Lmax, "window: too many landmarks for this handle");
+    LFVIO_REQUIRE(fl->n_proj >= 0 && fl->n_proj <= w->Rmax, "window: too many projection factors for this handle");
+    LFVIO_REQUIRE(fl->n_imu >= 0 && fl->n_imu <= w->F - 1, "window: too many IMU factors");
+    LFVIO_REQUIRE(o->max_num_iterations >= 0 && o->max_num_iterations < LFVIO_MAX_ITER_LOG, "window: bad max_num_iterations");
+    const int F = w->F, L = st->n_landmarks;
+    StateLayout lay{F, L};
+    uint8_t *hb = w->h_blob;
+    if (fl->n_proj) memcpy(hb + w->off_proj, fl->proj, sizeof(lfvio_proj_factor) * (size_t)fl->n_proj);
+    if (fl->n_imu) memcpy(hb + w->off_imu, fl->imu, sizeof(lfvio_imu_factor) * (size_t)fl->n_imu);
+    // landmark -> factor ranges (the reference inserts factors landmark by landmark, estimator.cpp:725-772)
+    int *lm = reinterpret_cast<int *>(hb + w->off_lm);
+    {
+        int k = 0;
+        for (int l = 0; l < L; l++) {
+            lm[l] = k;
+            while (k < fl->n_proj && fl->proj[k].landmark == l) {
+                const lfvio_proj_factor &f = fl->proj[k];
+                LFVIO_REQUIRE(f.frame_i >= 0 && f.frame_i < F && f.frame_j >= 0 && f.frame_j < F && f.frame_i != f.frame_j,
+                              "window: projection factor frame index out of range");
+                LFVIO_REQUIRE(f.frame_i == fl->proj[lm[l]].frame_i, "window: factors of one landmark must share the host frame");
+                k++;
+            }
+            LFVIO_REQUIRE(k - lm[l] <= kMaxObs, "window: too many observations of one landmark");
+        }
+        lm[L] = k;
+        LFVIO_REQUIRE(k == fl->n_proj, "window: projection factors must be grouped by ascending landmark index");
+    }
+    for (int k = 0; k < fl->n_imu; k++)
+        LFVIO_REQUIRE(fl->imu[k].frame_i >= 0 && fl->imu[k].frame_i < F - 1, "window: IMU factor frame index out of range");
+    DevProblem &P = w->P;
+    memset(&P, 0, sizeof(P));
+    P.lay = lay;
+    P.o = *o;
+    P.n_proj = fl->n_proj;
+    P.n_imu = fl->n_imu;
+    P.proj = reinterpret_cast<const lfvio_proj_factor *>(w->blob.p + w->off_proj);
+    P.imu = reinterpret_cast<const lfvio_imu_factor *>(w->blob.p + w->off_imu);
+    P.lm_first = reinterpret_cast<const int *>(w->blob.p + w->off_lm);
+    P.imu_sqrt_info = w->imu_sqrt_info.p;
+    if (fl->prior && fl->prior->n > 0) {
+        const lfvio_prior &p = *fl->prior;
+        LFVIO_REQUIRE(p.n <= w->nmax && p.n_blocks <= kMaxPriorBlocks, "window: prior too large for this handle");
+        P.prior.n = p.n;
+        P.prior.n_blocks = p.n_blocks;
+        int off = 0, lsum = 0;
+        for (int b = 0; b < p.n_blocks; b++) {
+            const int id = p.block_id[b];
+            LFVIO_REQUIRE(id >= 0 && id <= 2 * F + 1, "window: prior block id out of range");
+            P.prior.block_id[b] = id;
+            P.prior.block_idx[b] = p.block_idx[b];
+            P.prior.block_x0[b] = off;
+            off += lay.block_gsize(id);
+            lsum += lay.block_lsize(id);
+            LFVIO_REQUIRE(p.block_idx[b] >= 0 && p.block_idx[b] + lay.block_lsize(id) <= p.n, "window: prior block offset out of range");
+        }
+        LFVIO_REQUIRE(lsum == p.n, "window: prior size does not match its blocks");
+        memcpy(hb + w->off_px0, p.x0, sizeof(double) * off);
+        memcpy(hb + w->off_pJ0, p.J0, sizeof(double) * (size_t)p.n * p.n);
+        memcpy(hb + w->off_pr0, p.r0, sizeof(double) * p.n);
+        P.prior.x0 = reinterpret_cast<const double *>(w->blob.p + w->off_px0);
+        P.prior.J0 = reinterpret_cast<const double *>(w->blob.p + w->off_pJ0);
+        P.prior.r0 = reinterpret_cast<const double *>(w->blob.p + w->off_pr0);
+        P.prior.H0 = w->H0.p;
+    }
+    double *hx = reinterpret_cast<double *>(hb + w->off_x);
+    memcpy(hx + lay.pose(0), st->para_Pose, sizeof(double) * 7 * F);
+    memcpy(hx + lay.sb(0), st->para_SpeedBias, sizeof(double) * 9 * F);
+    memcpy(hx + lay.ex(), st->para_Ex_Pose, sizeof(double) * 7);
+    hx[lay.td()] = st->para_Td[0];
+    if (L) memcpy(hx + lay.feat(0), st->para_Feature, sizeof(double) * L);
+    // one DMA: everything up to the end of the state (unused capacity in between is skipped in three pieces)
+    cudaStream_t s = w->stream;
+    auto copy = [&](size_t off, size_t bytes) -> int {
+        if (bytes) LFVIO_CUDA_TRY(cudaMemcpyAsync(w->blob.p + off, hb + off, bytes, cudaMemcpyHostToDevice, s));
+        return LFVIO_OK;
+    };
+    LFVIO_TRY(copy(w->off_proj, sizeof(lfvio_proj_factor) * (size_t)fl->n_proj));
+    LFVIO_TRY(copy(w->off_imu, w->off_px0 - w->off_imu + (P.prior.n ? sizeof(double) * 9 * P.prior.n_blocks : 0)));
+    if (P.prior.n) {
+        LFVIO_TRY(copy(w->off_pJ0, sizeof(double) * (size_t)P.prior.n * P.prior.n));
+        LFVIO_TRY(copy(w->off_pr0, sizeof(double) * P.prior.n));
+    }
+    LFVIO_TRY(copy(w->off_x, sizeof(double) * lay.size()));
+    LFVIO_CUDA_TRY(cudaMemsetAsync(w->status.p, 0, sizeof(int) * 4, s));
+    LFVIO_TRY(launch_imu_prepare(P, w->imu_sqrt_info.p, w->status.p, s));
+    LFVIO_TRY(launch_prior_prepare(P, w->H0.p, s));
+    w->uploaded = true;
+    return LFVIO_OK;
+}
+
+// The whole ceres::Solve as a launch sequence (no host synchronisation).
+int enqueue_solve(lfvio_window *w) {
+    cudaStream_t s = w->stream;
+    const DevProblem &P = w->P;
+    const size_t xbytes = sizeof(double) * P.lay.size();
+    LFVIO_TRY(launch_solver_init(w->ctl.p, P.o, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->x[0].p, w->blob.p + w->off_x, xbytes, cudaMemcpyDeviceToDevice, s));
+    LFVIO_TRY(launch_evaluate(P, w->x[0].p, w->x[1].p, w->e[0], w->e[1], w->ctl.p, 0, 1, s));
+    LFVIO_TRY(launch_jacobi_scale(P, w->e[0], w->w, s));
+    for (int it = 0; it < P.o.max_num_iterations; it++) {
+        LFVIO_TRY(launch_accumulate(P, w->e[0], w->e[1], w->w, w->ctl.p, s));
+        LFVIO_TRY(launch_step(P, w->e[0], w->e[1], w->w, w->x[0].p, w->x[1].p, w->ctl.p, s));
+        LFVIO_TRY(launch_evaluate(P, w->x[0].p, w->x[1].p, w->e[0], w->e[1], w->ctl.p, 1, 1, s));
+    }
+    return LFVIO_OK;
+}
+
+__global__ void select_state_kernel(const double *x0, const double *x1, const SolverCtl *ctl, double *out, int n) {
+    const double *x = ctl->cur ? x1 : x0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) out[q] = x[q];
+}
+
+int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum) {
+    cudaStream_t s = w->stream;
+    const StateLayout lay = w->P.lay;
+    select_state_kernel<<<cdiv(lay.size(), 256), 256, 0, s>>>(w->x[0].p, w->x[1].p, w->ctl.p, w->x_out.p, lay.size());
+    LFVIO_LAUNCH_CHECK();
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_x, w->x_out.p, sizeof(double) * lay.size(), cudaMemcpyDeviceToHost, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_ctl, w->ctl.p, sizeof(SolverCtl), cudaMemcpyDeviceToHost, s));
+    int status[4];
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(status, w->status.p, sizeof(status), cudaMemcpyDeviceToHost, s));
+    LFVIO_CUDA_TRY(cudaStreamSynchronize(s));
+    if (st) {
+        memcpy(st->para_Pose, w->h_x + lay.pose(0), sizeof(double) * 7 * lay.F);
+        memcpy(st->para_SpeedBias, w->h_x + lay.sb(0), sizeof(double) * 9 * lay.F);
+        memcpy(st->para_Ex_Pose, w->h_x + lay.ex(), sizeof(double) * 7);
+        st->para_Td[0] = w->h_x[lay.td()];
+        if (lay.L) memcpy(st->para_Feature, w->h_x + lay.feat(0), sizeof(double) * lay.L);
+    }
+    const SolverCtl &c = *w->h_ctl;
+    if (sum) {
+        memset(sum, 0, sizeof(*sum));
+        sum->iterations = c.iter;
+        sum->num_successful_steps = c.successful;
+        sum->termination = c.done == 1 ? 1 : (c.done < 0 ? -1 : 0);
+        sum->initial_cost = c.cost_log[0];
+        sum->final_cost = c.cost;
+        for (int i = 0; i <= c.iter && i < LFVIO_MAX_ITER_LOG; i++) {
+            sum->cost[i] = c.cost_log[i];
+            sum->radius[i] = c.radius_log[i];
+            sum->accepted[i] = c.accepted_log[i];
+        }
+    }
+    if (status[0]) {
+        set_error("IMU covariance of a pre-integration is singular / not positive definite");
+        return LFVIO_ERR_NUMERIC;
+    }
+    if (c.done < 0) {
+        set_error("trust-region solve failed (non-finite cost or 5 invalid steps in a row)");
+        return LFVIO_ERR_NUMERIC;
+    }
+    return LFVIO_OK;
+}
+
+}  // namespace
+
+extern "C" void lfvio_solver_default_opts(lfvio_solver_opts *o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->max_num_iterations = 8;   // config/mindvision/mindvision.yaml:134
+    o->fixed_iterations = 0;
+    o->estimate_td = 1;          // mindvision.yaml:151
+    o->estimate_extrinsic = 1;   // mindvision.yaml:84
+    o->row = 960;
+    o->focal_length = 160.0;     // vins_estimator/src/parameters.h:11
+    o->tr = 0.0;
+    o->g[0] = 0.0;
+    o->g[1] = 0.0;
+    o->g[2] = 9.81007;           // mindvision.yaml:142
+    o->cauchy_a = 1.0;           // estimator.cpp:681
+    o->initial_trust_region_radius = 1e4;  // ceres::Solver::Options defaults (1.12.0)
+    o->max_trust_region_radius = 1e16;
+    o->min_trust_region_radius = 1e-32;
+    o->min_relative_decrease = 1e-3;
+    o->function_tolerance = 1e-6;
+    o->gradient_tolerance = 1e-10;
+    o->parameter_tolerance = 1e-8;
+}
+
+extern "C" int lfvio_window_create(int window_size, int max_landmarks, int max_proj, int device, lfvio_window **out) {
+    clear_error();
+    LFVIO_REQUIRE(out, "lfvio_window_create: null out");
+    LFVIO_REQUIRE(window_size >= 2 && window_size + 1 <= kMaxFrames, "lfvio_window_create: window_size out of range");
+    LFVIO_REQUIRE(max_landmarks > 0 && max_proj > 0, "lfvio_window_create: capacities must be positive");
+    lfvio_window *w = new (std::nothrow) lfvio_window();
+    LFVIO_REQUIRE(w, "lfvio_window_create: out of host memory");
+    const int st = window_init(w, window_size, max_landmarks, max_proj, device);
+    if (st != LFVIO_OK) {
+        lfvio_window_destroy(w);
+        return st;
+    }
+    *out = w;
+    return LFVIO_OK;
+}
+
+extern "C" void lfvio_window_destroy(lfvio_window *w) {
+    if (!w) return;
+    cudaSetDevice(w->device);
+    if (w->stream) {
+        cudaStreamSynchronize(w->stream);
+        cudaStreamDestroy(w->stream);
+    }
+    delete w;
+}
+
+extern "C" int lfvio_window_optimize(lfvio_window *w, lfvio_window_state *state, const lfvio_factor_list *factors,
+                                     const lfvio_solver_opts *opts, lfvio_solve_summary *summary) {
+    clear_error();
+    LFVIO_REQUIRE(w, "lfvio_window_optimize: null handle");
+    LFVIO_CUDA_TRY(cudaSetDevice(w->device));
+    LFVIO_TRY(upload(w, state, factors, opts));
+    LFVIO_TRY(enqueue_solve(w));
+    return download(w, state, summary);
+}
+
+extern "C" int lfvio_window_upload(lfvio_window *w, const lfvio_window_state *state, const lfvio_factor_list *factors,
+                                   const lfvio_solver_opts *opts) {
+    clear_error();
+    LFVIO_REQUIRE(w, "lfvio_window_upload: null handle");
+    LFVIO_CUDA_TRY(cudaSetDevice(w->device));
+    return upload(w, state, factors, opts);
+}
+
+extern "C" int lfvio_window_optimize_dev(lfvio_window *w, int with_marginalize, int margin_flag) {
+    clear_error();
+    LFVIO_REQUIRE(w && w->uploaded, "lfvio_window_optimize_dev: call lfvio_window_upload first");
+    LFVIO_CUDA_TRY(cudaSetDevice(w->device));
+    LFVIO_TRY(enqueue_solve(w));
+    (void)with_marginalize;
+    (void)margin_flag;
+    return LFVIO_OK;
+}
+
+extern "C" int lfvio_window_download(lfvio_window *w, lfvio_window_state *state, lfvio_solve_summary *summary) {
+    clear_error();
+    LFVIO_REQUIRE(w && w->uploaded, "lfvio_window_download: nothing uploaded");
+    LFVIO_CUDA_TRY(cudaSetDevice(w->device));
+    return download(w, state, summary);
+}
+
+extern "C" int lfvio_window_evaluate(lfvio_window *w, const lfvio_window_state *state, const lfvio_factor_list *factors,
+                                     const lfvio_solver_opts *opts, int robust, double *res_proj, double *jac_proj,
+                                     double *res_imu, double *jac_imu, double *res_prior, double *cost) {
+    clear_error();
+    LFVIO_REQUIRE(w, "lfvio_window_evaluate: null handle");
+    LFVIO_CUDA_TRY(cudaSetDevice(w->device));
+    LFVIO_TRY(upload(w, state, factors, opts));
+    cudaStream_t s = w->stream;
+    const DevProblem &P = w->P;
+    LFVIO_TRY(launch_solver_init(w->ctl.p, P.o, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->x[0].p, w->blob.p + w->off_x, sizeof(double) * P.lay.size(), cudaMemcpyDeviceToDevice, s));
+    LFVIO_TRY(launch_evaluate(P, w->x[0].p, w->x[1].p, w->e[0], w->e[1], w->ctl.p, 2, robust, s));
+    LFVIO_CUDA_TRY(cudaStreamSynchronize(s));
+    if (res_proj && P.n_proj) LFVIO_CUDA_TRY(cudaMemcpy(res_proj, w->rp[0].p, sizeof(double) * 2 * P.n_proj, cudaMemcpyDeviceToHost));
+    if (jac_proj && P.n_proj) LFVIO_CUDA_TRY(cudaMemcpy(jac_proj, w->Jp[0].p, sizeof(double) * 40 * P.n_proj, cudaMemcpyDeviceToHost));
+    if (res_imu && P.n_imu) LFVIO_CUDA_TRY(cudaMemcpy(res_imu, w->ri[0].p, sizeof(double) * 15 * P.n_imu, cudaMemcpyDeviceToHost));
+    if (jac_imu && P.n_imu) LFVIO_CUDA_TRY(cudaMemcpy(jac_imu, w->Ji[0].p, sizeof(double) * 450 * P.n_imu, cudaMemcpyDeviceToHost));
+    if (res_prior && P.prior.n) LFVIO_CUDA_TRY(cudaMemcpy(res_prior, w->rm[0].p, sizeof(double) * P.prior.n, cudaMemcpyDeviceToHost));
+    if (cost) {
+        SolverCtl c;
+        LFVIO_CUDA_TRY(cudaMemcpy(&c, w->ctl.p, sizeof(c), cudaMemcpyDeviceToHost));
+        *cost = c.cost;
+    }
+    int status[4];
+    LFVIO_CUDA_TRY(cudaMemcpy(status, w->status.p, sizeof(status), cudaMemcpyDeviceToHost));
+    if (status[0]) {
+        set_error("IMU covariance of a pre-integration is singular / not positive definite");
+        return LFVIO_ERR_NUMERIC;
+    }
+    return LFVIO_OK;
+}
+
+extern "C" int lfvio_window_marginalize(lfvio_window *w, const lfvio_window_state *state, const lfvio_factor_list *factors,
+                                        const lfvio_solver_opts *opts, int margin_flag, lfvio_prior *out) {
+    clear_error();
+    LFVIO_REQUIRE(w && out, "lfvio_window_marginalize: null argument");
+    (void)state;
+    (void)factors;
+    (void)opts;
+    (void)margin_flag;
+    set_error("lfvio_window_marginalize: device marginalisation not built yet");
+    return LFVIO_ERR_ARG;
+}
+
+extern "C" void *lfvio_window_stream(lfvio_window *w) { return w ? (void *)w->stream : nullptr; }

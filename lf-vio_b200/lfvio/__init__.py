@@ -303,3 +303,18 @@ class FeatureTracker:
         return {"cur_pts": self.cur_pts.copy(), "ids": self.ids.copy(), "track_cnt": self.track_cnt.copy(),
                 "cur_un_pts_3d": self.cur_un_pts_3d.copy(), "pts_velocity_3d": self.pts_velocity_3d.copy()}
 
+
+# ------------------------------------------------------------------------------------------------
+# sliding-window back end (structs + handle live in backend.py)
+# ------------------------------------------------------------------------------------------------
+from . import backend  # noqa: E402
+
+backend.bind(lib)
+
+
+def solver_default_opts() -> "backend.SolverOpts":
+    return backend.default_opts(lib)
+
+
+def Window(window_size: int = 10, max_landmarks: int = 1000, max_proj: int = 16384, device: int = 0) -> "backend.Window":
+    return backend.Window(lib, check, window_size, max_landmarks, max_proj, device)

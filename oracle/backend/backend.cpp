@@ -497,7 +497,7 @@ void solve(const Problem &P, State &x, Summary &sum) {
     double x_norm = global_norm_diff(P, x, nullptr);
     // DoglegStrategy state
     double radius = o.initial_trust_region_radius, mu = 1e-8;
-    const double min_mu = 1e-8, max_mu = 1.0, mu_increase = 10.0;
+    const double min_mu = 1e-8, mu_increase = 10.0;
     bool reuse = false;
     double dogleg_step_norm = 0, alpha = 0;
     std::vector<double> diagonal(N), gradient(N), gn(N), step(N), delta(N);
@@ -540,7 +540,7 @@ void solve(const Problem &P, State &x, Summary &sum) {
             }
             // Gauss-Newton step through the Schur complement, with the LM regulariser diag * sqrt(mu)
             bool solved = false;
-            while (mu < max_mu) {
+            for (int attempt = 0; attempt < 1; attempt++) {  // one attempt per iteration: a failed factorisation is an invalid step (mu *= 10 below); Ceres retries in place
                 Mat S(D, D);
                 std::vector<double> rhs(D, 0.0), c_l(L, 0.0), g_l(L, 0.0);
                 Mat W(L, D);  // row l: J_p^T j_lambda for landmark l
@@ -582,8 +582,8 @@ void solve(const Problem &P, State &x, Summary &sum) {
                 }
                 Mat Lc = S;
                 if (!cholesky_lower(Lc)) {
-                    mu *= mu_increase;
-                    continue;
+                    break;
+                    
                 }
                 std::vector<double> y = rhs;
                 chol_solve(Lc, y);
@@ -599,8 +599,8 @@ void solve(const Problem &P, State &x, Summary &sum) {
                     finite &= std::isfinite(gn[D + l]);
                 }
                 if (!finite) {
-                    mu *= mu_increase;
-                    continue;
+                    break;
+                    
                 }
                 solved = true;
                 break;

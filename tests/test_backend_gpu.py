@@ -1,0 +1,129 @@
+"""GPU parity tests of the sliding-window back end through the C-ABI (include/lfvio.h) against the fp64 oracle.
+
+Everything is fp64 on both sides; differences come from FMA contraction and summation order (atomics), amplified
+by the conditioning of the IMU information (covariance entries 1e-9..1e-4 are inverted, imu_factor.h:64).
+Stated tolerances: residuals/Jacobians 1e-7 relative to the block's largest entry; per-iteration cost 1e-6 relative;
+converged states 1e-6 absolute (metres / quaternion components / inverse depth).
+"""
+import numpy as np
+import pytest
+
+from lfvio import backend as B
+from lfvio import synthwin
+from oracle import backend as ob
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def win(lfvio_mod, gpu):
+    return lfvio_mod.Window(10, 1000, 16384, device=gpu)
+
+
+@pytest.fixture(scope="module")
+def problem(lfvio_mod):
+    return synthwin.make_window(seed=1, opts=lfvio_mod.solver_default_opts(), perturb=0.3)
+
+
+def test_default_opts_match_oracle(lfvio_mod):
+    a, b = lfvio_mod.solver_default_opts(), ob.default_opts()
+    assert bytes(a) == bytes(b)
+
+
+@pytest.mark.parametrize("robust", [False, True])
+def test_evaluate_matches_oracle(win, problem, robust):
+    g, o = win.evaluate(problem, robust), ob.evaluate(problem, robust)
+    assert rel_err(g.res_proj, o.res_proj) < 1e-9
+    assert rel_err(g.jac_proj, o.jac_proj) < 1e-9
+    assert rel_err(g.res_imu, o.res_imu) < 1e-7
+    assert rel_err(g.jac_imu, o.jac_imu) < 1e-7
+    assert abs(g.cost.value - o.cost.value) < 1e-7 * o.cost.value
+
+
+def test_evaluate_variants(lfvio_mod, win):
+    """estimate_td = 0 (ProjectionFactor), fixed extrinsics, rolling shutter term, no IMU factor for long gaps."""
+    for kw in (dict(estimate_td=0), dict(estimate_extrinsic=0), dict(tr=0.03), dict(long_gap=True)):
+        opts = lfvio_mod.solver_default_opts()
+        w = synthwin.make_window(seed=5, opts=opts, perturb=0.5, estimate_td=kw.get("estimate_td", 1))
+        if "estimate_extrinsic" in kw:
+            w.opts.estimate_extrinsic = 0
+        if "tr" in kw:
+            w.opts.tr = kw["tr"]
+        if kw.get("long_gap"):
+            w.imu[4].sum_dt = 11.0  # estimator.cpp:720-721: pre-integrations longer than 10 s are skipped
+        g, o = win.evaluate(w, True), ob.evaluate(w, True)
+        assert rel_err(g.res_proj, o.res_proj) < 1e-9, kw
+        assert rel_err(g.jac_proj, o.jac_proj) < 1e-9, kw
+        assert rel_err(g.res_imu, o.res_imu) < 1e-7, kw
+        assert rel_err(g.jac_imu, o.jac_imu) < 1e-7, kw
+        assert abs(g.cost.value - o.cost.value) < 1e-7 * o.cost.value, kw
+
+
+def _solve_both(win, w):
+    a, b = w.clone(), w.clone()
+    sg, so = win.optimize(a), ob.optimize(b)
+    return a, sg, b, so
+
+
+@pytest.mark.parametrize("seed,perturb", [(1, 0.3), (2, 1.0), (3, 0.1)])
+def test_optimize_matches_oracle(lfvio_mod, win, seed, perturb):
+    w = synthwin.make_window(seed=seed, opts=lfvio_mod.solver_default_opts(), perturb=perturb)
+    a, sg, b, so = _solve_both(win, w)
+    assert sg.iterations == so.iterations and sg.num_successful_steps == so.num_successful_steps
+    assert sg.termination == so.termination
+    for i in range(so.iterations + 1):
+        assert abs(sg.cost[i] - so.cost[i]) <= 1e-6 * abs(so.cost[i]) + 1e-9, (i, sg.cost[i], so.cost[i])
+        assert abs(sg.radius[i] - so.radius[i]) <= 1e-6 * so.radius[i], (i, sg.radius[i], so.radius[i])
+        assert sg.accepted[i] == so.accepted[i]
+    assert np.abs(a.pose - b.pose).max() < 1e-6
+    assert np.abs(a.sb - b.sb).max() < 1e-5
+    assert np.abs(a.ex - b.ex).max() < 1e-6
+    assert np.abs(a.feat - b.feat).max() < 1e-6
+    assert abs(a.td[0] - b.td[0]) < 1e-7
+
+
+def test_optimize_fixed_iterations_and_truth(lfvio_mod, win):
+    opts = lfvio_mod.solver_default_opts()
+    opts.fixed_iterations = 1
+    w = synthwin.make_window(seed=4, opts=opts, perturb=0.3)
+    a, sg, b, so = _solve_both(win, w)
+    assert sg.iterations == so.iterations == 8
+    assert np.abs(a.pose - b.pose).max() < 1e-6
+    assert np.abs(a.pose[:, :3] - w.truth["P"]).max() < 0.05
+
+
+def test_optimize_without_td_and_fixed_extrinsic(lfvio_mod, win):
+    opts = lfvio_mod.solver_default_opts()
+    w = synthwin.make_window(seed=6, opts=opts, perturb=0.3, estimate_td=0)
+    w.opts.estimate_extrinsic = 0
+    a, sg, b, so = _solve_both(win, w)
+    assert sg.iterations == so.iterations
+    assert np.array_equal(a.ex, w.ex) and a.td[0] == w.td[0]  # constant blocks are untouched
+    assert np.abs(a.pose - b.pose).max() < 1e-6
+
+
+def test_device_resident_solve_repeats(lfvio_mod, win, problem):
+    """upload once, solve twice from the uploaded state: identical results, equal to the host-buffer call."""
+    ref = problem.clone()
+    s_ref = win.optimize(ref)
+    win.upload(problem)
+    outs = []
+    for _ in range(2):
+        win.optimize_dev(False)
+        o = problem.clone()
+        s = win.download(o)
+        outs.append((o, s))
+    for o, s in outs:
+        assert s.iterations == s_ref.iterations
+        assert np.abs(o.pose - ref.pose).max() < 1e-9 and np.abs(o.feat - ref.feat).max() < 1e-9
+
+
+def test_bad_problem_is_rejected(lfvio_mod, win, problem):
+    w = problem.clone()
+    w.proj[3].landmark, w.proj[400].landmark = w.proj[400].landmark, w.proj[3].landmark  # breaks the grouping
+    with pytest.raises(lfvio_mod.LfvioError):
+        win.optimize(w)
