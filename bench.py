@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — VIO frames/sec (track + optimize, 10-keyframe window) on B200, next to the CPU path.
+
+One "step" = one camera frame through the hot path BASELINE.json's north_star names:
+  front end  FeatureTracker::readImage (CLAHE -> pyramidal LK -> border filter -> setMask -> Shi-Tomasi -> lift)
+  back end   Estimator::optimization   (8 dogleg iterations on an 11-frame window, DENSE_SCHUR semantics)
+Workload (config.workload): BASELINE.json configs[1] shape — synthetic 1280x960 panoramic frames @15 Hz published
+at 10 Hz, 150 features, 200 Hz IMU, 10-keyframe window, estimate_td = 1.  One independent stream per GPU (weak
+scaling, no data-path collective; NCCL only reduces the timing counters).
+
+JSON keys follow the driver contract: value (inputs resident in HBM), e2e (host buffers through the C-ABI, H2D/D2H
+inside the timed region), roofline (dominant kernel, live CUDA-event durations), cpu_baseline, clocks, gpu_launches.
+`--impl reference` times the reference's CPU path (cv2 with the reference's arguments + the fp64 C++ oracle of the
+back end; the reference itself — ROS/OpenCV-C++/Ceres/Eigen — cannot be built in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "lf-vio_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "VIO frames/sec (track+optimize, 10-kf window)"
+UNIT = "frames/s"
+CONFIGS = {
+    # name: (scale, max_cnt, window_size, n_landmarks for the synthetic window, camera Hz)
+    "palvio_id01_1280x960_150feat_10kf": (1.0, 150, 10, 260, 15.0),
+    "synthetic_1920x1440_500feat_10kf": (1.5, 500, 10, 900, 30.0),
+    "synthetic_3840x2880_2000feat_20kf": (3.0, 2000, 20, 3600, 60.0),
+}
+PUB_PATTERN = (1, 1, 0)  # 15 Hz camera published at 10 Hz (feature_tracker_node.cpp:50-62)
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.path = tempfile.mktemp(prefix="lfvio_clocks_", suffix=".csv")
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_workload(cfg_name: str, rank: int, n_frames_pool: int):
+    from lfvio import synth, synthwin
+    from lfvio.config import scaled_camera, tracker_defaults
+
+    scale, max_cnt, wsz, n_lm, hz = CONFIGS[cfg_name]
+    cam = scaled_camera(scale)
+    tcfg = tracker_defaults(scale, max_cnt)
+    rows, cols = cam["image_height"], cam["image_width"]
+    src = synth.FrameSource(rows, cols, seed=rank + 1)
+    frames = np.stack([src.frame(k) for k in range(n_frames_pool)])
+    return dict(cam=cam, tcfg=tcfg, rows=rows, cols=cols, frames=frames, hz=hz, window_size=wsz, n_landmarks=n_lm,
+                max_cnt=max_cnt, synthwin=synthwin)
+
+
+def make_window_problem(wl, opts, rank):
+    return wl["synthwin"].make_window(seed=rank + 1, n_frames=wl["window_size"] + 1, n_landmarks=wl["n_landmarks"],
+                                      feats_per_frame=wl["max_cnt"], opts=opts, perturb=0.3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm (reference path): cv2 front end + fp64 oracle back end
+# ---------------------------------------------------------------------------------------------------
+def cpu_arm(wl, steps: int, warmup: int, rank: int, with_marg: bool):
+    import cv2
+
+    from oracle import backend as ob
+    from oracle import frontend as fe
+
+    opts = ob.default_opts()
+    opts.fixed_iterations = 1
+    opts.row = wl["rows"]
+    w = make_window_problem(wl, opts, rank)
+    tr = fe.FeatureTrackerOracle(wl["cam"], wl["tcfg"], "cv2")
+    frames, hz = wl["frames"], wl["hz"]
+    n = len(frames)
+    t_front = t_back = 0.0
+    for k in range(warmup + steps):
+        img = frames[k % n]
+        t0 = time.perf_counter()
+        tr.read_image(img, k / hz, bool(PUB_PATTERN[k % len(PUB_PATTERN)]))
+        tr.update_ids()
+        t1 = time.perf_counter()
+        tb = ob.time_backend(w, with_marg, 0, 4, 1)
+        if k >= warmup:
+            t_front += t1 - t0
+            t_back += tb
+    total = t_front + t_back
+    return dict(fps=steps / total, ms_front=1e3 * t_front / steps, ms_back=1e3 * t_back / steps,
+                cores=os.cpu_count(), cv2_threads=cv2.getNumThreads(), n_proj=w.n_proj, n_landmarks=w.L)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="palvio_id01_1280x960_150feat_10kf", choices=list(CONFIGS))
+    ap.add_argument("--pool", type=int, default=0, help="distinct frames cycled (0 => enough to exceed L2)")
+    ap.add_argument("--cpu-sample", type=int, default=60, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--no-marginalize", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == "reference", "W >= 3 warm-up steps required"
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    with_marg = not args.no_marginalize
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        scale = CONFIGS[args.config][0]
+        wl = build_workload(args.config, 0, 32)
+        steps = min(args.steps, 200)
+        r = cpu_arm(wl, steps, min(args.warmup, 5), 0, with_marg)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["fps"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 5), "ms_per_step": 1e3 / r["fps"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/f32 front end, f64 back end", "data": "synthetic",
+            "config": {"workload": args.config, "scale": scale, "n_proj_factors": r["n_proj"], "n_landmarks": r["n_landmarks"],
+                       "iterations": 8, "marginalize": with_marg},
+            "cpu_baseline": {"value": r["fps"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                             "sample": f"{steps} frames; front end = cv2 (OpenCV {r['cv2_threads']} threads, the library the "
+                                       "reference calls) + restated control flow; back end = fp64 C++ oracle, 1 thread solve "
+                                       "+ 4 thread marginalisation (as the reference)",
+                             "ms_front": r["ms_front"], "ms_back": r["ms_back"]},
+            "e2e": {"value": r["fps"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+
+    import lfvio
+    from lfvio import backend as B
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    peaks, peak_kind = measured_peaks()
+
+    scale, max_cnt, wsz, n_lm, hz = CONFIGS[args.config]
+    rows, cols = int(round(960 * scale)), int(round(1280 * scale))
+    l2_bytes = 126 * 2 ** 20
+    pool = args.pool or max(16, int(np.ceil(1.25 * l2_bytes / (rows * cols))))
+    wl = build_workload(args.config, rank, pool)
+    frames_host = wl["frames"]
+    frames_dev = torch.from_numpy(frames_host).to(dev)
+    pinned = torch.from_numpy(frames_host).pin_memory() if frames_host.nbytes < 2 ** 31 else None
+    torch.cuda.synchronize()
+
+    tracker = lfvio.FeatureTracker(wl["cam"], wl["tcfg"], device=local_rank)
+    opts = lfvio.solver_default_opts()
+    opts.fixed_iterations = 1
+    opts.row = rows
+    wprob = make_window_problem(wl, opts, rank)
+    window = lfvio.Window(wsz, max(1000, 2 * wprob.L), max(16384, 2 * wprob.n_proj), device=local_rank)
+    window.upload(wprob)
+    t_stream = torch.cuda.ExternalStream(tracker.stream, device=dev)
+    w_stream = torch.cuda.ExternalStream(window.stream, device=dev)
+    frame_bytes = rows * cols
+
+    def step_dev(k):
+        tracker.read_image_dev(frames_dev[k % pool].data_ptr(), cols, k / hz, bool(PUB_PATTERN[k % len(PUB_PATTERN)]))
+        window.optimize_dev(with_marg, B.MARGIN_OLD)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM, no host synchronisation inside the timed region -------------
+    for k in range(args.warmup):
+        step_dev(k)
+    tracker.sync()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = lfvio.lib.lfvio_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record(t_stream)
+    ev[1].record(w_stream)
+    t_wall0 = time.perf_counter()
+    for k in range(args.warmup, args.warmup + args.steps):
+        step_dev(k)
+    ev[2].record(t_stream)
+    ev[3].record(w_stream)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = lfvio.lib.lfvio_launch_count() - launches0
+    clk = clocks.stop()
+    # both streams start together after the barrier; the step is done when both are
+    ms_total = max(ev[0].elapsed_time(ev[2]), ev[1].elapsed_time(ev[3]), ev[0].elapsed_time(ev[3]), ev[1].elapsed_time(ev[2]))
+    ms_total = max(ms_total, 0.0)
+    ms_tracker, ms_window = ev[0].elapsed_time(ev[2]), ev[1].elapsed_time(ev[3])
+    tracker.sync()
+    n_tracks = len(tracker.ids)
+    summ = window.download(wprob.clone())
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    barrier()
+
+    # ---- e2e: host buffers through the C-ABI, H2D + D2H inside the timed region ------------------------
+    e2e_steps = max(10, min(args.steps, 200))
+    work = wprob.clone()
+    init = (wprob.pose.copy(), wprob.sb.copy(), wprob.ex.copy(), wprob.feat.copy(), wprob.td.copy())
+    src_frames = pinned.numpy() if pinned is not None else frames_host
+
+    def step_host(k):
+        tracker.read_image(src_frames[k % pool], (args.warmup + args.steps + k) / hz, bool(PUB_PATTERN[k % len(PUB_PATTERN)]))
+        tracker.update_ids()
+        for dst, s in zip((work.pose, work.sb, work.ex, work.feat, work.td), init):
+            np.copyto(dst, s)
+        return window.optimize(work)
+
+    for k in range(3):
+        step_host(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(3, 3 + e2e_steps):
+        step_host(k)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    blob_bytes = wprob.n_proj * C.sizeof(B.ProjFactor) + wprob.n_imu * C.sizeof(B.ImuFactor) + 8 * (16 * (wsz + 1) + 8 + wprob.L)
+    h2d = frame_bytes + blob_bytes
+    d2h = max_cnt * (8 + 4 + 4 + 12 + 12) + 8 + 8 * (16 * (wsz + 1) + 8 + wprob.L) + 2048
+
+    # ---- per-kernel durations, live (CUDA events on the launching streams), same workload ---------------
+    prof_steps = min(args.steps, 200)
+    nt, nw = lfvio.lib.lfvio_tracker_stage_count(), lfvio.lib.lfvio_window_stage_count()
+    lfvio.check(lfvio.lib.lfvio_tracker_profile_begin(tracker.handle, prof_steps), "profile_begin")
+    lfvio.check(lfvio.lib.lfvio_window_profile_begin(window._h, prof_steps), "profile_begin")
+    window.upload(wprob)
+    for k in range(prof_steps):
+        step_dev(args.warmup + args.steps + k)
+    t_ms, t_cnt = (C.c_float * nt)(), (C.c_int * nt)()
+    w_ms, w_cnt = (C.c_float * nw)(), (C.c_int * nw)()
+    lfvio.check(lfvio.lib.lfvio_tracker_profile_end(tracker.handle, t_ms, t_cnt), "profile_end")
+    lfvio.check(lfvio.lib.lfvio_window_profile_end(window._h, w_ms, w_cnt), "profile_end")
+    tracker.sync()
+    stages = {}
+    for i in range(nt):
+        if t_cnt[i]:
+            stages[lfvio.lib.lfvio_tracker_stage_name(i).decode()] = (t_ms[i] / prof_steps, t_ms[i] / t_cnt[i], t_cnt[i] / prof_steps)
+    for i in range(nw):
+        if w_cnt[i]:
+            stages[lfvio.lib.lfvio_window_stage_name(i).decode()] = (w_ms[i] / prof_steps, w_ms[i] / w_cnt[i], w_cnt[i] / prof_steps)
+    # algorithmic bytes per launch group (SURVEY.md §8d / DESIGN.md)
+    px = rows * cols
+    n_lk = max(n_tracks, 1)
+    D = 15 * (wsz + 1) + 7
+    algo_bytes = {
+        "clahe(3 kernels)": 3.0 * px,
+        "pyr_down(3 kernels)": px * (1 + 0.25 + 0.0625 + 0.015625) + px * (0.25 + 0.0625),
+        "lk_kernel": n_lk * 4 * 2 * 43 * 43 + n_lk * 17,
+        "min_eig_kernel": 5.0 * px + px,
+        "candidates_kernel": 5.0 * px,
+        "mask_raster(copy+kernel)": 2.0 * px,
+        "evaluate_kernel(candidate)": wprob.n_proj * (144 + 336) + wprob.n_imu * (3720 + 3720),
+        "accumulate_kernel": wprob.n_proj * 336 + wprob.n_imu * 3720 + 8.0 * D * D,
+        "step_kernel": wprob.n_proj * 2 * 336 + 3 * 8.0 * D * D,
+    }
+    dom = max(stages.items(), key=lambda kv: kv[1][0])
+    dom_name, (dom_ms_step, dom_ms_launch, dom_per_step) = dom[0], dom[1]
+    ab = algo_bytes.get(dom_name)
+    achieved = (ab / (dom_ms_launch * 1e-3) / 1e9) if ab else None
+    roofline = {
+        "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None, "peak_kind": peak_kind,
+        "algorithmic_bytes_per_launch": ab, "avg_launch_ms": dom_ms_launch,
+        "stage_ms_per_step": {k: round(v[0], 5) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])},
+        "note": "configs 1-3 are launch/latency bound (a whole 1280x960 frame is ~3 us of HBM time, SURVEY.md §7)",
+    }
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -----------------------------------
+    cpu = None
+    if rank == 0 and world == 1:
+        r = cpu_arm(wl, args.cpu_sample, 3, 0, with_marg)
+        cpu = {"value": r["fps"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"{args.cpu_sample} frames of the same workload; cv2 front end ({r['cv2_threads']} threads) + fp64 C++ "
+                         "oracle back end (1 thread solve, 4 thread marginalisation)",
+               "ms_front": r["ms_front"], "ms_back": r["ms_back"]}
+
+    if rank == 0:
+        fps = world * args.steps / (ms_total * 1e-3)
+        line = {
+            "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/f32 front end, f64 back end", "data": "synthetic",
+            "config": {"workload": args.config, "image": f"{cols}x{rows}", "features": max_cnt, "tracked": n_tracks,
+                       "window_frames": wsz + 1, "n_proj_factors": wprob.n_proj, "n_landmarks": wprob.L,
+                       "iterations": int(summ.iterations), "marginalize": with_marg, "pub_pattern": list(PUB_PATTERN),
+                       "l2_policy": f"inputs larger than L2: {pool}-frame pool ({pool * px / 2**20:.0f} MiB) cycled",
+                       "streams": "one independent stream per GPU; front end and back end on separate CUDA streams"},
+            "ms_tracker_stream": ms_tracker / args.steps, "ms_window_stream": ms_window / args.steps,
+            "wall_ms_per_step": 1e3 * t_wall / args.steps,
+            "e2e": {"value": world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clk,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

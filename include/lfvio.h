@@ -276,6 +276,21 @@ int lfvio_window_upload(lfvio_window *w, const lfvio_window_state *state, const 
 int lfvio_window_optimize_dev(lfvio_window *w, int with_marginalize, int margin_flag);
 int lfvio_window_download(lfvio_window *w, lfvio_window_state *state, lfvio_solve_summary *summary);
 
+/* ------------------------------------------------------------------------------------------
+ * Live per-stage device timing (CUDA events recorded on the handle's own stream around each kernel
+ * group).  Replaces the reference's TicToc prints (feature_tracker.cpp:106,141,153,170,175;
+ * estimator.cpp:775,828,915,919) and gives bench.py the kernel durations its roofline line needs.
+ * ------------------------------------------------------------------------------------------ */
+int lfvio_tracker_stage_count(void);
+const char *lfvio_tracker_stage_name(int i);
+int lfvio_tracker_profile_begin(lfvio_tracker *t, int max_frames);
+/* Synchronises the stream; stage_ms[i] = total device ms, stage_records[i] = timed launches groups. */
+int lfvio_tracker_profile_end(lfvio_tracker *t, float *stage_ms, int *stage_records);
+int lfvio_window_stage_count(void);
+const char *lfvio_window_stage_name(int i);
+int lfvio_window_profile_begin(lfvio_window *w, int max_solves);
+int lfvio_window_profile_end(lfvio_window *w, float *stage_ms, int *stage_records);
+
 #ifdef __cplusplus
 }
 #endif

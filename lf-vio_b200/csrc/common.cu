@@ -30,6 +30,43 @@ int sm_count(int device) {
     return cached[device];
 }
 
+int StageProfiler::enable(int stages, int max_records) {
+    disable();
+    n_stages = stages;
+    cap = (size_t)max_records;
+    ev = new cudaEvent_t[2 * cap];
+    stage = new int[cap];
+    for (size_t i = 0; i < 2 * cap; i++) LFVIO_CUDA_TRY(cudaEventCreate(&ev[i]));
+    used = 0;
+    on = true;
+    return LFVIO_OK;
+}
+void StageProfiler::disable() {
+    if (ev) {
+        for (size_t i = 0; i < 2 * cap; i++) cudaEventDestroy(ev[i]);
+        delete[] ev;
+        delete[] stage;
+    }
+    ev = nullptr;
+    stage = nullptr;
+    cap = used = 0;
+    on = false;
+}
+int StageProfiler::collect(float *ms, int *counts) {
+    for (int i = 0; i < n_stages; i++) {
+        ms[i] = 0.f;
+        counts[i] = 0;
+    }
+    for (size_t r = 0; r < used; r++) {
+        float t = 0.f;
+        LFVIO_CUDA_TRY(cudaEventElapsedTime(&t, ev[2 * r], ev[2 * r + 1]));
+        ms[stage[r]] += t;
+        counts[stage[r]] += 1;
+    }
+    used = 0;
+    return LFVIO_OK;
+}
+
 }  // namespace lfvio
 
 extern "C" const char *lfvio_last_error(void) { return lfvio::g_err; }

@@ -51,6 +51,34 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // B200: 148 SMs.  Queried once per device and cached.
 int sm_count(int device);
 
+// Optional per-stage device timing (CUDA events on the handle's own stream), used by bench.py to measure the
+// average launch duration of each kernel group live, without a profiler attached.
+struct StageProfiler {
+    bool on = false;
+    int n_stages = 0;
+    size_t used = 0;
+    cudaEvent_t *ev = nullptr;  // 2 * cap events
+    int *stage = nullptr;
+    size_t cap = 0;
+    int enable(int stages, int max_records);
+    void disable();
+    void begin(int st, cudaStream_t s) {
+        if (on && used < cap) {
+            stage[used] = st;
+            cudaEventRecord(ev[2 * used], s);
+        }
+    }
+    void end(cudaStream_t s) {
+        if (on && used < cap) {
+            cudaEventRecord(ev[2 * used + 1], s);
+            used++;
+        }
+    }
+    // after a stream synchronise: per-stage total milliseconds and record counts; resets the record list
+    int collect(float *ms, int *counts);
+    ~StageProfiler() { disable(); }
+};
+
 }  // namespace lfvio
 
 #ifdef __CUDACC__

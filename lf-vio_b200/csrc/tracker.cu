@@ -125,7 +125,15 @@ LkParams default_lk(int rows, int cols, int border_check) {
 
 using namespace lfvio;
 
+enum TrackerStage { TS_CLAHE = 0, TS_PYRAMID, TS_LK, TS_COMPACT, TS_SETMASK, TS_MASK_RASTER, TS_MIN_EIG, TS_CANDIDATES,
+                    TS_SELECT, TS_UNDISTORT, TS_UPDATE_IDS, TS_COUNT };
+static const char *kTrackerStageNames[TS_COUNT] = {"clahe(3 kernels)", "pyr_down(3 kernels)", "lk_kernel", "compact_kernel",
+                                                   "set_mask_select_kernel", "mask_raster(copy+kernel)", "min_eig_kernel",
+                                                   "candidates_kernel", "select_kernel", "undistort_kernel",
+                                                   "update_ids_kernel"};
+
 struct lfvio_tracker {
+    StageProfiler prof;
     lfvio_tracker_cfg cfg;
     int device = 0, n_sm = 148, cap = 0, pitch = 0;
     cudaStream_t stream = nullptr;
@@ -226,39 +234,57 @@ int enqueue_frame(lfvio_tracker *t, const uint8_t *src, int src_pitch, double cu
     const int forw_slot = (t->frames == 0) ? t->cur_slot : (t->cur_slot ^ 1);
     Pyramid &forw = t->pyr[forw_slot];
     if (c.equalize) {
+        t->prof.begin(TS_CLAHE, s);
         LFVIO_TRY(launch_clahe(src, src_pitch, forw.lvl[0].data, forw.lvl[0].pitch, c.rows, c.cols, 3.0f,
                                t->clahe_hist.p, t->clahe_lut.p, t->n_sm, s));
+        t->prof.end(s);
     } else {
         LFVIO_CUDA_TRY(cudaMemcpy2DAsync(forw.lvl[0].data, forw.lvl[0].pitch, src, src_pitch, c.cols, c.rows,
                                          cudaMemcpyDeviceToDevice, s));
     }
-    LFVIO_TRY(launch_build_pyramid(forw, s));
+    t->prof.begin(TS_PYRAMID, s);
+        LFVIO_TRY(launch_build_pyramid(forw, s));
+        t->prof.end(s);
     Pyramid &cur = t->pyr[t->cur_slot];  // first frame: prev_img = cur_img = forw_img = img
     // forw_pts.clear(); if (cur_pts.size() > 0) calcOpticalFlowPyrLK ... reduceVector ...
     TrackArrays A = t->live(), B = t->spare();
     if (t->n_upper > 0) {
         const LkParams prm = default_lk(c.rows, c.cols, 1);
+        t->prof.begin(TS_LK, s);
         LFVIO_TRY(launch_lk(cur, forw, A.cur, A.forw, t->status.p, t->n_upper, t->n_dev.p, prm, s));
-        LFVIO_TRY(launch_compact(A, B, t->status.p, t->n_dev.p, t->cap, s));  // + track_cnt++
+        t->prof.end(s);
+        t->prof.begin(TS_COMPACT, s);
+        LFVIO_TRY(launch_compact(A, B, t->status.p, t->n_dev.p, t->cap, s));
+        t->prof.end(s);  // + track_cnt++
         t->a ^= 1;
         A = t->live();
         B = t->spare();
     }
     if (pub) {
         // rejectWithF(): SURVEY §8(f) rank 1, not built (cfg.ransac must be 0)
+        t->prof.begin(TS_SETMASK, s);
         LFVIO_TRY(launch_set_mask_select(A, B, t->n_dev.p, t->cap, t->base_mask.p, t->pitch, t->half_width.p, c.min_dist,
                                          t->sort_scratch.p, s));
+        t->prof.end(s);
         t->a ^= 1;
         A = t->live();
+        t->prof.begin(TS_MASK_RASTER, s);
         LFVIO_TRY(launch_mask_raster(t->mask.p, t->base_mask.p, c.rows, c.cols, t->pitch, A.forw, t->n_dev.p, t->cap,
                                      t->half_width.p, c.min_dist, s));
+        t->prof.end(s);
         // goodFeaturesToTrack(forw_img, n_pts, MAX_CNT - forw_pts.size(), 0.01, MIN_DIST, mask) + addPoints()
+        t->prof.begin(TS_MIN_EIG, s);
         LFVIO_TRY(launch_min_eig(forw.lvl[0].data, forw.lvl[0].pitch, t->mask.p, t->pitch, t->corners.eig.p, c.rows, c.cols,
                                  t->corners.max_bits.p, s));
+        t->prof.end(s);
+        t->prof.begin(TS_CANDIDATES, s);
         LFVIO_TRY(launch_corner_candidates(t->corners.eig.p, t->mask.p, t->pitch, c.rows, c.cols, t->corners.max_bits.p,
                                            0.01, t->corners.cs, s));
+        t->prof.end(s);
+        t->prof.begin(TS_SELECT, s);
         LFVIO_TRY(launch_corner_select(t->corners.cs, c.cols, (float)c.min_dist, c.max_cnt, t->n_dev.p, A.forw, A.ids,
                                        A.cnt, A.prev_valid, t->cap, s));
+        t->prof.end(s);
         t->n_upper = std::max(t->n_upper, c.max_cnt);
     }
     // prev_img = cur_img; cur_img = forw_img; cur_pts = forw_pts
@@ -266,12 +292,18 @@ int enqueue_frame(lfvio_tracker *t, const uint8_t *src, int src_pitch, double cu
     std::swap(t->store[t->a].cur.p, t->store[t->a].forw.p);
     A = t->live();
     const int hp = (int)(t->frames & 1);
-    LFVIO_TRY(launch_undistort(t->cam, A.cur, A.ids, A.bearing, A.prev_valid, t->bearing_out.p, t->vel_out.p,
+    t->prof.begin(TS_UNDISTORT, s);
+        LFVIO_TRY(launch_undistort(t->cam, A.cur, A.ids, A.bearing, A.prev_valid, t->bearing_out.p, t->vel_out.p,
                                t->n_dev.p, t->n_upper, cur_time - t->prev_time, t->have_prev.p + hp,
                                t->have_prev.p + (hp ^ 1), s));
+        t->prof.end(s);
     t->prev_time = cur_time;
     t->frames++;
-    if (ids_on_device) LFVIO_TRY(launch_update_ids(A.ids, t->n_dev.p, t->cap, t->n_id_dev.p, s));
+    if (ids_on_device) {
+        t->prof.begin(TS_UPDATE_IDS, s);
+        LFVIO_TRY(launch_update_ids(A.ids, t->n_dev.p, t->cap, t->n_id_dev.p, s));
+        t->prof.end(s);
+    }
     t->mirror_fresh = false;
     return LFVIO_OK;
 }
@@ -440,6 +472,24 @@ extern "C" int lfvio_tracker_set_points(lfvio_tracker *t, const float *cur_pts, 
 }
 
 extern "C" void *lfvio_tracker_stream(lfvio_tracker *t) { return t ? (void *)t->stream : nullptr; }
+
+extern "C" int lfvio_tracker_stage_count(void) { return TS_COUNT; }
+extern "C" const char *lfvio_tracker_stage_name(int i) { return (i >= 0 && i < TS_COUNT) ? kTrackerStageNames[i] : ""; }
+extern "C" int lfvio_tracker_profile_begin(lfvio_tracker *t, int max_frames) {
+    clear_error();
+    LFVIO_REQUIRE(t && max_frames > 0, "lfvio_tracker_profile_begin: bad arguments");
+    LFVIO_CUDA_TRY(cudaSetDevice(t->device));
+    return t->prof.enable(TS_COUNT, max_frames * TS_COUNT);
+}
+extern "C" int lfvio_tracker_profile_end(lfvio_tracker *t, float *stage_ms, int *stage_records) {
+    clear_error();
+    LFVIO_REQUIRE(t && stage_ms && stage_records, "lfvio_tracker_profile_end: bad arguments");
+    LFVIO_CUDA_TRY(cudaSetDevice(t->device));
+    LFVIO_CUDA_TRY(cudaStreamSynchronize(t->stream));
+    LFVIO_TRY(t->prof.collect(stage_ms, stage_records));
+    t->prof.disable();
+    return LFVIO_OK;
+}
 
 // ================================================================================================
 // Stage-level entry points (host buffers, synchronous)

@@ -39,7 +39,13 @@ size_t align8(size_t v) { return (v + 7) & ~size_t(7); }
 
 }  // namespace
 
+enum WindowStage { WS_PREPARE = 0, WS_EVAL_INITIAL, WS_JACOBI_SCALE, WS_ACCUMULATE, WS_STEP, WS_EVALUATE, WS_MARGINALIZE, WS_COUNT };
+static const char *kWindowStageNames[WS_COUNT] = {"prepare(init+imu_prepare+prior_prepare)", "evaluate_kernel(initial)",
+                                                  "jacobi_scale(2 kernels)", "accumulate_kernel", "step_kernel",
+                                                  "evaluate_kernel(candidate)", "marginalize"};
+
 struct lfvio_window {
+    StageProfiler prof;
     int device = 0, F = 0, Lmax = 0, Rmax = 0, nmax = 0;
     cudaStream_t stream = nullptr;
     // blob offsets (bytes)
@@ -236,14 +242,26 @@ int enqueue_solve(lfvio_window *w) {
     cudaStream_t s = w->stream;
     const DevProblem &P = w->P;
     const size_t xbytes = sizeof(double) * P.lay.size();
+    w->prof.begin(WS_PREPARE, s);
     LFVIO_TRY(launch_solver_init(w->ctl.p, P.o, s));
     LFVIO_CUDA_TRY(cudaMemcpyAsync(w->x[0].p, w->blob.p + w->off_x, xbytes, cudaMemcpyDeviceToDevice, s));
+    w->prof.end(s);
+    w->prof.begin(WS_EVAL_INITIAL, s);
     LFVIO_TRY(launch_evaluate(P, w->x[0].p, w->x[1].p, w->e[0], w->e[1], w->ctl.p, 0, 1, s));
+    w->prof.end(s);
+    w->prof.begin(WS_JACOBI_SCALE, s);
     LFVIO_TRY(launch_jacobi_scale(P, w->e[0], w->w, s));
+    w->prof.end(s);
     for (int it = 0; it < P.o.max_num_iterations; it++) {
+        w->prof.begin(WS_ACCUMULATE, s);
         LFVIO_TRY(launch_accumulate(P, w->e[0], w->e[1], w->w, w->ctl.p, s));
+        w->prof.end(s);
+        w->prof.begin(WS_STEP, s);
         LFVIO_TRY(launch_step(P, w->e[0], w->e[1], w->w, w->x[0].p, w->x[1].p, w->ctl.p, s));
+        w->prof.end(s);
+        w->prof.begin(WS_EVALUATE, s);
         LFVIO_TRY(launch_evaluate(P, w->x[0].p, w->x[1].p, w->e[0], w->e[1], w->ctl.p, 1, 1, s));
+        w->prof.end(s);
     }
     return LFVIO_OK;
 }
@@ -426,3 +444,21 @@ extern "C" int lfvio_window_marginalize(lfvio_window *w, const lfvio_window_stat
 }
 
 extern "C" void *lfvio_window_stream(lfvio_window *w) { return w ? (void *)w->stream : nullptr; }
+
+extern "C" int lfvio_window_stage_count(void) { return WS_COUNT; }
+extern "C" const char *lfvio_window_stage_name(int i) { return (i >= 0 && i < WS_COUNT) ? kWindowStageNames[i] : ""; }
+extern "C" int lfvio_window_profile_begin(lfvio_window *w, int max_solves) {
+    clear_error();
+    LFVIO_REQUIRE(w && max_solves > 0, "lfvio_window_profile_begin: bad arguments");
+    LFVIO_CUDA_TRY(cudaSetDevice(w->device));
+    return w->prof.enable(WS_COUNT, max_solves * (4 + 3 * LFVIO_MAX_ITER_LOG));
+}
+extern "C" int lfvio_window_profile_end(lfvio_window *w, float *stage_ms, int *stage_records) {
+    clear_error();
+    LFVIO_REQUIRE(w && stage_ms && stage_records, "lfvio_window_profile_end: bad arguments");
+    LFVIO_CUDA_TRY(cudaSetDevice(w->device));
+    LFVIO_CUDA_TRY(cudaStreamSynchronize(w->stream));
+    LFVIO_TRY(w->prof.collect(stage_ms, stage_records));
+    w->prof.disable();
+    return LFVIO_OK;
+}

@@ -98,6 +98,8 @@ void eval_projection(const lfvio_proj_factor &f, const double *pose_i, const dou
     const M3 tmp_r = A * Ri * ric;
     put(15, (-tmp_r) * skew(pts_camera_i) + skew(tmp_r * pts_camera_i) +
                 skew(ricT * (RjT * (Ri * Pe.p + Pi.p - Pj.p) - Pe.p)));  // d/dtheta_ic
+    if (!o.estimate_extrinsic)  // problem.SetParameterBlockConstant(para_Ex_Pose): the solver never sees these columns
+        for (int c = 12; c < 18; c++) J[0][c] = J[1][c] = 0.0;
     const V3 dl = (tmp_r * pts_i_td) * (-1.0 / (inv_dep_i * inv_dep_i));
     const V3 dt = (tmp_r * vel_i) * (-1.0 / inv_dep_i);
     for (int rr = 0; rr < 2; rr++) {
