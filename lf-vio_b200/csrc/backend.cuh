@@ -83,6 +83,7 @@ struct SolverCtl {
     double radius, mu, cost, cost_cand, x_norm, dogleg_step_norm, alpha, model_cost_change, step_norm;
     double cost_log[LFVIO_MAX_ITER_LOG], radius_log[LFVIO_MAX_ITER_LOG];
     int accepted_log[LFVIO_MAX_ITER_LOG];
+    long long phase_clk[16];  // clock64() at the phase boundaries of the last step_kernel (LFVIO_DEBUG_STEP=1 prints them)
 };
 
 #ifdef __CUDACC__

@@ -1,0 +1,33 @@
+// Marginalisation plan (host-built index bookkeeping) and device buffers, shared by marg.cu and window.cu.
+#pragma once
+#include "backend.cuh"
+
+namespace lfvio {
+
+// Column bookkeeping of MarginalizationInfo::marginalize (marginalization_factor.cpp:174-205) in a canonical
+// order: [dropped pose/speed-bias blocks (m_p columns) | kept blocks by ascending id (n columns)].  The dropped
+// inverse depths are eliminated landmark by landmark and never get a column.
+struct MargPlan {
+    int flag;                       // LFVIO_MARGIN_OLD / LFVIO_MARGIN_SECOND_NEW
+    int m_p, n, dim;                // dim = m_p + n
+    int use_prior, imu_index;       // imu_index < 0: no IMU factor to marginalise
+    int n_lm;                       // landmarks hosted in the dropped frame
+    const int *lm_list;             // device: their indices
+    int col[kMaxPriorBlocks];       // parameter-block id -> first column (-1: not involved)
+    int n_keep;
+    int keep_id[kMaxPriorBlocks];   // kept blocks in column order (ids BEFORE the addr_shift renaming)
+    int keep_x0[kMaxPriorBlocks];   // offset of each kept block's data in x0_out
+    int use_smem;
+};
+
+struct MargBuffers {
+    double *T;     // dim*dim + dim (system + right-hand side)
+    double *work;  // global fallback workspace of marg_finish_kernel
+    double *J0, *r0, *x0;
+};
+
+size_t marg_finish_workspace_doubles(int m_p, int n);
+int launch_marginalize(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const double *x0, const double *x1,
+                       const SolverCtl *ctl, MargPlan &plan, const MargBuffers &mb, cudaStream_t s);
+
+}  // namespace lfvio

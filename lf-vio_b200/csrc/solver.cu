@@ -26,9 +26,14 @@ namespace lfvio {
 namespace {
 
 constexpr int ACC_WARPS = 4;
-constexpr int STEP_THREADS = 1024;
+constexpr int STEP_THREADS = 512;  // 128 registers per thread: the fp64 panel solve keeps 16 doubles live
 constexpr int NB = 16;  // Cholesky panel width
 
+__device__ __forceinline__ long long gtimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return (long long)t;
+}
 __device__ __forceinline__ double clamp_diag(double v) { return fmin(fmax(v, 1e-6), 1e32); }
 
 // local column c (0..19) of a projection factor -> column of the full (reduced | landmark) system
@@ -355,7 +360,22 @@ __device__ double rows_reduce(const DevProblem &P, const EvalBuf &e, const doubl
 
 // Blocked right-looking Cholesky S = U^T U on the upper triangle of the row-major D x D matrix, one CTA.
 // Returns (to all threads) whether the matrix was positive definite.
-__device__ bool cholesky_upper(double *S, int D, double *s_panel /* NB x D */, double *s_diag /* NB x NB */, int *s_ok) {
+// The matrix is addressed through an accessor: MatFull = row-major D x D in global memory (any D), MatPacked =
+// packed upper triangle resident in shared memory (D <= ~220: the whole factorisation and both triangular
+// solves then run without a single global-memory round trip).
+struct MatFull {
+    double *p;
+    int D;
+    __device__ __forceinline__ double &at(int r, int c) const { return p[(size_t)r * D + c]; }
+};
+struct MatPacked {
+    double *p;
+    int D;
+    __device__ __forceinline__ double &at(int r, int c) const { return p[r * D - ((r * (r - 1)) >> 1) + (c - r)]; }
+};
+
+template <class M>
+__device__ bool cholesky_upper(M S, int D, double *s_panel /* NB x D */, double *s_diag /* NB x NB */, int *s_ok) {
     const int tid = threadIdx.x, nt = blockDim.x;
     if (tid == 0) *s_ok = 1;
     __syncthreads();
@@ -364,7 +384,7 @@ __device__ bool cholesky_upper(double *S, int D, double *s_panel /* NB x D */, d
         // diagonal block -> shared, factor with one warp
         for (int q = tid; q < nb * nb; q += nt) {
             const int r = q / nb, c = q % nb;
-            s_diag[r * NB + c] = (c >= r) ? S[(size_t)(j0 + r) * D + j0 + c] : 0.0;
+            s_diag[r * NB + c] = (c >= r) ? S.at(j0 + r, j0 + c) : 0.0;
         }
         __syncthreads();
         if (tid < 32) {
@@ -390,34 +410,73 @@ __device__ bool cholesky_upper(double *S, int D, double *s_panel /* NB x D */, d
         if (*s_ok == 0) return false;
         for (int q = tid; q < nb * nb; q += nt) {
             const int r = q / nb, c = q % nb;
-            if (c >= r) S[(size_t)(j0 + r) * D + j0 + c] = s_diag[r * NB + c];
+            if (c >= r) S.at(j0 + r, j0 + c) = s_diag[r * NB + c];
         }
         const int rest0 = j0 + nb, nrest = D - rest0;
         if (nrest > 0) {
             // row panel: U12 = U11^-T A12, one thread per column
             for (int c = tid; c < nrest; c += nt) {
                 double u[NB];
-                for (int r = 0; r < nb; r++) {
-                    double s = S[(size_t)(j0 + r) * D + rest0 + c];
-                    for (int t = 0; t < r; t++) s -= s_diag[t * NB + r] * u[t];
-                    u[r] = s / s_diag[r * NB + r];
+#pragma unroll
+                for (int r = 0; r < NB; r++) u[r] = (r < nb) ? S.at(j0 + r, rest0 + c) : 0.0;  // independent loads first
+#pragma unroll
+                for (int r = 0; r < NB; r++) {
+                    if (r < nb) {
+                        double s = u[r];
+#pragma unroll
+                        for (int t = 0; t < NB; t++)
+                            if (t < r) s -= s_diag[t * NB + r] * u[t];
+                        u[r] = s / s_diag[r * NB + r];
+                    }
                 }
-                for (int r = 0; r < nb; r++) {
-                    S[(size_t)(j0 + r) * D + rest0 + c] = u[r];
-                    s_panel[r * D + c] = u[r];
+#pragma unroll
+                for (int r = 0; r < NB; r++) {
+                    if (r < nb) {
+                        S.at(j0 + r, rest0 + c) = u[r];
+                        s_panel[r * D + c] = u[r];
+                    }
                 }
             }
+            // zero padding so the 4x4 register tiles below need no bounds checks inside the rank-nb loop
+            if (tid < NB * 4) {
+                const int r = tid >> 2, c = nrest + (tid & 3);
+                if (c < D) s_panel[r * D + c] = 0.0;
+            }
+            if (nb < NB)
+                for (int q = tid; q < (NB - nb) * D; q += nt) s_panel[nb * D + q] = 0.0;
             __syncthreads();
-            // trailing update of the upper triangle: A22[i][k] -= sum_t U12[t][i] U12[t][k], k >= i
-            // (flattened over the nrest x nrest square so that all threads have work; k fastest => coalesced)
-            for (int q = tid; q < nrest * nrest; q += nt) {
-                const int i = q / nrest, k = q - i * nrest;
-                if (k < i) continue;
-                double s = 0;
+            // trailing update of the upper triangle: A22[i][k] -= sum_t U12[t][i] U12[t][k], k >= i.
+            // 4x4 register tiles: 8 shared-memory loads per 16 DFMA (the one-element-per-thread form is bound by
+            // shared-memory bandwidth at 2 loads per DFMA).
+            const int nt4 = (nrest + 3) >> 2;
+            for (int q = tid; q < nt4 * nt4; q += nt) {
+                const int ti = q / nt4, tk = q - ti * nt4;
+                if (tk < ti) continue;
+                const int i0 = ti << 2, k0 = tk << 2;
+                double acc[4][4];
 #pragma unroll
-                for (int t = 0; t < NB; t++)
-                    if (t < nb) s += s_panel[t * D + i] * s_panel[t * D + k];
-                S[(size_t)(rest0 + i) * D + rest0 + k] -= s;
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
+#pragma unroll 4
+                for (int t = 0; t < NB; t++) {
+                    double a[4], b[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) a[u] = s_panel[t * D + i0 + u];
+#pragma unroll
+                    for (int v = 0; v < 4; v++) b[v] = s_panel[t * D + k0 + v];
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+#pragma unroll
+                        for (int v = 0; v < 4; v++) acc[u][v] += a[u] * b[v];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        const int i = i0 + u, k = k0 + v;
+                        if (i < nrest && k < nrest && k >= i) S.at(rest0 + i, rest0 + k) -= acc[u][v];
+                    }
             }
         }
         __syncthreads();
@@ -425,14 +484,65 @@ __device__ bool cholesky_upper(double *S, int D, double *s_panel /* NB x D */, d
     return true;
 }
 
+// U^T z = b (forward) then U y = z (backward) on a shared-memory vector y (in/out), blocked by NB: the 16-step
+// dependent chain of each diagonal block is run by warp 0, everything off the diagonal block is a parallel update
+// (forward: all threads own a column; backward: one warp per row does a dot product).  Whole CTA must call.
+template <class M>
+__device__ void solve_upper_blocked(M S, int D, double *y, double *s_tmp /* NB */) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    for (int j0 = 0; j0 < D; j0 += NB) {
+        const int nb = min(NB, D - j0);
+        if (wid == 0) {
+            for (int j = j0; j < j0 + nb; j++) {
+                const double zj = y[j] / S.at(j, j);
+                __syncwarp();
+                if (lane == 0) y[j] = zj;
+                const int k = j + 1 + lane;
+                if (k < j0 + nb) y[k] -= S.at(j, k) * zj;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int k = j0 + nb + tid; k < D; k += nt) {
+            double s = 0;
+#pragma unroll 4
+            for (int t = 0; t < nb; t++) s += S.at(j0 + t, k) * y[j0 + t];
+            y[k] -= s;
+        }
+        __syncthreads();
+    }
+    const int nblk = (D + NB - 1) / NB;
+    for (int bi = nblk - 1; bi >= 0; bi--) {
+        const int j0 = bi * NB, nb = min(NB, D - j0), k0 = j0 + nb;
+        for (int r = wid; r < nb; r += (nt >> 5)) {
+            double s = 0;
+            for (int k = k0 + lane; k < D; k += 32) s += S.at(j0 + r, k) * y[k];
+            s = warp_sum(s);
+            if (lane == 0) s_tmp[r] = s;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            for (int j = j0 + nb - 1; j >= j0; j--) {
+                double s = 0;
+                const int k = j + 1 + lane;
+                if (k < k0) s = S.at(j, k) * y[k];
+                s = warp_sum(s);
+                if (lane == 0) y[j] = (y[j] - s_tmp[j - j0] - s) / S.at(j, j);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(STEP_THREADS) step_kernel(DevProblem P, EvalBuf e0, EvalBuf e1, SolverScratch w, double *x0,
-                                                           double *x1, SolverCtl *ctl) {
+                                                           double *x1, SolverCtl *ctl, int use_smem) {
     if (ctl->done != 0) return;
     extern __shared__ double smem[];
     __shared__ double s_red[33];
     __shared__ double s_diag[NB * NB];
     __shared__ int s_ok;
-    __shared__ double s_sc[8];
+    __shared__ double s_sc[NB];
     const StateLayout lay = P.lay;
     const lfvio_solver_opts &o = P.o;
     const int D = lay.D(), L = lay.L, N = D + L;
@@ -441,7 +551,9 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(DevProblem P, EvalBu
     const EvalBuf &e = cur ? e1 : e0;
     double *x = cur ? x1 : x0, *xc = cur ? x0 : x1;
     double *s_panel = smem;                                  // NB * D doubles
-    int *pmap = reinterpret_cast<int *>(smem + (size_t)NB * D);  // prior column map
+    int *pmap = reinterpret_cast<int *>(smem + (size_t)NB * D);  // prior column map (15 * kMaxFrames + 8 ints)
+    double *s_y = smem + (size_t)NB * D + (15 * kMaxFrames + 8 + 1) / 2;  // D doubles
+    double *s_S = s_y + D;                                   // packed upper triangle when use_smem
     {
         const DevPrior &p = P.prior;
         for (int b = tid; b < p.n_blocks; b += nt) {
@@ -449,6 +561,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(DevProblem P, EvalBu
             for (int q = 0; q < ls; q++) pmap[p.block_idx[b] + q] = c0 + q;
         }
     }
+    if (tid == 0) ctl->phase_clk[0] = gtimer_ns();
     // x_norm over the non-constant parameter blocks (global sizes)
     {
         double a = 0;
@@ -479,8 +592,17 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(DevProblem P, EvalBu
             if (tid == 0) ctl->done = 1;
             return;
         }
-        for (int c = tid; c < D; c += nt) w.S[(size_t)c * D + c] += w.diagonal[c] * w.diagonal[c] * mu;
+        if (use_smem) {
+            const MatPacked Sp{s_S, D};
+            for (int q = tid; q < D * D; q += nt) {
+                const int r = q / D, c = q - r * D;
+                if (c >= r) Sp.at(r, c) = w.S[q] + (r == c ? w.diagonal[c] * w.diagonal[c] * mu : 0.0);
+            }
+        } else {
+            for (int c = tid; c < D; c += nt) w.S[(size_t)c * D + c] += w.diagonal[c] * w.diagonal[c] * mu;
+        }
         __syncthreads();
+    if (tid == 0) ctl->phase_clk[1] = gtimer_ns();
         // Cauchy point: alpha = |gradient|^2 / |J_s (gradient / diagonal)|^2
         for (int c = tid; c < N; c += nt) w.step[c] = w.gradient[c] / w.diagonal[c];  // step used as scratch
         double gg = 0;
@@ -489,34 +611,24 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(DevProblem P, EvalBu
         __syncthreads();
         const double jj = rows_reduce(P, e, w.scale, w.step, 0, pmap, s_red);
         if (tid == 0) ctl->alpha = gg / jj;
+    if (tid == 0) ctl->phase_clk[2] = gtimer_ns();
         // Gauss-Newton step through the reduced system
-        const bool pd = cholesky_upper(w.S, D, s_panel, s_diag, &s_ok);
+        const bool pd = use_smem ? cholesky_upper(MatPacked{s_S, D}, D, s_panel, s_diag, &s_ok)
+                                 : cholesky_upper(MatFull{w.S, D}, D, s_panel, s_diag, &s_ok);
         if (!pd) {
             step_valid = 0;
         } else {
             // U^T z = rhs (forward), U y = z (backward): one warp, row accesses are coalesced
-            for (int c = tid; c < D; c += nt) w.y[c] = w.rhs[c];
+    if (tid == 0) ctl->phase_clk[3] = gtimer_ns();
+            for (int c = tid; c < D; c += nt) s_y[c] = w.rhs[c];
             __syncthreads();
-            if (tid < 32) {
-                for (int j = 0; j < D; j++) {
-                    const double zj = w.y[j] / w.S[(size_t)j * D + j];
-                    __syncwarp();
-                    if (tid == 0) w.y[j] = zj;
-                    for (int k = j + 1 + tid; k < D; k += 32) w.y[k] -= w.S[(size_t)j * D + k] * zj;
-                    __syncwarp();
-                }
-                for (int j = D - 1; j >= 0; j--) {
-                    double s = 0;
-                    for (int k = j + 1 + tid; k < D; k += 32) s += w.S[(size_t)j * D + k] * w.y[k];
-                    s = warp_sum(s);
-                    if (tid == 0) w.y[j] = (w.y[j] - s) / w.S[(size_t)j * D + j];
-                    __syncwarp();
-                }
-            }
+            if (use_smem) solve_upper_blocked(MatPacked{s_S, D}, D, s_y, s_sc);
+            else solve_upper_blocked(MatFull{w.S, D}, D, s_y, s_sc);
             __syncthreads();
+    if (tid == 0) ctl->phase_clk[4] = gtimer_ns();
             int bad = 0;
             for (int c = tid; c < D; c += nt) {
-                const double yv = w.y[c];
+                const double yv = s_y[c];
                 if (!isfinite(yv)) bad = 1;
                 w.gn[c] = -w.diagonal[c] * yv;  // scaled GN step: D * (-(J^T J)^-1 g)
             }
@@ -528,13 +640,13 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(DevProblem P, EvalBu
                     const int fi = P.proj[k0].frame_i;
                     const double *ws = w.lm_ws + 13 * (size_t)l;
                     double s = w.lm_g[l];
-                    for (int a = 0; a < 6; a++) s -= ws[a] * w.y[lay.col_pose(fi) + a];
-                    for (int a = 0; a < 6; a++) s -= ws[6 + a] * w.y[lay.col_ex() + a];
-                    s -= ws[12] * w.y[lay.col_td()];
+                    for (int a = 0; a < 6; a++) s -= ws[a] * s_y[lay.col_pose(fi) + a];
+                    for (int a = 0; a < 6; a++) s -= ws[6 + a] * s_y[lay.col_ex() + a];
+                    s -= ws[12] * s_y[lay.col_td()];
                     for (int k = 0; k < K; k++) {
                         const double *wj = w.proj_wj + 6 * (size_t)(k0 + k);
                         const int cj = lay.col_pose(P.proj[k0 + k].frame_j);
-                        for (int a = 0; a < 6; a++) s -= wj[a] * w.y[cj + a];
+                        for (int a = 0; a < 6; a++) s -= wj[a] * s_y[cj + a];
                     }
                     const double c_l = w.lm_c[l];
                     yl = s / (c_l + clamp_diag(c_l) * mu);
@@ -548,6 +660,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(DevProblem P, EvalBu
     __syncthreads();
     double model_cost_change = 0, step_norm_x = 0;
     if (step_valid) {
+    if (tid == 0) ctl->phase_clk[5] = gtimer_ns();
         // ---- traditional dogleg ----
         double a0 = 0, a1 = 0, a2 = 0;
         for (int c = tid; c < N; c += nt) {
@@ -587,6 +700,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(DevProblem P, EvalBu
         sn = block_sum_1024(sn, s_red);
         if (dsn < 0) dsn = sqrt(sn);
         __syncthreads();
+    if (tid == 0) ctl->phase_clk[6] = gtimer_ns();
         // model_cost_change = -(J step) . (r + J step / 2)
         model_cost_change = rows_reduce(P, e, w.scale, w.step, 1, pmap, s_red);
         if (!(model_cost_change > 0.0)) step_valid = 0;
@@ -596,6 +710,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(DevProblem P, EvalBu
         }
     }
     if (step_valid) {
+    if (tid == 0) ctl->phase_clk[7] = gtimer_ns();
         // ---- candidate: x_plus_delta = Plus(x, step * scale) ----
         for (int q = tid; q < lay.size(); q += nt) xc[q] = x[q];
         __syncthreads();
@@ -624,6 +739,7 @@ __global__ void __launch_bounds__(STEP_THREADS) step_kernel(DevProblem P, EvalBu
         }
         step_norm_x = sqrt(block_sum_1024(a, s_red));
     }
+    if (tid == 0) ctl->phase_clk[8] = gtimer_ns();
     if (tid == 0) {
         (void)s_sc;
         ctl->step_valid = step_valid;
@@ -701,13 +817,17 @@ int launch_accumulate(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1,
 int launch_step(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const SolverScratch &w, double *x0, double *x1,
                 SolverCtl *ctl, cudaStream_t s) {
     const int D = P.lay.D();
-    const size_t smem = sizeof(double) * (size_t)NB * D + sizeof(int) * (size_t)(15 * kMaxFrames + 8);
+    const size_t base = sizeof(double) * ((size_t)NB * D + (15 * kMaxFrames + 8 + 1) / 2 + D);
+    const size_t packed = sizeof(double) * ((size_t)D * (D + 1) / 2);
+    const size_t limit = 220 * 1024;  // 227 KB per CTA minus the static arrays
+    const int use_smem = (base + packed <= limit) ? 1 : 0;
+    const size_t smem = base + (use_smem ? packed : 0);
     static bool attr_set = false;
     if (!attr_set) {
-        LFVIO_CUDA_TRY(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        LFVIO_CUDA_TRY(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
         attr_set = true;
     }
-    step_kernel<<<1, STEP_THREADS, smem, s>>>(P, e0, e1, w, x0, x1, ctl);
+    step_kernel<<<1, STEP_THREADS, smem, s>>>(P, e0, e1, w, x0, x1, ctl, use_smem);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

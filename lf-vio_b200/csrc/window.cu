@@ -7,14 +7,17 @@
 // (current / candidate) so an accepted step is a flag flip; the reduced system and dogleg vectors in one
 // scratch allocation.  The trust-region loop runs as a fixed launch sequence with a device-side control block
 // (no host synchronisation until the result is read back).
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
+#include <map>
+
 #include "backend.cuh"
+#include "marg.cuh"
 
 namespace lfvio {
 int launch_solver_init(SolverCtl *ctl, const lfvio_solver_opts &o, cudaStream_t s);
-int launch_marginalize(const DevProblem &P, const EvalBuf &e, const double *x, int flag, struct MargScratch &m, cudaStream_t s);
 }  // namespace lfvio
 
 using namespace lfvio;
@@ -63,11 +66,22 @@ struct lfvio_window {
     DevProblem P;
     EvalBuf e[2];
     bool uploaded = false;
+    // marginalisation (K14)
+    MargPlan plan[2];        // [LFVIO_MARGIN_OLD], [LFVIO_MARGIN_SECOND_NEW], rebuilt at every upload
+    bool plan_valid[2] = {false, false};
+    DBuf<int> lm_list[2];
+    DBuf<double> margT, marg_work, marg_J0, marg_r0, marg_x0;
+    double *h_marg = nullptr;  // pinned: [J0 nmax^2 | r0 nmax | x0 9*blocks]
+    int *h_lm[2] = {nullptr, nullptr};  // pinned staging of lm_list
+    int last_marg_flag = -1;
 
     ~lfvio_window() {
         if (h_blob) cudaFreeHost(h_blob);
         if (h_ctl) cudaFreeHost(h_ctl);
         if (h_x) cudaFreeHost(h_x);
+        if (h_marg) cudaFreeHost(h_marg);
+        for (int k = 0; k < 2; k++)
+            if (h_lm[k]) cudaFreeHost(h_lm[k]);
     }
 };
 
@@ -140,6 +154,111 @@ int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_pro
     LFVIO_CUDA_TRY(cudaMallocHost(&w->h_ctl, sizeof(SolverCtl)));
     LFVIO_CUDA_TRY(cudaMallocHost(&w->h_x, sizeof(double) * lay.size()));
     LFVIO_TRY(w->status.alloc(4));
+    {
+        const size_t dim = (size_t)w->nmax + 15;
+        for (int k = 0; k < 2; k++) {
+            LFVIO_TRY(w->lm_list[k].alloc(max_landmarks));
+            LFVIO_CUDA_TRY(cudaMallocHost(&w->h_lm[k], sizeof(int) * (size_t)max_landmarks));
+        }
+        LFVIO_TRY(w->margT.alloc(dim * dim + dim));
+        LFVIO_TRY(w->marg_work.alloc(marg_finish_workspace_doubles(15, w->nmax)));
+        LFVIO_TRY(w->marg_J0.alloc((size_t)w->nmax * w->nmax));
+        LFVIO_TRY(w->marg_r0.alloc(w->nmax));
+        LFVIO_TRY(w->marg_x0.alloc(9 * (size_t)kMaxPriorBlocks));
+        LFVIO_CUDA_TRY(cudaMallocHost(&w->h_marg, sizeof(double) * ((size_t)w->nmax * w->nmax + w->nmax + 9 * kMaxPriorBlocks)));
+    }
+    return LFVIO_OK;
+}
+
+// Which blocks are dropped / kept and in which column order (estimator.cpp:833-1005, marginalization_factor.cpp:174-205),
+// canonical order by block id instead of the reference's address-keyed unordered_map.
+int build_marg_plan(lfvio_window *w, int flag, const lfvio_factor_list *fl, const lfvio_solver_opts *o, int L) {
+    MargPlan &pl = w->plan[flag];
+    memset(&pl, 0, sizeof(pl));
+    w->plan_valid[flag] = false;
+    pl.flag = flag;
+    pl.imu_index = -1;
+    const int F = w->F;
+    const StateLayout lay{F, L};
+    for (int i = 0; i < kMaxPriorBlocks; i++) pl.col[i] = -1;
+    std::map<int, int> is_drop;
+    auto touch = [&](int id, bool drop) {
+        auto it = is_drop.find(id);
+        if (it == is_drop.end()) is_drop[id] = drop ? 1 : 0;
+        else if (drop) it->second = 1;
+    };
+    const bool have_prior = fl->prior && fl->prior->n > 0;
+    std::vector<int> lms;
+    if (flag == LFVIO_MARGIN_OLD) {
+        if (have_prior) {
+            pl.use_prior = 1;
+            for (int b = 0; b < fl->prior->n_blocks; b++) touch(fl->prior->block_id[b], fl->prior->block_id[b] <= 1);
+        }
+        for (int k = 0; k < fl->n_imu; k++)
+            if (fl->imu[k].frame_i == 0 && fl->imu[k].sum_dt < 10.0) {
+                pl.imu_index = k;
+                touch(0, true);
+                touch(1, true);
+                touch(2, false);
+                touch(3, false);
+            }
+        int last_l = -1;
+        for (int k = 0; k < fl->n_proj; k++)
+            if (fl->proj[k].frame_i == 0) {
+                touch(0, true);
+                touch(2 * fl->proj[k].frame_j, false);
+                touch(2 * F, false);
+                if (o->estimate_td) touch(2 * F + 1, false);
+                if (fl->proj[k].landmark != last_l) lms.push_back(last_l = fl->proj[k].landmark);
+            }
+    } else {
+        const int drop_id = 2 * (F - 2);  // para_Pose[WINDOW_SIZE - 1]
+        bool found = false;
+        if (have_prior)
+            for (int b = 0; b < fl->prior->n_blocks; b++) found |= (fl->prior->block_id[b] == drop_id);
+        if (!found) return LFVIO_OK;  // nothing to do (estimator.cpp:942-943)
+        pl.use_prior = 1;
+        for (int b = 0; b < fl->prior->n_blocks; b++) touch(fl->prior->block_id[b], fl->prior->block_id[b] == drop_id);
+    }
+    if (is_drop.empty()) return LFVIO_OK;
+    int pos = 0;
+    for (auto &kv : is_drop)
+        if (kv.second) {
+            pl.col[kv.first] = pos;
+            pos += lay.block_lsize(kv.first);
+        }
+    pl.m_p = pos;
+    LFVIO_REQUIRE(pl.m_p <= 15, "marginalize: more than one pose + speed-bias block to drop");
+    int off = 0;
+    for (auto &kv : is_drop)
+        if (!kv.second) {
+            pl.col[kv.first] = pos;
+            pos += lay.block_lsize(kv.first);
+            pl.keep_id[pl.n_keep] = kv.first;
+            pl.keep_x0[pl.n_keep] = off;
+            off += lay.block_gsize(kv.first);
+            pl.n_keep++;
+        }
+    pl.n = pos - pl.m_p;
+    pl.dim = pos;
+    pl.n_lm = (int)lms.size();
+    pl.lm_list = w->lm_list[flag].p;
+    if (pl.n_lm) {  // staged through pinned memory: no synchronisation on the upload path
+        memcpy(w->h_lm[flag], lms.data(), sizeof(int) * lms.size());
+        LFVIO_CUDA_TRY(cudaMemcpyAsync(w->lm_list[flag].p, w->h_lm[flag], sizeof(int) * lms.size(), cudaMemcpyHostToDevice, w->stream));
+    }
+    w->plan_valid[flag] = pl.n > 0;
+    return LFVIO_OK;
+}
+
+int enqueue_marginalize(lfvio_window *w, int flag, bool after_solve) {
+    if (!w->plan_valid[flag]) return LFVIO_OK;
+    MargBuffers mb{w->margT.p, w->marg_work.p, w->marg_J0.p, w->marg_r0.p, w->marg_x0.p};
+    w->prof.begin(WS_MARGINALIZE, w->stream);
+    LFVIO_TRY(launch_marginalize(w->P, w->e[0], w->e[1], w->x[0].p, w->x[1].p, after_solve ? w->ctl.p : nullptr, w->plan[flag], mb,
+                                 w->stream));
+    w->prof.end(w->stream);
+    w->last_marg_flag = flag;
     return LFVIO_OK;
 }
 
@@ -233,6 +352,8 @@ int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_lis
     LFVIO_CUDA_TRY(cudaMemsetAsync(w->status.p, 0, sizeof(int) * 4, s));
     LFVIO_TRY(launch_imu_prepare(P, w->imu_sqrt_info.p, w->status.p, s));
     LFVIO_TRY(launch_prior_prepare(P, w->H0.p, s));
+    LFVIO_TRY(build_marg_plan(w, LFVIO_MARGIN_OLD, fl, o, L));
+    LFVIO_TRY(build_marg_plan(w, LFVIO_MARGIN_SECOND_NEW, fl, o, L));
     w->uploaded = true;
     return LFVIO_OK;
 }
@@ -289,6 +410,10 @@ int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum) 
         if (lay.L) memcpy(st->para_Feature, w->h_x + lay.feat(0), sizeof(double) * lay.L);
     }
     const SolverCtl &c = *w->h_ctl;
+    if (getenv("LFVIO_DEBUG_STEP")) {
+        static const char *names[8] = {"norm+diag+copy", "cauchy", "cholesky", "tri-solve", "gn-landmarks", "dogleg", "model", "candidate"};
+        for (int i = 0; i < 8; i++) fprintf(stderr, "step phase %-16s %8.2f us\n", names[i], (c.phase_clk[i + 1] - c.phase_clk[i]) / 1000.0);
+    }
     if (sum) {
         memset(sum, 0, sizeof(*sum));
         sum->iterations = c.iter;
@@ -386,9 +511,9 @@ extern "C" int lfvio_window_optimize_dev(lfvio_window *w, int with_marginalize, 
     clear_error();
     LFVIO_REQUIRE(w && w->uploaded, "lfvio_window_optimize_dev: call lfvio_window_upload first");
     LFVIO_CUDA_TRY(cudaSetDevice(w->device));
+    LFVIO_REQUIRE(margin_flag == LFVIO_MARGIN_OLD || margin_flag == LFVIO_MARGIN_SECOND_NEW, "lfvio_window_optimize_dev: bad margin_flag");
     LFVIO_TRY(enqueue_solve(w));
-    (void)with_marginalize;
-    (void)margin_flag;
+    if (with_marginalize) LFVIO_TRY(enqueue_marginalize(w, margin_flag, true));
     return LFVIO_OK;
 }
 
@@ -435,12 +560,51 @@ extern "C" int lfvio_window_marginalize(lfvio_window *w, const lfvio_window_stat
                                         const lfvio_solver_opts *opts, int margin_flag, lfvio_prior *out) {
     clear_error();
     LFVIO_REQUIRE(w && out, "lfvio_window_marginalize: null argument");
-    (void)state;
-    (void)factors;
-    (void)opts;
-    (void)margin_flag;
-    set_error("lfvio_window_marginalize: device marginalisation not built yet");
-    return LFVIO_ERR_ARG;
+    LFVIO_REQUIRE(margin_flag == LFVIO_MARGIN_OLD || margin_flag == LFVIO_MARGIN_SECOND_NEW, "lfvio_window_marginalize: bad margin_flag");
+    LFVIO_CUDA_TRY(cudaSetDevice(w->device));
+    LFVIO_TRY(upload(w, state, factors, opts));
+    out->n = 0;
+    out->n_blocks = 0;
+    if (!w->plan_valid[margin_flag]) return LFVIO_OK;
+    cudaStream_t s = w->stream;
+    const DevProblem &P = w->P;
+    const MargPlan &pl = w->plan[margin_flag];
+    LFVIO_REQUIRE(pl.n <= out->cap_n && pl.n_keep <= out->cap_blocks, "lfvio_window_marginalize: output prior too small");
+    // preMarginalize(): evaluate the dropped factors (with the loss correction) at the given state
+    LFVIO_TRY(launch_solver_init(w->ctl.p, P.o, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->x[0].p, w->blob.p + w->off_x, sizeof(double) * P.lay.size(), cudaMemcpyDeviceToDevice, s));
+    LFVIO_TRY(launch_evaluate(P, w->x[0].p, w->x[1].p, w->e[0], w->e[1], w->ctl.p, 2, 1, s));
+    LFVIO_TRY(enqueue_marginalize(w, margin_flag, false));
+    const size_t nn = (size_t)pl.n * pl.n;
+    int x0_len = 0;
+    for (int b = 0; b < pl.n_keep; b++) x0_len += P.lay.block_gsize(pl.keep_id[b]);
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg, w->marg_J0.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg + nn, w->marg_r0.p, sizeof(double) * pl.n, cudaMemcpyDeviceToHost, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg + nn + pl.n, w->marg_x0.p, sizeof(double) * x0_len, cudaMemcpyDeviceToHost, s));
+    int status[4];
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(status, w->status.p, sizeof(status), cudaMemcpyDeviceToHost, s));
+    LFVIO_CUDA_TRY(cudaStreamSynchronize(s));
+    if (status[0]) {
+        set_error("IMU covariance of a pre-integration is singular / not positive definite");
+        return LFVIO_ERR_NUMERIC;
+    }
+    out->n = pl.n;
+    out->n_blocks = pl.n_keep;
+    const int F = w->F;
+    for (int b = 0; b < pl.n_keep; b++) {
+        const int id = pl.keep_id[b];
+        int new_id = id;  // addr_shift (estimator.cpp:921-931 / :980-1000)
+        if (id < 2 * F) {
+            if (margin_flag == LFVIO_MARGIN_OLD) new_id = id - 2;
+            else if ((id >> 1) == F - 1) new_id = id - 2;
+        }
+        out->block_id[b] = new_id;
+        out->block_idx[b] = pl.col[id] - pl.m_p;
+    }
+    memcpy(out->J0, w->h_marg, sizeof(double) * nn);
+    memcpy(out->r0, w->h_marg + nn, sizeof(double) * pl.n);
+    memcpy(out->x0, w->h_marg + nn + pl.n, sizeof(double) * x0_len);
+    return LFVIO_OK;
 }
 
 extern "C" void *lfvio_window_stream(lfvio_window *w) { return w ? (void *)w->stream : nullptr; }

@@ -318,3 +318,13 @@ def solver_default_opts() -> "backend.SolverOpts":
 
 def Window(window_size: int = 10, max_landmarks: int = 1000, max_proj: int = 16384, device: int = 0) -> "backend.Window":
     return backend.Window(lib, check, window_size, max_landmarks, max_proj, device)
+
+# live stage timing (bench.py)
+lib.lfvio_tracker_stage_name.restype = C.c_char_p
+lib.lfvio_tracker_stage_name.argtypes = [C.c_int]
+lib.lfvio_window_stage_name.restype = C.c_char_p
+lib.lfvio_window_stage_name.argtypes = [C.c_int]
+lib.lfvio_tracker_profile_begin.argtypes = [C.c_void_p, C.c_int]
+lib.lfvio_tracker_profile_end.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+lib.lfvio_window_profile_begin.argtypes = [C.c_void_p, C.c_int]
+lib.lfvio_window_profile_end.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]

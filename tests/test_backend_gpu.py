@@ -127,3 +127,60 @@ def test_bad_problem_is_rejected(lfvio_mod, win, problem):
     w.proj[3].landmark, w.proj[400].landmark = w.proj[400].landmark, w.proj[3].landmark  # breaks the grouping
     with pytest.raises(lfvio_mod.LfvioError):
         win.optimize(w)
+
+
+# ---- K14: marginalisation ------------------------------------------------------------------------------
+def _info_close(pg, po, tol=1e-7):
+    assert pg.n == po.n and pg.n_blocks == po.n_blocks
+    assert list(pg.block_id[: pg.n_blocks]) == list(po.block_id[: po.n_blocks])
+    assert list(pg.block_idx[: pg.n_blocks]) == list(po.block_idx[: po.n_blocks])
+    Ag, bg = pg.information()
+    Ao, bo = po.information()
+    assert np.abs(Ag - Ao).max() < tol * np.abs(Ao).max(), np.abs(Ag - Ao).max() / np.abs(Ao).max()
+    assert np.abs(bg - bo).max() < 1e-6 * max(np.abs(bo).max(), 1.0)
+    nx = sum(7 if (i < 2 * 11 and i % 2 == 0) or i == 22 else (9 if i < 22 else 1) for i in pg.block_id[: pg.n_blocks])
+    assert np.array_equal(pg.x0[:nx], po.x0[:nx])  # keep_block_data are plain copies
+
+
+def test_marginalize_old_matches_oracle(lfvio_mod, win):
+    w = synthwin.make_window(seed=1, opts=lfvio_mod.solver_default_opts(), perturb=0.3)
+    ob.optimize(w)
+    pg, po = win.marginalize(w, B.MARGIN_OLD), ob.marginalize(w, B.MARGIN_OLD)
+    assert pg.n == 6 * 10 + 9 + 6 + 1
+    _info_close(pg, po)
+
+
+def test_marginalize_chain_with_prior_and_second_new(lfvio_mod, win):
+    """Window k -> prior -> window k+1 (prior factor inside the solve) -> MARGIN_OLD and MARGIN_SECOND_NEW again."""
+    w = synthwin.make_window(seed=2, opts=lfvio_mod.solver_default_opts(), perturb=0.3)
+    win.optimize(w)
+    prior = win.marginalize(w, B.MARGIN_OLD)
+    nw = synthwin.make_window(seed=2, opts=lfvio_mod.solver_default_opts(), perturb=0.3)
+    nw.pose[:-1], nw.sb[:-1] = w.pose[1:], w.sb[1:]
+    nw.pose[-1], nw.sb[-1] = w.pose[-1], w.sb[-1]
+    nw.ex[:], nw.td[:] = w.ex, w.td
+    nw.prior = prior
+    # evaluation of the prior factor + full solve with the prior, device vs oracle
+    g, o = win.evaluate(nw), ob.evaluate(nw)
+    assert np.abs(g.res_prior - o.res_prior).max() < 1e-9 * max(1.0, np.abs(o.res_prior).max())
+    a, b = nw.clone(), nw.clone()
+    sg, so = win.optimize(a), ob.optimize(b)
+    assert sg.iterations == so.iterations
+    for i in range(so.iterations + 1):
+        assert abs(sg.cost[i] - so.cost[i]) <= 1e-6 * abs(so.cost[i]) + 1e-9
+    assert np.abs(a.pose - b.pose).max() < 1e-6
+    for flag in (B.MARGIN_OLD, B.MARGIN_SECOND_NEW):
+        pg, po = win.marginalize(b, flag), ob.marginalize(b, flag)
+        _info_close(pg, po, 1e-6)
+    assert win.marginalize(w, B.MARGIN_SECOND_NEW).n == 0  # no prior => nothing to do (estimator.cpp:942-943)
+
+
+def test_device_resident_solve_then_marginalize(lfvio_mod, win, problem):
+    win.upload(problem)
+    win.optimize_dev(True, B.MARGIN_OLD)
+    o = problem.clone()
+    s = win.download(o)
+    assert s.iterations > 0
+    po = ob.marginalize(o, B.MARGIN_OLD)
+    pg = win.marginalize(o, B.MARGIN_OLD)
+    _info_close(pg, po)
