@@ -273,13 +273,17 @@ def main():
     work = wprob.clone()
     init = (wprob.pose.copy(), wprob.sb.copy(), wprob.ex.copy(), wprob.feat.copy(), wprob.td.copy())
     src_frames = pinned.numpy() if pinned is not None else frames_host
+    prior_out = B.PriorData()
 
     def step_host(k):
         tracker.read_image(src_frames[k % pool], (args.warmup + args.steps + k) / hz, bool(PUB_PATTERN[k % len(PUB_PATTERN)]))
         tracker.update_ids()
         for dst, s in zip((work.pose, work.sb, work.ex, work.feat, work.td), init):
             np.copyto(dst, s)
-        return window.optimize(work)
+        summ_h = window.optimize(work)
+        if with_marg:  # Estimator::optimization(): solve, (double2vector gauge fix on host), then build the next prior
+            window.marginalize(work, B.MARGIN_OLD, prior_out)
+        return summ_h
 
     for k in range(3):
         step_host(k)

@@ -124,9 +124,13 @@ def test_device_resident_solve_repeats(lfvio_mod, win, problem):
 
 def test_bad_problem_is_rejected(lfvio_mod, win, problem):
     w = problem.clone()
-    w.proj[3].landmark, w.proj[400].landmark = w.proj[400].landmark, w.proj[3].landmark  # breaks the grouping
-    with pytest.raises(lfvio_mod.LfvioError):
-        win.optimize(w)
+    a, b = w.proj[3].landmark, w.proj[400].landmark
+    w.proj[3].landmark, w.proj[400].landmark = b, a  # breaks the grouping (the factor array is shared with `problem`)
+    try:
+        with pytest.raises(lfvio_mod.LfvioError):
+            win.optimize(w)
+    finally:
+        w.proj[3].landmark, w.proj[400].landmark = a, b
 
 
 # ---- K14: marginalisation ------------------------------------------------------------------------------
