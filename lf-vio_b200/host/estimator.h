@@ -1,0 +1,105 @@
+// Host-side mirror of the back-end part of class Estimator over the lfvio C-ABI (no Eigen / Ceres / ROS needed).
+//
+// Mirrors vins_estimator/src/estimator.h:25-137 for the hot path only:
+//   optimization()            estimator.cpp:676-1009   (problem build -> lfvio_window_optimize -> double2vector ->
+//                                                       lfvio_window_marginalize -> last_marginalization_*)
+//   vector2double()/double2vector()  estimator.cpp:488-530 / :532-626 (incl. the yaw / position gauge re-anchoring)
+//   FeatureManager::getFeatureCount/getDepthVector/setDepth   feature_manager.cpp:36-43,145-197
+// Everything else of Estimator (processIMU/processImage, initialisation, slideWindow, failure detection) is outside
+// SURVEY.md §8 (rows marked "next") and is not mirrored yet.  WINDOW_SIZE and NUM_OF_F are runtime values here
+// (compile-time constants in the reference, vins_estimator/src/parameters.h:12-13).
+#pragma once
+#include <array>
+#include <list>
+#include <vector>
+
+#include "lfvio.h"
+
+namespace lfvio_host {
+
+using Vec3 = std::array<double, 3>;
+using Mat3 = std::array<double, 9>;  // row-major
+
+// ---- vins_estimator/src/parameters.h globals ---------------------------------------------------------
+extern int ESTIMATE_TD, ESTIMATE_EXTRINSIC, NUM_ITERATIONS;
+extern double TR, TD, FOCAL_LENGTH;
+extern int EST_ROW;  // ROW of the estimator's parameters.cpp
+extern Vec3 G;
+
+struct FeaturePerFrame {  // feature_manager.h:17-41
+    Vec3 point{}, velocity{};
+    double cur_td = 0;
+    std::array<double, 2> uv{};
+};
+struct FeaturePerId {  // feature_manager.h:43-71
+    int feature_id = 0, start_frame = 0, used_num = 0, solve_flag = 0;
+    double estimated_depth = -1.0;
+    std::vector<FeaturePerFrame> feature_per_frame;
+};
+class FeatureManager {
+  public:
+    std::list<FeaturePerId> feature;
+    int window_size = 10;
+    int getFeatureCount();
+    std::vector<double> getDepthVector();
+    void setDepth(const std::vector<double> &x);
+};
+
+// IntegrationBase members the IMU factor reads (factor/integration_base.h:188-206) == lfvio_imu_factor
+using IntegrationBase = lfvio_imu_factor;
+
+struct MarginalizationInfo {  // what the reference keeps between frames (marginalization_factor.h:43-73)
+    int n = 0, n_blocks = 0;
+    std::vector<int> block_id, block_idx;
+    std::vector<double> x0, J0, r0;
+    bool valid() const { return n > 0; }
+};
+
+class Estimator {
+  public:
+    enum MarginalizationFlag { MARGIN_OLD = 0, MARGIN_SECOND_NEW = 1 };
+
+    explicit Estimator(int window_size = 10, int max_features = 1000, int device = 0);
+    ~Estimator();
+    Estimator(const Estimator &) = delete;
+    Estimator &operator=(const Estimator &) = delete;
+
+    void optimization();    // estimator.cpp:676-1009
+    void vector2double();   // :488-530
+    void double2vector();   // :532-626
+
+    const int WINDOW_SIZE;
+    // public state, names as in the reference (estimator.h:70-113)
+    std::vector<Vec3> Ps, Vs, Bas, Bgs;
+    std::vector<Mat3> Rs;
+    Vec3 tic[1];
+    Mat3 ric[1];
+    double td = 0;
+    std::vector<IntegrationBase *> pre_integrations;  // [0 .. WINDOW_SIZE], entry j connects frames j-1 and j
+    FeatureManager f_manager;
+    MarginalizationFlag marginalization_flag = MARGIN_OLD;
+    MarginalizationInfo last_marginalization_info;  // replaces MarginalizationInfo* + last_marginalization_parameter_blocks
+    bool failure_occur = false;
+    Mat3 last_R0{};
+    Vec3 last_P0{};
+    // flat parameter arrays (estimator.h:107-113)
+    std::vector<double> para_Pose, para_SpeedBias, para_Feature;
+    double para_Ex_Pose[1][7]{};
+    double para_Td[1][1]{};
+    lfvio_solve_summary summary{};
+    int last_status = 0;
+    const char *lastError() const;
+
+  private:
+    lfvio_window *m_window = nullptr;
+    int m_device;
+    std::vector<lfvio_proj_factor> m_proj;
+    std::vector<lfvio_imu_factor> m_imu;
+    void buildFactors();
+};
+
+// Utility::R2ypr / ypr2R (utility/utility.h:66-104), degrees
+Vec3 R2ypr(const Mat3 &R);
+Mat3 ypr2R(const Vec3 &ypr);
+
+}  // namespace lfvio_host
