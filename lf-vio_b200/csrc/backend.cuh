@@ -81,6 +81,13 @@ struct SolverCtl {
     unsigned int ticket; // last-block-done counter of the eval kernel
     int pad;
     double radius, mu, cost, cost_cand, x_norm, dogleg_step_norm, alpha, model_cost_change, step_norm;
+    double gnorm, gn_norm, gdot;  // |gradient_|, |gauss_newton_step_|, gradient_ . gauss_newton_step_ (kept while reuse_)
+    // per-iteration accumulators filled with atomics by the multi-CTA phases and consumed/zeroed by the phase that
+    // needs the total: [0] sum gradient^2  [1] sum (J g)^2  [2] max |J^T r| (as ordered bits)  [3] sum gn^2
+    // [4] sum gradient.gn  [5] model cost change  [6] |x - x_cand|^2
+    double acc[8];
+    unsigned int ticket2;  // last-block-done counter of cand_kernel
+    int pad2;
     double cost_log[LFVIO_MAX_ITER_LOG], radius_log[LFVIO_MAX_ITER_LOG];
     int accepted_log[LFVIO_MAX_ITER_LOG];
     long long phase_clk[16];  // clock64() at the phase boundaries of the last step_kernel (LFVIO_DEBUG_STEP=1 prints them)
@@ -266,6 +273,7 @@ int launch_evaluate(const DevProblem &P, const double *x0, const double *x1, con
 int launch_jacobi_scale(const DevProblem &P, const EvalBuf &e0, const SolverScratch &w, cudaStream_t s);
 int launch_accumulate(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const SolverScratch &w, SolverCtl *ctl,
                       cudaStream_t s);
+// One trust-region step up to (not including) the candidate evaluation: pre -> chol -> gnlm -> cand.
 int launch_step(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const SolverScratch &w, double *x0, double *x1,
                 SolverCtl *ctl, cudaStream_t s);
 
