@@ -29,6 +29,13 @@ constexpr int PRE_THREADS = 256;
 constexpr int CAND_THREADS = 256;
 constexpr int GNLM_WARPS = 8;
 
+__device__ __forceinline__ long long gtimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return (long long)t;
+}
+#define PHASE_MARK(i) do { if (threadIdx.x == 0) ctl->phase_clk[i] = gtimer_ns(); } while (0)
+
 __device__ __forceinline__ double block_sum(double v, double *s_red) {  // any blockDim (multiple of 32, <= 1024)
     v = warp_sum(v);
     __syncthreads();
@@ -161,55 +168,50 @@ struct MatPacked {  // packed upper triangle, row-major (c >= r)
     __device__ __forceinline__ double &at(int r, int c) const { return p[r * D - ((r * (r - 1)) >> 1) + (c - r)]; }
 };
 
-// Warp-level Cholesky of one nb x nb (nb <= 16) diagonal block, U^T U = A, entirely in registers: lane c owns column c.
-// Writes U back into S, and U^-1 (upper triangular, row-major, zero padded to 16 x 16) into s_X.  All 32 lanes must call.
-template <class M>
-__device__ bool factor_diag_block(M S, int j0, int nb, double *s_U, double *s_X) {
-    const int c = threadIdx.x & 31;
+// Warp-level Cholesky of one 16 x 16 diagonal block held in shared memory (identity-padded), U^T U = A, in registers:
+// lane c owns column c; pivots and row entries are exchanged with warp shuffles; no fp64 division or square root
+// (rsqrt + multiplies).  Overwrites s_U with U (upper, zeros below) and writes U^-1 (upper) into s_X.  All 32 lanes call.
+__device__ __noinline__ bool factor_diag_block(double *s_U, double *s_X) {
+    const int c = threadIdx.x & 15;  // lanes 16..31 mirror lanes 0..15 (keeps the shuffles convergent and cheap)
     double a[NB];
 #pragma unroll
-    for (int r = 0; r < NB; r++) a[r] = (c < nb && r <= c) ? S.at(j0 + r, j0 + c) : ((r == c) ? 1.0 : 0.0);
+    for (int r = 0; r < NB; r++) a[r] = s_U[r * NB + c];
     bool ok = true;
+    double invd[NB];
 #pragma unroll
     for (int j = 0; j < NB; j++) {
         double djj = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(djj > 0.0) || !isfinite(djj)) {
+        if (!(djj > 0.0) || !(djj < 1e300)) {
             ok = false;
             djj = 1.0;
         }
-        const double inv = 1.0 / sqrt(djj);
-        const double ujc = (c == j) ? djj * inv : a[j] * inv;  // U[j][c] (0 for c < j)
+        const double inv = rsqrt(djj);
+        invd[j] = inv;
+        // U[j][c] = a[j] / sqrt(djj) (lane j holds a[j] == djj).  Entries below the diagonal of a column (r > c) are
+        // never read by another lane, so they are updated unconditionally (no selects) and zeroed at write-out.
+        const double ujc = a[j] * inv;
         a[j] = ujc;
 #pragma unroll
         for (int r = j + 1; r < NB; r++) {
             const double ujr = __shfl_sync(0xffffffffu, ujc, r);
-            if (r <= c) a[r] -= ujr * ujc;
-        }
-    }
-    if (c < NB) {
-#pragma unroll
-        for (int r = 0; r < NB; r++) {
-            s_U[r * NB + c] = (r <= c) ? a[r] : 0.0;
-            if (c < nb && r <= c) S.at(j0 + r, j0 + c) = a[r];
+            a[r] = fma(-ujr, ujc, a[r]);
         }
     }
     __syncwarp();
+    if (threadIdx.x < NB) {
+#pragma unroll
+        for (int r = 0; r < NB; r++) s_U[r * NB + c] = (r <= c) ? a[r] : 0.0;
+    }
+    __syncwarp();
     // inverse, column c: x[c] = 1/U[c][c]; x[r] = -(sum_{k=r+1..c} U[r][k] x[k]) / U[r][r]
-    if (c < NB) {
+    if (threadIdx.x < NB) {
         double x[NB];
 #pragma unroll
         for (int r = NB - 1; r >= 0; r--) {
-            if (r > c) {
-                x[r] = 0.0;
-            } else if (r == c) {
-                x[r] = 1.0 / s_U[r * NB + r];
-            } else {
-                double s = 0;
+            double s = 0;
 #pragma unroll
-                for (int k = r + 1; k < NB; k++)
-                    if (k <= c) s += s_U[r * NB + k] * x[k];
-                x[r] = -s / s_U[r * NB + r];
-            }
+            for (int k = r + 1; k < NB; k++) s = fma(s_U[r * NB + k], x[k], s);  // x[k] == 0 for k > c
+            x[r] = (r > c) ? 0.0 : ((r == c) ? invd[r] : -s * invd[r]);
         }
 #pragma unroll
         for (int r = 0; r < NB; r++) s_X[r * NB + c] = x[r];
@@ -226,12 +228,22 @@ __device__ bool cholesky_upper(M S, int D, double *s_panel /* NB x D */, double 
     for (int j0 = 0, blk = 0; j0 < D; j0 += NB, blk++) {
         const int nb = min(NB, D - j0);
         double *s_X = s_Xall + blk * NB * NB;
+        // diagonal block -> shared (all threads), factor + invert (warp 0, registers), write back (all threads)
+        for (int q = tid; q < NB * NB; q += nt) {
+            const int r = q / NB, c = q % NB;
+            s_U[q] = (r < nb && c < nb && c >= r) ? S.at(j0 + r, j0 + c) : ((r == c) ? 1.0 : 0.0);
+        }
+        __syncthreads();
         if (tid < 32) {
-            const bool ok = factor_diag_block(S, j0, nb, s_U, s_X);
+            const bool ok = factor_diag_block(s_U, s_X);
             if (!ok && tid == 0) *s_ok = 0;
         }
         __syncthreads();
         if (*s_ok == 0) return false;
+        for (int q = tid; q < nb * nb; q += nt) {
+            const int r = q / nb, c = q % nb;
+            if (c >= r) S.at(j0 + r, j0 + c) = s_U[r * NB + c];
+        }
         const int rest0 = j0 + nb, nrest = D - rest0;
         if (nrest > 0) {
             // row panel U12 = U11^-T A12 = X^T A12: dependency-free, one thread per column
@@ -356,6 +368,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(DevProblem P, Solver
     double *s_y = s_panel + (size_t)NB * D;        // D
     double *s_X = s_y + D;                         // nblk * NB * NB inverted diagonal blocks
     double *s_S = s_X + (size_t)nblk * NB * NB;    // packed upper triangle when use_smem
+    PHASE_MARK(0);
     // ---- scalars of the Cauchy point; gradient tolerance ----
     if (tid == 0) {
         const double gg = ctl->acc[0], jj = ctl->acc[1];
@@ -383,6 +396,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(DevProblem P, Solver
     }
     const double mu = ctl->mu;
     bool pd;
+    PHASE_MARK(1);
     if (use_smem) {
         const MatPacked Sp{s_S, D};
         for (int q = tid; q < D * D; q += nt) {
@@ -390,6 +404,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(DevProblem P, Solver
             if (c >= r) Sp.at(r, c) = w.S[q] + (r == c ? w.diagonal[c] * w.diagonal[c] * mu : 0.0);
         }
         __syncthreads();
+        PHASE_MARK(2);
         pd = cholesky_upper(Sp, D, s_panel, s_U, s_X, &s_ok);
     } else {
         for (int c = tid; c < D; c += nt) w.S[(size_t)c * D + c] += w.diagonal[c] * w.diagonal[c] * mu;
@@ -400,11 +415,13 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(DevProblem P, Solver
         if (tid == 0) ctl->pad = 0;
         return;
     }
+    PHASE_MARK(3);
     for (int c = tid; c < D; c += nt) s_y[c] = w.rhs[c];
     __syncthreads();
     if (use_smem) solve_upper_blocked(MatPacked{s_S, D}, D, s_y, s_X, s_tmp);
     else solve_upper_blocked(MatFull{w.S, D}, D, s_y, s_X, s_tmp);
     __syncthreads();
+    PHASE_MARK(4);
     double gn2 = 0, gdot = 0;
     int bad = 0;
     for (int c = tid; c < D; c += nt) {
@@ -424,6 +441,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(DevProblem P, Solver
         ctl->acc[4] = gdot;
         if (bad) ctl->pad = 0;
     }
+    PHASE_MARK(5);
 }
 
 // =====================================================================================================

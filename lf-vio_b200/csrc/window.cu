@@ -411,8 +411,8 @@ int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum) 
     }
     const SolverCtl &c = *w->h_ctl;
     if (getenv("LFVIO_DEBUG_STEP")) {
-        static const char *names[8] = {"norm+diag+copy", "cauchy", "cholesky", "tri-solve", "gn-landmarks", "dogleg", "model", "candidate"};
-        for (int i = 0; i < 8; i++) fprintf(stderr, "step phase %-16s %8.2f us\n", names[i], (c.phase_clk[i + 1] - c.phase_clk[i]) / 1000.0);
+        static const char *names[5] = {"scalars+xnorm", "copy-to-smem", "cholesky", "tri-solve", "tail"};
+        for (int i = 0; i < 5; i++) fprintf(stderr, "step phase %-16s %8.2f us\n", names[i], (c.phase_clk[i + 1] - c.phase_clk[i]) / 1000.0);
     }
     if (sum) {
         memset(sum, 0, sizeof(*sum));

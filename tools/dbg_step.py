@@ -4,4 +4,4 @@ from lfvio import synthwin
 o=lfvio.solver_default_opts(); o.fixed_iterations=1
 w=synthwin.make_window(seed=1,opts=o,perturb=0.3)
 win=lfvio.Window(10,1000,16384)
-for _ in range(3): s=win.optimize(w.clone())
+for _ in range(30): s=win.optimize(w.clone())
