@@ -408,71 +408,89 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(DevProblem P, cons
 }
 
 // Eigen::LLT<Matrix15d>(covariance.inverse()).matrixL().transpose()  (imu_factor.h:64), once per solve.
-// One thread per factor: Gauss-Jordan with partial pivoting, then Cholesky (15x15 — latency irrelevant).
-__global__ void imu_prepare_kernel(const lfvio_imu_factor *imu, int n_imu, double *out, int *status) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per factor on a shared-memory 15 x 30 augmented matrix: Gauss-Jordan with partial pivoting (same pivot
+// rule and operation order as the oracle's invert()), then Cholesky of the inverse.
+__global__ void __launch_bounds__(32) imu_prepare_kernel(const lfvio_imu_factor *imu, int n_imu, double *out, int *status) {
+    const int k = blockIdx.x, lane = threadIdx.x;
     if (k >= n_imu) return;
-    double w[15][30];
-    for (int i = 0; i < 15; i++)
-        for (int j = 0; j < 15; j++) {
-            w[i][j] = imu[k].covariance[i * 15 + j];
-            w[i][15 + j] = (i == j) ? 1.0 : 0.0;
-        }
-    bool ok = imu[k].sum_dt <= 10.0;
-    if (!ok) {  // inactive factor: leave zeros
-        for (int q = 0; q < 225; q++) out[225 * (size_t)k + q] = 0.0;
+    __shared__ double w[15][31];
+    __shared__ double Lm[15][16];
+    if (imu[k].sum_dt > 10.0) {  // inactive factor: leave zeros
+        for (int q = lane; q < 225; q += 32) out[225 * (size_t)k + q] = 0.0;
         return;
     }
-    for (int col = 0; col < 15 && ok; col++) {
-        int piv = col;
-        double best = fabs(w[col][col]);
-        for (int i = col + 1; i < 15; i++)
-            if (fabs(w[i][col]) > best) {
-                best = fabs(w[i][col]);
-                piv = i;
+    for (int q = lane; q < 450; q += 32) {
+        const int i = q / 30, j = q % 30;
+        w[i][j] = j < 15 ? imu[k].covariance[i * 15 + j] : ((j - 15 == i) ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    bool ok = true;
+    for (int col = 0; col < 15; col++) {
+        // partial pivoting: first row (>= col) with the largest |w[i][col]|
+        double best = (lane >= col && lane < 15) ? fabs(w[lane][col]) : -1.0;
+        int piv = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int op = __shfl_xor_sync(0xffffffffu, piv, o);
+            if (ob > best || (ob == best && op < piv)) {
+                best = ob;
+                piv = op;
             }
-        if (best == 0.0) {
+        }
+        if (!(best > 0.0)) {
             ok = false;
             break;
         }
-        if (piv != col)
-            for (int j = 0; j < 30; j++) {
-                const double t = w[col][j];
-                w[col][j] = w[piv][j];
-                w[piv][j] = t;
-            }
+        if (piv != col && lane < 30) {
+            const double t = w[col][lane];
+            w[col][lane] = w[piv][lane];
+            w[piv][lane] = t;
+        }
+        __syncwarp();
         const double d = w[col][col];
-        for (int j = 0; j < 30; j++) w[col][j] /= d;
-        for (int i = 0; i < 15; i++) {
+        __syncwarp();
+        if (lane < 30) w[col][lane] /= d;
+        __syncwarp();
+        for (int q = lane; q < 15 * 30; q += 32) {
+            const int i = q / 30, j = q % 30;
             if (i == col) continue;
             const double f = w[i][col];
-            if (f == 0.0) continue;
-            for (int j = 0; j < 30; j++) w[i][j] -= f * w[col][j];
+            // every lane must read its multiplier before column `col` of row i is overwritten: j == col is done last
+            if (j != col && f != 0.0) w[i][j] -= f * w[col][j];
         }
+        __syncwarp();
+        if (lane < 15 && lane != col) w[lane][col] = 0.0;  // w[i][col] -= f * 1
+        __syncwarp();
     }
-    // Cholesky of the inverse (right half), lower triangle
-    double L[15][15];
-    for (int j = 0; j < 15 && ok; j++) {
-        double d = w[j][15 + j];
-        for (int q = 0; q < j; q++) d -= L[j][q] * L[j][q];
-        if (!(d > 0.0)) {
-            ok = false;
-            break;
-        }
-        d = sqrt(d);
-        L[j][j] = d;
-        for (int i = j + 1; i < 15; i++) {
-            double s = w[i][15 + j];
-            for (int q = 0; q < j; q++) s -= L[i][q] * L[j][q];
-            L[i][j] = s / d;
+    // Cholesky (lower) of the inverse held in w[:, 15:30]
+    if (ok) {
+        for (int j = 0; j < 15; j++) {
+            double d = w[j][15 + j];
+            for (int q = 0; q < j; q++) d -= Lm[j][q] * Lm[j][q];
+            if (!(d > 0.0)) {
+                ok = false;
+                break;
+            }
+            d = sqrt(d);
+            __syncwarp();
+            if (lane == 0) Lm[j][j] = d;
+            if (lane > j && lane < 15) {
+                double s = w[lane][15 + j];
+                for (int q = 0; q < j; q++) s -= Lm[lane][q] * Lm[j][q];
+                Lm[lane][j] = s / d;
+            }
+            __syncwarp();
         }
     }
     if (!ok) {
-        *status = 1;
+        if (lane == 0) *status = 1;
         return;
     }
-    for (int i = 0; i < 15; i++)
-        for (int j = 0; j < 15; j++) out[225 * (size_t)k + i * 15 + j] = (j >= i) ? L[j][i] : 0.0;  // L^T
+    for (int q = lane; q < 225; q += 32) {
+        const int i = q / 15, j = q % 15;
+        out[225 * (size_t)k + q] = (j >= i) ? Lm[j][i] : 0.0;  // L^T
+    }
 }
 
 // H0 = J0^T J0 of the prior (constant during a solve).
@@ -488,7 +506,7 @@ __global__ void prior_prepare_kernel(const double *J0, int n, double *H0) {
 
 int launch_imu_prepare(const DevProblem &P, double *imu_sqrt_info, int *status, cudaStream_t s) {
     if (P.n_imu == 0) return LFVIO_OK;
-    imu_prepare_kernel<<<cdiv(P.n_imu, 32), 32, 0, s>>>(P.imu, P.n_imu, imu_sqrt_info, status);
+    imu_prepare_kernel<<<P.n_imu, 32, 0, s>>>(P.imu, P.n_imu, imu_sqrt_info, status);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

@@ -24,6 +24,7 @@
 // Jacobian by sqrt(rho') — exactly what evaluate_kernel already stored.
 #include "backend.cuh"
 #include "marg.cuh"
+#include "chol16.cuh"
 
 namespace lfvio {
 
@@ -204,7 +205,7 @@ __device__ void jacobi_eig_warp(double *A, double *V, int n, double *s_c, double
         }
         off = warp_sum(off);
         dg = warp_sum(dg);
-        if (off <= 1e-30 * (dg + off) || off == 0.0) break;
+        if (off <= 1e-24 * (dg + off) || off == 0.0) break;
         for (int round = 0; round < m - 1; round++) {
             if (lane < half) {
                 int a, b;  // circle method: player m-1 is fixed, the others rotate
@@ -261,66 +262,110 @@ __device__ void jacobi_eig_warp(double *A, double *V, int n, double *s_c, double
     }
 }
 
-// Rank-revealing factorisation A' = R^T R of the symmetric PSD n x n matrix by Cholesky with diagonal pivoting
-// (left-looking: row k of R is built from A and the previous rows, so A itself is never updated).  Pivots <= tol end
-// the factorisation: every remaining entry is then <= tol in magnitude (|a_ij|^2 <= a_ii a_jj), i.e. exactly the
-// directions the reference's "eigenvalue > eps" test discards, to within eps.  R is stored in the ORIGINAL column
-// order (R[k][i] = 0 for columns pivoted earlier), so J0 = R and r0 = R^-T b' satisfy J0^T J0 = A', J0^T r0 = b'.
-// Whole CTA calls.  d: n doubles, done: n ints (shared).
-__device__ void pivoted_cholesky(const double *A, const double *b, int n, double tol, double *R, double *r0, double *d, int *done,
-                                 double *s_red, int *s_idx) {
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+// Rank-revealing factorisation A' = R^T R of the symmetric PSD n x n matrix by Cholesky with diagonal pivoting,
+// right-looking: at step k the largest remaining diagonal entry is the pivot, row k of R is the scaled pivot column
+// and the remaining (full, symmetric) matrix gets a rank-1 update: warp w owns rows w, w + 16, ..., lanes own columns.
+// The next pivot is found in the same pass (per-warp arg-max of the freshly updated diagonal, double-buffered), so
+// a step costs ONE block barrier.  Pivots <= tol end the factorisation: every remaining entry is then <= tol in
+// magnitude (|a_ij|^2 <= a_ii a_jj), i.e. the directions the reference's "eigenvalue > eps" test discards, to within
+// eps.  R is stored in the ORIGINAL column order (R[k][i] = 0 for columns pivoted earlier), so J0 = R and
+// r0 = R^-T b' satisfy J0^T J0 = A', J0^T r0 = b'.  A and b are destroyed.  Whole CTA calls (blockDim multiple of 32).
+__device__ void pivoted_cholesky(double *A, double *b, int n, double tol, double *R, double *r0, int *done, double *s_best,
+                                 int *s_bidx) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
     for (int i = tid; i < n; i += nt) {
-        d[i] = A[i * n + i];
         done[i] = 0;
         r0[i] = 0.0;
     }
     for (int q = tid; q < n * n; q += nt) R[q] = 0.0;
+    // initial pivot candidates: warp w scans its rows' diagonal entries
+    {
+        double best = -1.0;
+        int bi = -1;
+        for (int i = wid + nw * lane; i < n; i += nw * 32) {
+            const double d = A[i * n + i];
+            if (d > best) {
+                best = d;
+                bi = i;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) {
+                best = ob;
+                bi = oi;
+            }
+        }
+        if (lane == 0) {
+            s_best[wid] = best;
+            s_bidx[wid] = bi;
+        }
+    }
     __syncthreads();
     for (int k = 0; k < n; k++) {
-        if (wid == 0) {  // argmax of the remaining diagonal (ties: smallest index)
-            double best = -1.0;
-            int bi = -1;
-            for (int i = lane; i < n; i += 32)
-                if (!done[i] && d[i] > best) {
-                    best = d[i];
+        const int par = k & 1;
+        // every thread reduces the per-warp candidates of the previous pass (ties: smallest index)
+        double dmax = -1.0;
+        int p = -1;
+        for (int q = 0; q < nw; q++) {
+            const double ob = s_best[par * 32 + q];
+            const int oi = s_bidx[par * 32 + q];
+            if (ob > dmax || (ob == dmax && oi >= 0 && (p < 0 || oi < p))) {
+                dmax = ob;
+                p = oi;
+            }
+        }
+        if (p < 0 || !(dmax > tol)) break;
+        const double inv = 1.0 / sqrt(dmax);
+        const double rk = b[p] * inv;
+        // this lane's columns of the pivot row
+        double vj[5];  // up to 160 columns (n = 136 at F = 21)
+        int cj[5];
+#pragma unroll
+        for (int u = 0; u < 5; u++) {
+            const int j = lane + 32 * u;
+            cj[u] = (j < n && (j == p || !done[j])) ? j : -1;  // done[p] may already be set by thread 0 (below)
+            vj[u] = cj[u] >= 0 ? A[p * n + j] * inv : 0.0;
+            if (wid == 0 && cj[u] >= 0) R[k * n + j] = vj[u];
+        }
+        if (tid == 0) {
+            r0[k] = rk;
+            done[p] = 1;  // every read of done[] in this step is guarded by an explicit test against p
+        }
+        double best = -1.0;
+        int bi = -1;
+        for (int i = wid; i < n; i += nw) {
+            if (i == p || done[i]) continue;
+            const double vi = A[p * n + i] * inv;
+#pragma unroll
+            for (int u = 0; u < 5; u++) {
+                const int j = cj[u];
+                if (j < 0 || j == p) continue;
+                const double v = A[i * n + j] - vi * vj[u];
+                A[i * n + j] = v;
+                if (j == i && v > best) {
+                    best = v;
                     bi = i;
                 }
+            }
+            if (lane == 0) b[i] -= vi * rk;
+        }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) {
-                    best = ob;
-                    bi = oi;
-                }
-            }
-            if (lane == 0) {
-                s_red[0] = best;
-                s_idx[0] = bi;
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) {
+                best = ob;
+                bi = oi;
             }
         }
-        __syncthreads();
-        const double dmax = s_red[0];
-        const int p = s_idx[0];
-        if (p < 0 || !(dmax > tol)) break;
-        const double rk = sqrt(dmax);
-        for (int i = tid; i < n + 1; i += nt) {
-            if (i == n) {  // right-hand side rides along: r0[k] = (b[p] - sum_t R[t][p] r0[t]) / rk
-                double s = b[p];
-                for (int t = 0; t < k; t++) s -= R[t * n + p] * r0[t];
-                r0[k] = s / rk;
-            } else if (!done[i]) {
-                double s = A[p * n + i];
-                for (int t = 0; t < k; t++) s -= R[t * n + p] * R[t * n + i];
-                const double v = (i == p) ? rk : s / rk;
-                R[k * n + i] = v;
-                d[i] -= v * v;
-            }
+        if (lane == 0) {
+            s_best[(par ^ 1) * 32 + wid] = best;
+            s_bidx[(par ^ 1) * 32 + wid] = bi;
         }
-        __syncthreads();
-        if (tid == 0) done[p] = 1;
-        __syncthreads();
+        __syncthreads();  // A, b, done[] and the candidates of this step are visible to everybody
     }
     __syncthreads();
 }
@@ -330,8 +375,8 @@ __global__ void __launch_bounds__(MF_THREADS) marg_finish_kernel(DevProblem P, c
                                                                 const double *bvec, double *work, double *J0_out,
                                                                 double *r0_out, double *x0_out) {
     extern __shared__ double smem[];
-    __shared__ double s_c[32], s_s[32], s_red[4], s_d[15 * kMaxFrames + 8];
-    __shared__ int s_p[32], s_q[32], s_idx[4], s_done[15 * kMaxFrames + 8];
+    __shared__ double s_c[32], s_s[32], s_best[64];
+    __shared__ int s_p[32], s_q[32], s_bidx[64], s_done[15 * kMaxFrames + 8];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int mp = plan.m_p, n = plan.n, ld = plan.dim;
     const double *x = (ctl && ctl->cur) ? x1 : x0;
@@ -355,17 +400,41 @@ __global__ void __launch_bounds__(MF_THREADS) marg_finish_kernel(DevProblem P, c
         Amm[q] = 0.5 * (T[(size_t)r * ld + c] + T[(size_t)c * ld + r]);
     }
     __syncthreads();
-    if (tid < 32) jacobi_eig_warp(Amm, Vm, mp, s_c, s_s, s_p, s_q);
+    // Amm^+ (marginalization_factor.cpp:267-272).  Fast path: the block is comfortably positive definite (it carries the
+    // IMU factor and/or the previous prior), so its inverse is X X^T with X = U^-1 from the warp-level Cholesky; the
+    // reference's thresholded eigen-decomposition is kept for the (near-)singular case.
+    __shared__ double s_U16[NB * NB], s_X16[NB * NB];
+    __shared__ int s_fast;
+    for (int q = tid; q < NB * NB; q += nt) {
+        const int r = q / NB, c = q % NB;
+        s_U16[q] = (r < mp && c < mp && c >= r) ? Amm[r * mp + c] : ((r == c) ? 1.0 : 0.0);
+    }
     __syncthreads();
-    // Amm^+ = V diag(1/w > eps) V^T   (marginalization_factor.cpp:267-272)
-    for (int q = tid; q < mp * mp; q += nt) {
-        const int r = q / mp, c = q % mp;
-        double s = 0;
-        for (int k = 0; k < mp; k++) {
-            const double wk = Amm[k * mp + k];
-            if (wk > kEps) s += Vm[r * mp + k] * Vm[c * mp + k] / wk;
+    if (tid < 32) {
+        double pmin = 0, pmax = 0;
+        const bool pd = factor_diag_block(s_U16, s_X16, &pmin, &pmax);
+        if (tid == 0) s_fast = (pd && pmin > 1e-6 && pmin > 1e-12 * pmax) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_fast) {
+        for (int q = tid; q < mp * mp; q += nt) {
+            const int r = q / mp, c = q % mp;
+            double s = 0;
+            for (int k = max(r, c); k < mp; k++) s += s_X16[r * NB + k] * s_X16[c * NB + k];
+            Minv[q] = s;
         }
-        Minv[q] = s;
+    } else {
+        if (tid < 32) jacobi_eig_warp(Amm, Vm, mp, s_c, s_s, s_p, s_q);
+        __syncthreads();
+        for (int q = tid; q < mp * mp; q += nt) {
+            const int r = q / mp, c = q % mp;
+            double s = 0;
+            for (int k = 0; k < mp; k++) {
+                const double wk = Amm[k * mp + k];
+                if (wk > kEps) s += Vm[r * mp + k] * Vm[c * mp + k] / wk;
+            }
+            Minv[q] = s;
+        }
     }
     __syncthreads();
     for (int q = tid; q < n * mp; q += nt) {
@@ -393,7 +462,7 @@ __global__ void __launch_bounds__(MF_THREADS) marg_finish_kernel(DevProblem P, c
     // (J0, r0) with J0^T J0 = A', J0^T r0 = b'.  The reference takes J0 = sqrt(S) V^T from a second dense
     // eigen-decomposition (:283-291); any square root of A' defines the same prior factor, and the pivoted Cholesky
     // factor is ~100x cheaper on a GPU than a 76 x 76 Jacobi sweep sequence.
-    pivoted_cholesky(Ar, br, n, kEps, R, r0, s_d, s_done, s_red, s_idx);
+    pivoted_cholesky(Ar, br, n, kEps, R, r0, s_done, s_best, s_bidx);
     for (int q = tid; q < n * n; q += nt) J0_out[q] = R[q];
     for (int k = tid; k < n; k += nt) r0_out[k] = r0[k];
 }
