@@ -241,46 +241,116 @@ inline bool invert(const Mat &A, Mat &inv) {
     return true;
 }
 
-// Cyclic Jacobi eigen-decomposition of a symmetric matrix: A = V diag(w) V^T (stands in for
-// Eigen::SelfAdjointEigenSolver; eigenvector order/sign are not unique, callers use invariants only).
+// Symmetric eigen-decomposition A = V diag(w) V^T by Householder tridiagonalisation + implicit-shift QL (the
+// textbook tred2 / tqli pair; stands in for Eigen::SelfAdjointEigenSolver, which uses the same two stages).
+// Eigenvector order/sign are not unique, callers use invariants only.
 inline void sym_eig(const Mat &Ain, std::vector<double> &w, Mat &V) {
     const int n = Ain.r;
-    Mat A = Ain;
-    V = Mat(n, n);
-    for (int i = 0; i < n; i++) V(i, i) = 1.0;
-    for (int sweep = 0; sweep < 60; sweep++) {
-        double off = 0.0, diag = 0.0;
-        for (int i = 0; i < n; i++) {
-            diag += A(i, i) * A(i, i);
-            for (int j = i + 1; j < n; j++) off += A(i, j) * A(i, j);
-        }
-        if (off <= 1e-30 * (diag + off) || off == 0.0) break;
-        for (int p = 0; p < n - 1; p++)
-            for (int q = p + 1; q < n; q++) {
-                const double apq = A(p, q);
-                if (apq == 0.0) continue;
-                const double theta = (A(q, q) - A(p, p)) / (2.0 * apq);
-                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < n; k++) {
-                    const double akp = A(k, p), akq = A(k, q);
-                    A(k, p) = c * akp - s * akq;
-                    A(k, q) = s * akp + c * akq;
+    V = Ain;
+    w.assign(n, 0.0);
+    if (n == 0) return;
+    std::vector<double> e(n, 0.0);
+    Mat &a = V;
+    std::vector<double> &d = w;
+    // ---- tred2 ----
+    for (int i = n - 1; i >= 1; i--) {
+        const int l = i - 1;
+        double h = 0.0, scale = 0.0;
+        if (l > 0) {
+            for (int k = 0; k <= l; k++) scale += std::fabs(a(i, k));
+            if (scale == 0.0) {
+                e[i] = a(i, l);
+            } else {
+                for (int k = 0; k <= l; k++) {
+                    a(i, k) /= scale;
+                    h += a(i, k) * a(i, k);
                 }
-                for (int k = 0; k < n; k++) {
-                    const double apk = A(p, k), aqk = A(q, k);
-                    A(p, k) = c * apk - s * aqk;
-                    A(q, k) = s * apk + c * aqk;
+                double f = a(i, l);
+                double g = (f >= 0.0 ? -std::sqrt(h) : std::sqrt(h));
+                e[i] = scale * g;
+                h -= f * g;
+                a(i, l) = f - g;
+                f = 0.0;
+                for (int j = 0; j <= l; j++) {
+                    a(j, i) = a(i, j) / h;
+                    g = 0.0;
+                    for (int k = 0; k <= j; k++) g += a(j, k) * a(i, k);
+                    for (int k = j + 1; k <= l; k++) g += a(k, j) * a(i, k);
+                    e[j] = g / h;
+                    f += e[j] * a(i, j);
                 }
-                for (int k = 0; k < n; k++) {
-                    const double vkp = V(k, p), vkq = V(k, q);
-                    V(k, p) = c * vkp - s * vkq;
-                    V(k, q) = s * vkp + c * vkq;
+                const double hh = f / (h + h);
+                for (int j = 0; j <= l; j++) {
+                    f = a(i, j);
+                    e[j] = g = e[j] - hh * f;
+                    for (int k = 0; k <= j; k++) a(j, k) -= (f * e[k] + g * a(i, k));
                 }
             }
+        } else {
+            e[i] = a(i, l);
+        }
+        d[i] = h;
     }
-    w.resize(n);
-    for (int i = 0; i < n; i++) w[i] = A(i, i);
+    d[0] = 0.0;
+    e[0] = 0.0;
+    for (int i = 0; i < n; i++) {
+        const int l = i - 1;
+        if (d[i] != 0.0) {
+            for (int j = 0; j <= l; j++) {
+                double g = 0.0;
+                for (int k = 0; k <= l; k++) g += a(i, k) * a(k, j);
+                for (int k = 0; k <= l; k++) a(k, j) -= g * a(k, i);
+            }
+        }
+        d[i] = a(i, i);
+        a(i, i) = 1.0;
+        for (int j = 0; j <= l; j++) a(j, i) = a(i, j) = 0.0;
+    }
+    // ---- tqli ----
+    for (int i = 1; i < n; i++) e[i - 1] = e[i];
+    e[n - 1] = 0.0;
+    for (int l = 0; l < n; l++) {
+        int iter = 0, m;
+        do {
+            for (m = l; m < n - 1; m++) {
+                const double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+                if (std::fabs(e[m]) <= 2.3e-16 * dd) break;
+            }
+            if (m != l) {
+                if (iter++ == 200) break;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = std::hypot(g, 1.0);
+                g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? std::fabs(r) : -std::fabs(r)));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                for (i = m - 1; i >= l; i--) {
+                    double f = s * e[i];
+                    const double bb = c * e[i];
+                    e[i + 1] = (r = std::hypot(f, g));
+                    if (r == 0.0) {
+                        d[i + 1] -= p;
+                        e[m] = 0.0;
+                        break;
+                    }
+                    s = f / r;
+                    c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * bb;
+                    d[i + 1] = g + (p = s * r);
+                    g = c * r - bb;
+                    for (int k = 0; k < n; k++) {
+                        f = a(k, i + 1);
+                        a(k, i + 1) = s * a(k, i) + c * f;
+                        a(k, i) = c * a(k, i) - s * f;
+                    }
+                }
+                if (r == 0.0 && i >= l) continue;
+                d[l] -= p;
+                e[l] = g;
+                e[m] = 0.0;
+            }
+        } while (m != l);
+    }
 }
 
 }  // namespace ob

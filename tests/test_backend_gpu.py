@@ -188,3 +188,25 @@ def test_device_resident_solve_then_marginalize(lfvio_mod, win, problem):
     po = ob.marginalize(o, B.MARGIN_OLD)
     pg = win.marginalize(o, B.MARGIN_OLD)
     _info_close(pg, po)
+
+
+# ---- larger windows (BASELINE.json configs 3/4 shapes): global-memory Cholesky path, more landmarks ------------
+@pytest.mark.parametrize("n_frames,n_lm,feats", [(11, 900, 500), (21, 1500, 800)])
+def test_large_window_matches_oracle(lfvio_mod, gpu, n_frames, n_lm, feats):
+    opts = lfvio_mod.solver_default_opts()
+    w = synthwin.make_window(seed=7, n_frames=n_frames, n_landmarks=n_lm, feats_per_frame=feats, opts=opts, perturb=0.3)
+    win = lfvio_mod.Window(n_frames - 1, 4096, 65536, device=gpu)
+    g, o = win.evaluate(w), ob.evaluate(w)
+    assert rel_err(g.res_proj, o.res_proj) < 1e-9 and rel_err(g.jac_imu, o.jac_imu) < 1e-7
+    a, b = w.clone(), w.clone()
+    sg, so = win.optimize(a), ob.optimize(b)
+    assert sg.iterations == so.iterations and sg.num_successful_steps == so.num_successful_steps
+    for i in range(so.iterations + 1):
+        assert abs(sg.cost[i] - so.cost[i]) <= 1e-6 * abs(so.cost[i]) + 1e-9, (i, sg.cost[i], so.cost[i])
+    assert np.abs(a.pose - b.pose).max() < 1e-6 and np.abs(a.feat - b.feat).max() < 1e-6
+    pg, po = win.marginalize(b, B.MARGIN_OLD), ob.marginalize(b, B.MARGIN_OLD)
+    assert pg.n == po.n
+    Ag, bg = pg.information()
+    Ao, bo = po.information()
+    assert np.abs(Ag - Ao).max() < 1e-6 * np.abs(Ao).max()
+    win.close()
