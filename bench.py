@@ -106,7 +106,7 @@ def build_workload(cfg_name: str, rank: int, n_frames_pool: int):
     cam = scaled_camera(scale)
     tcfg = tracker_defaults(scale, max_cnt)
     rows, cols = cam["image_height"], cam["image_width"]
-    src = synth.FrameSource(rows, cols, seed=rank + 1)
+    src = synth.FrameSource(rows, cols, seed=rank + 1)  # lfvio.multi.stream_seed: one independent stream per rank
     frames = np.stack([src.frame(k) for k in range(n_frames_pool)])
     return dict(cam=cam, tcfg=tcfg, rows=rows, cols=cols, frames=frames, hz=hz, window_size=wsz, n_landmarks=n_lm,
                 max_cnt=max_cnt, synthwin=synthwin)
@@ -262,10 +262,9 @@ def main():
     tracker.sync()
     n_tracks = len(tracker.ids)
     summ = window.download(wprob.clone())
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    from lfvio import multi
+
+    ms_total, frames_total = multi.reduce_counters(ms_total, args.steps, dev)  # MAX of times, SUM of frames (NCCL)
     barrier()
 
     # ---- e2e: host buffers through the C-ABI, H2D + D2H inside the timed region ------------------------
@@ -314,10 +313,8 @@ def main():
         estimator_node(0, 1)
     torch.cuda.synchronize()
     e2e_seq_ms = 1e3 * (time.perf_counter() - t0) / n_seq
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_ms, e2e_frames = multi.reduce_counters(1e3 * e2e_s, e2e_steps, dev)
+    e2e_s = e2e_ms * 1e-3
     blob_bytes = wprob.n_proj * C.sizeof(B.ProjFactor) + wprob.n_imu * C.sizeof(B.ImuFactor) + 8 * (16 * (wsz + 1) + 8 + wprob.L)
     h2d = frame_bytes + blob_bytes
     d2h = max_cnt * (8 + 4 + 4 + 12 + 12) + 8 + 8 * (16 * (wsz + 1) + 8 + wprob.L) + 2048
@@ -379,7 +376,7 @@ def main():
                "ms_front": r["ms_front"], "ms_back": r["ms_back"]}
 
     if rank == 0:
-        fps = world * args.steps / (ms_total * 1e-3)
+        fps = frames_total / (ms_total * 1e-3)
         line = {
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -391,7 +388,7 @@ def main():
                        "streams": "one independent stream per GPU; front end and back end on separate CUDA streams"},
             "ms_tracker_stream": ms_tracker / args.steps, "ms_window_stream": ms_window / args.steps,
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
-            "e2e": {"value": world * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e_frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "host_threads": 2, "single_thread_ms_per_frame": e2e_seq_ms,
                     "note": "two host threads = the reference's two ROS nodes; each makes blocking C-ABI calls with host buffers"},
             "gpu_launches": int(launches),
