@@ -249,3 +249,28 @@ def test_device_async_path_equals_sync_path(lfvio_mod, gpu, golden_dir):
     assert np.array_equal(tr.ids, g[f"f{k}_ids"]) and np.array_equal(tr.track_cnt, g[f"f{k}_track_cnt"])
     assert np.abs(tr.cur_pts - g[f"f{k}_cur_pts"]).max() < 5e-3
     tr.close()
+
+
+# ---- BASELINE.json configs 3 and 4 shapes (larger frames, more features) against the live cv2 oracle -------------
+@pytest.mark.parametrize("scale,max_cnt,n_frames", [(1.5, 500, 3), (3.0, 2000, 2)])
+def test_tracker_large_configs_match_cv2_oracle(lfvio_mod, gpu, scale, max_cnt, n_frames):
+    pytest.importorskip("cv2")
+    from lfvio.config import scaled_camera
+
+    cam, cfg = scaled_camera(scale), tracker_defaults(scale, max_cnt)
+    rows, cols = cam["image_height"], cam["image_width"]
+    src = synth.FrameSource(rows, cols, seed=5, margin=int(160 * scale))
+    dev_tr = lfvio_mod.FeatureTracker(cam, cfg, device=gpu)
+    ref_tr = fe.FeatureTrackerOracle(cam, cfg, "cv2")
+    for k in range(n_frames):
+        img = src.frame(2 * k)
+        for t in (dev_tr, ref_tr):
+            t.read_image(img, 3.0 + k / 30.0, True)
+            t.update_ids()
+        assert len(dev_tr.ids) == len(ref_tr.ids), f"frame {k}: {len(dev_tr.ids)} vs {len(ref_tr.ids)} tracks"
+        assert np.array_equal(dev_tr.ids, ref_tr.ids), f"frame {k}: ids"
+        assert np.array_equal(dev_tr.track_cnt, ref_tr.track_cnt), f"frame {k}: track_cnt"
+        assert np.abs(dev_tr.cur_pts - ref_tr.cur_pts).max() < 5e-3, f"frame {k}: cur_pts"
+        assert np.array_equal(dev_tr.mask, ref_tr.mask), f"frame {k}: mask"
+    assert len(dev_tr.ids) > 0.9 * max_cnt
+    dev_tr.close()
