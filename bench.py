@@ -288,9 +288,10 @@ def main():
         for k in range(k0, k0 + n):
             for dst, s in zip((work.pose, work.sb, work.ex, work.feat, work.td), init):
                 np.copyto(dst, s)
-            window.optimize(work)
-            if with_marg:  # Estimator::optimization(): solve, (double2vector on host), then build the next prior
-                window.marginalize(work, B.MARGIN_OLD, prior_out)
+            if with_marg:  # Estimator::optimization() in one call: solve, double2vector gauge fix, next prior (all on device)
+                window.optimize_full(work, B.MARGIN_OLD, prior_out)
+            else:
+                window.optimize(work)
 
     def run_nodes(k0, n):
         th = [threading.Thread(target=tracker_node, args=(k0, n)), threading.Thread(target=estimator_node, args=(k0, n))]

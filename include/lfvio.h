@@ -260,6 +260,13 @@ int lfvio_window_optimize(lfvio_window *w, lfvio_window_state *state, const lfvi
  * (addr_shift).  out->n == 0 if nothing is to be marginalised (SECOND_NEW without a matching prior).  */
 int lfvio_window_marginalize(lfvio_window *w, const lfvio_window_state *state, const lfvio_factor_list *factors,
                              const lfvio_solver_opts *opts, int margin_flag, lfvio_prior *out);
+/* The whole Estimator::optimization() (estimator.cpp:676-1009) in one call, one upload and one synchronisation:
+ * solve, then double2vector()/vector2double() (estimator.cpp:488-626: the window is rotated about gravity and shifted so
+ * that frame 0 keeps the yaw and position it had on entry), then the next prior at the re-anchored state.  `state` returns
+ * the re-anchored parameters; prior_out as in lfvio_window_marginalize.                                              */
+int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *state, const lfvio_factor_list *factors,
+                               const lfvio_solver_opts *opts, int margin_flag, lfvio_solve_summary *summary,
+                               lfvio_prior *prior_out);
 /* ceres::CostFunction::Evaluate of every factor at `state` (debug / parity hook): residuals are
  * written factor by factor (2 per projection factor incl. the Cauchy correction when robust != 0,
  * 15 per IMU factor, prior.n for the prior); jacobians likewise in LOCAL parameterisation, row-major:

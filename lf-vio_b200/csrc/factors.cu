@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(DevProblem P, cons
     if (active) {
         const double *x = target ? x1 : x0;
         const EvalBuf &e = target ? e1 : e0;
-        double *cost_acc = (mode == 1) ? &ctl->cost_cand : &ctl->cost;
+        double *cost_acc = (mode == 1) ? &ctl->cost_cand : (mode == 2 ? &ctl->acc[7] : &ctl->cost);  // mode 2 never touches the solve's cost
         const int b = blockIdx.x;
         if (b < nbp) {
             const int k = b * EV_THREADS + tid;

@@ -392,11 +392,82 @@ __global__ void select_state_kernel(const double *x0, const double *x1, const So
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) out[q] = x[q];
 }
 
-int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum) {
+// Estimator::double2vector() gauge re-anchoring (estimator.cpp:532-583) followed by vector2double() (:488-530), on device:
+// the optimised window is rotated about gravity so that frame 0 keeps the yaw it had before the solve, and translated so
+// that frame 0 keeps its position; poses go through the same quaternion -> matrix -> quaternion round trip as on the host.
+__device__ DM3 dev_ypr2R(double y_deg, double p_deg, double r_deg) {
+    const double y = y_deg / 180.0 * M_PI, p = p_deg / 180.0 * M_PI, r = r_deg / 180.0 * M_PI;
+    DM3 Rz = dm3_identity(), Ry = dm3_identity(), Rx = dm3_identity();
+    Rz.m[0][0] = cos(y); Rz.m[0][1] = -sin(y); Rz.m[1][0] = sin(y); Rz.m[1][1] = cos(y);
+    Ry.m[0][0] = cos(p); Ry.m[0][2] = sin(p); Ry.m[2][0] = -sin(p); Ry.m[2][2] = cos(p);
+    Rx.m[1][1] = cos(r); Rx.m[1][2] = -sin(r); Rx.m[2][1] = sin(r); Rx.m[2][2] = cos(r);
+    return Rz * Ry * Rx;
+}
+__device__ D3 dev_R2ypr(const DM3 &R) {  // Utility::R2ypr, degrees
+    const D3 n = d3(R.m[0][0], R.m[1][0], R.m[2][0]), o = d3(R.m[0][1], R.m[1][1], R.m[2][1]), a = d3(R.m[0][2], R.m[1][2], R.m[2][2]);
+    const double y = atan2(n.y, n.x);
+    const double p = atan2(-n.z, n.x * cos(y) + n.y * sin(y));
+    const double r = atan2(a.x * sin(y) - a.y * cos(y), -o.x * sin(y) + o.y * cos(y));
+    return d3(y / M_PI * 180.0, p / M_PI * 180.0, r / M_PI * 180.0);
+}
+__device__ void dev_rot_to_quat(const DM3 &m, double *q /* x y z w */) {  // Eigen::Quaterniond(Matrix3d)
+    double t = m.m[0][0] + m.m[1][1] + m.m[2][2];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        q[3] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (m.m[2][1] - m.m[1][2]) * t;
+        q[1] = (m.m[0][2] - m.m[2][0]) * t;
+        q[2] = (m.m[1][0] - m.m[0][1]) * t;
+    } else {
+        int i = 0;
+        if (m.m[1][1] > m.m[0][0]) i = 1;
+        if (m.m[2][2] > m.m[i][i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(m.m[i][i] - m.m[j][j] - m.m[k][k] + 1.0);
+        q[i] = 0.5 * t;
+        t = 0.5 / t;
+        q[3] = (m.m[k][j] - m.m[j][k]) * t;
+        q[j] = (m.m[j][i] + m.m[i][j]) * t;
+        q[k] = (m.m[k][i] + m.m[i][k]) * t;
+    }
+}
+__global__ void gauge_fix_kernel(StateLayout lay, const double *x_init, const double *x0, const double *x1, const SolverCtl *ctl,
+                                 double *out) {
+    const double *x = ctl->cur ? x1 : x0;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int q = lay.ex() + tid; q < lay.size(); q += nth) out[q] = x[q];  // extrinsic, td, inverse depths: unchanged
+    if (tid >= lay.F) return;
+    D3 P0i, P0o;
+    DQ Q0i, Q0o;
+    load_pose(x_init + lay.pose(0), &P0i, &Q0i);
+    load_pose(x + lay.pose(0), &P0o, &Q0o);
+    const DM3 R0_init = qrot(Q0i), R00 = qrot(Q0o);
+    const D3 origin_R0 = dev_R2ypr(R0_init), origin_R00 = dev_R2ypr(R00);
+    DM3 rot_diff = dev_ypr2R(origin_R0.x - origin_R00.x, 0.0, 0.0);
+    if (fabs(fabs(origin_R0.y) - 90) < 1.0 || fabs(fabs(origin_R00.y) - 90) < 1.0) rot_diff = R0_init * transpose3(R00);  // euler singular point
+    const int f = tid;
+    D3 p;
+    DQ qf;
+    load_pose(x + lay.pose(f), &p, &qf);
+    const DM3 Rf = rot_diff * qrot(qnormalized(qf));
+    const D3 Pf = rot_diff * (p - P0o) + P0i;
+    const double *sb = x + lay.sb(f);
+    const D3 Vf = rot_diff * d3(sb[0], sb[1], sb[2]);
+    double *po = out + lay.pose(f), *so = out + lay.sb(f);
+    po[0] = Pf.x; po[1] = Pf.y; po[2] = Pf.z;
+    dev_rot_to_quat(Rf, po + 3);
+    so[0] = Vf.x; so[1] = Vf.y; so[2] = Vf.z;
+    for (int k = 3; k < 9; k++) so[k] = sb[k];
+}
+
+int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum, bool select_state = true) {
     cudaStream_t s = w->stream;
     const StateLayout lay = w->P.lay;
-    select_state_kernel<<<cdiv(lay.size(), 256), 256, 0, s>>>(w->x[0].p, w->x[1].p, w->ctl.p, w->x_out.p, lay.size());
-    LFVIO_LAUNCH_CHECK();
+    if (select_state) {
+        select_state_kernel<<<cdiv(lay.size(), 256), 256, 0, s>>>(w->x[0].p, w->x[1].p, w->ctl.p, w->x_out.p, lay.size());
+        LFVIO_LAUNCH_CHECK();
+    }
     LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_x, w->x_out.p, sizeof(double) * lay.size(), cudaMemcpyDeviceToHost, s));
     LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_ctl, w->ctl.p, sizeof(SolverCtl), cudaMemcpyDeviceToHost, s));
     int status[4];
@@ -499,6 +570,63 @@ extern "C" int lfvio_window_optimize(lfvio_window *w, lfvio_window_state *state,
     return download(w, state, summary);
 }
 
+// Estimator::optimization() in one call: solve -> double2vector/vector2double gauge fix -> next prior, one upload, one sync.
+extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *state, const lfvio_factor_list *factors,
+                                          const lfvio_solver_opts *opts, int margin_flag, lfvio_solve_summary *summary,
+                                          lfvio_prior *prior_out) {
+    clear_error();
+    LFVIO_REQUIRE(w && prior_out, "lfvio_window_optimize_full: null argument");
+    LFVIO_REQUIRE(margin_flag == LFVIO_MARGIN_OLD || margin_flag == LFVIO_MARGIN_SECOND_NEW, "lfvio_window_optimize_full: bad margin_flag");
+    LFVIO_CUDA_TRY(cudaSetDevice(w->device));
+    LFVIO_TRY(upload(w, state, factors, opts));
+    LFVIO_TRY(enqueue_solve(w));
+    cudaStream_t s = w->stream;
+    const DevProblem &P = w->P;
+    gauge_fix_kernel<<<cdiv(std::max(P.lay.size(), P.lay.F), 256), 256, 0, s>>>(P.lay, reinterpret_cast<const double *>(w->blob.p + w->off_x),
+                                                                            w->x[0].p, w->x[1].p, w->ctl.p, w->x_out.p);
+    LFVIO_LAUNCH_CHECK();
+    prior_out->n = 0;
+    prior_out->n_blocks = 0;
+    const bool do_marg = w->plan_valid[margin_flag];
+    const MargPlan &pl = w->plan[margin_flag];
+    size_t nn = 0;
+    int x0_len = 0;
+    if (do_marg) {
+        LFVIO_REQUIRE(pl.n <= prior_out->cap_n && pl.n_keep <= prior_out->cap_blocks, "lfvio_window_optimize_full: output prior too small");
+        // preMarginalize() at the re-anchored state: evaluate into buffer 0, then eliminate
+        LFVIO_TRY(launch_evaluate(P, w->x_out.p, w->x_out.p, w->e[0], w->e[1], w->ctl.p, 2, 1, s));
+        MargBuffers mb{w->margT.p, w->marg_work.p, w->marg_J0.p, w->marg_r0.p, w->marg_x0.p};
+        w->prof.begin(WS_MARGINALIZE, s);
+        LFVIO_TRY(launch_marginalize(P, w->e[0], w->e[1], w->x_out.p, w->x_out.p, nullptr, w->plan[margin_flag], mb, s));
+        w->prof.end(s);
+        nn = (size_t)pl.n * pl.n;
+        for (int b = 0; b < pl.n_keep; b++) x0_len += P.lay.block_gsize(pl.keep_id[b]);
+        LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg, w->marg_J0.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, s));
+        LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg + nn, w->marg_r0.p, sizeof(double) * pl.n, cudaMemcpyDeviceToHost, s));
+        LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg + nn + pl.n, w->marg_x0.p, sizeof(double) * x0_len, cudaMemcpyDeviceToHost, s));
+    }
+    LFVIO_TRY(download(w, state, summary, false));
+    if (do_marg) {
+        prior_out->n = pl.n;
+        prior_out->n_blocks = pl.n_keep;
+        const int F = w->F;
+        for (int b = 0; b < pl.n_keep; b++) {
+            const int id = pl.keep_id[b];
+            int new_id = id;  // addr_shift (estimator.cpp:921-931 / :980-1000)
+            if (id < 2 * F) {
+                if (margin_flag == LFVIO_MARGIN_OLD) new_id = id - 2;
+                else if ((id >> 1) == F - 1) new_id = id - 2;
+            }
+            prior_out->block_id[b] = new_id;
+            prior_out->block_idx[b] = pl.col[id] - pl.m_p;
+        }
+        memcpy(prior_out->J0, w->h_marg, sizeof(double) * nn);
+        memcpy(prior_out->r0, w->h_marg + nn, sizeof(double) * pl.n);
+        memcpy(prior_out->x0, w->h_marg + nn + pl.n, sizeof(double) * x0_len);
+    }
+    return LFVIO_OK;
+}
+
 extern "C" int lfvio_window_upload(lfvio_window *w, const lfvio_window_state *state, const lfvio_factor_list *factors,
                                    const lfvio_solver_opts *opts) {
     clear_error();
@@ -545,7 +673,7 @@ extern "C" int lfvio_window_evaluate(lfvio_window *w, const lfvio_window_state *
     if (cost) {
         SolverCtl c;
         LFVIO_CUDA_TRY(cudaMemcpy(&c, w->ctl.p, sizeof(c), cudaMemcpyDeviceToHost));
-        *cost = c.cost;
+        *cost = c.acc[7];
     }
     int status[4];
     LFVIO_CUDA_TRY(cudaMemcpy(status, w->status.p, sizeof(status), cudaMemcpyDeviceToHost));

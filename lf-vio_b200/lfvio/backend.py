@@ -142,6 +142,8 @@ def bind(lib):
                                           C.POINTER(SolveSummary)]
     lib.lfvio_window_marginalize.argtypes = [C.c_void_p, C.POINTER(WindowState), C.POINTER(FactorList), C.POINTER(SolverOpts),
                                              C.c_int, C.POINTER(Prior)]
+    lib.lfvio_window_optimize_full.argtypes = [C.c_void_p, C.POINTER(WindowState), C.POINTER(FactorList), C.POINTER(SolverOpts),
+                                               C.c_int, C.POINTER(SolveSummary), C.POINTER(Prior)]
     lib.lfvio_window_evaluate.argtypes = [C.c_void_p, C.POINTER(WindowState), C.POINTER(FactorList), C.POINTER(SolverOpts),
                                           C.c_int, _dp, _dp, _dp, _dp, _dp, _dp]
     lib.lfvio_window_stream.argtypes = [C.c_void_p]
@@ -205,6 +207,15 @@ class Window:
         self._check(self._lib.lfvio_window_optimize(self._h, C.byref(st), C.byref(fl), C.byref(w.opts), C.byref(s)),
                     "lfvio_window_optimize")
         return s
+
+    def optimize_full(self, w: WindowProblem, flag: int = MARGIN_OLD, out: PriorData | None = None):
+        """solve + gauge re-anchoring + next prior in one call; returns (summary, prior)."""
+        out = out or PriorData()
+        s = SolveSummary()
+        st, fl = w.state(), w.factors()
+        self._check(self._lib.lfvio_window_optimize_full(self._h, C.byref(st), C.byref(fl), C.byref(w.opts), flag, C.byref(s),
+                                                         C.byref(out.c)), "lfvio_window_optimize_full")
+        return s, out
 
     def marginalize(self, w: WindowProblem, flag: int, out: PriorData | None = None) -> PriorData:
         out = out or PriorData()

@@ -94,3 +94,32 @@ def test_estimator_class_optimization_roundtrip(lfvio_mod, gpu, host):
     Ag, bg = prior.information()
     Ao, bo = po.information()
     assert np.abs(Ag - Ao).max() < 1e-6 * np.abs(Ao).max()
+
+
+def test_fused_optimize_full_equals_host_class_path(lfvio_mod, gpu, host):
+    """lfvio_window_optimize_full (gauge fix on device) == Estimator::optimization() of the host mirror
+    (solve, double2vector on the host, marginalise at the re-anchored state)."""
+    w0 = synthwin.make_window(seed=4, opts=lfvio_mod.solver_default_opts(), perturb=0.3)
+    # make frame 0 itself move during the solve so that the re-anchoring is not a no-op
+    w0.pose[0, :3] += 0.02
+    F, L = w0.F, w0.L
+    pose, sb, ex, feat, td = np.zeros((F, 7)), np.zeros((F, 9)), np.zeros(7), np.zeros(L), np.zeros(1)
+    prior_h = B.PriorData()
+    it = C.c_int(0)
+    st, fl = w0.state(), w0.factors()
+    host.lfvio_host_estimator_roundtrip.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p, C.c_void_p]
+    assert host.lfvio_host_estimator_roundtrip(C.byref(st), C.byref(fl), 1, 0, pose.ctypes.data, sb.ctypes.data, ex.ctypes.data,
+                                               feat.ctypes.data, td.ctypes.data, C.byref(prior_h.c), C.byref(it)) == 0
+    win = lfvio_mod.Window(10, 1000, 16384, device=gpu)
+    w = w0.clone()
+    summ, prior_d = win.optimize_full(w, B.MARGIN_OLD)
+    assert summ.iterations == it.value
+    assert np.abs(w.pose - pose).max() < 1e-7 and np.abs(w.sb - sb).max() < 1e-6
+    assert np.allclose(w.pose[0, :3], w0.pose[0, :3], atol=1e-9)  # frame 0 keeps its position
+    assert np.abs(w.feat - feat).max() < 1e-7 and abs(w.td[0] - td[0]) < 1e-9
+    assert prior_d.n == prior_h.n and list(prior_d.block_id[: prior_d.n_blocks]) == list(prior_h.block_id[: prior_h.n_blocks])
+    Ad, bd = prior_d.information()
+    Ah, bh = prior_h.information()
+    assert np.abs(Ad - Ah).max() < 1e-6 * np.abs(Ah).max()
+    assert np.abs(bd - bh).max() < 1e-5 * max(np.abs(bh).max(), 1.0)
+    win.close()
