@@ -2,6 +2,8 @@
 // Each mirrors one third-party call the reference's FeatureTracker::readImage makes
 // (feature_tracker/src/feature_tracker.cpp:95-184); arithmetic follows SURVEY.md Appendix B.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched from the driver at run time)
+
 #include "common.cuh"
 #include "lift.cuh"
 
@@ -20,6 +22,15 @@ struct Pyramid {
     ImgLevel lvl[kMaxPyrLevels];
     int levels;  // number of valid levels (maxLevel + 1 after the "<= winSize" early stop)
 };
+
+// TMA descriptors of the first pyramid levels (u8, box 64 x 44 covers the 44 x 44 LK tile at any x), passed to lk_kernel as __grid_constant__.
+constexpr int kTmaLevels = 4;
+struct alignas(64) PyrTmaps {
+    CUtensorMap m[kTmaLevels];
+    int valid;  // 0: descriptors could not be encoded (the kernel then stages every tile with plain loads)
+};
+// Encodes one descriptor per level with cuTensorMapEncodeTiled (entry point resolved through cudaGetDriverEntryPoint).
+void make_pyramid_tmaps(const Pyramid &p, PyrTmaps *out);
 
 // ---- K1 CLAHE -------------------------------------------------------------------------------
 // hist: 64*256 u32 scratch (zeroed inside), lut: 64*256 u8 scratch.
@@ -43,7 +54,7 @@ struct LkParams {
     int rows, cols;     // level-0 size for inBorder
 };
 // n_dev: optional device count (if non-null the kernel uses min(*n_dev, n_max)); grid is n_max CTAs.
-int launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *prev_pts, float2 *next_pts,
+int launch_lk(const Pyramid &prev, const PyrTmaps &prev_tm, const Pyramid &next, const float2 *prev_pts, float2 *next_pts,
               uint8_t *status, int n_max, const int *n_dev, const LkParams &prm, cudaStream_t s);
 
 // ---- K4 Shi-Tomasi --------------------------------------------------------------------------

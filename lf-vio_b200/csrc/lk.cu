@@ -9,7 +9,7 @@
 //   oscillation back-off, level-0 bounds => status 0 (incl. the extra bounds check of the `err` pass).
 //
 // One CTA (4 warps) per feature, all pyramid levels inside the CTA (coarse -> fine is a serial chain).
-// Per level the 44x44 u8 tile of the previous image is staged in shared memory, the Scharr gradients and
+// Per level the 44x44 u8 tile of the previous image is staged in shared memory (TMA box load for interior tiles), the Scharr gradients and
 // the 41x41 template are built there once, and every iteration samples the next image (L1/L2-resident)
 // and reduces the 2x2 normal-equation right-hand side with warp shuffles.  The sums are accumulated in
 // exact integer arithmetic (int32 per thread, int64 across the CTA) — order independent, deterministic —
@@ -25,7 +25,7 @@ namespace {
 constexpr int WIN = 41;
 constexpr int HALF = 20;
 constexpr int TILE = WIN + 3;     // 44: I at ip-1 .. ip+42
-constexpr int TILE_P = 48;        // padded row
+constexpr int TILE_P = 64;        // row pitch == TMA box width: 44 columns + up to 15 of 16-byte alignment slack
 constexpr int DW = WIN + 1;       // 42: derivative positions ip .. ip+41
 constexpr int LK_THREADS = 128;
 constexpr int SEGS = 3, SEG_LEN = 14;  // 41 rows x 3 segments = 123 working threads
@@ -63,14 +63,47 @@ __device__ __forceinline__ void block_sum(long long (&v)[K], long long *buf) {
     for (int k = 0; k < K; k++) v[k] = buf[0 * K + k] + buf[1 * K + k] + buf[2 * K + k] + buf[3 * K + k];
 }
 
-__global__ void __launch_bounds__(LK_THREADS) lk_kernel(Pyramid prev, Pyramid next, const float2 *__restrict__ prev_pts,
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+// one 48 x 44 u8 box whose top-left pixel is (x, y); out-of-range bytes (x >= cols) are zero-filled by the TMA unit
+__device__ __forceinline__ void tma_load_tile(void *dst, const CUtensorMap *tmap, int x, int y, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__global__ void __launch_bounds__(LK_THREADS) lk_kernel(Pyramid prev, const __grid_constant__ PyrTmaps prev_tm, Pyramid next,
+                                                        const float2 *__restrict__ prev_pts,
                                                         float2 *__restrict__ next_pts, uint8_t *__restrict__ status,
                                                         int n_max, const int *__restrict__ n_dev, LkParams prm) {
     const int p = blockIdx.x;
     const int n = n_dev ? min(*n_dev, n_max) : n_max;
     if (p >= n) return;
 
-    __shared__ uint8_t s_I[TILE][TILE_P];
+    __shared__ __align__(128) uint8_t s_I[TILE][TILE_P];  // 44 rows x 64 bytes == one TMA box
+    __shared__ uint64_t s_mbar;
     __shared__ short s_dx[DW][DW + 2], s_dy[DW][DW + 2];
     __shared__ short s_Iw[WIN][WIN + 1], s_Ix[WIN][WIN + 1], s_Iy[WIN][WIN + 1];
     __shared__ long long s_red[2][4 * 3];
@@ -81,6 +114,9 @@ __global__ void __launch_bounds__(LK_THREADS) lk_kernel(Pyramid prev, Pyramid ne
     const int wx0 = (tid % SEGS) * SEG_LEN;
     const int wx1 = min(WIN, wx0 + SEG_LEN);
 
+    if (threadIdx.x == 0) mbar_init(&s_mbar, 1);
+    uint32_t tma_phase = 0;
+    __syncthreads();
     const float2 pt0 = prev_pts[p];
     const float FLT_SCALE = 1.f / (1 << 20);
     const float halfWin = (float)HALF;
@@ -104,13 +140,30 @@ __global__ void __launch_bounds__(LK_THREADS) lk_kernel(Pyramid prev, Pyramid ne
             continue;
         }
         __syncthreads();  // previous level's shared tiles are dead
-        // ---- stage the 44x44 tile of I (virtual coords ip-1 ..), REFLECT_101 ----
-        for (int k = tid; k < TILE * TILE; k += LK_THREADS) {
-            const int ty = k / TILE, tx = k % TILE;
-            const int y = reflect101(ipy - 1 + ty, I.rows), x = reflect101(ipx - 1 + tx, I.cols);
-            s_I[ty][tx] = I.data[(size_t)y * I.pitch + x];
+        // ---- stage the 44x44 tile of I (virtual coords ip-1 ..) ----
+        // interior tiles: one TMA box load (cp.async.bulk.tensor.2d) issued by one thread, completion on an mbarrier;
+        // tiles touching the image border need REFLECT_101 and are gathered with plain loads.
+        const bool tile_inside = (ipx - 1 >= 0) && (ipy - 1 >= 0) && (ipx - 1 + TILE <= I.cols) && (ipy - 1 + TILE <= I.rows);
+        int xo = 0;  // column of the tile's first pixel inside s_I rows
+        if (prev_tm.valid && level < kTmaLevels && tile_inside) {
+            // a TMA box row must start on a 16-byte boundary of the image row (u8: x % 16 == 0, measured: any other
+            // start faults), so the box starts at the aligned column below ip-1 and the tile sits xo bytes into it
+            xo = (ipx - 1) & 15;
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads of s_I are done
+                mbar_expect_tx(&s_mbar, TILE * TILE_P);
+                tma_load_tile(&s_I[0][0], &prev_tm.m[level], (ipx - 1) - xo, ipy - 1, &s_mbar);
+            }
+            mbar_wait(&s_mbar, tma_phase);
+            tma_phase ^= 1;
+        } else {
+            for (int k = tid; k < TILE * TILE; k += LK_THREADS) {
+                const int ty = k / TILE, tx = k % TILE;
+                const int y = reflect101(ipy - 1 + ty, I.rows), x = reflect101(ipx - 1 + tx, I.cols);
+                s_I[ty][tx] = I.data[(size_t)y * I.pitch + x];
+            }
+            __syncthreads();
         }
-        __syncthreads();
         // ---- Scharr gradients at ip .. ip+41 (zero outside the image) ----
         for (int k = tid; k < DW * DW; k += LK_THREADS) {
             const int dy = k / DW, dx = k % DW;
@@ -118,9 +171,10 @@ __global__ void __launch_bounds__(LK_THREADS) lk_kernel(Pyramid prev, Pyramid ne
             short gx = 0, gy = 0;
             if (x >= 0 && x < I.cols && y >= 0 && y < I.rows) {
                 // tile index of (y, x) is (dy+1, dx+1)
-                const int a00 = s_I[dy][dx], a01 = s_I[dy][dx + 1], a02 = s_I[dy][dx + 2];
-                const int a10 = s_I[dy + 1][dx], a12 = s_I[dy + 1][dx + 2];
-                const int a20 = s_I[dy + 2][dx], a21 = s_I[dy + 2][dx + 1], a22 = s_I[dy + 2][dx + 2];
+                const uint8_t *r0 = &s_I[dy][dx + xo], *r1 = r0 + TILE_P, *r2 = r1 + TILE_P;
+                const int a00 = r0[0], a01 = r0[1], a02 = r0[2];
+                const int a10 = r1[0], a12 = r1[2];
+                const int a20 = r2[0], a21 = r2[1], a22 = r2[2];
                 // Ix = smooth_y[3 10 3](x+1) - smooth_y(x-1);  Iy = smooth_x[3 10 3] of (row+1 - row-1)
                 gx = (short)(((a02 + a22) * 3 + a12 * 10) - ((a00 + a20) * 3 + a10 * 10));
                 gy = (short)(((a20 - a00) + (a22 - a02)) * 3 + (a21 - a01) * 10);
@@ -136,8 +190,8 @@ __global__ void __launch_bounds__(LK_THREADS) lk_kernel(Pyramid prev, Pyramid ne
             int a11 = 0, a12 = 0, a22 = 0;
             const int y = wrow;
             for (int x = wx0; x < wx1; x++) {
-                const int iv = descale(s_I[y + 1][x + 1] * w.w00 + s_I[y + 1][x + 2] * w.w01 + s_I[y + 2][x + 1] * w.w10 +
-                                           s_I[y + 2][x + 2] * w.w11, W_BITS - 5);
+                const uint8_t *q0 = &s_I[y + 1][x + 1 + xo], *q1 = q0 + TILE_P;
+                const int iv = descale(q0[0] * w.w00 + q0[1] * w.w01 + q1[0] * w.w10 + q1[1] * w.w11, W_BITS - 5);
                 const int ix = descale(s_dx[y][x] * w.w00 + s_dx[y][x + 1] * w.w01 + s_dx[y + 1][x] * w.w10 +
                                            s_dx[y + 1][x + 1] * w.w11, W_BITS);
                 const int iy = descale(s_dy[y][x] * w.w00 + s_dy[y][x + 1] * w.w01 + s_dy[y + 1][x] * w.w10 +
@@ -254,11 +308,11 @@ __global__ void __launch_bounds__(LK_THREADS) lk_kernel(Pyramid prev, Pyramid ne
 
 }  // namespace
 
-int launch_lk(const Pyramid &prev, const Pyramid &next, const float2 *prev_pts, float2 *next_pts,
+int launch_lk(const Pyramid &prev, const PyrTmaps &prev_tm, const Pyramid &next, const float2 *prev_pts, float2 *next_pts,
               uint8_t *status, int n_max, const int *n_dev, const LkParams &prm, cudaStream_t s) {
     if (n_max <= 0) return LFVIO_OK;
     LFVIO_REQUIRE(prm.win == WIN, "launch_lk: only the reference's 41x41 window is built");
-    lk_kernel<<<n_max, LK_THREADS, 0, s>>>(prev, next, prev_pts, next_pts, status, n_max, n_dev, prm);
+    lk_kernel<<<n_max, LK_THREADS, 0, s>>>(prev, prev_tm, next, prev_pts, next_pts, status, n_max, n_dev, prm);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

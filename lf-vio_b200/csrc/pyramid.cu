@@ -8,6 +8,8 @@
 //
 // Tile kernel: a CTA produces 32x8 output pixels from a 67x19 input tile staged in shared memory
 // (separable: horizontal pass into smem, vertical pass out).  Traffic: read 1 B/px, write 1/4 B/px.
+#include <cstring>
+
 #include "frontend.cuh"
 
 namespace lfvio {
@@ -56,6 +58,33 @@ int launch_pyr_down(const ImgLevel &src, const ImgLevel &dst, cudaStream_t s) {
 int launch_build_pyramid(const Pyramid &p, cudaStream_t s) {
     for (int l = 1; l < p.levels; l++) LFVIO_TRY(launch_pyr_down(p.lvl[l - 1], p.lvl[l], s));
     return LFVIO_OK;
+}
+
+void make_pyramid_tmaps(const Pyramid &p, PyrTmaps *out) {
+    typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    memset(out, 0, sizeof(*out));
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    EncodeTiled encode = reinterpret_cast<EncodeTiled>(fn);
+    for (int l = 0; l < p.levels && l < kTmaLevels; l++) {
+        const ImgLevel &L = p.lvl[l];
+        if ((reinterpret_cast<uintptr_t>(L.data) & 15) || (L.pitch & 15)) return;  // TMA needs 16-byte aligned base and pitch
+        const cuuint64_t gdim[2] = {(cuuint64_t)L.cols, (cuuint64_t)L.rows};
+        const cuuint64_t gstride[1] = {(cuuint64_t)L.pitch};
+        const cuuint32_t box[2] = {64, 44};  // the 44 x 44 LK tile + 16-byte alignment slack of the row start
+        const cuuint32_t estride[2] = {1, 1};
+        if (encode(&out->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, L.data, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return;
+    }
+    out->valid = 1;
 }
 
 void make_pyramid_layout(Pyramid *p, int rows, int cols, int max_level, int win) {

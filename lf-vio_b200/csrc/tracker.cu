@@ -142,6 +142,7 @@ struct lfvio_tracker {
     DevBuf<uint8_t> raw, mask, base_mask;
     std::vector<DevBuf<uint8_t>> pyr_store[2];
     Pyramid pyr[2];
+    PyrTmaps pyr_tm[2];
     int cur_slot = 0;
     long frames = 0;
     // CLAHE scratch
@@ -185,7 +186,10 @@ int tracker_init(lfvio_tracker *t, const lfvio_tracker_cfg *cfg, int device) {
     LFVIO_TRY(t->raw.alloc(img_bytes));
     LFVIO_TRY(t->mask.alloc(img_bytes));
     LFVIO_TRY(t->base_mask.alloc(img_bytes));
-    for (int k = 0; k < 2; k++) LFVIO_TRY(alloc_pyramid(&t->pyr[k], &t->pyr_store[k], rows, cols, 3, 41));
+    for (int k = 0; k < 2; k++) {
+        LFVIO_TRY(alloc_pyramid(&t->pyr[k], &t->pyr_store[k], rows, cols, 3, 41));
+        make_pyramid_tmaps(t->pyr[k], &t->pyr_tm[k]);
+    }
     LFVIO_TRY(t->clahe_hist.alloc(kClaheTiles * kClaheTiles * 256));
     LFVIO_TRY(t->clahe_lut.alloc(kClaheTiles * kClaheTiles * 256));
     for (int k = 0; k < 2; k++) LFVIO_TRY(t->store[k].alloc(t->cap));
@@ -251,7 +255,7 @@ int enqueue_frame(lfvio_tracker *t, const uint8_t *src, int src_pitch, double cu
     if (t->n_upper > 0) {
         const LkParams prm = default_lk(c.rows, c.cols, 1);
         t->prof.begin(TS_LK, s);
-        LFVIO_TRY(launch_lk(cur, forw, A.cur, A.forw, t->status.p, t->n_upper, t->n_dev.p, prm, s));
+        LFVIO_TRY(launch_lk(cur, t->pyr_tm[t->cur_slot], forw, A.cur, A.forw, t->status.p, t->n_upper, t->n_dev.p, prm, s));
         t->prof.end(s);
         t->prof.begin(TS_COMPACT, s);
         LFVIO_TRY(launch_compact(A, B, t->status.p, t->n_dev.p, t->cap, s));
@@ -570,7 +574,9 @@ extern "C" int lfvio_calc_optical_flow_pyr_lk(const uint8_t *prev, const uint8_t
     LFVIO_TRY(st.alloc(n));
     LFVIO_CUDA_TRY(cudaMemcpy(p0.p, prev_pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
     const LkParams prm = default_lk(rows, cols, 0);
-    LFVIO_TRY(launch_lk(pa, pb, p0.p, p1.p, st.p, n, nullptr, prm, 0));
+    PyrTmaps tma;
+    make_pyramid_tmaps(pa, &tma);
+    LFVIO_TRY(launch_lk(pa, tma, pb, p0.p, p1.p, st.p, n, nullptr, prm, 0));
     LFVIO_CUDA_TRY(cudaDeviceSynchronize());
     LFVIO_CUDA_TRY(cudaMemcpy(next_pts, p1.p, sizeof(float2) * n, cudaMemcpyDeviceToHost));
     LFVIO_CUDA_TRY(cudaMemcpy(status, st.p, n, cudaMemcpyDeviceToHost));
