@@ -274,6 +274,9 @@ int launch_jacobi_scale(const DevProblem &P, const EvalBuf &e0, const SolverScra
 int launch_accumulate(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const SolverScratch &w, SolverCtl *ctl,
                       cudaStream_t s);
 // One trust-region step up to (not including) the candidate evaluation: pre -> chol -> gnlm -> cand.
+#ifdef LFVIO_CHOL_PROFILE
+void chol_profile_read(long long *out);
+#endif
 int launch_step(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const SolverScratch &w, double *x0, double *x1,
                 SolverCtl *ctl, cudaStream_t s);
 

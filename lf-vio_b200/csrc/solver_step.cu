@@ -35,6 +35,16 @@ __device__ __forceinline__ long long gtimer_ns() {
     return (long long)t;
 }
 #define PHASE_MARK(i) do { if (threadIdx.x == 0) ctl->phase_clk[i] = gtimer_ns(); } while (0)
+#ifdef LFVIO_CHOL_PROFILE
+#define SUB_T0() long long sub_t = clock64(); long long sub_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define SUB_MARK(i) do { const long long now = clock64(); sub_acc[i] += now - sub_t; sub_t = now; } while (0)
+#define SUB_FLUSH() do { if (threadIdx.x == 0 || threadIdx.x == 32) for (int i = 0; i < 8; i++) g_sub[(threadIdx.x >> 5) * 8 + i] = sub_acc[i]; } while (0)
+__device__ long long g_sub[16];
+#else
+#define SUB_T0()
+#define SUB_MARK(i)
+#define SUB_FLUSH()
+#endif
 
 __device__ __forceinline__ double block_sum(double v, double *s_red) {  // any blockDim (multiple of 32, <= 1024)
     v = warp_sum(v);
@@ -157,144 +167,229 @@ __global__ void __launch_bounds__(PRE_THREADS) pre_kernel(DevProblem P, EvalBuf 
 }
 
 // =====================================================================================================
+// row pitch of the shared panel: trailing columns rounded up to the 4-wide tiles, + one tile whose last column holds the rhs
+__host__ __device__ inline int chol_panel_pitch(int D) { return ((D + 3) & ~3) + 4; }
+
 struct MatFull {
     double *p;
     int D;
     __device__ __forceinline__ double &at(int r, int c) const { return p[(size_t)r * D + c]; }
+    __device__ __forceinline__ double *row(int r) const { return p + (size_t)r * D; }  // row(r)[c] == at(r, c)
 };
 struct MatPacked {  // packed upper triangle, row-major (c >= r)
     double *p;
     int D;
     __device__ __forceinline__ double &at(int r, int c) const { return p[r * D - ((r * (r - 1)) >> 1) + (c - r)]; }
+    __device__ __forceinline__ double *row(int r) const { return p + (r * D - ((r * (r - 1)) >> 1) - r); }  // valid for c >= r
 };
 
-template <class M>
-__device__ bool cholesky_upper(M S, int D, double *s_panel /* NB x D */, double *s_U /* NB x NB */, double *s_Xall, int *s_ok) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) *s_ok = 1;
-    __syncthreads();
-    for (int j0 = 0, blk = 0; j0 < D; j0 += NB, blk++) {
-        const int nb = min(NB, D - j0);
-        double *s_X = s_Xall + blk * NB * NB;
-        // diagonal block -> shared (all threads), factor + invert (warp 0, registers), write back (all threads)
-        for (int q = tid; q < NB * NB; q += nt) {
-            const int r = q / NB, c = q % NB;
-            s_U[q] = (r < nb && c < nb && c >= r) ? S.at(j0 + r, j0 + c) : ((r == c) ? 1.0 : 0.0);
-        }
-        __syncthreads();
-        if (tid < 32) {
-            const bool ok = factor_diag_block(s_U, s_X);
-            if (!ok && tid == 0) *s_ok = 0;
-        }
-        __syncthreads();
-        if (*s_ok == 0) return false;
-        for (int q = tid; q < nb * nb; q += nt) {
-            const int r = q / nb, c = q % nb;
-            if (c >= r) S.at(j0 + r, j0 + c) = s_U[r * NB + c];
-        }
-        const int rest0 = j0 + nb, nrest = D - rest0;
-        if (nrest > 0) {
-            // row panel U12 = U11^-T A12 = X^T A12: dependency-free, one thread per column
-            for (int c = tid; c < nrest; c += nt) {
-                double a[NB], u[NB];
+// ---- look-ahead blocked Cholesky + fused forward substitution ---------------------------------------------------
+// S = U^T U on the upper triangle, 16-column block steps, one CTA.  Warp 0 is the "diagonal warp": while the other
+// warps (workers) apply block step k to the trailing matrix, warp 0 already solves the 16 panel columns of block k+1,
+// applies step k to diagonal block k+1 and factors it in registers — the serial pivot chain of block k+1 overlaps the
+// throughput-bound trailing update of block k.  The right-hand side rides along as one extra panel column, so the
+// forward substitution U^T z = b costs nothing extra; solve_upper_back finishes with U y = z.
+// Barriers: id 1 = "diagonal block ready / trailing update done" (all threads), id 2 = "panel complete"
+// (workers wait, warp 0 only arrives).
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// one panel column: a <- U11^-T a by substitution with the factored diagonal block (broadcast reads of U, 1/pivot)
+__device__ __forceinline__ void panel_column_solve(double (&a)[NB], const double *U, const double *invd) {
 #pragma unroll
-                for (int r = 0; r < NB; r++) a[r] = (r < nb) ? S.at(j0 + r, rest0 + c) : 0.0;
+    for (int j = 0; j < NB; j++) {
+        const double u = a[j] * invd[j];
+        a[j] = u;
 #pragma unroll
-                for (int r = 0; r < NB; r++) {
-                    double s = 0;
-#pragma unroll
-                    for (int t = 0; t < NB; t++)
-                        if (t <= r) s += s_X[t * NB + r] * a[t];
-                    u[r] = s;
-                }
-#pragma unroll
-                for (int r = 0; r < NB; r++) {
-                    if (r < nb) S.at(j0 + r, rest0 + c) = u[r];
-                    s_panel[r * D + c] = (r < nb) ? u[r] : 0.0;
-                }
-            }
-            if (tid < NB * 4) {  // zero padding so that the 4x4 tiles need no bounds checks inside the rank-16 loop
-                const int r = tid >> 2, c = nrest + (tid & 3);
-                if (c < D) s_panel[r * D + c] = 0.0;
-            }
-            __syncthreads();
-            // trailing update A22[i][k] -= sum_t U12[t][i] U12[t][k] (k >= i), 4x4 register tiles
-            const int nt4 = (nrest + 3) >> 2;
-            for (int q = tid; q < nt4 * nt4; q += nt) {
-                const int ti = q / nt4, tk = q - ti * nt4;
-                if (tk < ti) continue;
-                const int i0 = ti << 2, k0 = tk << 2;
-                double acc[4][4];
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-#pragma unroll
-                    for (int v = 0; v < 4; v++) acc[u][v] = 0.0;
-#pragma unroll 4
-                for (int t = 0; t < NB; t++) {
-                    double a[4], b[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) a[u] = s_panel[t * D + i0 + u];
-#pragma unroll
-                    for (int v = 0; v < 4; v++) b[v] = s_panel[t * D + k0 + v];
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-#pragma unroll
-                        for (int v = 0; v < 4; v++) acc[u][v] += a[u] * b[v];
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-#pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        const int i = i0 + u, k = k0 + v;
-                        if (i < nrest && k < nrest && k >= i) S.at(rest0 + i, rest0 + k) -= acc[u][v];
-                    }
-            }
-        }
-        __syncthreads();
+        for (int r = j + 1; r < NB; r++) a[r] = fma(-U[j * NB + r], u, a[r]);
     }
+}
+
+template <class M>
+__device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, int PW, double *s_U /* 2 x NB x NB */,
+                                   double *s_invd /* nblk x NB */, double *s_y /* D: b in, z out */, int *s_okv /* nblk */, double *s_row /* 2 x NB */) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int nblk = (D + NB - 1) / NB;
+    const int nworkers = nt - 32, wtid = tid - 32;
+    const int nbar = nt;  // threads taking part in the named barriers
+    const int zc = PW - 1;           // panel column of the right-hand side
+    SUB_T0();
+    if (wid == 0) {  // factor diagonal block 0
+        const int nb = min(NB, D);
+        for (int q = lane; q < NB * NB; q += 32) {
+            const int r = q / NB, c = q % NB;
+            s_U[q] = (r < nb && c < nb && c >= r) ? S.at(r, c) : ((r == c) ? 1.0 : 0.0);
+        }
+        __syncwarp();
+        const bool ok = factor_diag_block_split(s_U, s_invd, s_row);
+        if (lane == 0) s_okv[0] = ok ? 1 : 0;
+        for (int q = lane; q < NB * NB; q += 32) {
+            const int r = q / NB, c = q % NB;
+            if (c >= r && c < nb) S.at(r, c) = s_U[q];
+        }
+    }
+    bar_sync(1, nbar);
+#ifdef LFVIO_CHOL_PROFILE
+    sub_t = clock64();
+#endif
+    for (int blk = 0; blk < nblk; blk++) {
+        if (s_okv[blk] == 0) return false;
+        const int j0 = blk * NB, nb = min(NB, D - j0);
+        const int rest0 = j0 + nb, nrest = D - rest0, nb1 = min(NB, nrest);
+        const double *U = s_U + (blk & 1) * NB * NB, *invd = s_invd + blk * NB;
+        if (wid == 0) {
+            // ---- diagonal warp: panel columns of block blk+1, then look ahead ----
+            double *Un = s_U + ((blk + 1) & 1) * NB * NB;
+            if (lane < nb1) {
+                double a[NB];
+#pragma unroll
+                for (int r = 0; r < NB; r++) a[r] = (r < nb) ? S.at(j0 + r, rest0 + lane) : 0.0;
+                panel_column_solve(a, U, invd);
+#pragma unroll
+                for (int r = 0; r < NB; r++) {
+                    if (r < nb) S.at(j0 + r, rest0 + lane) = a[r];
+                    s_panel[r * PW + lane] = a[r];
+                }
+            }
+            __threadfence_block();
+            bar_arrive(2, nbar);
+            SUB_MARK(0);
+            if (nb1 > 0) {
+                __syncwarp();
+                // step blk applied to diagonal block blk+1: lane (h, c) owns rows 8h .. 8h+7 of column c
+                const int c = lane & 15, i0 = (lane >> 4) * 8;
+                double acc[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc[u] = 0.0;
+                if (c < nb1) {
+#pragma unroll 4
+                    for (int t = 0; t < NB; t++) {
+                        const double pc = s_panel[t * PW + c];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) acc[u] = fma(s_panel[t * PW + i0 + u], pc, acc[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u;
+                    Un[i * NB + c] = (i <= c && c < nb1) ? S.at(rest0 + i, rest0 + c) - acc[u] : ((i == c) ? 1.0 : 0.0);
+                }
+                __syncwarp();
+                SUB_MARK(1);
+                const bool ok = factor_diag_block_split(Un, s_invd + (blk + 1) * NB, s_row);
+                if (lane == 0) s_okv[blk + 1] = ok ? 1 : 0;
+                for (int q = lane; q < NB * NB; q += 32) {
+                    const int r = q / NB, cc = q % NB;
+                    if (cc >= r && cc < nb1) S.at(rest0 + r, rest0 + cc) = Un[q];
+                }
+                SUB_MARK(2);
+            }
+        } else {
+            // ---- workers: remaining panel columns + right-hand side ----
+            const int ncol = nrest - nb1 + 1;  // last one is the right-hand side
+            // (one pass: D < number of workers, checked by launch_step)
+            if (const int q = wtid; q < ncol) {
+                const bool is_rhs = q == ncol - 1;
+                const int c = nb1 + q;  // column inside the trailing matrix
+                double a[NB];
+#pragma unroll
+                for (int r = 0; r < NB; r++) a[r] = (r < nb) ? (is_rhs ? s_y[j0 + r] : S.at(j0 + r, rest0 + c)) : 0.0;
+                SUB_MARK(4);
+                panel_column_solve(a, U, invd);
+                SUB_MARK(5);
+                const int pc = is_rhs ? zc : c;
+#pragma unroll
+                for (int r = 0; r < NB; r++) {
+                    if (r < nb) {
+                        if (is_rhs) s_y[j0 + r] = a[r];
+                        else S.at(j0 + r, rest0 + c) = a[r];
+                    }
+                    s_panel[r * PW + pc] = a[r];
+                }
+            }
+            SUB_MARK(0);
+            bar_sync(2, nbar);
+            SUB_MARK(1);
+            // ---- trailing update A22[i][k] -= sum_t U12[t][i] U12[t][k] (k >= i) in 16 x 16 blocks: 16 threads per
+            //      block, thread y owns column y of it (16 accumulators).  Per rank-1 step the 16 row factors are one
+            //      broadcast read and the column factor one conflict-free read; the read-modify-write of S touches 16
+            //      consecutive doubles per row.  Block (0, 0) — diagonal block blk+1 — belongs to warp 0. ----
+            const int nbk = (nrest + NB - 1) / NB, nunits = nbk * (nbk + 1) / 2;
+            const int y = wtid & 15;
+            for (int q = 1 + (wtid >> 4); q < nunits; q += nworkers >> 4) {
+                int bi = 0, rem = q;
+                while (rem >= nbk - bi) {
+                    rem -= nbk - bi;
+                    bi++;
+                }
+                const int bk = bi + rem, i0 = bi * NB, k = bk * NB + y;
+                double acc[NB];
+#pragma unroll
+                for (int u = 0; u < NB; u++) acc[u] = 0.0;
+#pragma unroll 2
+                for (int t = 0; t < NB; t++) {
+                    const double pk = s_panel[t * PW + k];
+                    const double2 *ap = reinterpret_cast<const double2 *>(&s_panel[t * PW + i0]);
+#pragma unroll
+                    for (int u2 = 0; u2 < NB / 2; u2++) {
+                        const double2 av = ap[u2];
+                        acc[2 * u2] = fma(av.x, pk, acc[2 * u2]);
+                        acc[2 * u2 + 1] = fma(av.y, pk, acc[2 * u2 + 1]);
+                    }
+                }
+                if (k < nrest) {
+#pragma unroll
+                    for (int u = 0; u < NB; u++) {
+                        const int i = i0 + u;
+                        if (i <= k) S.row(rest0 + i)[rest0 + k] -= acc[u];  // (i <= k < nrest)
+                    }
+                }
+            }
+            // right-hand side: b_rest -= U12^T z (taken by the workers that got the fewest tiles)
+            for (int i = nworkers - 1 - wtid; i < nrest; i += nworkers) {
+                double sacc = 0;
+#pragma unroll 4
+                for (int t = 0; t < NB; t++) sacc = fma(s_panel[t * PW + i], s_panel[t * PW + zc], sacc);
+                s_y[rest0 + i] -= sacc;
+            }
+            SUB_MARK(2);
+        }
+        bar_sync(1, nbar);
+        SUB_MARK(3);
+    }
+    SUB_FLUSH();
     return true;
 }
 
-// U^T z = b, U y = z on the shared vector y (in/out) using the inverted diagonal blocks: per block one 16x16 mat-vec
-// by 16 threads plus a parallel update — no dependent scalar chain.  Whole CTA calls.
+// U y = z on the shared vector y (in/out), last block first: warp 0 back-substitutes the 16 x 16 diagonal block with
+// shuffles, then every thread folds the 16 new unknowns into the rows above.  Whole CTA calls.
 template <class M>
-__device__ void solve_upper_blocked(M S, int D, double *y, const double *s_Xall, double *s_tmp /* NB */) {
-    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+__device__ void solve_upper_back(M S, int D, double *y, const double *s_invd) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const int nblk = (D + NB - 1) / NB;
-    for (int blk = 0; blk < nblk; blk++) {
-        const int j0 = blk * NB, nb = min(NB, D - j0);
-        const double *X = s_Xall + blk * NB * NB;
-        double z = 0;
-        if (tid < nb) {  // z[r] = sum_{t <= r} X[t][r] b[t]
-            for (int t = 0; t <= tid; t++) z += X[t * NB + tid] * y[j0 + t];
-        }
-        __syncthreads();
-        if (tid < nb) y[j0 + tid] = z;
-        __syncthreads();
-        for (int k = j0 + nb + tid; k < D; k += nt) {
-            double s = 0;
-#pragma unroll 4
-            for (int t = 0; t < nb; t++) s += S.at(j0 + t, k) * y[j0 + t];
-            y[k] -= s;
-        }
-        __syncthreads();
-    }
     for (int blk = nblk - 1; blk >= 0; blk--) {
-        const int j0 = blk * NB, nb = min(NB, D - j0), k0 = j0 + nb;
-        const double *X = s_Xall + blk * NB * NB;
-        for (int r = wid; r < nb; r += (nt >> 5)) {  // s_tmp[r] = sum_{k > block} U[j0+r][k] y[k]
-            double s = 0;
-            for (int k = k0 + lane; k < D; k += 32) s += S.at(j0 + r, k) * y[k];
-            s = warp_sum(s);
-            if (lane == 0) s_tmp[r] = s;
+        const int j0 = blk * NB, nb = min(NB, D - j0);
+        if (tid < 32) {
+            const int r = lane & 15;
+            double urow[NB];
+#pragma unroll
+            for (int t = 0; t < NB; t++) urow[t] = (r < nb && t > r && t < nb) ? S.at(j0 + r, j0 + t) : 0.0;
+            double wv = (r < nb) ? y[j0 + r] : 0.0;
+            const double inv = (r < nb) ? s_invd[blk * NB + r] : 1.0;
+#pragma unroll
+            for (int t = NB - 1; t >= 0; t--) {
+                const double yt = __shfl_sync(0xffffffffu, wv * inv, t);
+                wv = fma(-urow[t], yt, wv);  // urow[t] == 0 for t <= r
+            }
+            if (lane < nb) y[j0 + lane] = wv * inv;
         }
         __syncthreads();
-        double v = 0;
-        if (tid < nb) {  // y[r] = sum_{t >= r} X[r][t] (z[t] - s_tmp[t])
-            for (int t = tid; t < nb; t++) v += X[tid * NB + t] * (y[j0 + t] - s_tmp[t]);
+        for (int i = tid; i < j0; i += nt) {
+            double sacc = 0;
+#pragma unroll 4
+            for (int t = 0; t < nb; t++) sacc = fma(S.at(i, j0 + t), y[j0 + t], sacc);
+            y[i] -= sacc;
         }
-        __syncthreads();
-        if (tid < nb) y[j0 + tid] = v;
         __syncthreads();
     }
 }
@@ -304,18 +399,19 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(DevProblem P, Solver
     if (ctl->done != 0 || ctl->reuse != 0) return;
     extern __shared__ double smem[];
     __shared__ double s_red[33];
-    __shared__ double s_U[NB * NB];
-    __shared__ double s_tmp[NB];
-    __shared__ int s_ok;
+    __shared__ __align__(16) double s_U[2 * NB * NB];
+    __shared__ __align__(16) double s_row[2 * NB];
+    __shared__ int s_okv[kMaxFrames * 15 / NB + 4];
     const StateLayout lay = P.lay;
     const lfvio_solver_opts &o = P.o;
     const int D = lay.D();
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nblk = (D + NB - 1) / NB;
-    double *s_panel = smem;                        // NB * D
-    double *s_y = s_panel + (size_t)NB * D;        // D
-    double *s_X = s_y + D;                         // nblk * NB * NB inverted diagonal blocks
-    double *s_S = s_X + (size_t)nblk * NB * NB;    // packed upper triangle when use_smem
+    const int PW = chol_panel_pitch(D);
+    double *s_panel = smem;                        // NB * PW (16-byte aligned rows)
+    double *s_y = s_panel + (size_t)NB * PW;       // D (padded to even)
+    double *s_invd = s_y + ((D + 1) & ~1);         // nblk * NB reciprocal pivots
+    double *s_S = s_invd + (size_t)nblk * NB;      // packed upper triangle when use_smem
     PHASE_MARK(0);
     // ---- scalars of the Cauchy point; gradient tolerance ----
     if (tid == 0) {
@@ -345,30 +441,30 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(DevProblem P, Solver
     const double mu = ctl->mu;
     bool pd;
     PHASE_MARK(1);
+    for (int q = tid; q < NB * PW; q += nt) s_panel[q] = 0.0;
+    for (int c = tid; c < D; c += nt) s_y[c] = w.rhs[c];
     if (use_smem) {
         const MatPacked Sp{s_S, D};
-        for (int q = tid; q < D * D; q += nt) {
-            const int r = q / D, c = q - r * D;
-            if (c >= r) Sp.at(r, c) = w.S[q] + (r == c ? w.diagonal[c] * w.diagonal[c] * mu : 0.0);
+        for (int r = tid >> 5; r < D; r += nt >> 5) {  // one warp per row: coalesced reads of the upper triangle
+            const double *src = w.S + (size_t)r * D;
+            double *dst = &Sp.at(r, r) - r;
+            for (int c = r + (tid & 31); c < D; c += 32) dst[c] = src[c] + (r == c ? w.diagonal[c] * w.diagonal[c] * mu : 0.0);
         }
         __syncthreads();
         PHASE_MARK(2);
-        pd = cholesky_upper(Sp, D, s_panel, s_U, s_X, &s_ok);
+        pd = cholesky_lookahead(Sp, D, s_panel, PW, s_U, s_invd, s_y, s_okv, s_row);
     } else {
         for (int c = tid; c < D; c += nt) w.S[(size_t)c * D + c] += w.diagonal[c] * w.diagonal[c] * mu;
         __syncthreads();
-        pd = cholesky_upper(MatFull{w.S, D}, D, s_panel, s_U, s_X, &s_ok);
+        pd = cholesky_lookahead(MatFull{w.S, D}, D, s_panel, PW, s_U, s_invd, s_y, s_okv, s_row);
     }
     if (!pd) {
         if (tid == 0) ctl->pad = 0;
         return;
     }
     PHASE_MARK(3);
-    for (int c = tid; c < D; c += nt) s_y[c] = w.rhs[c];
-    __syncthreads();
-    if (use_smem) solve_upper_blocked(MatPacked{s_S, D}, D, s_y, s_X, s_tmp);
-    else solve_upper_blocked(MatFull{w.S, D}, D, s_y, s_X, s_tmp);
-    __syncthreads();
+    if (use_smem) solve_upper_back(MatPacked{s_S, D}, D, s_y, s_invd);
+    else solve_upper_back(MatFull{w.S, D}, D, s_y, s_invd);
     PHASE_MARK(4);
     double gn2 = 0, gdot = 0;
     int bad = 0;
@@ -570,6 +666,10 @@ __global__ void __launch_bounds__(CAND_THREADS) cand_kernel(DevProblem P, EvalBu
 
 }  // namespace
 
+#ifdef LFVIO_CHOL_PROFILE
+void chol_profile_read(long long *out) { cudaMemcpyFromSymbol(out, g_sub, sizeof(long long) * 16); }
+#endif
+
 int launch_step(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const SolverScratch &w, double *x0, double *x1,
                 SolverCtl *ctl, cudaStream_t s) {
     const int D = P.lay.D(), L = P.lay.L;
@@ -577,8 +677,9 @@ int launch_step(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const
     const int grid_rows = std::max(1, std::min(cdiv(work, PRE_THREADS), 148));
     pre_kernel<<<grid_rows, PRE_THREADS, 0, s>>>(P, e0, e1, w, ctl);
     LFVIO_LAUNCH_CHECK();
+    LFVIO_REQUIRE(D + 1 <= CHOL_THREADS - 32, "window too large for the single-pass panel solve (15 F + 8 <= 480)");
     const int nblk = cdiv(D, NB);
-    const size_t base = sizeof(double) * ((size_t)NB * D + D + (size_t)nblk * NB * NB);
+    const size_t base = sizeof(double) * ((size_t)NB * chol_panel_pitch(D) + ((D + 1) & ~1) + (size_t)nblk * NB);
     const size_t packed = sizeof(double) * ((size_t)D * (D + 1) / 2);
     const size_t limit = 220 * 1024;
     const int use_smem = (base + packed <= limit) ? 1 : 0;

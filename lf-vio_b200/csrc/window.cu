@@ -481,6 +481,14 @@ int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum, 
         if (lay.L) memcpy(st->para_Feature, w->h_x + lay.feat(0), sizeof(double) * lay.L);
     }
     const SolverCtl &c = *w->h_ctl;
+#ifdef LFVIO_CHOL_PROFILE
+    if (getenv("LFVIO_DEBUG_STEP")) {
+        long long sub[16];
+        chol_profile_read(sub);
+        static const char *sn[16] = {"w0 panel16", "w0 diag-upd", "w0 factor", "w0 wait", "-", "-", "-", "-", "wk panel-store", "wk wait-panel", "wk trailing", "wk wait", "wk panel-load", "wk panel-solve", "-", "-"};
+        for (int i = 0; i < 16; i++) fprintf(stderr, "chol sub-phase %-12s %8.0f cycles\n", sn[i], (double)sub[i]);
+    }
+#endif
     if (getenv("LFVIO_DEBUG_STEP")) {
         static const char *names[5] = {"scalars+xnorm", "copy-to-smem", "cholesky", "tri-solve", "tail"};
         for (int i = 0; i < 5; i++) fprintf(stderr, "step phase %-16s %8.2f us\n", names[i], (c.phase_clk[i + 1] - c.phase_clk[i]) / 1000.0);
