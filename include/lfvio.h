@@ -85,6 +85,15 @@ int lfvio_calc_optical_flow_pyr_lk(const uint8_t *prev, const uint8_t *next, int
 /* cv::cornerMinEigenVal(img, out, 3, 3): out rows x cols f32 (dense)                            */
 int lfvio_corner_min_eigen_val(const uint8_t *img, int rows, int cols, int stride, float *out,
                                int device);
+/* FeatureTracker::rejectWithF (feature_tracker.cpp:329-386) on n >= 0 point pairs: lifts cur_pts / forw_pts
+ * (n x 2 f32 pixels) to the unit sphere, runs myfindFundamentalMat (:266-327: 100 spherical 8-point hypotheses,
+ * float score, refit on the inliers of the best) and writes status (n u8, 1 = keep; all ones when n < 8).
+ * Sample sets: word k of hypothesis h is the top half of splitmix64(seed + frame*C1 + h*C2 + k*C3), consumed by
+ * create_random_array's procedure (random_array.cc:22-49).  Optional outputs: E_out (9 f64, row-major, the refit
+ * E_21), scores_out (100 f32, score of every hypothesis), best_out (index of the winning hypothesis).          */
+int lfvio_reject_with_f(const lfvio_ocam *cam, const float *cur_pts, const float *forw_pts, int n,
+                        unsigned long long seed, unsigned frame, unsigned char *status, double *E_out,
+                        float *scores_out, int *best_out);
 /* cv::goodFeaturesToTrack(img, corners, max_corners, quality, min_distance, mask)
  * feature_tracker.cpp:166.  mask may be NULL.  corners: max_corners x 2 f32; *n_out <= max_corners. */
 int lfvio_good_features_to_track(const uint8_t *img, int rows, int cols, int stride,
@@ -106,8 +115,10 @@ typedef struct lfvio_tracker_cfg {
     double center_x, center_y; /* CENTER_X/Y (YAML center_x/center_y), truncated like cv::Point */
     int max_r, min_r;          /* MAX_R, MIN_R: annular mask radii                           */
     int capacity;              /* device track capacity; 0 => max_cnt                        */
-    int ransac;                /* reserved: rejectWithF; must be 0       */
+    int ransac;                /* 1: run rejectWithF() on published frames (feature_tracker.cpp:149) */
     lfvio_ocam cam;            /* m_camera                                                   */
+    unsigned long long ransac_seed; /* injected random source of rejectWithF's sample sets: the reference seeds
+                                * a new mt19937 from std::random_device per call (random_array.cc:12-20)   */
 } lfvio_tracker_cfg;
 
 /* Caller-allocated SoA view of the public members the ROS node reads after readImage

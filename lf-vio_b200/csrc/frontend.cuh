@@ -93,8 +93,21 @@ struct TrackArrays {  // SoA per-track state, capacity cap
     uint8_t *prev_valid;  // id was != -1 when `bearing` was stored (prev_un_pts_map_3d membership)
 };
 // Stable compaction by status, track_cnt++ (feature_tracker.cpp:132-145).  n_dev in/out.
-int launch_compact(const TrackArrays &in, const TrackArrays &out, const uint8_t *status, int *n_dev, int cap,
+int launch_compact(const TrackArrays &in, const TrackArrays &out, const uint8_t *status, int *n_dev, int cap, int cnt_add,
                    cudaStream_t s);
+
+// ---- K7 rejectWithF (feature_tracker.cpp:329-386): spherical 8-point RANSAC, ransac.cu --------------------------
+struct RansacScratch {
+    double3 *b1, *b2;  // cap unit bearings of cur_pts / forw_pts
+    double *E;         // 100 x 9 hypotheses
+    float *score;      // 100
+    uint8_t *flags;    // 100 x cap inlier flags per hypothesis
+    double *E_best;    // 9: refit essential matrix (row-major)
+    int *best;         // index of the winning hypothesis
+};
+// status[i] = 1 for the tracks rejectWithF keeps (all ones below 8 tracks).  seed/frame: injected random source.
+int launch_reject_with_f(const OcamDev &cam, const float2 *cur, const float2 *forw, const int *n_dev, int n_upper, int cap,
+                         unsigned long long seed, unsigned frame, const RansacScratch &rs, uint8_t *status, cudaStream_t s);
 // setMask (feature_tracker.cpp:46-83): sort (libstdc++ introsort order), greedy keep, reorder.
 // half_width: circle_spans(min_dist) table (min_dist+1 ints), base_mask: the annulus.
 int launch_set_mask_select(const TrackArrays &in, const TrackArrays &out, int *n_dev, int cap,

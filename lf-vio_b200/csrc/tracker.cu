@@ -125,9 +125,10 @@ LkParams default_lk(int rows, int cols, int border_check) {
 
 using namespace lfvio;
 
-enum TrackerStage { TS_CLAHE = 0, TS_PYRAMID, TS_LK, TS_COMPACT, TS_SETMASK, TS_MASK_RASTER, TS_MIN_EIG, TS_CANDIDATES,
+enum TrackerStage { TS_CLAHE = 0, TS_PYRAMID, TS_LK, TS_COMPACT, TS_RANSAC, TS_SETMASK, TS_MASK_RASTER, TS_MIN_EIG, TS_CANDIDATES,
                     TS_SELECT, TS_UNDISTORT, TS_UPDATE_IDS, TS_COUNT };
 static const char *kTrackerStageNames[TS_COUNT] = {"clahe(3 kernels)", "pyr_down(3 kernels)", "lk_kernel", "compact_kernel",
+                                                   "reject_with_f(4 kernels + compact)",
                                                    "set_mask_select_kernel", "mask_raster(copy+kernel)", "min_eig_kernel",
                                                    "candidates_kernel", "select_kernel", "undistort_kernel",
                                                    "update_ids_kernel"};
@@ -153,6 +154,15 @@ struct lfvio_tracker {
     int a = 0;           // index of the live store
     bool swapped_cf[2] = {false, false};
     DevBuf<uint8_t> status;
+    // rejectWithF scratch (cfg.ransac)
+    DevBuf<double> rs_b1, rs_b2, rs_E, rs_E_best;
+    DevBuf<float> rs_score;
+    DevBuf<uint8_t> rs_flags;
+    DevBuf<int> rs_best;
+    RansacScratch ransac() {
+        return RansacScratch{reinterpret_cast<double3 *>(rs_b1.p), reinterpret_cast<double3 *>(rs_b2.p), rs_E.p, rs_score.p, rs_flags.p,
+                             rs_E_best.p, rs_best.p};
+    }
     DevBuf<int> n_dev, have_prev, n_id_dev, sort_scratch, half_width;
     DevBuf<float> bearing_out, vel_out;
     CornerStore corners;
@@ -194,6 +204,15 @@ int tracker_init(lfvio_tracker *t, const lfvio_tracker_cfg *cfg, int device) {
     LFVIO_TRY(t->clahe_lut.alloc(kClaheTiles * kClaheTiles * 256));
     for (int k = 0; k < 2; k++) LFVIO_TRY(t->store[k].alloc(t->cap));
     LFVIO_TRY(t->status.alloc(t->cap));
+    if (t->cfg.ransac) {
+        LFVIO_TRY(t->rs_b1.alloc(3 * (size_t)t->cap));
+        LFVIO_TRY(t->rs_b2.alloc(3 * (size_t)t->cap));
+        LFVIO_TRY(t->rs_E.alloc(100 * 9));
+        LFVIO_TRY(t->rs_E_best.alloc(9));
+        LFVIO_TRY(t->rs_score.alloc(100));
+        LFVIO_TRY(t->rs_flags.alloc(100 * (size_t)t->cap));
+        LFVIO_TRY(t->rs_best.alloc(1));
+    }
     LFVIO_TRY(t->n_dev.alloc(1));
     LFVIO_TRY(t->have_prev.alloc(2));
     LFVIO_TRY(t->n_id_dev.alloc(1));
@@ -258,14 +277,23 @@ int enqueue_frame(lfvio_tracker *t, const uint8_t *src, int src_pitch, double cu
         LFVIO_TRY(launch_lk(cur, t->pyr_tm[t->cur_slot], forw, A.cur, A.forw, t->status.p, t->n_upper, t->n_dev.p, prm, s));
         t->prof.end(s);
         t->prof.begin(TS_COMPACT, s);
-        LFVIO_TRY(launch_compact(A, B, t->status.p, t->n_dev.p, t->cap, s));
+        LFVIO_TRY(launch_compact(A, B, t->status.p, t->n_dev.p, t->cap, 1, s));
         t->prof.end(s);  // + track_cnt++
         t->a ^= 1;
         A = t->live();
         B = t->spare();
     }
     if (pub) {
-        // rejectWithF(): SURVEY §8(f) rank 1, not built (cfg.ransac must be 0)
+        if (c.ransac && t->n_upper > 0) {  // rejectWithF() :149, :329-386
+            t->prof.begin(TS_RANSAC, s);
+            LFVIO_TRY(launch_reject_with_f(t->cam, A.cur, A.forw, t->n_dev.p, t->n_upper, t->cap, c.ransac_seed, (unsigned)t->frames,
+                                           t->ransac(), t->status.p, s));
+            LFVIO_TRY(launch_compact(A, B, t->status.p, t->n_dev.p, t->cap, 0, s));
+            t->prof.end(s);
+            t->a ^= 1;
+            A = t->live();
+            B = t->spare();
+        }
         t->prof.begin(TS_SETMASK, s);
         LFVIO_TRY(launch_set_mask_select(A, B, t->n_dev.p, t->cap, t->base_mask.p, t->pitch, t->half_width.p, c.min_dist,
                                          t->sort_scratch.p, s));
@@ -343,12 +371,49 @@ int download(lfvio_tracker *t) {
 
 }  // namespace
 
+extern "C" int lfvio_reject_with_f(const lfvio_ocam *cam, const float *cur_pts, const float *forw_pts, int n,
+                                   unsigned long long seed, unsigned frame, unsigned char *status, double *E_out,
+                                   float *scores_out, int *best_out) {
+    clear_error();
+    LFVIO_REQUIRE(cam && cur_pts && forw_pts && status && n >= 0, "lfvio_reject_with_f: bad arguments");
+    if (n == 0) return LFVIO_OK;
+    OcamDev dc = make_ocam_dev(*cam);
+    DevBuf<float2> c, f;
+    DevBuf<double> b1, b2, E, Eb;
+    DevBuf<float> score;
+    DevBuf<uint8_t> flags, st;
+    DevBuf<int> nd, best;
+    LFVIO_TRY(c.alloc(n));
+    LFVIO_TRY(f.alloc(n));
+    LFVIO_TRY(b1.alloc(3 * (size_t)n));
+    LFVIO_TRY(b2.alloc(3 * (size_t)n));
+    LFVIO_TRY(E.alloc(900));
+    LFVIO_TRY(Eb.alloc(9));
+    LFVIO_TRY(score.alloc(100));
+    LFVIO_TRY(flags.alloc(100 * (size_t)n));
+    LFVIO_TRY(st.alloc(n));
+    LFVIO_TRY(nd.alloc(1));
+    LFVIO_TRY(best.alloc(1));
+    LFVIO_CUDA_TRY(cudaMemcpy(c.p, cur_pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
+    LFVIO_CUDA_TRY(cudaMemcpy(f.p, forw_pts, sizeof(float2) * n, cudaMemcpyHostToDevice));
+    LFVIO_CUDA_TRY(cudaMemcpy(nd.p, &n, sizeof(int), cudaMemcpyHostToDevice));
+    LFVIO_CUDA_TRY(cudaMemset(Eb.p, 0, sizeof(double) * 9));
+    LFVIO_CUDA_TRY(cudaMemset(score.p, 0, sizeof(float) * 100));
+    LFVIO_CUDA_TRY(cudaMemset(best.p, 0xff, sizeof(int)));
+    const RansacScratch rs{reinterpret_cast<double3 *>(b1.p), reinterpret_cast<double3 *>(b2.p), E.p, score.p, flags.p, Eb.p, best.p};
+    LFVIO_TRY(launch_reject_with_f(dc, c.p, f.p, nd.p, n, n, seed, frame, rs, st.p, 0));
+    LFVIO_CUDA_TRY(cudaMemcpy(status, st.p, n, cudaMemcpyDeviceToHost));
+    if (E_out) LFVIO_CUDA_TRY(cudaMemcpy(E_out, Eb.p, sizeof(double) * 9, cudaMemcpyDeviceToHost));
+    if (scores_out) LFVIO_CUDA_TRY(cudaMemcpy(scores_out, score.p, sizeof(float) * 100, cudaMemcpyDeviceToHost));
+    if (best_out) LFVIO_CUDA_TRY(cudaMemcpy(best_out, best.p, sizeof(int), cudaMemcpyDeviceToHost));
+    return LFVIO_OK;
+}
+
 extern "C" int lfvio_tracker_create(const lfvio_tracker_cfg *cfg, int device, lfvio_tracker **out) {
     clear_error();
     LFVIO_REQUIRE(cfg && out, "lfvio_tracker_create: null argument");
     LFVIO_REQUIRE(cfg->rows > 41 && cfg->cols > 41, "lfvio_tracker_create: image must exceed the 41x41 LK window");
     LFVIO_REQUIRE(cfg->max_cnt > 0 && cfg->min_dist >= 1, "lfvio_tracker_create: max_cnt > 0 and min_dist >= 1 required");
-    LFVIO_REQUIRE(cfg->ransac == 0, "lfvio_tracker_create: rejectWithF (ransac) is not built yet; pass 0");
     LFVIO_REQUIRE(cfg->max_r >= 0 && cfg->min_r >= 0, "lfvio_tracker_create: bad annulus radii");
     lfvio_tracker *t = new (std::nothrow) lfvio_tracker();
     LFVIO_REQUIRE(t, "lfvio_tracker_create: out of host memory");

@@ -78,7 +78,7 @@ __device__ __forceinline__ void copy_track(const TrackArrays &in, int i, const T
 }
 
 __global__ void __launch_bounds__(BT) compact_kernel(TrackArrays in, TrackArrays out, const uint8_t *__restrict__ status,
-                                                     int *n_dev, int cap) {
+                                                     int *n_dev, int cap, int cnt_add) {
     __shared__ int s_warp[33];
     const int n = min(*n_dev, cap);
     int carry = 0;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(BT) compact_kernel(TrackArrays in, TrackArrays
         const int keep = (i < n && status[i]) ? 1 : 0;
         int total;
         const int ex = block_excl_scan(keep, s_warp, &total);
-        if (keep) copy_track(in, i, out, carry + ex, 1);  // for (auto &n : track_cnt) n++
+        if (keep) copy_track(in, i, out, carry + ex, cnt_add);  // 1 after LK: for (auto &n : track_cnt) n++
         carry += total;
         __syncthreads();
     }
@@ -363,9 +363,9 @@ __global__ void __launch_bounds__(BT) update_ids_kernel(int *ids, const int *__r
 
 }  // namespace
 
-int launch_compact(const TrackArrays &in, const TrackArrays &out, const uint8_t *status, int *n_dev, int cap,
+int launch_compact(const TrackArrays &in, const TrackArrays &out, const uint8_t *status, int *n_dev, int cap, int cnt_add,
                    cudaStream_t s) {
-    compact_kernel<<<1, BT, 0, s>>>(in, out, status, n_dev, cap);
+    compact_kernel<<<1, BT, 0, s>>>(in, out, status, n_dev, cap, cnt_add);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

@@ -13,6 +13,8 @@ int ROW = 960, COL = 1280, MAX_CNT = 150, MIN_DIST = 20, EQUALIZE = 1, FISHEYE =
 bool PUB_THIS_FRAME = false;
 double CENTER_X = 640.991301, CENTER_Y = 490.937512;
 int MAX_R = 500, MIN_R = 160;
+int REJECT_WITH_F = 1;
+unsigned long long RANSAC_SEED = 0x5eed5eed5eedull;
 int FeatureTracker::n_id = 0;
 
 namespace {
@@ -145,7 +147,8 @@ bool FeatureTracker::ensureHandle() {
     cfg.max_r = MAX_R;
     cfg.min_r = MIN_R;
     cfg.capacity = 0;
-    cfg.ransac = 0;
+    cfg.ransac = REJECT_WITH_F;
+    cfg.ransac_seed = RANSAC_SEED;
     cfg.cam = m_params;
     return lfvio_tracker_create(&cfg, device, &m_handle) == LFVIO_OK;
 }
@@ -219,6 +222,7 @@ extern "C" int lfvio_host_tracker_run(const lfvio_ocam *cam, const uint8_t *fram
     MAX_CNT = max_cnt;
     MIN_DIST = min_dist;
     EQUALIZE = 1;
+    REJECT_WITH_F = 0;  // the golden sequences of tests/golden were generated without RANSAC
     FeatureTracker::n_id = 0;
     FeatureTracker tr;
     tr.setCamera(std::make_shared<camodocal::OCAMCamera>(*cam), *cam);

@@ -37,6 +37,10 @@ extern int ROW, COL, MAX_CNT, MIN_DIST, EQUALIZE, FISHEYE, FREQ;
 extern bool PUB_THIS_FRAME;
 extern double CENTER_X, CENTER_Y;
 extern int MAX_R, MIN_R;
+// rejectWithF (feature_tracker.cpp:149, :329-386) runs on every published frame in the reference.  Its sample sets
+// come from std::random_device there; here the random source is the counter-based generator seeded by RANSAC_SEED.
+extern int REJECT_WITH_F;
+extern unsigned long long RANSAC_SEED;
 // readParameters(): the YAML keys of config/mindvision/mindvision.yaml (image_height, image_width, max_cnt,
 // min_dist, freq, equalize, center_x, center_y, max_r, min_r).  Returns false if the file cannot be read.
 bool readParameters(const std::string &config_file);

@@ -168,6 +168,26 @@ def good_features_to_track(img: np.ndarray, max_corners: int, quality: float, mi
     return out[: n.value].copy()
 
 
+lib.lfvio_reject_with_f.argtypes = [C.POINTER(Ocam), _fp, _fp, C.c_int, C.c_uint64, C.c_uint, _u8p, C.POINTER(C.c_double),
+                                    _fp, _ip]
+
+
+def reject_with_f(cam: dict, cur_pts: np.ndarray, forw_pts: np.ndarray, seed: int, frame: int):
+    """FeatureTracker::rejectWithF (feature_tracker.cpp:329-386).  Returns (status u8[n], E 3x3, scores f32[100], best)."""
+    cur = np.ascontiguousarray(cur_pts, np.float32).reshape(-1, 2)
+    forw = np.ascontiguousarray(forw_pts, np.float32).reshape(-1, 2)
+    n = len(cur)
+    status = np.zeros(n, np.uint8)
+    E = np.zeros(9, np.float64)
+    scores = np.zeros(100, np.float32)
+    best = np.zeros(1, np.int32)
+    oc = Ocam.from_dict(cam)
+    check(lib.lfvio_reject_with_f(C.byref(oc), _as(cur, C.c_float), _as(forw, C.c_float), n, seed, frame, _as(status, C.c_uint8),
+                                  E.ctypes.data_as(C.POINTER(C.c_double)), _as(scores, C.c_float), _as(best, C.c_int)),
+          "lfvio_reject_with_f")
+    return status, E.reshape(3, 3), scores, int(best[0])
+
+
 # ------------------------------------------------------------------------------------------------
 # FeatureTracker handle
 # ------------------------------------------------------------------------------------------------
@@ -175,7 +195,7 @@ class TrackerCfg(C.Structure):
     _fields_ = [
         ("rows", C.c_int), ("cols", C.c_int), ("max_cnt", C.c_int), ("min_dist", C.c_int), ("equalize", C.c_int),
         ("center_x", C.c_double), ("center_y", C.c_double), ("max_r", C.c_int), ("min_r", C.c_int),
-        ("capacity", C.c_int), ("ransac", C.c_int), ("cam", Ocam),
+        ("capacity", C.c_int), ("ransac", C.c_int), ("cam", Ocam), ("ransac_seed", C.c_uint64),
     ]
 
 
@@ -212,7 +232,8 @@ class FeatureTracker:
         c.max_cnt, c.min_dist, c.equalize = cfg["max_cnt"], cfg["min_dist"], cfg.get("equalize", 1)
         c.center_x, c.center_y = cfg["center_x"], cfg["center_y"]
         c.max_r, c.min_r = cfg["max_r"], cfg["min_r"]
-        c.capacity, c.ransac = capacity, 0
+        c.capacity, c.ransac = capacity, int(bool(cfg.get("ransac", 0)))
+        c.ransac_seed = int(cfg.get("ransac_seed", 0))
         c.cam = Ocam.from_dict(cam)
         self.rows, self.cols = c.rows, c.cols
         self._cap = max(capacity, c.max_cnt)

@@ -427,8 +427,9 @@ class FeatureTrackerOracle:
 
     backend "cv2": image operators are the cv2 calls the reference makes (the oracle of record and the
     CPU baseline that is timed).  backend "restated": the numpy restatements above.
-    RANSAC (rejectWithF, feature_tracker.cpp:329-386) is seeded from std::random_device in the reference
-    and is SURVEY §8(f) rank 1; it is skipped unless a `ransac` callable is injected.
+    RANSAC (rejectWithF, feature_tracker.cpp:329-386) is seeded from std::random_device in the reference; it runs
+    when a `ransac` callable is injected (oracle.ransac.make_injected(seed) is the restatement with the injected
+    random source the CUDA path shares).
     """
 
     def __init__(self, cam: dict, cfg: dict, backend: str = "cv2", ransac=None):
@@ -438,6 +439,7 @@ class FeatureTrackerOracle:
         self.cam, self.cfg, self.backend, self.ransac = cam, cfg, backend, ransac
         self.ROW, self.COL = cam["image_height"], cam["image_width"]
         self.n_id = 0
+        self.frames_seen = 0
         self.prev_img = self.cur_img = self.forw_img = None
         self.cur_pts = np.zeros((0, 2), f32)
         self.forw_pts = np.zeros((0, 2), f32)
@@ -546,6 +548,7 @@ class FeatureTrackerOracle:
         self.cur_pts = self.forw_pts
         self.undistorted_points()
         self.prev_time = self.cur_time
+        self.frames_seen += 1
 
     # -- feature_tracker.cpp:441-504 --------------------------------------------------------------
     def undistorted_points(self):
