@@ -104,7 +104,9 @@ def build_workload(cfg_name: str, rank: int, n_frames_pool: int):
 
     scale, max_cnt, wsz, n_lm, hz = CONFIGS[cfg_name]
     cam = scaled_camera(scale)
-    tcfg = tracker_defaults(scale, max_cnt)
+    # rejectWithF runs on every published frame in the reference (feature_tracker.cpp:149); the device arm does the same.
+    # FeatureTrackerOracle (CPU arm) ignores these two keys: it has no native RANSAC port, so the CPU baseline does LESS work.
+    tcfg = dict(tracker_defaults(scale, max_cnt), ransac=1, ransac_seed=rank + 1)
     rows, cols = cam["image_height"], cam["image_width"]
     src = synth.FrameSource(rows, cols, seed=rank + 1)  # lfvio.multi.stream_seed: one independent stream per rank
     frames = np.stack([src.frame(k) for k in range(n_frames_pool)])
@@ -384,7 +386,7 @@ def main():
             "dtype": "u8/f32 front end, f64 back end", "data": "synthetic",
             "config": {"workload": args.config, "image": f"{cols}x{rows}", "features": max_cnt, "tracked": n_tracks,
                        "window_frames": wsz + 1, "n_proj_factors": wprob.n_proj, "n_landmarks": wprob.L,
-                       "iterations": int(summ.iterations), "marginalize": with_marg, "pub_pattern": list(PUB_PATTERN),
+                       "iterations": int(summ.iterations), "marginalize": with_marg, "pub_pattern": list(PUB_PATTERN), "reject_with_f": "device arm: on, every published frame; cpu arms: off (no native CPU port; the CPU arms do less work)",
                        "l2_policy": f"inputs larger than L2: {pool}-frame pool ({pool * px / 2**20:.0f} MiB) cycled",
                        "streams": "one independent stream per GPU; front end and back end on separate CUDA streams"},
             "ms_tracker_stream": ms_tracker / args.steps, "ms_window_stream": ms_window / args.steps,
