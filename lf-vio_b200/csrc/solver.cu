@@ -10,11 +10,11 @@
 // being retried with 10x mu inside the same iteration.
 //
 // Per trust-region iteration, all on device (the control block SolverCtl never visits the host):
-//   accumulate_kernel  one warp per landmark: loads its factors' Jacobians (Jacobi-scaled) into shared memory,
+//   accumulate_kernel  one CTA (4 warps) per landmark: loads its factors' Jacobians (Jacobi-scaled) into shared memory,
 //                      forms the landmark's 1x1 pivot c_l, the coupling vector w_l and adds the landmark's
 //                      complete contribution  sum_k J_k^T J_k - w_l w_l^T / c_l  to the reduced system with
 //                      fp64 atomics (upper triangle) — the Schur complement is never materialised per landmark;
-//                      one warp per IMU factor (15x30 block), one CTA for the prior (precomputed J0^T J0).
+//                      one CTA per IMU factor (15x30 block), PRIOR_CTAS CTAs for the prior (precomputed J0^T J0).
 //   pre/chol/gnlm/cand (solver_step.cu) Cauchy point (multi-CTA), Cholesky + triangular solves of the D x D reduced
 //                      system (one CTA, shared-memory resident), landmark back-substitution (warp per landmark),
 //                      dogleg + model cost + candidate state x (+) delta (multi-CTA).
@@ -26,7 +26,8 @@ namespace lfvio {
 
 namespace {
 
-constexpr int ACC_WARPS = 4;
+constexpr int ACC_WARPS = 4;    // warps of one CTA; they split the rows of an item's local block
+constexpr int PRIOR_CTAS = 8;   // CTAs that share the prior's n x n block and its gradient
 
 // ---- Jacobi scaling: scale = 1 / (1 + sqrt(sum_i J_ic^2)) at the initial point ---------------------
 __global__ void colnorm_kernel(DevProblem P, EvalBuf e, double *scale) {
@@ -82,10 +83,10 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const double mu = ctl->mu;
     if ((int)blockIdx.x < n_lm_cta) {
-        const int item = blockIdx.x * ACC_WARPS + wid;
-        // per-warp shared memory: sJ[max_obs][40], sR[max_obs][2], sW[max_obs][6], sWs[13], sFj[max_obs] (as double slots)
-        const int per_warp = max_obs * 40 + max_obs * 2 + max_obs * 6 + 16 + max_obs;
-        double *sJ = smem + (size_t)wid * per_warp;
+        const int item = blockIdx.x;
+        const int tid = threadIdx.x;
+        // shared memory: sJ[max_obs][40], sR[max_obs][2], sW[max_obs][6], sWs[13], sFj[max_obs] (as double slots)
+        double *sJ = smem;
         double *sR = sJ + max_obs * 40;
         double *sW = sR + max_obs * 2;
         double *sWs = sW + max_obs * 6;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
             const int l = item;
             const int k0 = P.lm_first[l], K = min(P.lm_first[l + 1] - k0, max_obs);
             if (K <= 0) {
-                if (lane == 0) {
+                if (tid == 0) {
                     w.lm_c[l] = 0.0;
                     w.lm_g[l] = 0.0;
                 }
@@ -103,16 +104,17 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
             }
             const int fi = P.proj[k0].frame_i;
             const double sc_l = w.scale[D + l];
-            for (int k = lane; k < K; k += 32) sFj[k] = P.proj[k0 + k].frame_j;
-            __syncwarp();
-            for (int q = lane; q < K * 40; q += 32) {
+            for (int k = tid; k < K; k += ACC_WARPS * 32) sFj[k] = P.proj[k0 + k].frame_j;
+            __syncthreads();
+            for (int q = tid; q < K * 40; q += ACC_WARPS * 32) {
                 const int k = q / 40, c = (q % 40) % 20;
                 const int col = proj_col(lay, fi, sFj[k], l, c);
                 sJ[q] = e.Jp[40 * (size_t)(k0 + k) + (q % 40)] * w.scale[col];
             }
-            for (int q = lane; q < K * 2; q += 32) sR[q] = e.rp[2 * (size_t)k0 + q];
-            __syncwarp();
+            for (int q = tid; q < K * 2; q += ACC_WARPS * 32) sR[q] = e.rp[2 * (size_t)k0 + q];
+            __syncthreads();
             (void)sc_l;
+            // pivot and landmark gradient (every warp computes them, identically)
             // pivot and landmark gradient
             double c_l = 0, g_l = 0;
             for (int q = lane; q < K * 2; q += 32) {
@@ -126,24 +128,24 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
             const double inv_c = 1.0 / c_reg;
             // shared columns a: 0..5 pose_i, 6..11 ex, 12 td -> factor-local column
             auto shared_c = [](int a) { return a < 6 ? a : (a < 12 ? a + 6 : 19); };
-            if (lane < 13) {
-                const int c = shared_c(lane);
+            if (tid < 13) {
+                const int c = shared_c(tid);
                 double s = 0;
                 for (int k = 0; k < K; k++) s += sJ[k * 40 + c] * sJ[k * 40 + 18] + sJ[k * 40 + 20 + c] * sJ[k * 40 + 38];
-                sWs[lane] = s;
+                sWs[tid] = s;
             }
-            for (int q = lane; q < K * 6; q += 32) {
+            for (int q = tid; q < K * 6; q += ACC_WARPS * 32) {
                 const int k = q / 6, c = 6 + q % 6;
                 sW[q] = sJ[k * 40 + c] * sJ[k * 40 + 18] + sJ[k * 40 + 20 + c] * sJ[k * 40 + 38];
             }
-            __syncwarp();
+            __syncthreads();
             // persist what the back-substitution needs
-            if (lane == 0) {
+            if (tid == 0) {
                 w.lm_c[l] = c_l;
                 w.lm_g[l] = g_l;
             }
-            if (lane < 13) w.lm_ws[13 * (size_t)l + lane] = sWs[lane];
-            for (int q = lane; q < K * 6; q += 32) w.proj_wj[6 * (size_t)k0 + q] = sW[q];
+            if (tid < 13) w.lm_ws[13 * (size_t)l + tid] = sWs[tid];
+            for (int q = tid; q < K * 6; q += ACC_WARPS * 32) w.proj_wj[6 * (size_t)k0 + q] = sW[q];
             // local index A in [0, 13 + 6K): global column and accessors
             const int n_l = 13 + 6 * K;
             auto gcol = [&](int A) {
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
             };
             auto wval = [&](int A) { return A < 13 ? sWs[A] : sW[A - 13]; };
             // gradient, squared column norms, reduced right-hand side
-            for (int A = lane; A < n_l; A += 32) {
+            for (int A = tid; A < n_l; A += ACC_WARPS * 32) {
                 double g = 0, d2 = 0;
                 if (A < 13) {
                     const int c = shared_c(A);
@@ -175,8 +177,8 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
                 const double rr = g - wval(A) * g_l * inv_c;
                 if (rr != 0.0) atomicAdd(&w.rhs[gc], rr);
             }
-            // reduced-system contribution: every unordered local pair (A <= B) exactly once
-            for (int A = 0; A < n_l; A++) {
+            // reduced-system contribution: every unordered local pair (A <= B) exactly once; the warps interleave the rows
+            for (int A = wid; A < n_l; A += ACC_WARPS) {
                 const int gA = gcol(A);
                 const double wA = wval(A);
                 for (int B = A + lane; B < n_l; B += 32) {
@@ -207,23 +209,23 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
             if (P.imu[k].sum_dt > 10.0) return;
             const int fi = P.imu[k].frame_i;
             double *sI = sJ;  // 450 doubles fit (per_warp >= 49 * max_obs + 16 >= 450 is ensured by the launcher)
-            for (int q = lane; q < 450; q += 32) sI[q] = e.Ji[450 * (size_t)k + q] * w.scale[imu_col(lay, fi, q % 30)];
+            for (int q = tid; q < 450; q += ACC_WARPS * 32) sI[q] = e.Ji[450 * (size_t)k + q] * w.scale[imu_col(lay, fi, q % 30)];
             double *sRi = sI + 450;
-            for (int q = lane; q < 15; q += 32) sRi[q] = e.ri[15 * (size_t)k + q];
-            __syncwarp();
-            if (lane < 30) {
+            for (int q = tid; q < 15; q += ACC_WARPS * 32) sRi[q] = e.ri[15 * (size_t)k + q];
+            __syncthreads();
+            if (tid < 30) {
                 double g = 0, d2 = 0;
                 for (int r = 0; r < 15; r++) {
-                    const double j = sI[r * 30 + lane];
+                    const double j = sI[r * 30 + tid];
                     g += j * sRi[r];
                     d2 += j * j;
                 }
-                const int gc = imu_col(lay, fi, lane);
+                const int gc = imu_col(lay, fi, tid);
                 atomicAdd(&w.grad[gc], g);
                 atomicAdd(&w.rhs[gc], g);
                 atomicAdd(&w.diag2[gc], d2);
             }
-            for (int A = 0; A < 30; A++) {
+            for (int A = wid; A < 30; A += ACC_WARPS) {
                 const int gA = imu_col(lay, fi, A);
                 for (int B = A + lane; B < 30; B += 32) {
                     double v = 0;
@@ -234,9 +236,10 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
         }
         return;
     }
-    // ===== prior CTA: S += scale (J0^T J0) scale, gradient += scale J0^T r =====
+    // ===== prior CTAs: S += scale (J0^T J0) scale, gradient += scale J0^T r =====
     const DevPrior &p = P.prior;
     if (p.n <= 0) return;
+    const int pj = blockIdx.x - n_lm_cta, ptid = pj * blockDim.x + threadIdx.x, pnt = PRIOR_CTAS * blockDim.x;
     int *pmap = reinterpret_cast<int *>(smem);
     for (int b = threadIdx.x; b < p.n_blocks; b += blockDim.x) {
         const int ls = lay.block_lsize(p.block_id[b]), c0 = lay.block_col(p.block_id[b]);
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
     }
     __syncthreads();
     const int n = p.n;
-    for (int q = threadIdx.x; q < n * n; q += blockDim.x) {
+    for (int q = ptid; q < n * n; q += pnt) {
         const int a = q / n, b = q % n;
         const int ga = pmap[a], gb = pmap[b];
         if (ga <= gb) {
@@ -253,9 +256,9 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
             if (a == b) atomicAdd(&w.diag2[ga], v);
         }
     }
-    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+    for (int a = threadIdx.x; a < n; a += blockDim.x) {  // CTA pj sums the rows i = pj, pj + PRIOR_CTAS, ...
         double g = 0;
-        for (int i = 0; i < n; i++) g += p.J0[(size_t)i * n + a] * e.rm[i];
+        for (int i = pj; i < n; i += PRIOR_CTAS) g += p.J0[(size_t)i * n + a] * e.rm[i];
         g *= w.scale[pmap[a]];
         atomicAdd(&w.grad[pmap[a]], g);
         atomicAdd(&w.rhs[pmap[a]], g);
@@ -312,15 +315,15 @@ int launch_accumulate(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1,
     LFVIO_CUDA_TRY(cudaMemsetAsync(w.S, 0, w.zero_bytes, s));
     int max_obs = std::max(P.lay.F - 1, 10);  // 49 * 10 + 16 = 506 doubles >= 465 needed by an IMU warp
     const int items = P.lay.L + P.n_imu;
-    const int n_lm_cta = cdiv(items, ACC_WARPS);
-    size_t smem = sizeof(double) * (size_t)acc_per_warp_doubles(max_obs) * ACC_WARPS;
+    const int n_lm_cta = items;
+    size_t smem = sizeof(double) * (size_t)acc_per_warp_doubles(max_obs);
     smem = std::max(smem, sizeof(int) * (size_t)(15 * kMaxFrames + 8));
     static bool attr_set = false;
     if (!attr_set) {
         LFVIO_CUDA_TRY(cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    accumulate_kernel<<<n_lm_cta + 1, ACC_WARPS * 32, smem, s>>>(P, e0, e1, w, ctl, n_lm_cta, max_obs);
+    accumulate_kernel<<<n_lm_cta + PRIOR_CTAS, ACC_WARPS * 32, smem, s>>>(P, e0, e1, w, ctl, n_lm_cta, max_obs);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }
