@@ -50,24 +50,46 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  The sampler is
+    started before the warm-up (nvidia-smi needs some hundred ms to produce its first line) and only the samples whose
+    timestamp falls inside [mark_begin, mark_end] are used; if the region is shorter than the sampling period the
+    samples taken under load since the warm-up are used instead and "window" says so."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
         self.path = tempfile.mktemp(prefix="lfvio_clocks_", suffix=".csv")
         self.proc = None
         self.device = device
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.device)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def wait_ready(self, timeout=5.0):
+        t_end = time.time() + timeout
+        while self.proc is not None and time.time() < t_end:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                pass
+            time.sleep(0.02)
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self) -> dict:
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -76,25 +98,33 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[2]), float(f[3]), f[6:10]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        window = "timed region"
+        if not inside:
+            inside = [r for r in rows if self.t1 is None or r[0] <= self.t1 + 0.05][-25:]
+            window = "warm-up + timed region (timed region shorter than the sampling period)"
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if inside:
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                       reasons=sorted(reasons), samples=len(inside), window=window)
         return out
 
 
@@ -114,9 +144,12 @@ def build_workload(cfg_name: str, rank: int, n_frames_pool: int):
                 max_cnt=max_cnt, synthwin=synthwin)
 
 
-def make_window_problem(wl, opts, rank):
-    return wl["synthwin"].make_window(seed=rank + 1, n_frames=wl["window_size"] + 1, n_landmarks=wl["n_landmarks"],
-                                      feats_per_frame=wl["max_cnt"], opts=opts, perturb=0.3)
+def make_window_problem(wl, opts, rank, optimize, marginalize):
+    """Steady-state Estimator::optimization() input: projection + IMU factors AND the marginalisation prior left by the
+    previous frame (n = 76 at F = 11), produced by `optimize` / `marginalize` of the arm that is being timed."""
+    return wl["synthwin"].make_window_with_prior(optimize, marginalize, seed=rank + 1, n_frames=wl["window_size"] + 1,
+                                                 n_landmarks=wl["n_landmarks"], feats_per_frame=wl["max_cnt"], opts=opts,
+                                                 perturb=0.3)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -131,7 +164,7 @@ def cpu_arm(wl, steps: int, warmup: int, rank: int, with_marg: bool):
     opts = ob.default_opts()
     opts.fixed_iterations = 1
     opts.row = wl["rows"]
-    w = make_window_problem(wl, opts, rank)
+    w = make_window_problem(wl, opts, rank, ob.optimize, ob.marginalize)
     tr = fe.FeatureTrackerOracle(wl["cam"], wl["tcfg"], "cv2")
     frames, hz = wl["frames"], wl["hz"]
     n = len(frames)
@@ -148,7 +181,8 @@ def cpu_arm(wl, steps: int, warmup: int, rank: int, with_marg: bool):
             t_back += tb
     total = t_front + t_back
     return dict(fps=steps / total, ms_front=1e3 * t_front / steps, ms_back=1e3 * t_back / steps,
-                cores=os.cpu_count(), cv2_threads=cv2.getNumThreads(), n_proj=w.n_proj, n_landmarks=w.L)
+                cores=os.cpu_count(), cv2_threads=cv2.getNumThreads(), n_proj=w.n_proj, n_landmarks=w.L,
+                prior_n=int(w.prior.n) if w.prior is not None else 0)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -181,7 +215,7 @@ def main():
             "impl": "reference", "metric": METRIC, "value": r["fps"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 5), "ms_per_step": 1e3 / r["fps"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/f32 front end, f64 back end", "data": "synthetic",
-            "config": {"workload": args.config, "scale": scale, "n_proj_factors": r["n_proj"], "n_landmarks": r["n_landmarks"],
+            "config": {"workload": args.config, "scale": scale, "n_proj_factors": r["n_proj"], "n_landmarks": r["n_landmarks"], "prior_n": r["prior_n"],
                        "iterations": 8, "marginalize": with_marg},
             "cpu_baseline": {"value": r["fps"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                              "sample": f"{steps} frames; front end = cv2 (OpenCV {r['cv2_threads']} threads, the library the "
@@ -220,8 +254,8 @@ def main():
     opts = lfvio.solver_default_opts()
     opts.fixed_iterations = 1
     opts.row = rows
-    wprob = make_window_problem(wl, opts, rank)
-    window = lfvio.Window(wsz, max(1000, 2 * wprob.L), max(16384, 2 * wprob.n_proj), device=local_rank)
+    window = lfvio.Window(wsz, max(1000, 2 * n_lm), max(16384, 24 * n_lm), device=local_rank)
+    wprob = make_window_problem(wl, opts, rank, window.optimize, window.marginalize)
     window.upload(wprob)
     t_stream = torch.cuda.ExternalStream(tracker.stream, device=dev)
     w_stream = torch.cuda.ExternalStream(window.stream, device=dev)
@@ -238,23 +272,47 @@ def main():
             torch.cuda.synchronize()
 
     # ---- value: inputs resident in HBM, no host synchronisation inside the timed region -------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    clocks.wait_ready()
     for k in range(args.warmup):
         step_dev(k)
     tracker.sync()
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark_begin()
     launches0 = lfvio.lib.lfvio_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     ev[0].record(t_stream)
     ev[1].record(w_stream)
+    # Two host threads, as in the reference (feature_tracker_node / estimator_node are two processes): each enqueues its
+    # own CUDA stream; nothing inside the loops synchronises with the device.
+    import threading
+
+    enq = [0.0, 0.0]
+
+    def enqueue_tracker():
+        t0 = time.perf_counter()
+        for k in range(args.warmup, args.warmup + args.steps):
+            tracker.read_image_dev(frames_dev[k % pool].data_ptr(), cols, k / hz, bool(PUB_PATTERN[k % len(PUB_PATTERN)]))
+        enq[0] = time.perf_counter() - t0
+
+    def enqueue_window():
+        t0 = time.perf_counter()
+        for k in range(args.warmup, args.warmup + args.steps):
+            window.optimize_dev(with_marg, B.MARGIN_OLD)
+        enq[1] = time.perf_counter() - t0
+
     t_wall0 = time.perf_counter()
-    for k in range(args.warmup, args.warmup + args.steps):
-        step_dev(k)
+    th = [threading.Thread(target=enqueue_tracker), threading.Thread(target=enqueue_window)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
     ev[2].record(t_stream)
     ev[3].record(w_stream)
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
+    clocks.mark_end()
     launches = lfvio.lib.lfvio_launch_count() - launches0
     clk = clocks.stop()
     # both streams start together after the barrier; the step is done when both are
@@ -319,6 +377,8 @@ def main():
     e2e_ms, e2e_frames = multi.reduce_counters(1e3 * e2e_s, e2e_steps, dev)
     e2e_s = e2e_ms * 1e-3
     blob_bytes = wprob.n_proj * C.sizeof(B.ProjFactor) + wprob.n_imu * C.sizeof(B.ImuFactor) + 8 * (16 * (wsz + 1) + 8 + wprob.L)
+    if wprob.prior is not None:  # MarginalizationInfo travels with the problem: J0 (n x n), r0, x0, block tables
+        blob_bytes += 8 * (int(wprob.prior.n) ** 2 + 3 * int(wprob.prior.n) + 64)
     h2d = frame_bytes + blob_bytes
     d2h = max_cnt * (8 + 4 + 4 + 12 + 12) + 8 + 8 * (16 * (wsz + 1) + 8 + wprob.L) + 2048
 
@@ -346,6 +406,7 @@ def main():
     px = rows * cols
     n_lk = max(n_tracks, 1)
     D = 15 * (wsz + 1) + 7
+    pn = int(wprob.prior.n) if wprob.prior is not None else 0
     algo_bytes = {
         "clahe(3 kernels)": 3.0 * px,
         "pyr_down(3 kernels)": px * (1 + 0.25 + 0.0625 + 0.015625) + px * (0.25 + 0.0625),
@@ -353,9 +414,9 @@ def main():
         "min_eig_kernel": 5.0 * px + px,
         "candidates_kernel": 5.0 * px,
         "mask_raster(copy+kernel)": 2.0 * px,
-        "evaluate_kernel(candidate)": wprob.n_proj * (144 + 336) + wprob.n_imu * (3720 + 3720),
-        "accumulate_kernel": wprob.n_proj * 336 + wprob.n_imu * 3720 + 8.0 * D * D,
-        "step_kernel": wprob.n_proj * 2 * 336 + 3 * 8.0 * D * D,
+        "evaluate_kernel(candidate)": wprob.n_proj * (144 + 336) + wprob.n_imu * (3720 + 3720) + 8.0 * pn * pn,
+        "accumulate_kernel": wprob.n_proj * 336 + wprob.n_imu * 3720 + 8.0 * D * D + 8.0 * pn * pn,
+        "step_kernel": wprob.L * 13 * 8 * 2 + wprob.n_proj * 6 * 8 * 2 + 8.0 * D * (D + 1) / 2 + 6 * 8.0 * (D + wprob.L),
     }
     dom = max(stages.items(), key=lambda kv: kv[1][0])
     dom_name, (dom_ms_step, dom_ms_launch, dom_per_step) = dom[0], dom[1]
@@ -367,6 +428,10 @@ def main():
         "algorithmic_bytes_per_launch": ab, "avg_launch_ms": dom_ms_launch,
         "stage_ms_per_step": {k: round(v[0], 5) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])},
         "note": "configs 1-3 are launch/latency bound (a whole 1280x960 frame is ~3 us of HBM time, SURVEY.md §7)",
+        # every stage that has an algorithmic byte count: [avg launch-group us, achieved GB/s, fraction of the measured HBM peak]
+        "per_stage": {k: [round(1e3 * v[1], 2), round(algo_bytes[k] / (v[1] * 1e-3) / 1e9, 1),
+                          round(algo_bytes[k] / (v[1] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)]
+                      for k, v in stages.items() if k in algo_bytes and v[1] > 0},
     }
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -----------------------------------
@@ -386,11 +451,12 @@ def main():
             "dtype": "u8/f32 front end, f64 back end", "data": "synthetic",
             "config": {"workload": args.config, "image": f"{cols}x{rows}", "features": max_cnt, "tracked": n_tracks,
                        "window_frames": wsz + 1, "n_proj_factors": wprob.n_proj, "n_landmarks": wprob.L,
-                       "iterations": int(summ.iterations), "marginalize": with_marg, "pub_pattern": list(PUB_PATTERN), "reject_with_f": "device arm: on, every published frame; cpu arms: off (no native CPU port; the CPU arms do less work)",
+                       "prior_n": int(wprob.prior.n) if wprob.prior is not None else 0, "iterations": int(summ.iterations), "marginalize": with_marg, "pub_pattern": list(PUB_PATTERN), "reject_with_f": "device arm: on, every published frame; cpu arms: off (no native CPU port; the CPU arms do less work)",
                        "l2_policy": f"inputs larger than L2: {pool}-frame pool ({pool * px / 2**20:.0f} MiB) cycled",
                        "streams": "one independent stream per GPU; front end and back end on separate CUDA streams"},
             "ms_tracker_stream": ms_tracker / args.steps, "ms_window_stream": ms_window / args.steps,
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
+            "host_enqueue_ms_per_step": {"tracker_thread": 1e3 * enq[0] / args.steps, "window_thread": 1e3 * enq[1] / args.steps},
             "e2e": {"value": e2e_frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "host_threads": 2, "single_thread_ms_per_frame": e2e_seq_ms,
                     "note": "two host threads = the reference's two ROS nodes; each makes blocking C-ABI calls with host buffers"},

@@ -21,10 +21,12 @@ struct StateLayout {
     __host__ __device__ int td() const { return 16 * F + 7; }
     __host__ __device__ int feat(int l) const { return 16 * F + 8 + l; }
     __host__ __device__ int size() const { return 16 * F + 8 + L; }
-    // local (tangent) columns of the reduced system: [pose_f 6 | sb_f 9] per frame, ex 6, td 1, then landmarks
+    // local (tangent) columns of the reduced system, then the landmarks.  Elimination order of the dense solve:
+    // [sb_{F-1} .. sb_1 | sb_0 | pose_{F-1} .. pose_0 | ex 6 | td 1] — speed-bias blocks first, newest first, so that
+    // their fill stays inside a pose prefix (chol_blocked.cuh: WindowProfile).
     __host__ __device__ int D() const { return 15 * F + 7; }
-    __host__ __device__ int col_pose(int f) const { return 15 * f; }
-    __host__ __device__ int col_sb(int f) const { return 15 * f + 6; }
+    __host__ __device__ int col_pose(int f) const { return 9 * F + 6 * (F - 1 - f); }
+    __host__ __device__ int col_sb(int f) const { return 9 * (F - 1 - f); }
     __host__ __device__ int col_ex() const { return 15 * F; }
     __host__ __device__ int col_td() const { return 15 * F + 6; }
     __host__ __device__ int block_col(int id) const {
@@ -82,6 +84,7 @@ struct SolverCtl {
     int pad;
     double radius, mu, cost, cost_cand, x_norm, dogleg_step_norm, alpha, model_cost_change, step_norm;
     double gnorm, gn_norm, gdot;  // |gradient_|, |gauss_newton_step_|, gradient_ . gauss_newton_step_ (kept while reuse_)
+    double jj, mu_solve;          // |J_s (gradient_/diagonal_)|^2 and the mu of the last linear solve (kept while reuse_)
     // per-iteration accumulators filled with atomics by the multi-CTA phases and consumed/zeroed by the phase that
     // needs the total: [0] sum gradient^2  [1] sum (J g)^2  [2] max |J^T r| (as ordered bits)  [3] sum gn^2
     // [4] sum gradient.gn  [5] model cost change  [6] |x - x_cand|^2
@@ -257,6 +260,8 @@ struct SolverScratch {
     double *lm_g;      // L : j_lambda^T r
     double *lm_ws;     // L x 13 : [pose_i 6 | ex 6 | td] part of w_l
     double *proj_wj;   // n_proj x 6 : pose_j part of w_l
+    int *lm_coli;      // L : reduced column of the host pose block (pose_i) of landmark l, -1 if it has no factor
+    int *proj_colj;    // n_proj : reduced column of the pose_j block of factor k
     double *scale;     // D + L Jacobi scaling
     double *diagonal;  // D + L
     double *gradient;  // D + L (divided by diagonal)

@@ -1,0 +1,295 @@
+// Blocked look-ahead Cholesky (one CTA) shared by the solver's reduced system (solver_step.cu) and the square root of
+// the marginalisation's Schur complement (marg.cu).  See cholesky_lookahead below for the scheme.
+#pragma once
+#include "chol16.cuh"
+
+namespace lfvio {
+
+#ifdef __CUDACC__
+#ifdef LFVIO_CHOL_PROFILE
+#define SUB_T0() long long sub_t = clock64(); long long sub_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define SUB_MARK(i) do { const long long now = clock64(); sub_acc[i] += now - sub_t; sub_t = now; } while (0)
+#define SUB_FLUSH() do { if (threadIdx.x == 0 || threadIdx.x == 32) for (int i = 0; i < 8; i++) g_sub[(threadIdx.x >> 5) * 8 + i] = sub_acc[i]; } while (0)
+static __device__ long long g_sub[16];
+#else
+#define SUB_T0()
+#define SUB_MARK(i)
+#define SUB_FLUSH()
+#endif
+// row pitch of the shared panel: trailing columns rounded up to the 4-wide tiles, + one tile whose last column holds the rhs
+__host__ __device__ inline int chol_panel_pitch(int D) { return ((D + 3) & ~3) + 4; }
+
+struct MatFull {
+    double *p;
+    int D;
+    __device__ __forceinline__ double &at(int r, int c) const { return p[(size_t)r * D + c]; }
+    __device__ __forceinline__ double *row(int r) const { return p + (size_t)r * D; }  // row(r)[c] == at(r, c)
+};
+struct MatPacked {  // packed upper triangle, row-major (c >= r)
+    double *p;
+    int D;
+    __device__ __forceinline__ double &at(int r, int c) const { return p[r * D - ((r * (r - 1)) >> 1) + (c - r)]; }
+    __device__ __forceinline__ double *row(int r) const { return p + (r * D - ((r * (r - 1)) >> 1) - r); }  // valid for c >= r
+};
+
+// ---- look-ahead blocked Cholesky + fused forward substitution ---------------------------------------------------
+// S = U^T U on the upper triangle, 16-column block steps, one CTA.  Warp 0 is the "diagonal warp": while the other
+// warps (workers) apply block step k to the trailing matrix, warp 0 already solves the 16 panel columns of block k+1,
+// applies step k to diagonal block k+1 and factors it in registers — the serial pivot chain of block k+1 overlaps the
+// throughput-bound trailing update of block k.  The right-hand side rides along as one extra panel column, so the
+// forward substitution U^T z = b costs nothing extra; solve_upper_back finishes with U y = z.
+// Barriers: id 1 = "diagonal block ready / trailing update done" (all threads), id 2 = "panel complete"
+// (workers wait, warp 0 only arrives).
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// one panel column: a <- U11^-T a by substitution with the factored diagonal block (broadcast reads of U, 1/pivot)
+__device__ __forceinline__ void panel_column_solve(double (&a)[NB], const double *U, const double *invd) {
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+        const double u = a[j] * invd[j];
+        a[j] = u;
+#pragma unroll
+        for (int r = j + 1; r < NB; r++) a[r] = fma(-U[j * NB + r], u, a[r]);
+    }
+}
+
+// Sparsity profiles: which trailing columns a block step [j0, j0 + nb) can touch, as two contiguous ranges
+// [rest0, rest0 + lenA) and [startB, startB + lenB) (lenA >= nb1 so that the look-ahead block is always inside).
+struct DenseProfile {
+    __device__ __forceinline__ void active(int j0, int nb, int D, int nb1, int &lenA, int &startB, int &lenB) const {
+        lenA = D - (j0 + nb);
+        startB = 0;
+        lenB = 0;
+    }
+};
+// Reduced system of the sliding window in the column order of StateLayout: [sb_{F-1} .. sb_1 | sb_0 | pose_{F-1} ..
+// pose_0 | ex | td].  A speed-bias block sb_k (k >= 1) is coupled only to sb_{k+-1} and pose_{k-1..k+1} (IMU factors);
+// eliminating sb_{F-1}, sb_{F-2}, ... in this order the fill of row sb_k stays inside sb_{k-1} and pose_{F-1} .. pose_{k-1},
+// a PREFIX of the pose section.  Everything from sb_0 on (prior, landmarks' Schur complement) is dense.
+struct WindowProfile {
+    int F;
+    __device__ __forceinline__ void active(int j0, int nb, int D, int nb1, int &lenA, int &startB, int &lenB) const {
+        const int rest0 = j0 + nb, jl = rest0 - 1;
+        lenA = D - rest0;
+        startB = 0;
+        lenB = 0;
+        if (jl >= 9 * (F - 1)) return;               // the block reaches sb_0: dense tail
+        const int k_lo = F - 1 - jl / 9;             // lowest speed-bias index inside the block (>= 1)
+        const int a_end = 9 * (F - k_lo + 1);        // end of sb_{k_lo - 1}
+        const int la = max(a_end - rest0, nb1), sb = 9 * F, lb = 6 * (F - k_lo + 1);
+        if (rest0 + la >= sb) {
+            lenA = sb + lb - rest0;                  // ranges touch: one contiguous range up to the end of the pose prefix
+            return;
+        }
+        lenA = la;
+        startB = sb;
+        lenB = lb;
+    }
+};
+
+template <class M, class Prof = DenseProfile>
+__device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, int PW, double *s_U /* 2 x NB x NB */,
+                                   double *s_invd /* nblk x NB */, double *s_y /* D: b in, z out */, int *s_okv /* nblk */, double *s_row /* 2 x NB */,
+                                   Prof prof = Prof(), bool leave_last = false) {
+    // leave_last: stop before the last diagonal block — on return it holds the fully updated (unfactored) Schur
+    // complement of the leading blocks and s_y its updated right-hand side; the caller factors it its own way
+    // (marg.cu: with diagonal pivoting, because that is where a gauge-deficient matrix shows its tiny pivots).
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int nblk = (D + NB - 1) / NB;
+    const int nworkers = nt - 32, wtid = tid - 32;
+    const int nbar = nt;  // threads taking part in the named barriers
+    const int zc = PW - 1;           // panel column of the right-hand side
+    SUB_T0();
+    if (wid == 0) {  // factor diagonal block 0
+        const int nb = min(NB, D);
+        for (int q = lane; q < NB * NB; q += 32) {
+            const int r = q / NB, c = q % NB;
+            s_U[q] = (r < nb && c < nb && c >= r) ? S.at(r, c) : ((r == c) ? 1.0 : 0.0);
+        }
+        __syncwarp();
+        const bool ok = factor_diag_block_split(s_U, s_invd, s_row);
+        if (lane == 0) s_okv[0] = ok ? 1 : 0;
+        for (int q = lane; q < NB * NB; q += 32) {
+            const int r = q / NB, c = q % NB;
+            if (c >= r && c < nb) S.at(r, c) = s_U[q];
+        }
+    }
+    bar_sync(1, nbar);
+#ifdef LFVIO_CHOL_PROFILE
+    sub_t = clock64();
+#endif
+    for (int blk = 0; blk < nblk; blk++) {
+        if (s_okv[blk] == 0) return false;
+        if (leave_last && blk == nblk - 1) break;
+        const int j0 = blk * NB, nb = min(NB, D - j0);
+        const int rest0 = j0 + nb, nrest = D - rest0, nb1 = min(NB, nrest);
+        const double *U = s_U + (blk & 1) * NB * NB, *invd = s_invd + blk * NB;
+        if (wid == 0) {
+            // ---- diagonal warp: panel columns of block blk+1, then look ahead ----
+            double *Un = s_U + ((blk + 1) & 1) * NB * NB;
+            if (lane < nb1) {
+                double a[NB];
+#pragma unroll
+                for (int r = 0; r < NB; r++) a[r] = (r < nb) ? S.at(j0 + r, rest0 + lane) : 0.0;
+                panel_column_solve(a, U, invd);
+#pragma unroll
+                for (int r = 0; r < NB; r++) {
+                    if (r < nb) S.at(j0 + r, rest0 + lane) = a[r];
+                    s_panel[r * PW + lane] = a[r];
+                }
+            }
+            __threadfence_block();
+            bar_arrive(2, nbar);
+            SUB_MARK(0);
+            if (nb1 > 0) {
+                __syncwarp();
+                // step blk applied to diagonal block blk+1: lane (h, c) owns rows 8h .. 8h+7 of column c
+                const int c = lane & 15, i0 = (lane >> 4) * 8;
+                double acc[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) acc[u] = 0.0;
+                if (c < nb1) {
+#pragma unroll 4
+                    for (int t = 0; t < NB; t++) {
+                        const double pc = s_panel[t * PW + c];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) acc[u] = fma(s_panel[t * PW + i0 + u], pc, acc[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = i0 + u;
+                    Un[i * NB + c] = (i <= c && c < nb1) ? S.at(rest0 + i, rest0 + c) - acc[u] : ((i == c) ? 1.0 : 0.0);
+                }
+                __syncwarp();
+                SUB_MARK(1);
+                const bool ok = (leave_last && blk + 1 == nblk - 1) ? true : factor_diag_block_split(Un, s_invd + (blk + 1) * NB, s_row);
+                if (lane == 0) s_okv[blk + 1] = ok ? 1 : 0;
+                for (int q = lane; q < NB * NB; q += 32) {
+                    const int r = q / NB, cc = q % NB;
+                    if (cc >= r && cc < nb1) S.at(rest0 + r, rest0 + cc) = Un[q];
+                }
+                SUB_MARK(2);
+            }
+        } else {
+            // ---- workers: remaining panel columns + right-hand side ----
+            // The trailing matrix is addressed through COMPACT indices 0 .. nact-1 over the profile's two ranges;
+            // the panel is stored compactly, only the reads/writes of S translate to real columns.
+            int lenA, startB, lenB;
+            prof.active(j0, nb, D, nb1, lenA, startB, lenB);
+            const int nact = lenA + lenB;
+            auto ccol = [&](int c) { return c < lenA ? rest0 + c : startB + (c - lenA); };
+            const int ncol = nact - nb1 + 1;  // last one is the right-hand side
+            // (one pass: D < number of workers, checked by launch_step)
+            if (const int q = wtid; q < ncol) {
+                const bool is_rhs = q == ncol - 1;
+                const int c = nb1 + q;  // compact column inside the trailing matrix
+                const int rc = ccol(c);
+                double a[NB];
+#pragma unroll
+                for (int r = 0; r < NB; r++) a[r] = (r < nb) ? (is_rhs ? s_y[j0 + r] : S.at(j0 + r, rc)) : 0.0;
+                SUB_MARK(4);
+                panel_column_solve(a, U, invd);
+                SUB_MARK(5);
+                const int pc = is_rhs ? zc : c;
+#pragma unroll
+                for (int r = 0; r < NB; r++) {
+                    if (r < nb) {
+                        if (is_rhs) s_y[j0 + r] = a[r];
+                        else S.at(j0 + r, rc) = a[r];
+                    }
+                    s_panel[r * PW + pc] = a[r];
+                }
+            }
+            SUB_MARK(0);
+            bar_sync(2, nbar);
+            SUB_MARK(1);
+            // ---- trailing update A22[i][k] -= sum_t U12[t][i] U12[t][k] (k >= i) in 16 x 16 blocks: 16 threads per
+            //      block, thread y owns column y of it (16 accumulators).  Per rank-1 step the 16 row factors are one
+            //      broadcast read and the column factor one conflict-free read; the read-modify-write of S touches 16
+            //      consecutive doubles per row.  Block (0, 0) — diagonal block blk+1 — belongs to warp 0. ----
+            const int nbk = (nact + NB - 1) / NB, nunits = nbk * (nbk + 1) / 2;
+            const int y = wtid & 15;
+            for (int q = 1 + (wtid >> 4); q < nunits; q += nworkers >> 4) {
+                int bi = 0, rem = q;
+                while (rem >= nbk - bi) {
+                    rem -= nbk - bi;
+                    bi++;
+                }
+                const int bk = bi + rem, i0 = bi * NB, k = bk * NB + y;
+                double acc[NB];
+#pragma unroll
+                for (int u = 0; u < NB; u++) acc[u] = 0.0;
+#pragma unroll 2
+                for (int t = 0; t < NB; t++) {
+                    const double pk = s_panel[t * PW + k];
+                    const double2 *ap = reinterpret_cast<const double2 *>(&s_panel[t * PW + i0]);
+#pragma unroll
+                    for (int u2 = 0; u2 < NB / 2; u2++) {
+                        const double2 av = ap[u2];
+                        acc[2 * u2] = fma(av.x, pk, acc[2 * u2]);
+                        acc[2 * u2 + 1] = fma(av.y, pk, acc[2 * u2 + 1]);
+                    }
+                }
+                if (k < nact) {
+                    const int rk = ccol(k);
+#pragma unroll
+                    for (int u = 0; u < NB; u++) {
+                        const int i = i0 + u;
+                        if (i <= k) S.row(ccol(i))[rk] -= acc[u];  // (i <= k < nact; the mapping is monotone)
+                    }
+                }
+            }
+            // right-hand side: b_rest -= U12^T z (taken by the workers that got the fewest tiles)
+            for (int i = nworkers - 1 - wtid; i < nact; i += nworkers) {
+                double sacc = 0;
+#pragma unroll 4
+                for (int t = 0; t < NB; t++) sacc = fma(s_panel[t * PW + i], s_panel[t * PW + zc], sacc);
+                s_y[ccol(i)] -= sacc;
+            }
+            SUB_MARK(2);
+        }
+        bar_sync(1, nbar);
+        SUB_MARK(3);
+    }
+    SUB_FLUSH();
+    return true;
+}
+
+// U y = z on the shared vector y (in/out), last block first: warp 0 back-substitutes the 16 x 16 diagonal block with
+// shuffles, then every thread folds the 16 new unknowns into the rows above.  Whole CTA calls.
+template <class M>
+__device__ void solve_upper_back(M S, int D, double *y, const double *s_invd) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int nblk = (D + NB - 1) / NB;
+    for (int blk = nblk - 1; blk >= 0; blk--) {
+        const int j0 = blk * NB, nb = min(NB, D - j0);
+        if (tid < 32) {
+            const int r = lane & 15;
+            double urow[NB];
+#pragma unroll
+            for (int t = 0; t < NB; t++) urow[t] = (r < nb && t > r && t < nb) ? S.at(j0 + r, j0 + t) : 0.0;
+            double wv = (r < nb) ? y[j0 + r] : 0.0;
+            const double inv = (r < nb) ? s_invd[blk * NB + r] : 1.0;
+#pragma unroll
+            for (int t = NB - 1; t >= 0; t--) {
+                const double yt = __shfl_sync(0xffffffffu, wv * inv, t);
+                wv = fma(-urow[t], yt, wv);  // urow[t] == 0 for t <= r
+            }
+            if (lane < nb) y[j0 + lane] = wv * inv;
+        }
+        __syncthreads();
+        for (int i = tid; i < j0; i += nt) {
+            double sacc = 0;
+#pragma unroll 4
+            for (int t = 0; t < nb; t++) sacc = fma(S.at(i, j0 + t), y[j0 + t], sacc);
+            y[i] -= sacc;
+        }
+        __syncthreads();
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace lfvio

@@ -25,6 +25,7 @@
 #include "backend.cuh"
 #include "marg.cuh"
 #include "chol16.cuh"
+#include "chol_blocked.cuh"
 
 namespace lfvio {
 
@@ -33,6 +34,10 @@ namespace {
 constexpr int MA_WARPS = 4;
 constexpr int MF_THREADS = 512;
 constexpr double kEps = 1e-8;  // MarginalizationInfo::eps (marginalization_factor.h:70)
+
+// phase boundaries of the last marg_finish_kernel (LFVIO_DEBUG_STEP=1 prints them); [7] = fast path taken
+__device__ long long g_marg_clk[8];
+#define MARG_MARK(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_marg_clk[i] = (long long)t_; } } while (0)
 
 __device__ __forceinline__ void add_sym(double *T, int ld, int a, int b, double v) {
     if (v == 0.0) return;
@@ -49,9 +54,9 @@ __global__ void __launch_bounds__(MA_WARPS * 32) marg_accumulate_kernel(DevProbl
     const int ld = plan.dim;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if ((int)blockIdx.x < n_item_cta) {
-        const int item = blockIdx.x * MA_WARPS + wid;
-        const int per_warp = max_obs * 40 + max_obs * 2 + max_obs * 6 + 16 + max_obs;
-        double *sJ = smem + (size_t)wid * per_warp;
+        const int item = blockIdx.x;  // one CTA per item; its warps interleave the rows of the item's local block
+        const int tid = threadIdx.x;
+        double *sJ = smem;
         double *sR = sJ + max_obs * 40;
         double *sW = sR + max_obs * 2;
         double *sWs = sW + max_obs * 6;
@@ -62,10 +67,10 @@ __global__ void __launch_bounds__(MA_WARPS * 32) marg_accumulate_kernel(DevProbl
             const int k0 = P.lm_first[l], K = min(P.lm_first[l + 1] - k0, max_obs);
             if (K <= 0) return;
             const int fi = P.proj[k0].frame_i;
-            for (int k = lane; k < K; k += 32) sFj[k] = P.proj[k0 + k].frame_j;
-            for (int q = lane; q < K * 40; q += 32) sJ[q] = e.Jp[40 * (size_t)k0 + q];
-            for (int q = lane; q < K * 2; q += 32) sR[q] = e.rp[2 * (size_t)k0 + q];
-            __syncwarp();
+            for (int k = tid; k < K; k += MA_WARPS * 32) sFj[k] = P.proj[k0 + k].frame_j;
+            for (int q = tid; q < K * 40; q += MA_WARPS * 32) sJ[q] = e.Jp[40 * (size_t)k0 + q];
+            for (int q = tid; q < K * 2; q += MA_WARPS * 32) sR[q] = e.rp[2 * (size_t)k0 + q];
+            __syncthreads();
             double c_l = 0, g_l = 0;
             for (int q = lane; q < K * 2; q += 32) {
                 const double jl = sJ[(q >> 1) * 40 + (q & 1) * 20 + 18];
@@ -76,17 +81,17 @@ __global__ void __launch_bounds__(MA_WARPS * 32) marg_accumulate_kernel(DevProbl
             g_l = warp_sum(g_l);
             const double inv_c = c_l > kEps ? 1.0 / c_l : 0.0;
             auto shared_c = [](int a) { return a < 6 ? a : (a < 12 ? a + 6 : 19); };
-            if (lane < 13) {
-                const int c = shared_c(lane);
+            if (tid < 13) {
+                const int c = shared_c(tid);
                 double s = 0;
                 for (int k = 0; k < K; k++) s += sJ[k * 40 + c] * sJ[k * 40 + 18] + sJ[k * 40 + 20 + c] * sJ[k * 40 + 38];
-                sWs[lane] = s;
+                sWs[tid] = s;
             }
-            for (int q = lane; q < K * 6; q += 32) {
+            for (int q = tid; q < K * 6; q += MA_WARPS * 32) {
                 const int k = q / 6, c = 6 + q % 6;
                 sW[q] = sJ[k * 40 + c] * sJ[k * 40 + 18] + sJ[k * 40 + 20 + c] * sJ[k * 40 + 38];
             }
-            __syncwarp();
+            __syncthreads();
             const int n_l = 13 + 6 * K;
             const bool has_td = P.o.estimate_td != 0;
             auto mcol = [&](int A) {  // column in the marginalisation ordering, -1 if the block is absent
@@ -96,7 +101,7 @@ __global__ void __launch_bounds__(MA_WARPS * 32) marg_accumulate_kernel(DevProbl
                 return plan.col[2 * sFj[(A - 13) / 6]] + (A - 13) % 6;
             };
             auto wval = [&](int A) { return A < 13 ? sWs[A] : sW[A - 13]; };
-            for (int A = lane; A < n_l; A += 32) {
+            for (int A = tid; A < n_l; A += MA_WARPS * 32) {
                 const int ca = mcol(A);
                 if (ca < 0) continue;
                 double g = 0;
@@ -110,7 +115,7 @@ __global__ void __launch_bounds__(MA_WARPS * 32) marg_accumulate_kernel(DevProbl
                 const double v = g - wval(A) * g_l * inv_c;
                 if (v != 0.0) atomicAdd(&bvec[ca], v);
             }
-            for (int A = 0; A < n_l; A++) {
+            for (int A = wid; A < n_l; A += MA_WARPS) {
                 const int ca = mcol(A);
                 if (ca < 0) continue;
                 const double wA = wval(A);
@@ -142,22 +147,22 @@ __global__ void __launch_bounds__(MA_WARPS * 32) marg_accumulate_kernel(DevProbl
             // ===== IMUFactor(pre_integrations[1]) between frames 0 and 1 =====
             const int k = plan.imu_index;
             double *sI = sJ;
-            for (int q = lane; q < 450; q += 32) sI[q] = e.Ji[450 * (size_t)k + q];
+            for (int q = tid; q < 450; q += MA_WARPS * 32) sI[q] = e.Ji[450 * (size_t)k + q];
             double *sRi = sI + 450;
-            for (int q = lane; q < 15; q += 32) sRi[q] = e.ri[15 * (size_t)k + q];
-            __syncwarp();
+            for (int q = tid; q < 15; q += MA_WARPS * 32) sRi[q] = e.ri[15 * (size_t)k + q];
+            __syncthreads();
             auto icol = [&](int c) {
                 if (c < 6) return plan.col[0] + c;
                 if (c < 15) return plan.col[1] + (c - 6);
                 if (c < 21) return plan.col[2] + (c - 15);
                 return plan.col[3] + (c - 21);
             };
-            if (lane < 30) {
+            if (tid < 30) {
                 double g = 0;
-                for (int r = 0; r < 15; r++) g += sI[r * 30 + lane] * sRi[r];
-                atomicAdd(&bvec[icol(lane)], g);
+                for (int r = 0; r < 15; r++) g += sI[r * 30 + tid] * sRi[r];
+                atomicAdd(&bvec[icol(tid)], g);
             }
-            for (int A = 0; A < 30; A++)
+            for (int A = wid; A < 30; A += MA_WARPS)
                 for (int B = A + lane; B < 30; B += 32) {
                     double v = 0;
                     for (int r = 0; r < 15; r++) v += sI[r * 30 + A] * sI[r * 30 + B];
@@ -395,11 +400,21 @@ __global__ void __launch_bounds__(MF_THREADS) marg_finish_kernel(DevProblem P, c
     double *br = R + n * n;
     double *r0 = br + n;
     double *Tm = r0 + n;  // n x mp : T_rm * Amm^+
+    // T (ld x ld, symmetric up to atomics round-off) staged once into shared memory; the same region later holds the
+    // fast path's Cholesky panel.  With the global workspace (large windows) T is read in place.
+    double *Ts = Tm + (((size_t)n * mp + (Tm - base) + 1) & ~(size_t)1) - (Tm - base);  // 16-byte aligned
+    MARG_MARK(0);
+    if (plan.use_smem) {
+        for (int q = tid; q < ld * ld; q += nt) Ts[q] = T[q];
+        __syncthreads();
+        T = Ts;
+    }
     for (int q = tid; q < mp * mp; q += nt) {
         const int r = q / mp, c = q % mp;
         Amm[q] = 0.5 * (T[(size_t)r * ld + c] + T[(size_t)c * ld + r]);
     }
     __syncthreads();
+    MARG_MARK(1);
     // Amm^+ (marginalization_factor.cpp:267-272).  Fast path: the block is comfortably positive definite (it carries the
     // IMU factor and/or the previous prior), so its inverse is X X^T with X = U^-1 from the warp-level Cholesky; the
     // reference's thresholded eigen-decomposition is kept for the (near-)singular case.
@@ -437,6 +452,7 @@ __global__ void __launch_bounds__(MF_THREADS) marg_finish_kernel(DevProblem P, c
         }
     }
     __syncthreads();
+    MARG_MARK(2);
     for (int q = tid; q < n * mp; q += nt) {
         const int i = q / mp, j = q % mp;
         double s = 0;
@@ -459,17 +475,127 @@ __global__ void __launch_bounds__(MF_THREADS) marg_finish_kernel(DevProblem P, c
         br[i] = s;
     }
     __syncthreads();
+    MARG_MARK(3);
     // (J0, r0) with J0^T J0 = A', J0^T r0 = b'.  The reference takes J0 = sqrt(S) V^T from a second dense
     // eigen-decomposition (:283-291); any square root of A' defines the same prior factor, and the pivoted Cholesky
     // factor is ~100x cheaper on a GPU than a 76 x 76 Jacobi sweep sequence.
-    pivoted_cholesky(Ar, br, n, kEps, R, r0, s_done, s_best, s_bidx);
+    // Fast path (shared-memory workspace only).  In the steady state A' is well conditioned EXCEPT for the gauge of a
+    // visual-inertial window (global position + yaw): conditioned on every other kept variable, one pose block has ~4
+    // directions with no information (eigenvalues ~1e-6 or round-off).  So: move one pose block to the end, run the
+    // solver's blocked look-ahead Cholesky (no pivoting) on the leading blocks, and factor only the last diagonal block
+    // (<= 16 columns, containing that pose) with diagonal pivoting and the reference's eps cut-off.  J0 = U P (P the
+    // column permutation), r0 = U^-T P b'.  Accepted only if every leading pivot exceeds 10 eps; otherwise (e.g. the
+    // first windows, whose prior is rank deficient elsewhere) the fully pivoted factorisation below runs on the intact A'.
+    bool fast_ok = false;
+    const int nblk_f = (n + NB - 1) / NB, c0_f = (nblk_f - 1) * NB, nl_f = n - c0_f;
+    if (plan.use_smem && n + 1 <= (int)blockDim.x - 32 && nblk_f >= 2 && nl_f >= 6) {
+        const int PW = chol_panel_pitch(n);
+        double *s_panel = Ts;  // T is dead: A' and b' are formed
+        double *s_y = s_panel + (size_t)NB * PW;
+        double *s_invd = s_y + ((n + 1) & ~1);
+        __shared__ __align__(16) double s_U[2 * NB * NB];
+        __shared__ __align__(16) double s_row[2 * NB];
+        __shared__ int s_okv[kMaxFrames * 15 / NB + 4];
+        __shared__ int s_perm[15 * kMaxFrames + 8];
+        // permutation: the 6 columns of the last kept pose block go to the end
+        int pb = -1;
+        for (int b2 = 0; b2 < plan.n_keep; b2++)
+            if (plan.keep_id[b2] < 2 * P.lay.F && (plan.keep_id[b2] & 1) == 0) pb = b2;
+        const int pc0 = pb >= 0 ? plan.col[plan.keep_id[pb]] - mp : n - 6;
+        for (int i = tid; i < n; i += nt) s_perm[i] = i < pc0 ? i : (i < n - 6 ? i + 6 : pc0 + (i - (n - 6)));
+        for (int q = tid; q < NB * PW; q += nt) s_panel[q] = 0.0;
+        __syncthreads();
+        for (int q = tid; q < n * n; q += nt) {
+            const int i = q / n, j = q % n;
+            R[q] = (i <= j) ? Ar[s_perm[i] * n + s_perm[j]] : 0.0;
+        }
+        for (int i = tid; i < n; i += nt) s_y[i] = br[s_perm[i]];
+        __syncthreads();
+        fast_ok = cholesky_lookahead(MatFull{R, n}, n, s_panel, PW, s_U, s_invd, s_y, s_okv, s_row, DenseProfile(), true);
+        __syncthreads();
+        if (fast_ok) {
+            int bad = 0;
+            for (int i = tid; i < c0_f; i += nt) {
+                const double inv = s_invd[i];  // 1 / U_ii
+                if (!(inv * inv * (10.0 * kEps) < 1.0)) bad = 1;
+            }
+            fast_ok = __syncthreads_or(bad) == 0;
+        }
+        if (fast_ok) {
+            // last diagonal block: rank-revealing Cholesky with diagonal pivoting by one warp (lane j = column j)
+            if (tid < 32) {
+                double *Bk = s_U;            // nl x nl symmetric copy of the block, then scratch
+                double *Uo = s_U + NB * NB;  // rows of the factor in pivot order, original column positions
+                const int lane = tid;
+                for (int q = lane; q < NB * NB; q += 32) {
+                    const int i = q / NB, j = q % NB;
+                    Bk[q] = (i < nl_f && j < nl_f) ? R[(c0_f + min(i, j)) * n + c0_f + max(i, j)] : 0.0;
+                    Uo[q] = 0.0;
+                }
+                __syncwarp();
+                double zj = lane < nl_f ? s_y[c0_f + lane] : 0.0;
+                double zout = 0.0;  // lane k keeps r0 of pivot step k
+                bool done = lane >= nl_f;
+                for (int k = 0; k < nl_f; k++) {
+                    double best = done ? -1.0 : Bk[lane * NB + lane];
+                    int bi = done ? -1 : lane;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) {
+                            best = ob;
+                            bi = oi;
+                        }
+                    }
+                    if (bi < 0 || !(best > kEps)) break;
+                    const double inv = rsqrt(best);
+                    const double uj = done ? 0.0 : Bk[bi * NB + lane] * inv;  // row k of the factor (column `lane`)
+                    const double rk = __shfl_sync(0xffffffffu, zj, bi) * inv;
+                    if (lane < nl_f) Uo[k * NB + lane] = uj;
+                    if (lane == k) zout = rk;
+                    __syncwarp();
+                    if (!done && lane != bi) {
+                        for (int i = 0; i < nl_f; i++) Bk[i * NB + lane] -= Uo[k * NB + i] * uj;  // rows of finished pivots hold zeros in Uo
+                        zj -= uj * rk;
+                    }
+                    if (lane == bi) done = true;
+                    __syncwarp();
+                }
+                for (int q = lane; q < nl_f * nl_f; q += 32) {
+                    const int k = q / nl_f, j = q % nl_f;
+                    R[(c0_f + k) * n + c0_f + j] = Uo[k * NB + j];
+                }
+                if (lane < nl_f) s_y[c0_f + lane] = zout;
+            }
+            __syncthreads();
+            // un-permute the columns: J0[:, perm[c]] = U[:, c]   (Ar is free now)
+            for (int q = tid; q < n * n; q += nt) Ar[(q / n) * n + s_perm[q % n]] = R[q];
+            for (int i = tid; i < n; i += nt) r0[i] = s_y[i];
+            __syncthreads();
+            for (int q = tid; q < n * n; q += nt) R[q] = Ar[q];
+            __syncthreads();
+        }
+    }
+    MARG_MARK(4);
+    if (!fast_ok) pivoted_cholesky(Ar, br, n, kEps, R, r0, s_done, s_best, s_bidx);
+    __syncthreads();
+    MARG_MARK(5);
+    if (tid == 0) g_marg_clk[7] = fast_ok ? 1 : 0;
     for (int q = tid; q < n * n; q += nt) J0_out[q] = R[q];
     for (int k = tid; k < n; k += nt) r0_out[k] = r0[k];
+    MARG_MARK(6);
 }
 
 }  // namespace
 
-size_t marg_finish_workspace_doubles(int m_p, int n) { return (size_t)3 * m_p * m_p + 2 * (size_t)n * n + 2 * (size_t)n + (size_t)n * m_p; }
+void marg_profile_read(long long *out) { cudaMemcpyFromSymbol(out, g_marg_clk, sizeof(long long) * 8); }
+
+size_t marg_finish_workspace_doubles(int m_p, int n) {
+    const size_t chol = (size_t)NB * chol_panel_pitch(n) + (size_t)((n + 1) & ~1) + (size_t)((n + NB - 1) / NB) * NB;  // fast-path panel, rhs, pivots
+    const size_t tdim = (size_t)(m_p + n) * (m_p + n);                                                                   // staged T (same region)
+    return (size_t)3 * m_p * m_p + 2 * (size_t)n * n + 2 * (size_t)n + (size_t)n * m_p + std::max(chol, tdim) + 2;
+}
 
 int launch_marginalize(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const double *x0, const double *x1,
                        const SolverCtl *ctl, MargPlan &plan, const MargBuffers &mb, cudaStream_t s) {
@@ -477,9 +603,9 @@ int launch_marginalize(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1
     LFVIO_CUDA_TRY(cudaMemsetAsync(mb.T, 0, sizeof(double) * ((size_t)dim * dim + dim), s));
     const int max_obs = std::max(P.lay.F - 1, 10);
     const int items = plan.n_lm + 1;
-    const int n_item_cta = cdiv(items, MA_WARPS);
-    const int per_warp = max_obs * 40 + max_obs * 2 + max_obs * 6 + 16 + max_obs;
-    size_t smem = sizeof(double) * (size_t)per_warp * MA_WARPS;
+    const int n_item_cta = items;
+    const int per_item = max_obs * 40 + max_obs * 2 + max_obs * 6 + 16 + max_obs;
+    size_t smem = sizeof(double) * (size_t)per_item;
     smem = std::max(smem, sizeof(int) * (size_t)(15 * kMaxFrames + 8));
     static bool a1 = false, a2 = false;
     if (!a1) {

@@ -27,6 +27,7 @@ struct MargBuffers {
 };
 
 size_t marg_finish_workspace_doubles(int m_p, int n);
+void marg_profile_read(long long *out);  // debug: phase boundaries (ns) of the last marg_finish_kernel
 int launch_marginalize(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const double *x0, const double *x1,
                        const SolverCtl *ctl, MargPlan &plan, const MargBuffers &mb, cudaStream_t s);
 

@@ -48,17 +48,11 @@ __global__ void colnorm_kernel(DevProblem P, EvalBuf e, double *scale) {
         for (int r = 0; r < 15; r++) v += J[r * 30 + c] * J[r * 30 + c];
         if (v != 0.0) atomicAdd(&scale[imu_col(lay, P.imu[k].frame_i, c)], v);
     }
+    // prior: squared column norms of J0 = diagonal of H0 = J0^T J0 (prior_prepare_kernel, once per upload)
     const DevPrior &p = P.prior;
     for (int b = 0; b < p.n_blocks; b++) {
         const int ls = lay.block_lsize(p.block_id[b]), c0 = lay.block_col(p.block_id[b]);
-        for (int q = tid; q < ls; q += nth) {
-            double v = 0;
-            for (int i = 0; i < p.n; i++) {
-                const double j = p.J0[(size_t)i * p.n + p.block_idx[b] + q];
-                v += j * j;
-            }
-            atomicAdd(&scale[c0 + q], v);
-        }
+        for (int q = tid; q < ls; q += nth) atomicAdd(&scale[c0 + q], p.H0[(size_t)(p.block_idx[b] + q) * (p.n + 1)]);
     }
 }
 __global__ void scale_finalize_kernel(double *scale, int n) {
@@ -99,6 +93,7 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
                 if (tid == 0) {
                     w.lm_c[l] = 0.0;
                     w.lm_g[l] = 0.0;
+                    w.lm_coli[l] = -1;
                 }
                 return;
             }
@@ -143,7 +138,9 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
             if (tid == 0) {
                 w.lm_c[l] = c_l;
                 w.lm_g[l] = g_l;
+                w.lm_coli[l] = lay.col_pose(fi);
             }
+            for (int k = tid; k < K; k += ACC_WARPS * 32) w.proj_colj[k0 + k] = lay.col_pose(sFj[k]);
             if (tid < 13) w.lm_ws[13 * (size_t)l + tid] = sWs[tid];
             for (int q = tid; q < K * 6; q += ACC_WARPS * 32) w.proj_wj[6 * (size_t)k0 + q] = sW[q];
             // local index A in [0, 13 + 6K): global column and accessors
@@ -286,6 +283,8 @@ __global__ void solver_init_kernel(SolverCtl *ctl, lfvio_solver_opts o) {
     ctl->model_cost_change = 0.0;
     ctl->step_norm = 0.0;
     ctl->gnorm = ctl->gn_norm = ctl->gdot = 0.0;
+    ctl->jj = 0.0;
+    ctl->mu_solve = 1e-8;
     ctl->ticket2 = 0;
     for (int i = 0; i < 8; i++) ctl->acc[i] = 0.0;
 }

@@ -131,7 +131,7 @@ int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_pro
     LFVIO_TRY(w->H0.alloc((size_t)w->nmax * w->nmax));
     // scratch: [S D*D | rhs D | diag2 D | grad D | lm_c L | lm_g L] (zeroed per iteration) | lm_ws | proj_wj | scale | ...
     const size_t D = lay.D(), L = max_landmarks, N = D + L;
-    const size_t n_scr = D * D + 3 * D + 2 * L + 13 * L + 6 * (size_t)max_proj + 5 * N + D;
+    const size_t n_scr = D * D + 3 * D + 2 * L + 13 * L + 6 * (size_t)max_proj + 5 * N + D + (L + (size_t)max_proj) / 2 + 2;
     LFVIO_TRY(w->scratch.alloc(n_scr));
     double *p = w->scratch.p;
     SolverScratch &s = w->w;
@@ -150,6 +150,8 @@ int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_pro
     s.gn = p;         p += N;
     s.step = p;       p += N;
     s.y = p;          p += D;
+    s.lm_coli = reinterpret_cast<int *>(p);
+    s.proj_colj = s.lm_coli + L;
     LFVIO_TRY(w->ctl.alloc(1));
     LFVIO_CUDA_TRY(cudaMallocHost(&w->h_ctl, sizeof(SolverCtl)));
     LFVIO_CUDA_TRY(cudaMallocHost(&w->h_x, sizeof(double) * lay.size()));
@@ -490,8 +492,8 @@ int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum, 
     }
 #endif
     if (getenv("LFVIO_DEBUG_STEP")) {
-        static const char *names[5] = {"scalars+xnorm", "copy-to-smem", "cholesky", "tri-solve", "tail"};
-        for (int i = 0; i < 5; i++) fprintf(stderr, "step phase %-16s %8.2f us\n", names[i], (c.phase_clk[i + 1] - c.phase_clk[i]) / 1000.0);
+        static const char *names[6] = {"cauchy+xnorm", "copy+quadform", "cholesky", "tri-solve", "gn+backsub", "cand_tail"};
+        for (int i = 0; i < 6; i++) fprintf(stderr, "step phase %-16s %8.2f us\n", names[i], (c.phase_clk[i + 1] - c.phase_clk[i]) / 1000.0);
     }
     if (sum) {
         memset(sum, 0, sizeof(*sum));
@@ -614,6 +616,13 @@ extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *s
         LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg + nn + pl.n, w->marg_x0.p, sizeof(double) * x0_len, cudaMemcpyDeviceToHost, s));
     }
     LFVIO_TRY(download(w, state, summary, false));
+    if (do_marg && getenv("LFVIO_DEBUG_STEP")) {
+        long long mc[8];
+        marg_profile_read(mc);
+        static const char *names[6] = {"stage T, Amm", "Amm^+", "Tm, A', b'", "blocked chol+tail", "pivoted chol", "write-out"};
+        for (int i = 0; i < 6; i++) fprintf(stderr, "marg_finish phase %-14s %8.2f us\n", names[i], (mc[i + 1] - mc[i]) / 1000.0);
+        fprintf(stderr, "marg_finish fast path: %lld\n", mc[7]);
+    }
     if (do_marg) {
         prior_out->n = pl.n;
         prior_out->n_blocks = pl.n_keep;

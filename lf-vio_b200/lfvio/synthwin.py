@@ -266,3 +266,22 @@ def make_window(seed: int = 1, n_frames: int = 11, n_landmarks: int = 260, feats
     w = B.WindowProblem(F, pose, sb, ex, np.array(feat_depth), td_true + perturb * 0.003, proj, imu, None, opts)
     w.truth = dict(P=np.array(Ps), R=np.array(Rs), V=np.array(Vs), ba=ba_true, bg=bg_true, td=td_true)
     return w
+
+
+def make_window_with_prior(optimize, marginalize, seed: int = 1, t0: float = 5.0, frame_dt: float = 0.1, depth: int = 3,
+                           **kw) -> B.WindowProblem:
+    """Steady-state window: the `depth` windows before t0 (same trajectory, one frame apart) are optimised in turn and
+    their oldest frame marginalised (MARGIN_OLD, estimator.cpp:833-939), each one carrying the prior left by its
+    predecessor; the last prior (n = 6 (F - 1) + 9 + 6 + 1) is attached to the window at t0, whose frames 0 .. F-2 are
+    the frames 1 .. F-1 that prior was linearised on.  depth >= 3 reaches the regime a running estimator is in (the
+    prior's information matrix numerically positive definite apart from the gauge directions).
+    optimize(w) / marginalize(w, flag) are the device or the oracle implementations (same signatures)."""
+    prior = None
+    for k in range(depth, 0, -1):
+        prev = make_window(seed=seed, t0=t0 - k * frame_dt, frame_dt=frame_dt, **kw)
+        prev.prior = prior
+        optimize(prev)
+        prior = marginalize(prev, B.MARGIN_OLD)
+    w = make_window(seed=seed, t0=t0, frame_dt=frame_dt, **kw)
+    w.prior = prior
+    return w
