@@ -294,6 +294,41 @@ int lfvio_window_upload(lfvio_window *w, const lfvio_window_state *state, const 
 int lfvio_window_optimize_dev(lfvio_window *w, int with_marginalize, int margin_flag);
 int lfvio_window_download(lfvio_window *w, lfvio_window_state *state, lfvio_solve_summary *summary);
 
+/* ==========================================================================================
+ * The two steps right before optimization(): they produce the constants the
+ * factors above consume.
+ * ========================================================================================== */
+typedef struct lfvio_imu_noise { /* ACC_N GYR_N ACC_W GYR_W (vins_estimator/src/parameters.cpp:58-61) */
+    double acc_n, gyr_n, acc_w, gyr_w;
+} lfvio_imu_noise;
+
+typedef struct lfvio_imu_interval { /* one IntegrationBase: the IMU samples between two camera frames */
+    int first, count;              /* samples [first, first + count) of the dt / acc / gyr arrays          */
+    int frame_i;                   /* copied to lfvio_imu_factor.frame_i                                   */
+    int propagate;                 /* != 0: also run the nominal-state prediction of Estimator::processIMU */
+    double acc_0[3], gyr_0[3];     /* IntegrationBase(acc_0, gyr_0, ...)   integration_base.h:13-16        */
+    double ba[3], bg[3];           /* ... linearized_ba, linearized_bg (Bas[j], Bgs[j], estimator.cpp:97)  */
+    double P[3], V[3], R[9];       /* Ps[j], Vs[j], Rs[j] (row-major) before the first sample              */
+} lfvio_imu_interval;
+
+/* IntegrationBase::push_back for every sample of every interval (factor/integration_base.h:31-157: mid-point
+ * integration of delta_p/q/v, jacobian <- F jacobian, covariance <- F covariance F^T + V noise V^T), i.e. what
+ * Estimator::processIMU (estimator.cpp:86-120) does at 200 Hz and IntegrationBase::repropagate (:39-53) does after a
+ * bias change.  out[i] is the IMUFactor input for interval i.  state_out (may be NULL): n_intervals x 15 =
+ * [P 3 | V 3 | R 9 row-major], the predicted Ps[j], Vs[j], Rs[j] (estimator.cpp:107-116) when propagate != 0. */
+int lfvio_preintegrate(const lfvio_imu_interval *intervals, int n_intervals, const double *dt, const double *acc,
+                       const double *gyr, int n_samples, const lfvio_imu_noise *noise, const double *g /* 3 */,
+                       lfvio_imu_factor *out, double *state_out, int device);
+
+/* FeatureManager::triangulate (vins_estimator/src/feature_manager.cpp:199-253).  Feature l was first seen in frame
+ * start_frame[l] and has the unit bearings obs_pts[obs_first[l] .. obs_first[l+1]) (x y z each) in consecutive frames.
+ * Ps (n_frames x 3) / Rs (n_frames x 9 row-major) are the IMU poses, tic / ric the camera extrinsics.  depth[l] is
+ * in/out like FeaturePerId::estimated_depth: entries > 0 are left untouched (:207), features with fewer than two
+ * observations or start_frame >= WINDOW_SIZE - 2 are skipped (:204), a negative result becomes init_depth (:246-249). */
+int lfvio_triangulate(const double *Ps, const double *Rs, int n_frames, const double *tic, const double *ric,
+                      const int *start_frame, const int *obs_first, const double *obs_pts, int n_features,
+                      double init_depth, double *depth, int device);
+
 /* ------------------------------------------------------------------------------------------
  * Live per-stage device timing (CUDA events recorded on the handle's own stream around each kernel
  * group).  Replaces the reference's TicToc prints (feature_tracker.cpp:106,141,153,170,175;

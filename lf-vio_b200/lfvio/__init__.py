@@ -349,3 +349,18 @@ lib.lfvio_tracker_profile_begin.argtypes = [C.c_void_p, C.c_int]
 lib.lfvio_tracker_profile_end.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
 lib.lfvio_window_profile_begin.argtypes = [C.c_void_p, C.c_int]
 lib.lfvio_window_profile_end.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+
+# ------------------------------------------------------------------------------------------------
+# the two steps before optimization(): IMU pre-integration and triangulation (prestep.py)
+# ------------------------------------------------------------------------------------------------
+from . import prestep  # noqa: E402
+
+prestep.bind(lib)
+
+
+def preintegrate(intervals, dt, acc, gyr, noise, g, device: int = 0):
+    return prestep.preintegrate(lib, check, intervals, dt, acc, gyr, noise, g, device)
+
+
+def triangulate(Ps, Rs, tic, ric, start_frame, obs_first, obs_pts, depth, init_depth: float = 5.0, device: int = 0):
+    return prestep.triangulate(lib, check, Ps, Rs, tic, ric, start_frame, obs_first, obs_pts, depth, init_depth, device)
