@@ -110,11 +110,35 @@ void FeatureManager::setDepth(const std::vector<double> &x) {
     }
 }
 
+int FeatureManager::triangulate(const std::vector<Vec3> &Ps, const std::vector<Mat3> &Rs, const Vec3 tic[], const Mat3 ric[], int device) {
+    std::vector<int> start, first{0};
+    std::vector<double> pts, depth;
+    for (auto &it : feature) {
+        it.used_num = (int)it.feature_per_frame.size();
+        start.push_back(it.start_frame);
+        for (const auto &o : it.feature_per_frame) pts.insert(pts.end(), o.point.begin(), o.point.end());
+        first.push_back((int)(pts.size() / 3));
+        depth.push_back(it.estimated_depth);
+    }
+    if (start.empty()) return LFVIO_OK;
+    std::vector<double> P, R;
+    for (const auto &p : Ps) P.insert(P.end(), p.begin(), p.end());
+    for (const auto &r : Rs) R.insert(R.end(), r.begin(), r.end());
+    const int st = lfvio_triangulate(P.data(), R.data(), (int)Ps.size(), tic[0].data(), ric[0].data(), start.data(), first.data(),
+                                     pts.data(), (int)start.size(), init_depth, depth.data(), device);
+    if (st != LFVIO_OK) return st;
+    size_t i = 0;
+    for (auto &it : feature) it.estimated_depth = depth[i++];
+    return LFVIO_OK;
+}
+
 // ---- Estimator ---------------------------------------------------------------------------------------
 Estimator::Estimator(int window_size, int max_features, int device)
     : WINDOW_SIZE(window_size), Ps(window_size + 1), Vs(window_size + 1), Bas(window_size + 1), Bgs(window_size + 1),
       Rs(window_size + 1, Mat3{1, 0, 0, 0, 1, 0, 0, 0, 1}), pre_integrations(window_size + 1, nullptr),
-      para_Pose(7 * (window_size + 1)), para_SpeedBias(9 * (window_size + 1)), para_Feature(max_features), m_device(device) {
+      dt_buf(window_size + 1), linear_acceleration_buf(window_size + 1), angular_velocity_buf(window_size + 1),
+      para_Pose(7 * (window_size + 1)), para_SpeedBias(9 * (window_size + 1)), para_Feature(max_features), m_device(device),
+      m_iv(window_size + 1), m_pre(window_size + 1) {
     tic[0] = Vec3{0, 0, 0};
     ric[0] = Mat3{1, 0, 0, 0, 1, 0, 0, 0, 1};
     f_manager.window_size = window_size;
@@ -124,6 +148,87 @@ Estimator::~Estimator() {
     if (m_window) lfvio_window_destroy(m_window);
 }
 const char *Estimator::lastError() const { return lfvio_last_error(); }
+
+void Estimator::processIMU(double dt, const Vec3 &linear_acceleration, const Vec3 &angular_velocity) {
+    if (!first_imu) {
+        first_imu = true;
+        acc_0 = linear_acceleration;
+        gyr_0 = angular_velocity;
+    }
+    const int j = frame_count;
+    Interval &iv = m_iv[j];
+    if (!iv.open) {  // new IntegrationBase{acc_0, gyr_0, Bas[frame_count], Bgs[frame_count]}  (estimator.cpp:95-98)
+        iv.open = true;
+        iv.acc_start = acc_0;
+        iv.gyr_start = gyr_0;
+        iv.ba = Bas[j];
+        iv.bg = Bgs[j];
+        iv.P = Ps[j];
+        iv.V = Vs[j];
+        iv.R = Rs[j];
+        iv.dirty = true;
+    }
+    if (j != 0) {
+        dt_buf[j].push_back(dt);
+        linear_acceleration_buf[j].push_back(linear_acceleration);
+        angular_velocity_buf[j].push_back(angular_velocity);
+        iv.dirty = true;
+    }
+    acc_0 = linear_acceleration;
+    gyr_0 = angular_velocity;
+}
+
+int Estimator::integrate(int j, bool propagate) {
+    Interval &iv = m_iv[j];
+    const int n = (int)dt_buf[j].size();
+    lfvio_imu_interval I{};
+    I.first = 0;
+    I.count = n;
+    I.frame_i = j - 1;
+    I.propagate = propagate ? 1 : 0;
+    for (int k = 0; k < 3; k++) {
+        I.acc_0[k] = iv.acc_start[k];
+        I.gyr_0[k] = iv.gyr_start[k];
+        I.ba[k] = iv.ba[k];
+        I.bg[k] = iv.bg[k];
+        I.P[k] = iv.P[k];
+        I.V[k] = iv.V[k];
+    }
+    for (int k = 0; k < 9; k++) I.R[k] = iv.R[k];
+    std::vector<double> acc(3 * (size_t)n + 3), gyr(3 * (size_t)n + 3);
+    for (int k = 0; k < n; k++)
+        for (int a = 0; a < 3; a++) {
+            acc[3 * k + a] = linear_acceleration_buf[j][k][a];
+            gyr[3 * k + a] = angular_velocity_buf[j][k][a];
+        }
+    double state[15];
+    const int st = lfvio_preintegrate(&I, 1, dt_buf[j].data(), acc.data(), gyr.data(), n, &imu_noise, G.data(), &m_pre[j], state, m_device);
+    if (st != LFVIO_OK) return st;
+    pre_integrations[j] = &m_pre[j];
+    if (propagate) {
+        Ps[j] = Vec3{state[0], state[1], state[2]};
+        Vs[j] = Vec3{state[3], state[4], state[5]};
+        for (int k = 0; k < 9; k++) Rs[j][k] = state[6 + k];
+    }
+    iv.dirty = false;
+    return LFVIO_OK;
+}
+
+int Estimator::flushIMU() {
+    for (int j = 0; j <= WINDOW_SIZE; j++)
+        if (m_iv[j].open && m_iv[j].dirty) {
+            last_status = integrate(j, true);
+            if (last_status != LFVIO_OK) return last_status;
+        }
+    return LFVIO_OK;
+}
+
+int Estimator::repropagate(int j, const Vec3 &ba, const Vec3 &bg) {
+    if (!m_iv[j].open) return LFVIO_OK;
+    m_iv[j].ba = ba;
+    m_iv[j].bg = bg;
+    return last_status = integrate(j, false);  // repropagate() re-integrates the deltas only (integration_base.h:39-53)
+}
 
 void Estimator::vector2double() {
     for (int i = 0; i <= WINDOW_SIZE; i++) {
@@ -223,6 +328,7 @@ void Estimator::buildFactors() {
 
 void Estimator::optimization() {
     if (!m_window) return;
+    if (flushIMU() != LFVIO_OK) return;  // pre_integrations[] and the predicted newest state up to date
     vector2double();
     buildFactors();
     lfvio_solver_opts o;
@@ -375,5 +481,70 @@ extern "C" int lfvio_host_estimator_roundtrip(const lfvio_window_state *st, cons
         memcpy(prior_out->r0, m.r0.data(), sizeof(double) * m.n);
         memcpy(prior_out->x0, m.x0.data(), sizeof(double) * 9 * m.n_blocks);
     }
+    return LFVIO_OK;
+}
+
+// Test hook: drives Estimator::processIMU / flushIMU and FeatureManager::triangulate of the host mirror from Python.
+extern "C" int lfvio_host_process_imu(int frame, const double *P, const double *V, const double *R, const double *ba, const double *bg,
+                                      const double *g, const double *noise, const double *acc0, const double *gyr0, const double *dt,
+                                      const double *acc, const double *gyr, int n, lfvio_imu_factor *out, double *state_out) {
+    using namespace lfvio_host;
+    Estimator est(10, 8, 0);
+    if (est.last_status != LFVIO_OK) return est.last_status;
+    G = Vec3{g[0], g[1], g[2]};
+    est.imu_noise = lfvio_imu_noise{noise[0], noise[1], noise[2], noise[3]};
+    est.frame_count = frame;
+    est.Ps[frame] = Vec3{P[0], P[1], P[2]};
+    est.Vs[frame] = Vec3{V[0], V[1], V[2]};
+    for (int k = 0; k < 9; k++) est.Rs[frame][k] = R[k];
+    est.Bas[frame] = Vec3{ba[0], ba[1], ba[2]};
+    est.Bgs[frame] = Vec3{bg[0], bg[1], bg[2]};
+    est.first_imu = true;  // the previous frame's last sample
+    est.acc_0 = Vec3{acc0[0], acc0[1], acc0[2]};
+    est.gyr_0 = Vec3{gyr0[0], gyr0[1], gyr0[2]};
+    for (int k = 0; k < n; k++)
+        est.processIMU(dt[k], Vec3{acc[3 * k], acc[3 * k + 1], acc[3 * k + 2]}, Vec3{gyr[3 * k], gyr[3 * k + 1], gyr[3 * k + 2]});
+    const int st = est.flushIMU();
+    if (st != LFVIO_OK) return st;
+    if (!est.pre_integrations[frame]) return LFVIO_ERR_ARG;
+    *out = *est.pre_integrations[frame];
+    for (int k = 0; k < 3; k++) {
+        state_out[k] = est.Ps[frame][k];
+        state_out[3 + k] = est.Vs[frame][k];
+    }
+    for (int k = 0; k < 9; k++) state_out[6 + k] = est.Rs[frame][k];
+    return LFVIO_OK;
+}
+
+extern "C" int lfvio_host_triangulate(const double *Ps, const double *Rs, int n_frames, const double *tic, const double *ric,
+                                      const int *start_frame, const int *obs_first, const double *obs_pts, int n, double *depth) {
+    using namespace lfvio_host;
+    FeatureManager fm;
+    fm.window_size = n_frames - 1;
+    for (int l = 0; l < n; l++) {
+        FeaturePerId fp;
+        fp.feature_id = l;
+        fp.start_frame = start_frame[l];
+        fp.estimated_depth = depth[l];
+        for (int k = obs_first[l]; k < obs_first[l + 1]; k++) {
+            FeaturePerFrame o;
+            o.point = Vec3{obs_pts[3 * k], obs_pts[3 * k + 1], obs_pts[3 * k + 2]};
+            fp.feature_per_frame.push_back(o);
+        }
+        fm.feature.push_back(fp);
+    }
+    std::vector<Vec3> P(n_frames);
+    std::vector<Mat3> R(n_frames);
+    for (int f = 0; f < n_frames; f++) {
+        P[f] = Vec3{Ps[3 * f], Ps[3 * f + 1], Ps[3 * f + 2]};
+        for (int k = 0; k < 9; k++) R[f][k] = Rs[9 * f + k];
+    }
+    Vec3 t[1] = {Vec3{tic[0], tic[1], tic[2]}};
+    Mat3 r[1];
+    for (int k = 0; k < 9; k++) r[0][k] = ric[k];
+    const int st = fm.triangulate(P, R, t, r, 0);
+    if (st != LFVIO_OK) return st;
+    int l = 0;
+    for (const auto &it : fm.feature) depth[l++] = it.estimated_depth;
     return LFVIO_OK;
 }

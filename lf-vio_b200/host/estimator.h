@@ -43,6 +43,10 @@ class FeatureManager {
     int getFeatureCount();
     std::vector<double> getDepthVector();
     void setDepth(const std::vector<double> &x);
+    // feature_manager.cpp:199-253 — every untriangulated eligible track in ONE lfvio_triangulate call.
+    // Returns the C-ABI status (the reference returns void).
+    int triangulate(const std::vector<Vec3> &Ps, const std::vector<Mat3> &Rs, const Vec3 tic[], const Mat3 ric[], int device = 0);
+    double init_depth = 5.0;  // INIT_DEPTH (parameters.cpp:116)
 };
 
 // IntegrationBase members the IMU factor reads (factor/integration_base.h:188-206) == lfvio_imu_factor
@@ -64,6 +68,13 @@ class Estimator {
     Estimator(const Estimator &) = delete;
     Estimator &operator=(const Estimator &) = delete;
 
+    // estimator.cpp:86-120.  Samples are buffered per frame exactly like dt_buf / linear_acceleration_buf /
+    // angular_velocity_buf; the pre-integration record and the predicted Ps/Vs/Rs[frame_count] are brought up to date by
+    // flushIMU() (one lfvio_preintegrate call over the frame's whole interval), which optimization() calls itself.
+    void processIMU(double dt, const Vec3 &linear_acceleration, const Vec3 &angular_velocity);
+    int flushIMU();
+    // IntegrationBase::repropagate (integration_base.h:39-53) for frame j with new linearisation biases
+    int repropagate(int j, const Vec3 &ba, const Vec3 &bg);
     void optimization();    // estimator.cpp:676-1009
     void vector2double();   // :488-530
     void double2vector();   // :532-626
@@ -76,6 +87,12 @@ class Estimator {
     Mat3 ric[1];
     double td = 0;
     std::vector<IntegrationBase *> pre_integrations;  // [0 .. WINDOW_SIZE], entry j connects frames j-1 and j
+    int frame_count = 0;
+    bool first_imu = false;
+    Vec3 acc_0{}, gyr_0{};
+    std::vector<std::vector<double>> dt_buf;                                   // estimator.h:96-98
+    std::vector<std::vector<Vec3>> linear_acceleration_buf, angular_velocity_buf;
+    lfvio_imu_noise imu_noise{0.08, 0.004, 0.00004, 2.0e-6};                  // ACC_N GYR_N ACC_W GYR_W
     FeatureManager f_manager;
     MarginalizationFlag marginalization_flag = MARGIN_OLD;
     MarginalizationInfo last_marginalization_info;  // replaces MarginalizationInfo* + last_marginalization_parameter_blocks
@@ -96,6 +113,15 @@ class Estimator {
     std::vector<lfvio_proj_factor> m_proj;
     std::vector<lfvio_imu_factor> m_imu;
     void buildFactors();
+    // per-frame interval bookkeeping of processIMU / flushIMU
+    struct Interval {
+        bool open = false, dirty = false;
+        Vec3 acc_start{}, gyr_start{}, ba{}, bg{}, P{}, V{};
+        Mat3 R{};
+    };
+    std::vector<Interval> m_iv;
+    std::vector<lfvio_imu_factor> m_pre;  // storage behind pre_integrations[] filled by flushIMU
+    int integrate(int j, bool propagate);
 };
 
 // Utility::R2ypr / ypr2R (utility/utility.h:66-104), degrees

@@ -123,3 +123,44 @@ def test_fused_optimize_full_equals_host_class_path(lfvio_mod, gpu, host):
     assert np.abs(Ad - Ah).max() < 1e-6 * np.abs(Ah).max()
     assert np.abs(bd - bh).max() < 1e-5 * max(np.abs(bh).max(), 1.0)
     win.close()
+
+
+def test_estimator_process_imu_and_triangulate_mirrors(lfvio_mod, gpu, host):
+    """Estimator::processIMU (+ flushIMU) and FeatureManager::triangulate of the C++ host mirror give what the C-ABI
+    entry points give (which tests/test_prestep_gpu.py holds against the oracle)."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from lfvio import prestep as PS
+    from prestep_data import G, NOISE, imu_stream, tracks
+
+    s = imu_stream(7, n_intervals=3)
+    tr, t = s["traj"], s["times"]
+    i = 1
+    first, count, a0, g0 = s["intervals"][i]
+    P, V, R = tr.pos(t[i]), tr.vel(t[i]), tr.rot(t[i])
+    iv = PS.make_interval(first, count, i, a0, g0, s["ba"], s["bg"], P, V, R)
+    want, wstate = lfvio_mod.preintegrate([iv], s["dt"], s["acc"], s["gyr"], NOISE, G, device=gpu)
+    out = B.ImuFactor()
+    state = np.zeros(15)
+    dp = lambda a: np.ascontiguousarray(a, np.float64).ctypes.data_as(C.c_void_p)
+    host.lfvio_host_process_imu.argtypes = [C.c_int] + [C.c_void_p] * 12 + [C.c_int, C.c_void_p, C.c_void_p]
+    sl = slice(first, first + count)
+    keep = [np.ascontiguousarray(x, np.float64) for x in (P, V, R, s["ba"], s["bg"], G, NOISE, a0, g0, s["dt"][sl], s["acc"][sl], s["gyr"][sl])]
+    rc = host.lfvio_host_process_imu(i + 1, *[k.ctypes.data_as(C.c_void_p) for k in keep], count, C.byref(out), state.ctypes.data_as(C.c_void_p))
+    assert rc == 0, lfvio_mod.lib.lfvio_last_error()
+    assert out.frame_i == i and out.sum_dt == want[0].sum_dt
+    assert np.array_equal(np.array(out.jacobian), np.array(want[0].jacobian))
+    assert np.array_equal(np.array(out.covariance), np.array(want[0].covariance))
+    assert np.array_equal(np.array(out.delta_p), np.array(want[0].delta_p)) and np.array_equal(state, wstate[0])
+
+    d = tracks(4, n_feat=120)
+    depth0 = -np.ones(120)
+    want_d = lfvio_mod.triangulate(d["Ps"], d["Rs"], d["tic"], d["ric"], d["start_frame"], d["obs_first"], d["obs_pts"], depth0, 5.0, device=gpu)
+    got_d = depth0.copy()
+    host.lfvio_host_triangulate.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    arrs = [np.ascontiguousarray(d["Ps"], np.float64), np.ascontiguousarray(d["Rs"], np.float64), np.ascontiguousarray(d["tic"], np.float64),
+            np.ascontiguousarray(d["ric"], np.float64), d["start_frame"], d["obs_first"], np.ascontiguousarray(d["obs_pts"], np.float64)]
+    rc = host.lfvio_host_triangulate(arrs[0].ctypes.data, arrs[1].ctypes.data, len(d["Ps"]), arrs[2].ctypes.data, arrs[3].ctypes.data,
+                                     arrs[4].ctypes.data, arrs[5].ctypes.data, arrs[6].ctypes.data, 120, got_d.ctypes.data)
+    assert rc == 0 and np.array_equal(got_d, want_d) and (got_d > 0).sum() > 40
