@@ -39,6 +39,9 @@ CONFIGS = {
     "synthetic_1920x1440_500feat_10kf": (1.5, 500, 10, 900, 30.0),
     "synthetic_3840x2880_2000feat_20kf": (3.0, 2000, 20, 3600, 60.0),
 }
+ATE_SCENARIO = ("closed-loop sliding window (processIMU -> triangulate -> optimization -> MARGIN_OLD -> slideWindow) on a synthetic "
+                "hand-held trajectory: 150 bearings/frame at 0.3 px (f = 160), 10 Hz keyframes, 200 Hz IMU with the PAL noise values, "
+                "estimate_td = 1, bootstrap from perturbed ground truth; PALVIO itself is not available offline")
 PUB_PATTERN = (1, 1, 0)  # 15 Hz camera published at 10 Hz (feature_tracker_node.cpp:50-62)
 
 
@@ -185,6 +188,18 @@ def cpu_arm(wl, steps: int, warmup: int, rank: int, with_marg: bool):
                 prior_n=int(w.prior.n) if w.prior is not None else 0)
 
 
+def closed_loop_ate(ops, opts, n_frames=50, seed=1):
+    """Second half of BASELINE.json's metric ("ATE vs CPU ref"): a closed-loop sliding-window run (lfvio.violoop) over a
+    synthetic 150-feature / 200 Hz IMU stream with the arm's own numeric steps; ATE = RMSE after SE(3) alignment."""
+    from lfvio import violoop
+
+    world = violoop.World(seed=seed, n_frames=n_frames)
+    loop = violoop.VioLoop(world, ops, opts).run()
+    ate, ks = violoop.trajectory_error(loop)
+    path = float(sum(np.linalg.norm(world.truth(k + 1)[0] - world.truth(k)[0]) for k in ks[:-1]))
+    return loop, {"ate_rmse_m": ate, "frames": len(ks), "path_m": path}
+
+
 # ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -211,8 +226,14 @@ def main():
         wl = build_workload(args.config, 0, 32)
         steps = min(args.steps, 200)
         r = cpu_arm(wl, steps, min(args.warmup, 5), 0, with_marg)
+        from oracle import backend as ob_
+        from oracle import loop_ops
+
+        o_ = ob_.default_opts()
+        o_.row = 960
+        _, ate_cpu = closed_loop_ate(loop_ops.oracle_ops(), o_)
         line = {
-            "impl": "reference", "metric": METRIC, "value": r["fps"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "impl": "reference", "ate": {"cpu_ref": ate_cpu, "scenario": ATE_SCENARIO}, "metric": METRIC, "value": r["fps"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 5), "ms_per_step": 1e3 / r["fps"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8/f32 front end, f64 back end", "data": "synthetic",
             "config": {"workload": args.config, "scale": scale, "n_proj_factors": r["n_proj"], "n_landmarks": r["n_landmarks"], "prior_n": r["prior_n"],
@@ -443,6 +464,24 @@ def main():
                          "oracle back end (1 thread solve, 4 thread marginalisation)",
                "ms_front": r["ms_front"], "ms_back": r["ms_back"]}
 
+    # ---- ATE of the closed loop, device arm next to the CPU reference arm (rank 0, N = 1 only) ------------------
+    ate = None
+    if rank == 0 and world == 1:
+        from lfvio import violoop
+        from oracle import backend as ob_
+        from oracle import loop_ops
+
+        d_opts = lfvio.solver_default_opts()
+        d_opts.row = 960
+        o_opts = ob_.default_opts()
+        o_opts.row = 960
+        win2 = lfvio.Window(10, 1000, 16384, device=local_rank)
+        dev_loop, ate_dev = closed_loop_ate(violoop.device_ops(lfvio, win2, local_rank), d_opts)
+        cpu_loop, ate_cpu = closed_loop_ate(loop_ops.oracle_ops(), o_opts)
+        win2.close()
+        diff = max(float(np.abs(dev_loop.estimates[k][0] - cpu_loop.estimates[k][0]).max()) for k in cpu_loop.estimates)
+        ate = {"device": ate_dev, "cpu_ref": ate_cpu, "max_position_difference_m": diff, "scenario": ATE_SCENARIO}
+
     if rank == 0:
         fps = frames_total / (ms_total * 1e-3)
         line = {
@@ -463,6 +502,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "ate": ate,
             "clocks": clk,
         }
         print(json.dumps(line))
