@@ -235,46 +235,186 @@ __device__ void std_sort_desc(long long *a, int n) {
     }
 }
 
+// ---- the same std::sort, level-parallel ------------------------------------------------------------------
+// libstdc++'s result for equal keys depends on every swap it makes, so the algorithm itself is replayed — but its
+// independent pieces run in parallel:
+//   * __introsort_loop: all sub-ranges of one recursion level are partitioned concurrently, one warp per range.
+//     __unguarded_partition is a pure function of the range's ORIGINAL contents: with l_1 < l_2 < ... the positions
+//     (from the left) whose key is <= the pivot's and r_1 > r_2 > ... the positions (from the right) whose key is >= it,
+//     it swaps (l_k, r_k) for k = 1 .. K, K = #{k : l_k < r_k}, and returns cut = min(l_{K+1}, r_K) — ballots and
+//     prefix counts instead of two dependent pointer walks.
+//   * depth exhausted -> heap sort of that range by one lane (as rare as in the reference);
+//   * __final_insertion_sort is a STABLE sort of whatever the loop left, i.e. rank(i) = #{key_j > key_i} + #{j < i :
+//     key_j == key_i}: one pass of comparisons per element, all threads.
+struct SortShared {
+    long long *a;   // cap records (key << 32 | source index)
+    long long *tmp; // cap records (stable-sort scatter target)
+    int *lpos;      // cap: L-stopper positions of each range, stored at the range's own offset
+    int *rpos;      // cap: R-stopper positions (left to right)
+    int *rf, *rl, *rd;  // two range lists of max_ranges each: first / last / depth
+};
+
+__device__ void parallel_std_sort_desc(const SortShared &S, int n, int max_ranges, int *s_cnt /* 2 ints */) {
+    DescByKey comp;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
+    if (n <= 1) return;
+    long long *a = S.a;
+    if (n > 16) {
+        if (tid == 0) {
+            S.rf[0] = 0;
+            S.rl[0] = n;
+            S.rd[0] = 2 * (31 - __clz(n));
+            s_cnt[0] = 1;
+            s_cnt[1] = 0;
+        }
+        __syncthreads();
+        for (int level = 0;; level++) {
+            const int cur = level & 1, nxt = cur ^ 1;
+            const int n_cur = s_cnt[cur];
+            if (n_cur == 0) break;
+            const int *cf = S.rf + cur * max_ranges, *cl = S.rl + cur * max_ranges, *cd = S.rd + cur * max_ranges;
+            int *nf = S.rf + nxt * max_ranges, *nl = S.rl + nxt * max_ranges, *nd = S.rd + nxt * max_ranges;
+            for (int ri = wid; ri < n_cur; ri += nwarp) {
+                const int first = cf[ri], last = cl[ri];
+                int depth = cd[ri];
+                if (depth == 0) {
+                    if (lane == 0) heap_sort(a + first, last - first, comp);
+                    continue;
+                }
+                --depth;
+                if (lane == 0) {  // __move_median_to_first(first, first + 1, mid, last - 1)
+                    const int mid = first + (last - first) / 2;
+                    const int ia = first + 1, ib = mid, ic = last - 1;
+                    int m;
+                    if (comp(a[ia], a[ib])) {
+                        if (comp(a[ib], a[ic])) m = ib;
+                        else if (comp(a[ia], a[ic])) m = ic;
+                        else m = ia;
+                    } else if (comp(a[ia], a[ic])) m = ia;
+                    else if (comp(a[ib], a[ic])) m = ic;
+                    else m = ib;
+                    const long long t = a[first];
+                    a[first] = a[m];
+                    a[m] = t;
+                }
+                __syncwarp();
+                const int pk = (int)(a[first] >> 32);
+                int nL = 0, nR = 0;
+                for (int p0 = first + 1; p0 < last; p0 += 32) {
+                    const int p = p0 + lane;
+                    const int key = p < last ? (int)(a[p] >> 32) : 0;
+                    const bool isL = p < last && key <= pk, isR = p < last && key >= pk;
+                    const unsigned bl = __ballot_sync(0xffffffffu, isL), br = __ballot_sync(0xffffffffu, isR);
+                    const unsigned below = (1u << lane) - 1u;
+                    if (isL) S.lpos[first + nL + __popc(bl & below)] = p;
+                    if (isR) S.rpos[first + nR + __popc(br & below)] = p;
+                    nL += __popc(bl);
+                    nR += __popc(br);
+                }
+                __syncwarp();
+                // k-th (1-based) stopper from the left: lpos[first + k - 1]; from the right: rpos[first + nR - k]
+                int K = 0;
+                for (int k = 1 + lane; k <= min(nL, nR); k += 32)
+                    if (S.lpos[first + k - 1] < S.rpos[first + nR - k]) K++;
+                K = warp_sum(K);
+                for (int k = 1 + lane; k <= K; k += 32) {
+                    const int l = S.lpos[first + k - 1], r = S.rpos[first + nR - k];
+                    const long long t = a[l];
+                    a[l] = a[r];
+                    a[r] = t;
+                }
+                const int c1 = K < nL ? S.lpos[first + K] : 0x7fffffff, c2 = K >= 1 ? S.rpos[first + nR - K] : 0x7fffffff;
+                const int cut = min(c1, c2);
+                if (lane == 0) {
+                    if (last - cut > 16) {
+                        const int q = atomicAdd(&s_cnt[nxt], 1);
+                        nf[q] = cut;
+                        nl[q] = last;
+                        nd[q] = depth;
+                    }
+                    if (cut - first > 16) {
+                        const int q = atomicAdd(&s_cnt[nxt], 1);
+                        nf[q] = first;
+                        nl[q] = cut;
+                        nd[q] = depth;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_cnt[cur] = 0;
+            __syncthreads();
+        }
+    }
+    // __final_insertion_sort == stable sort of the current order
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const int ki = (int)(a[i] >> 32);
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            const int kj = (int)(a[j] >> 32);
+            rank += (kj > ki) || (kj == ki && j < i);
+        }
+        S.tmp[rank] = a[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) a[i] = S.tmp[i];
+    __syncthreads();
+}
+
+// setMask (feature_tracker.cpp:46-83): sort by track_cnt (std::sort order), then the greedy keep loop.  One CTA; the
+// sort records, pixel coordinates and kept list live in shared memory; the keep loop is run by ONE warp (ballots, no
+// block barriers) over coordinates and mask bits gathered in parallel beforehand.
 __global__ void __launch_bounds__(BT) set_mask_select_kernel(TrackArrays in, TrackArrays out, int *n_dev, int cap,
                                                              const uint8_t *__restrict__ base_mask, int mask_pitch,
-                                                             const int *__restrict__ half_width, int min_dist,
-                                                             long long *sort_buf, int *kept_xy) {
+                                                             const int *__restrict__ half_width, int min_dist, int max_ranges) {
+    extern __shared__ long long smem_ll[];
+    __shared__ int s_cnt[2];
     __shared__ int s_nkept;
-    __shared__ int s_flag;
+    SortShared S;
+    S.a = smem_ll;
+    S.tmp = S.a + cap;
+    S.lpos = reinterpret_cast<int *>(S.tmp + cap);
+    S.rpos = S.lpos + cap;
+    S.rf = S.rpos + cap;
+    S.rl = S.rf + 2 * max_ranges;
+    S.rd = S.rl + 2 * max_ranges;
+    int *s_px = S.rd + 2 * max_ranges, *s_py = s_px + cap, *s_ok = s_py + cap, *kept = s_ok + cap;  // kept: indices into the sorted order
     const int n = min(*n_dev, cap);
-    for (int i = threadIdx.x; i < n; i += BT) sort_buf[i] = ((long long)in.cnt[i] << 32) | (unsigned)i;
+    for (int i = threadIdx.x; i < n; i += BT) S.a[i] = ((long long)in.cnt[i] << 32) | (unsigned)i;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        std_sort_desc(sort_buf, n);
-        s_nkept = 0;
-    }
-    __syncthreads();
-    // sequential keep loop; kept_xy holds rounded pixel coords of kept tracks (x, y interleaved)
-    for (int k = 0; k < n; k++) {
-        const int src = (int)(sort_buf[k] & 0xffffffffu);
+    parallel_std_sort_desc(S, n, max_ranges, s_cnt);
+    for (int k = threadIdx.x; k < n; k += BT) {
+        const int src = (int)(S.a[k] & 0xffffffffu);
         const float2 pt = in.forw[src];
         const int px = cv_round(pt.x), py = cv_round(pt.y);  // Mat::at<uchar>(Point2f -> Point)
-        const int nk = s_nkept;
-        if (threadIdx.x == 0) s_flag = (base_mask[(size_t)py * mask_pitch + px] == 255) ? 0 : 1;
-        __syncthreads();
-        int hit = 0;
-        for (int j = threadIdx.x; j < nk; j += BT) {
-            const int dx = abs(px - kept_xy[2 * j]), dy = abs(py - kept_xy[2 * j + 1]);
-            if (dy <= min_dist && dx <= half_width[dy]) hit = 1;
-        }
-        const int any = __syncthreads_or(hit | s_flag);
-        if (!any) {
-            if (threadIdx.x == 0) {
-                kept_xy[2 * nk] = px;
-                kept_xy[2 * nk + 1] = py;
-                sort_buf[nk] = (sort_buf[nk] & ~0xffffffffLL) | (unsigned)src;  // kept order -> source index (nk <= k)
-                s_nkept = nk + 1;
+        s_px[k] = px;
+        s_py[k] = py;
+        s_ok[k] = base_mask[(size_t)py * mask_pitch + px] == 255;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int nk = 0;
+        for (int k = 0; k < n; k++) {
+            if (!s_ok[k]) continue;  // (uniform)
+            const int px = s_px[k], py = s_py[k];
+            int hit = 0;
+            for (int j = lane; j < nk; j += 32) {
+                const int q = kept[j];
+                const int dx = abs(px - s_px[q]), dy = abs(py - s_py[q]);
+                if (dy <= min_dist && dx <= half_width[dy]) hit = 1;
+            }
+            if (!__any_sync(0xffffffffu, hit)) {
+                if (lane == 0) kept[nk] = k;
+                nk++;
+                __syncwarp();
             }
         }
-        __syncthreads();
+        if (lane == 0) s_nkept = nk;
     }
+    __syncthreads();
     const int nkept = s_nkept;
-    for (int o = threadIdx.x; o < nkept; o += BT) copy_track(in, (int)(sort_buf[o] & 0xffffffffu), out, o, 0);
+    for (int o = threadIdx.x; o < nkept; o += BT) copy_track(in, (int)(S.a[kept[o]] & 0xffffffffu), out, o, 0);
     __syncthreads();
     if (threadIdx.x == 0) *n_dev = nkept;
 }
@@ -373,11 +513,16 @@ int launch_compact(const TrackArrays &in, const TrackArrays &out, const uint8_t 
 int launch_set_mask_select(const TrackArrays &in, const TrackArrays &out, int *n_dev, int cap,
                            const uint8_t *base_mask, int mask_pitch, const int *half_width, int min_dist,
                            int *sort_scratch, cudaStream_t s) {
-    // sort_scratch: 2*cap ints viewed as cap int64 sort records, followed by 2*cap ints of kept (x, y)
-    long long *sort_buf = reinterpret_cast<long long *>(sort_scratch);
-    int *kept_xy = sort_scratch + 2 * cap;
-    set_mask_select_kernel<<<1, BT, 0, s>>>(in, out, n_dev, cap, base_mask, mask_pitch, half_width, min_dist,
-                                            sort_buf, kept_xy);
+    (void)sort_scratch;  // (the sort records live in shared memory now)
+    const int max_ranges = cap / 8 + 8;
+    const size_t smem = sizeof(long long) * 2 * (size_t)cap + sizeof(int) * (2 * (size_t)cap + 6 * (size_t)max_ranges + 4 * (size_t)cap);
+    LFVIO_REQUIRE(smem <= 200 * 1024, "setMask: too many tracks for the shared-memory sort (max_cnt <= ~5000)");
+    static bool attr_set = false;
+    if (!attr_set) {
+        LFVIO_CUDA_TRY(cudaFuncSetAttribute(set_mask_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    set_mask_select_kernel<<<1, BT, smem, s>>>(in, out, n_dev, cap, base_mask, mask_pitch, half_width, min_dist, max_ranges);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }
