@@ -277,7 +277,9 @@ int launch_evaluate(const DevProblem &P, const double *x0, const double *x1, con
                     SolverCtl *ctl, int mode, int robust, cudaStream_t s);
 int launch_jacobi_scale(const DevProblem &P, const EvalBuf &e0, const SolverScratch &w, cudaStream_t s);
 int launch_accumulate(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const SolverScratch &w, SolverCtl *ctl,
-                      cudaStream_t s);
+                      cudaStream_t s, bool clear_done = false);
+// true when launch_step's chol_kernel clears [S | rhs | diag2 | grad] itself while consuming them (fused step, S in smem)
+bool step_zeroes_system(const DevProblem &P);
 // One trust-region step up to (not including) the candidate evaluation: pre -> chol -> gnlm -> cand.
 #ifdef LFVIO_CHOL_PROFILE
 void chol_profile_read(long long *out);

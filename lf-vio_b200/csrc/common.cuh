@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 
 #include "../../include/lfvio.h"
 
@@ -47,6 +48,31 @@ void count_launch(int n = 1);
     } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+#ifdef __CUDACC__
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may be scheduled while its predecessor in
+// the stream is still running; pdl_prologue() at the top of BOTH kernels (a) lets the successor's CTAs become resident
+// right away and (b) blocks until the predecessor has completed and its writes are visible.  For chains of short,
+// strictly dependent kernels (the trust-region loop) this removes the launch/scheduling gap between them.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // B200: 148 SMs.  Queried once per device and cached.
 int sm_count(int device);

@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(DevProblem P, cons
     __shared__ double s_red[EV_THREADS / 32];
     __shared__ int s_last;
     const int tid = threadIdx.x;
+    pdl_prologue();
     bool active = true;
     int target = 0;
     if (mode == 0) {
@@ -523,7 +524,7 @@ int launch_evaluate(const DevProblem &P, const double *x0, const double *x1, con
     const int nbp = cdiv(P.n_proj, EV_THREADS);
     const int grid = nbp + P.n_imu + (P.prior.n > 0 ? 1 : 0);
     if (grid == 0) return LFVIO_OK;
-    evaluate_kernel<<<grid, EV_THREADS, 0, s>>>(P, x0, x1, e0, e1, ctl, mode, robust, nbp);
+    LFVIO_CUDA_TRY(launch_pdl(evaluate_kernel, dim3(grid), dim3(EV_THREADS), 0, s, P, x0, x1, e0, e1, ctl, mode, robust, nbp));
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

@@ -69,6 +69,7 @@ __device__ __forceinline__ void add_upper(double *S, int D, int ga, int gb, doub
 
 __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P, EvalBuf e0, EvalBuf e1, SolverScratch w,
                                                                    const SolverCtl *ctl, int n_lm_cta, int max_obs) {
+    pdl_prologue();
     if (ctl->done != 0 || ctl->reuse != 0) return;
     extern __shared__ double smem[];
     const EvalBuf &e = ctl->cur ? e1 : e0;
@@ -310,8 +311,10 @@ int launch_jacobi_scale(const DevProblem &P, const EvalBuf &e0, const SolverScra
 static int acc_per_warp_doubles(int max_obs) { return max_obs * 40 + max_obs * 2 + max_obs * 6 + 16 + max_obs; }
 
 int launch_accumulate(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const SolverScratch &w, SolverCtl *ctl,
-                      cudaStream_t s) {
-    LFVIO_CUDA_TRY(cudaMemsetAsync(w.S, 0, w.zero_bytes, s));
+                      cudaStream_t s, bool clear_done) {
+    // [S | rhs | diag2 | grad] must be zero on entry.  When the whole step runs in chol_kernel with S in shared memory
+    // (step_zeroes_system), that kernel clears them as it consumes them; otherwise clear them here.
+    if (!clear_done) LFVIO_CUDA_TRY(cudaMemsetAsync(w.S, 0, w.zero_bytes, s));
     int max_obs = std::max(P.lay.F - 1, 10);  // 49 * 10 + 16 = 506 doubles >= 465 needed by an IMU warp
     const int items = P.lay.L + P.n_imu;
     const int n_lm_cta = items;
@@ -322,7 +325,8 @@ int launch_accumulate(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1,
         LFVIO_CUDA_TRY(cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    accumulate_kernel<<<n_lm_cta + PRIOR_CTAS, ACC_WARPS * 32, smem, s>>>(P, e0, e1, w, ctl, n_lm_cta, max_obs);
+    LFVIO_CUDA_TRY(launch_pdl(accumulate_kernel, dim3(n_lm_cta + PRIOR_CTAS), dim3(ACC_WARPS * 32), smem, s, P, e0, e1, w,
+                              (const SolverCtl *)ctl, n_lm_cta, max_obs));
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

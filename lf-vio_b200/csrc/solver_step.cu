@@ -123,6 +123,7 @@ __device__ double rows_partial(const DevProblem &P, const EvalBuf &e, const doub
 
 // =====================================================================================================
 __global__ void __launch_bounds__(PRE_THREADS) pre_kernel(DevProblem P, EvalBuf e0, EvalBuf e1, SolverScratch w, SolverCtl *ctl) {
+    pdl_prologue();
     if (ctl->done != 0 || ctl->reuse != 0) return;
     __shared__ double s_red[33];
     __shared__ int pmap[15 * kMaxFrames + 8];
@@ -322,6 +323,7 @@ __device__ __forceinline__ void landmark_backsub(const DevProblem &P, const Solv
 // gnlm_kernel finishes (back-substitution over many CTAs, cand_tail in its last CTA).
 __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(DevProblem P, SolverScratch w, double *x0, double *x1,
                                                            SolverCtl *ctl, int use_smem, int fused) {
+    pdl_prologue();
     if (ctl->done != 0) return;
     extern __shared__ double smem[];
     __shared__ double s_red[33];
@@ -358,7 +360,13 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(DevProblem P, Solver
             w.gradient[c] = gs;
             gga += gs * gs;
             gm = fmax(gm, fabs(g / w.scale[c]));  // un-scaled gradient J^T r
-            if (c < D) s_a[c] = g / d2;
+            if (c < D) {
+                s_a[c] = g / d2;
+                if (use_smem) {  // consumed: clear for the next accumulation (see launch_accumulate)
+                    w.diag2[c] = 0.0;
+                    w.grad[c] = 0.0;
+                }
+            }
         }
         gg = block_sum(gga, s_red);
         gmax = block_max(gm, s_red);
@@ -389,7 +397,11 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(DevProblem P, Solver
     bool pd;
     PHASE_MARK(1);
     for (int q = tid; q < NB * PW; q += nt) s_panel[q] = 0.0;
-    for (int c = tid; c < D; c += nt) s_y[c] = w.rhs[c];
+    const bool clear_sys = fused && use_smem;
+    for (int c = tid; c < D; c += nt) {
+        s_y[c] = w.rhs[c];
+        if (clear_sys) w.rhs[c] = 0.0;
+    }
     // copy (or regularise in place) and, when fused, a_p^T S a_p on the way: one warp per row, coalesced upper triangle
     const MatPacked Sp{s_S, D};
     for (int r = wid; r < D; r += nwarp) {
@@ -406,6 +418,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(DevProblem P, Solver
                 if (c >= D) continue;
                 if (fused) jj_part += ar * v[u] * s_a[c] * (c == r ? 1.0 : 2.0);
                 if (use_smem) dst[c] = v[u] + (r == c ? w.diagonal[c] * w.diagonal[c] * mu : 0.0);
+                if (clear_sys) src[c] = 0.0;
                 else if (r == c) dst[c] = v[u] + w.diagonal[c] * w.diagonal[c] * mu;
             }
         }
@@ -465,6 +478,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(DevProblem P, Solver
 // =====================================================================================================
 // Large windows only (L > kFuseMaxL): landmark back-substitution over many CTAs; the last CTA to finish runs cand_tail.
 __global__ void __launch_bounds__(GNLM_WARPS * 32) gnlm_kernel(DevProblem P, SolverScratch w, double *x0, double *x1, SolverCtl *ctl) {
+    pdl_prologue();
     if (ctl->done != 0) return;
     __shared__ double s_red[33];
     __shared__ int s_last;
@@ -504,13 +518,20 @@ __global__ void __launch_bounds__(GNLM_WARPS * 32) gnlm_kernel(DevProblem P, Sol
 void chol_profile_read(long long *out) { cudaMemcpyFromSymbol(out, g_sub, sizeof(long long) * 16); }
 #endif
 
+static size_t chol_base_bytes(int D) {
+    return sizeof(double) * ((size_t)NB * chol_panel_pitch(D) + 2 * (size_t)((D + 1) & ~1) + (size_t)cdiv(D, NB) * NB);
+}
+static bool chol_in_smem(int D) { return chol_base_bytes(D) + sizeof(double) * ((size_t)D * (D + 1) / 2) <= 220 * 1024; }
+
+bool step_zeroes_system(const DevProblem &P) { return P.lay.L <= kFuseMaxL && chol_in_smem(P.lay.D()); }
+
 int launch_step(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const SolverScratch &w, double *x0, double *x1,
                 SolverCtl *ctl, cudaStream_t s) {
     const int D = P.lay.D(), L = P.lay.L;
     const int fused = (L <= kFuseMaxL) ? 1 : 0;
     if (!fused) {
         const int work = std::max(std::max(D + L, P.n_proj), 1);
-        pre_kernel<<<std::max(1, std::min(cdiv(work, PRE_THREADS), 148)), PRE_THREADS, 0, s>>>(P, e0, e1, w, ctl);
+        LFVIO_CUDA_TRY(launch_pdl(pre_kernel, dim3(std::max(1, std::min(cdiv(work, PRE_THREADS), 148))), dim3(PRE_THREADS), 0, s, P, e0, e1, w, ctl));
         LFVIO_LAUNCH_CHECK();
     }
     LFVIO_REQUIRE(D + 1 <= CHOL_THREADS - 32, "window too large for the single-pass panel solve (15 F + 8 <= 480)");
@@ -524,10 +545,10 @@ int launch_step(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const
         LFVIO_CUDA_TRY(cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
         attr_set = true;
     }
-    chol_kernel<<<1, CHOL_THREADS, base + (use_smem ? packed : 0), s>>>(P, w, x0, x1, ctl, use_smem, fused);
+    LFVIO_CUDA_TRY(launch_pdl(chol_kernel, dim3(1), dim3(CHOL_THREADS), base + (use_smem ? packed : 0), s, P, w, x0, x1, ctl, use_smem, fused));
     LFVIO_LAUNCH_CHECK();
     if (!fused) {
-        gnlm_kernel<<<std::max(1, std::min(cdiv(L, GNLM_WARPS * 32), 148)), GNLM_WARPS * 32, 0, s>>>(P, w, x0, x1, ctl);
+        LFVIO_CUDA_TRY(launch_pdl(gnlm_kernel, dim3(std::max(1, std::min(cdiv(L, GNLM_WARPS * 32), 148))), dim3(GNLM_WARPS * 32), 0, s, P, w, x0, x1, ctl));
         LFVIO_LAUNCH_CHECK();
     }
     return LFVIO_OK;

@@ -375,9 +375,11 @@ int enqueue_solve(lfvio_window *w) {
     w->prof.begin(WS_JACOBI_SCALE, s);
     LFVIO_TRY(launch_jacobi_scale(P, w->e[0], w->w, s));
     w->prof.end(s);
+    const bool self_clearing = step_zeroes_system(P);
+    if (self_clearing) LFVIO_CUDA_TRY(cudaMemsetAsync(w->w.S, 0, w->w.zero_bytes, s));  // once; chol_kernel keeps it clear
     for (int it = 0; it < P.o.max_num_iterations; it++) {
         w->prof.begin(WS_ACCUMULATE, s);
-        LFVIO_TRY(launch_accumulate(P, w->e[0], w->e[1], w->w, w->ctl.p, s));
+        LFVIO_TRY(launch_accumulate(P, w->e[0], w->e[1], w->w, w->ctl.p, s, self_clearing));
         w->prof.end(s);
         w->prof.begin(WS_STEP, s);
         LFVIO_TRY(launch_step(P, w->e[0], w->e[1], w->w, w->x[0].p, w->x[1].p, w->ctl.p, s));
