@@ -443,9 +443,17 @@ def main():
     dom_name, (dom_ms_step, dom_ms_launch, dom_per_step) = dom[0], dom[1]
     ab = algo_bytes.get(dom_name)
     achieved = (ab / (dom_ms_launch * 1e-3) / 1e9) if ab else None
+    # dram__bytes_read + dram__bytes_write per launch of the dominant kernel from the committed `ncu --set full` capture
+    # of this command at the default workload (profiles/r1_traffic.json); null for other workloads / kernels
+    traffic = None
+    try:
+        if args.config == "palvio_id01_1280x960_150feat_10kf":
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["dram_bytes_per_launch"].get(dom_name)
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-        "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": None, "peak_kind": peak_kind,
+        "frac": (achieved / peaks["hbm_gbs"]) if achieved else None, "traffic": traffic, "peak_kind": peak_kind,
         "algorithmic_bytes_per_launch": ab, "avg_launch_ms": dom_ms_launch,
         "stage_ms_per_step": {k: round(v[0], 5) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])},
         "note": "configs 1-3 are launch/latency bound (a whole 1280x960 frame is ~3 us of HBM time, SURVEY.md §7)",
