@@ -258,6 +258,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; stdout carries the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     peaks, peak_kind = measured_peaks()
 
