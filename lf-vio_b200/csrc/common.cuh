@@ -69,7 +69,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (s == nullptr) ? 0 : 1;  // stage-level entry points run on the default stream: plain launch there
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 #endif
