@@ -362,12 +362,17 @@ def main():
     # with two host threads, each making the blocking C-ABI calls of its node (ctypes releases the GIL in the calls).
     import threading
 
+    node_s = {"tracker": 0.0, "estimator": 0.0}
+
     def tracker_node(k0, n):
+        t_node = time.perf_counter()
         for k in range(k0, k0 + n):
             tracker.read_image(src_frames[k % pool], (args.warmup + args.steps + k) / hz, bool(PUB_PATTERN[k % len(PUB_PATTERN)]))
             tracker.update_ids()
+        node_s["tracker"] = time.perf_counter() - t_node
 
     def estimator_node(k0, n):
+        t_node = time.perf_counter()
         for k in range(k0, k0 + n):
             for dst, s in zip((work.pose, work.sb, work.ex, work.feat, work.td), init):
                 np.copyto(dst, s)
@@ -375,6 +380,7 @@ def main():
                 window.optimize_full(work, B.MARGIN_OLD, prior_out)
             else:
                 window.optimize(work)
+        node_s["estimator"] = time.perf_counter() - t_node
 
     def run_nodes(k0, n):
         th = [threading.Thread(target=tracker_node, args=(k0, n)), threading.Thread(target=estimator_node, args=(k0, n))]
@@ -389,6 +395,7 @@ def main():
     run_nodes(0, 3)
     barrier()
     e2e_s = run_nodes(3, e2e_steps)
+    e2e_node_ms = {k: 1e3 * v / e2e_steps for k, v in node_s.items()}
     # the same calls made back to back by ONE thread (latency of a frame through both halves)
     t0 = time.perf_counter()
     n_seq = max(5, e2e_steps // 4)
@@ -507,7 +514,7 @@ def main():
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
             "host_enqueue_ms_per_step": {"tracker_thread": 1e3 * enq[0] / args.steps, "window_thread": 1e3 * enq[1] / args.steps},
             "e2e": {"value": e2e_frames / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "host_threads": 2, "single_thread_ms_per_frame": e2e_seq_ms,
+                    "steps": e2e_steps, "host_threads": 2, "single_thread_ms_per_frame": e2e_seq_ms, "node_ms_per_frame": e2e_node_ms,
                     "note": "two host threads = the reference's two ROS nodes; each makes blocking C-ABI calls with host buffers"},
             "gpu_launches": int(launches),
             "roofline": roofline,

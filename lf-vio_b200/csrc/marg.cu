@@ -32,6 +32,7 @@ namespace lfvio {
 namespace {
 
 constexpr int MA_WARPS = 4;
+constexpr int MARG_PRIOR_CTAS = 8;  // CTAs that share the previous prior's n x n block
 constexpr int MF_THREADS = 512;
 constexpr double kEps = 1e-8;  // MarginalizationInfo::eps (marginalization_factor.h:70)
 
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(MA_WARPS * 32) marg_accumulate_kernel(DevProbl
         }
         return;
     }
-    // ===== previous prior: T += P (J0^T J0) P^T, b += P J0^T r(x) =====
+    // ===== previous prior: T += P (J0^T J0) P^T, b += P J0^T r(x), shared by MARG_PRIOR_CTAS CTAs =====
     if (!plan.use_prior) return;
     const DevPrior &p = P.prior;
     int *pmap = reinterpret_cast<int *>(smem);
@@ -181,14 +182,15 @@ __global__ void __launch_bounds__(MA_WARPS * 32) marg_accumulate_kernel(DevProbl
     }
     __syncthreads();
     const int n = p.n;
-    for (int q = threadIdx.x; q < n * n; q += blockDim.x) {
+    const int pj = blockIdx.x - n_item_cta, ptid = pj * blockDim.x + threadIdx.x, pnt = MARG_PRIOR_CTAS * blockDim.x;
+    for (int q = ptid; q < n * n; q += pnt) {
         const int a = q / n, b = q % n;
         const double v = p.H0[q];
         if (v != 0.0) atomicAdd(&T[(size_t)pmap[a] * ld + pmap[b]], v);
     }
-    for (int a = threadIdx.x; a < n; a += blockDim.x) {
+    for (int a = threadIdx.x; a < n; a += blockDim.x) {  // CTA pj sums the rows i = pj, pj + MARG_PRIOR_CTAS, ...
         double g = 0;
-        for (int i = 0; i < n; i++) g += p.J0[(size_t)i * n + a] * e.rm[i];
+        for (int i = pj; i < n; i += MARG_PRIOR_CTAS) g += p.J0[(size_t)i * n + a] * e.rm[i];
         atomicAdd(&bvec[pmap[a]], g);
     }
 }
@@ -612,7 +614,7 @@ int launch_marginalize(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1
         LFVIO_CUDA_TRY(cudaFuncSetAttribute(marg_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         a1 = true;
     }
-    marg_accumulate_kernel<<<n_item_cta + 1, MA_WARPS * 32, smem, s>>>(P, e0, e1, ctl, plan, mb.T, mb.T + (size_t)dim * dim,
+    marg_accumulate_kernel<<<n_item_cta + MARG_PRIOR_CTAS, MA_WARPS * 32, smem, s>>>(P, e0, e1, ctl, plan, mb.T, mb.T + (size_t)dim * dim,
                                                                       n_item_cta, max_obs);
     LFVIO_LAUNCH_CHECK();
     const size_t ws = sizeof(double) * marg_finish_workspace_doubles(plan.m_p, plan.n);
