@@ -8,7 +8,7 @@
 namespace lfvio_host {
 
 int ESTIMATE_TD = 1, ESTIMATE_EXTRINSIC = 1, NUM_ITERATIONS = 8, EST_ROW = 960;
-double TR = 0.0, TD = -0.008, FOCAL_LENGTH = 160.0;
+double TR = 0.0, TD = -0.008, FOCAL_LENGTH = 160.0, MIN_PARALLAX = 10.0 / 160.0;
 Vec3 G{0.0, 0.0, 9.81007};
 
 namespace {
@@ -110,6 +110,100 @@ void FeatureManager::setDepth(const std::vector<double> &x) {
     }
 }
 
+bool FeatureManager::addFeatureCheckParallax(int frame_count, const ImageFeatures &image, double td) {
+    double parallax_sum = 0;
+    int parallax_num = 0;
+    last_track_num = 0;
+    for (const auto &id_pts : image) {
+        const std::array<double, 8> &p = id_pts.second[0].second;
+        FeaturePerFrame f;  // FeaturePerFrame(_point, td)  (feature_manager.h:21-35)
+        f.point = Vec3{p[0], p[1], p[2]};
+        f.uv = {p[3], p[4]};
+        f.velocity = Vec3{p[5], p[6], p[7]};
+        f.cur_td = td;
+        const int feature_id = id_pts.first;
+        auto it = feature.begin();
+        for (; it != feature.end(); ++it)
+            if (it->feature_id == feature_id) break;
+        if (it == feature.end()) {
+            FeaturePerId fp;
+            fp.feature_id = feature_id;
+            fp.start_frame = frame_count;
+            fp.feature_per_frame.push_back(f);
+            feature.push_back(fp);
+        } else {
+            it->feature_per_frame.push_back(f);
+            last_track_num++;
+        }
+    }
+    if (frame_count < 2 || last_track_num < 20) return true;
+    for (const auto &it : feature) {
+        if (it.start_frame <= frame_count - 2 && it.start_frame + (int)it.feature_per_frame.size() - 1 >= frame_count - 1) {
+            const Vec3 &pi = it.feature_per_frame[frame_count - 2 - it.start_frame].point;
+            const Vec3 &pj = it.feature_per_frame[frame_count - 1 - it.start_frame].point;
+            parallax_sum += std::acos(pi[0] * pj[0] + pi[1] * pj[1] + pi[2] * pj[2]) * 10;  // compensatedParallax2
+            parallax_num++;
+        }
+    }
+    if (parallax_num == 0) return true;
+    return parallax_sum / parallax_num >= MIN_PARALLAX;
+}
+
+void FeatureManager::removeBackShiftDepth(const Mat3 &marg_R, const Vec3 &marg_P, const Mat3 &new_R, const Vec3 &new_P) {
+    for (auto it = feature.begin(), it_next = feature.begin(); it != feature.end(); it = it_next) {
+        it_next++;
+        if (it->start_frame != 0) {
+            it->start_frame--;
+            continue;
+        }
+        const Vec3 uv_i = it->feature_per_frame[0].point;
+        it->feature_per_frame.erase(it->feature_per_frame.begin());
+        if (it->feature_per_frame.size() < 2) {
+            feature.erase(it);
+            continue;
+        }
+        const Vec3 pts_i{uv_i[0] * it->estimated_depth, uv_i[1] * it->estimated_depth, uv_i[2] * it->estimated_depth};
+        const Vec3 w = matvec(marg_R, pts_i);
+        const Vec3 d{w[0] + marg_P[0] - new_P[0], w[1] + marg_P[1] - new_P[1], w[2] + marg_P[2] - new_P[2]};
+        const Vec3 pts_j = matvec(transpose(new_R), d);
+        const double dep_j = std::sqrt(pts_j[0] * pts_j[0] + pts_j[1] * pts_j[1] + pts_j[2] * pts_j[2]);
+        it->estimated_depth = dep_j > 0 ? dep_j : init_depth;
+    }
+}
+
+void FeatureManager::removeBack() {
+    for (auto it = feature.begin(), it_next = feature.begin(); it != feature.end(); it = it_next) {
+        it_next++;
+        if (it->start_frame != 0) {
+            it->start_frame--;
+        } else {
+            it->feature_per_frame.erase(it->feature_per_frame.begin());
+            if (it->feature_per_frame.empty()) feature.erase(it);
+        }
+    }
+}
+
+void FeatureManager::removeFront(int frame_count) {
+    for (auto it = feature.begin(), it_next = feature.begin(); it != feature.end(); it = it_next) {
+        it_next++;
+        if (it->start_frame == frame_count) {
+            it->start_frame--;
+        } else {
+            const int j = window_size - 1 - it->start_frame;
+            if (it->start_frame + (int)it->feature_per_frame.size() - 1 < frame_count - 1) continue;
+            it->feature_per_frame.erase(it->feature_per_frame.begin() + j);
+            if (it->feature_per_frame.empty()) feature.erase(it);
+        }
+    }
+}
+
+void FeatureManager::removeFailures() {
+    for (auto it = feature.begin(), it_next = feature.begin(); it != feature.end(); it = it_next) {
+        it_next++;
+        if (it->solve_flag == 2) feature.erase(it);
+    }
+}
+
 int FeatureManager::triangulate(const std::vector<Vec3> &Ps, const std::vector<Mat3> &Rs, const Vec3 tic[], const Mat3 ric[], int device) {
     std::vector<int> start, first{0};
     std::vector<double> pts, depth;
@@ -167,6 +261,7 @@ void Estimator::processIMU(double dt, const Vec3 &linear_acceleration, const Vec
         iv.V = Vs[j];
         iv.R = Rs[j];
         iv.dirty = true;
+        iv.predict = true;
     }
     if (j != 0) {
         dt_buf[j].push_back(dt);
@@ -217,7 +312,8 @@ int Estimator::integrate(int j, bool propagate) {
 int Estimator::flushIMU() {
     for (int j = 0; j <= WINDOW_SIZE; j++)
         if (m_iv[j].open && m_iv[j].dirty) {
-            last_status = integrate(j, true);
+            last_status = integrate(j, m_iv[j].predict);
+            m_iv[j].predict = false;
             if (last_status != LFVIO_OK) return last_status;
         }
     return LFVIO_OK;
@@ -228,6 +324,127 @@ int Estimator::repropagate(int j, const Vec3 &ba, const Vec3 &bg) {
     m_iv[j].ba = ba;
     m_iv[j].bg = bg;
     return last_status = integrate(j, false);  // repropagate() re-integrates the deltas only (integration_base.h:39-53)
+}
+
+void Estimator::processImage(const ImageFeatures &image, double header_stamp) {
+    marginalization_flag = f_manager.addFeatureCheckParallax(frame_count, image, td) ? MARGIN_OLD : MARGIN_SECOND_NEW;
+    if ((int)Headers.size() <= WINDOW_SIZE) Headers.resize(WINDOW_SIZE + 1, 0.0);
+    Headers[frame_count] = header_stamp;
+    if (solver_flag == INITIAL) {
+        // initialStructure() is not part of this mirror: the window fills, then slides until the caller has initialised
+        // the states and set solver_flag = NON_LINEAR (the reference does the same while its initialisation fails, :177-178)
+        if (frame_count == WINDOW_SIZE) {
+            if (flushIMU() != LFVIO_OK) return;
+            slideWindow();
+        } else {
+            frame_count++;
+        }
+        return;
+    }
+    solveOdometry();
+    if (last_status != LFVIO_OK) return;
+    if (failureDetection()) {
+        failure_occur = true;  // the reference reboots here (clearState + setParameter); left to the caller
+        return;
+    }
+    slideWindow();
+    f_manager.removeFailures();
+    key_poses.assign(Ps.begin(), Ps.end());
+    last_R = Rs[WINDOW_SIZE];
+    last_P = Ps[WINDOW_SIZE];
+    last_R0 = Rs[0];
+    last_P0 = Ps[0];
+}
+
+void Estimator::solveOdometry() {
+    if (frame_count < WINDOW_SIZE) return;
+    if (solver_flag == NON_LINEAR) {
+        if (flushIMU() != LFVIO_OK) return;  // Ps/Vs/Rs[WINDOW_SIZE] predicted before triangulating against them
+        last_status = f_manager.triangulate(Ps, Rs, tic, ric, m_device);
+        if (last_status != LFVIO_OK) return;
+        optimization();
+    }
+}
+
+bool Estimator::failureDetection() {
+    auto norm = [](const Vec3 &v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+    if (norm(Bgs[WINDOW_SIZE]) > 1.0) return true;
+    const Vec3 &p = Ps[WINDOW_SIZE];
+    if (norm(Vec3{p[0] - last_P[0], p[1] - last_P[1], p[2] - last_P[2]}) > 5) return true;
+    if (std::fabs(p[2] - last_P[2]) > 1) return true;
+    return false;  // (the little-feature, big-acc-bias and big-angle tests only log in the reference)
+}
+
+void Estimator::slideWindow() {
+    if (marginalization_flag == MARGIN_OLD) {
+        back_R0 = Rs[0];
+        back_P0 = Ps[0];
+        if (frame_count == WINDOW_SIZE) {
+            for (int i = 0; i < WINDOW_SIZE; i++) {
+                std::swap(Rs[i], Rs[i + 1]);
+                std::swap(m_pre[i], m_pre[i + 1]);
+                std::swap(m_iv[i], m_iv[i + 1]);
+                dt_buf[i].swap(dt_buf[i + 1]);
+                linear_acceleration_buf[i].swap(linear_acceleration_buf[i + 1]);
+                angular_velocity_buf[i].swap(angular_velocity_buf[i + 1]);
+                Headers[i] = Headers[i + 1];
+                std::swap(Ps[i], Ps[i + 1]);
+                std::swap(Vs[i], Vs[i + 1]);
+                std::swap(Bas[i], Bas[i + 1]);
+                std::swap(Bgs[i], Bgs[i + 1]);
+            }
+            Headers[WINDOW_SIZE] = Headers[WINDOW_SIZE - 1];
+            Ps[WINDOW_SIZE] = Ps[WINDOW_SIZE - 1];
+            Vs[WINDOW_SIZE] = Vs[WINDOW_SIZE - 1];
+            Rs[WINDOW_SIZE] = Rs[WINDOW_SIZE - 1];
+            Bas[WINDOW_SIZE] = Bas[WINDOW_SIZE - 1];
+            Bgs[WINDOW_SIZE] = Bgs[WINDOW_SIZE - 1];
+            // new IntegrationBase{acc_0, gyr_0, Bas[WINDOW_SIZE], Bgs[WINDOW_SIZE]}: opened by the next processIMU
+            m_iv[WINDOW_SIZE] = Interval{};
+            dt_buf[WINDOW_SIZE].clear();
+            linear_acceleration_buf[WINDOW_SIZE].clear();
+            angular_velocity_buf[WINDOW_SIZE].clear();
+            for (int i = 0; i <= WINDOW_SIZE; i++) pre_integrations[i] = m_iv[i].open ? &m_pre[i] : nullptr;
+            slideWindowOld();
+        }
+    } else if (frame_count == WINDOW_SIZE) {
+        const int fc = frame_count;
+        for (size_t i = 0; i < dt_buf[fc].size(); i++) {  // the newest interval is appended to the previous one
+            dt_buf[fc - 1].push_back(dt_buf[fc][i]);
+            linear_acceleration_buf[fc - 1].push_back(linear_acceleration_buf[fc][i]);
+            angular_velocity_buf[fc - 1].push_back(angular_velocity_buf[fc][i]);
+        }
+        if (!dt_buf[fc].empty()) m_iv[fc - 1].dirty = true;  // re-integrated from its own start by the next flushIMU
+        Headers[fc - 1] = Headers[fc];
+        Ps[fc - 1] = Ps[fc];
+        Vs[fc - 1] = Vs[fc];
+        Rs[fc - 1] = Rs[fc];
+        Bas[fc - 1] = Bas[fc];
+        Bgs[fc - 1] = Bgs[fc];
+        m_iv[WINDOW_SIZE] = Interval{};
+        pre_integrations[WINDOW_SIZE] = nullptr;
+        dt_buf[WINDOW_SIZE].clear();
+        linear_acceleration_buf[WINDOW_SIZE].clear();
+        angular_velocity_buf[WINDOW_SIZE].clear();
+        slideWindowNew();
+    }
+}
+
+void Estimator::slideWindowNew() {
+    sum_of_front++;
+    f_manager.removeFront(frame_count);
+}
+
+void Estimator::slideWindowOld() {
+    sum_of_back++;
+    if (solver_flag == NON_LINEAR) {
+        const Mat3 R0 = matmul(back_R0, ric[0]), R1 = matmul(Rs[0], ric[0]);
+        const Vec3 a = matvec(back_R0, tic[0]), b = matvec(Rs[0], tic[0]);
+        const Vec3 P0{back_P0[0] + a[0], back_P0[1] + a[1], back_P0[2] + a[2]}, P1{Ps[0][0] + b[0], Ps[0][1] + b[1], Ps[0][2] + b[2]};
+        f_manager.removeBackShiftDepth(R0, P0, R1, P1);
+    } else {
+        f_manager.removeBack();
+    }
 }
 
 void Estimator::vector2double() {
@@ -546,5 +763,105 @@ extern "C" int lfvio_host_triangulate(const double *Ps, const double *Rs, int n_
     if (st != LFVIO_OK) return st;
     int l = 0;
     for (const auto &it : fm.feature) depth[l++] = it.estimated_depth;
+    return LFVIO_OK;
+}
+
+// ---- test hooks: the C++ Estimator driven frame by frame from Python (closed loop, tests/test_host_classes_gpu.py) ----
+extern "C" void *lfvio_host_estimator_create(int window_size, int max_features, int device) {
+    auto *e = new lfvio_host::Estimator(window_size, max_features, device);
+    if (e->last_status != LFVIO_OK) {
+        delete e;
+        return nullptr;
+    }
+    return e;
+}
+extern "C" void lfvio_host_estimator_destroy(void *h) { delete static_cast<lfvio_host::Estimator *>(h); }
+
+extern "C" int lfvio_host_estimator_set_params(void *h, const double *noise4, const double *g3, const double *tic3, const double *ric9,
+                                               double td, double min_parallax, int estimate_td, const double *ba3, const double *bg3) {
+    using namespace lfvio_host;
+    auto *e = static_cast<Estimator *>(h);
+    e->imu_noise = lfvio_imu_noise{noise4[0], noise4[1], noise4[2], noise4[3]};
+    G = Vec3{g3[0], g3[1], g3[2]};
+    e->tic[0] = Vec3{tic3[0], tic3[1], tic3[2]};
+    for (int k = 0; k < 9; k++) e->ric[0][k] = ric9[k];
+    e->td = td;
+    MIN_PARALLAX = min_parallax;
+    ESTIMATE_TD = estimate_td;
+    for (int i = 0; i <= e->WINDOW_SIZE; i++) {
+        e->Bas[i] = Vec3{ba3[0], ba3[1], ba3[2]};
+        e->Bgs[i] = Vec3{bg3[0], bg3[1], bg3[2]};
+    }
+    return LFVIO_OK;
+}
+
+// acc0/gyr0 (may be NULL): override acc_0 / gyr_0 before the interval, for streams whose intervals do not share a sample
+extern "C" int lfvio_host_estimator_process_imu(void *h, const double *acc0, const double *gyr0, const double *dt, const double *acc,
+                                                const double *gyr, int n) {
+    using namespace lfvio_host;
+    auto *e = static_cast<Estimator *>(h);
+    if (acc0 && gyr0) {
+        e->first_imu = true;
+        e->acc_0 = Vec3{acc0[0], acc0[1], acc0[2]};
+        e->gyr_0 = Vec3{gyr0[0], gyr0[1], gyr0[2]};
+    }
+    for (int k = 0; k < n; k++)
+        e->processIMU(dt[k], Vec3{acc[3 * k], acc[3 * k + 1], acc[3 * k + 2]}, Vec3{gyr[3 * k], gyr[3 * k + 1], gyr[3 * k + 2]});
+    return LFVIO_OK;
+}
+
+// states of all window frames (replaces initialStructure); pending intervals are integrated first so that their
+// state prediction cannot overwrite what is set here
+extern "C" int lfvio_host_estimator_set_states(void *h, const double *P, const double *R, const double *V, int nonlinear) {
+    using namespace lfvio_host;
+    auto *e = static_cast<Estimator *>(h);
+    const int st = e->flushIMU();
+    if (st != LFVIO_OK) return st;
+    for (int i = 0; i <= e->WINDOW_SIZE; i++) {
+        e->Ps[i] = Vec3{P[3 * i], P[3 * i + 1], P[3 * i + 2]};
+        e->Vs[i] = Vec3{V[3 * i], V[3 * i + 1], V[3 * i + 2]};
+        for (int k = 0; k < 9; k++) e->Rs[i][k] = R[9 * i + k];
+    }
+    e->last_P = e->Ps[e->WINDOW_SIZE];
+    e->last_R = e->Rs[e->WINDOW_SIZE];
+    e->last_P0 = e->Ps[0];
+    e->last_R0 = e->Rs[0];
+    if (nonlinear) e->solver_flag = Estimator::NON_LINEAR;
+    return LFVIO_OK;
+}
+
+extern "C" int lfvio_host_estimator_process_image(void *h, const int *ids, const double *feat8, int n, double stamp) {
+    using namespace lfvio_host;
+    auto *e = static_cast<Estimator *>(h);
+    ImageFeatures image;
+    for (int i = 0; i < n; i++) {
+        std::array<double, 8> p;
+        for (int k = 0; k < 8; k++) p[k] = feat8[8 * i + k];
+        image[ids[i]].emplace_back(0, p);
+    }
+    e->processImage(image, stamp);
+    return e->last_status;
+}
+
+extern "C" int lfvio_host_estimator_get(void *h, double *P, double *R, double *V, double *ba, double *bg, double *td, int *info) {
+    using namespace lfvio_host;
+    auto *e = static_cast<Estimator *>(h);
+    for (int i = 0; i <= e->WINDOW_SIZE; i++)
+        for (int k = 0; k < 3; k++) {
+            P[3 * i + k] = e->Ps[i][k];
+            V[3 * i + k] = e->Vs[i][k];
+            ba[3 * i + k] = e->Bas[i][k];
+            bg[3 * i + k] = e->Bgs[i][k];
+        }
+    for (int i = 0; i <= e->WINDOW_SIZE; i++)
+        for (int k = 0; k < 9; k++) R[9 * i + k] = e->Rs[i][k];
+    *td = e->td;
+    info[0] = (int)e->marginalization_flag;
+    info[1] = (int)e->f_manager.feature.size();
+    info[2] = e->summary.iterations;
+    info[3] = e->frame_count;
+    info[4] = e->failure_occur ? 1 : 0;
+    info[5] = e->sum_of_back;
+    info[6] = e->sum_of_front;
     return LFVIO_OK;
 }

@@ -11,6 +11,8 @@
 #pragma once
 #include <array>
 #include <list>
+#include <map>
+#include <utility>
 #include <vector>
 
 #include "lfvio.h"
@@ -22,7 +24,7 @@ using Mat3 = std::array<double, 9>;  // row-major
 
 // ---- vins_estimator/src/parameters.h globals ---------------------------------------------------------
 extern int ESTIMATE_TD, ESTIMATE_EXTRINSIC, NUM_ITERATIONS;
-extern double TR, TD, FOCAL_LENGTH;
+extern double TR, TD, FOCAL_LENGTH, MIN_PARALLAX;  // MIN_PARALLAX = keyframe_parallax / FOCAL_LENGTH (parameters.cpp:56-57)
 extern int EST_ROW;  // ROW of the estimator's parameters.cpp
 extern Vec3 G;
 
@@ -36,10 +38,21 @@ struct FeaturePerId {  // feature_manager.h:43-71
     double estimated_depth = -1.0;
     std::vector<FeaturePerFrame> feature_per_frame;
 };
+// what estimator_node hands to processImage: feature id -> [(camera id, [x y z u v vx vy vz])]  (estimator_node.cpp:290-310)
+using ImageFeatures = std::map<int, std::vector<std::pair<int, std::array<double, 8>>>>;
+
 class FeatureManager {
   public:
     std::list<FeaturePerId> feature;
     int window_size = 10;
+    int last_track_num = 0;
+    void clearState() { feature.clear(); }
+    // feature_manager.cpp:46-105 (bearing parallax: acos(p_i . p_j) * 10, :353-369)
+    bool addFeatureCheckParallax(int frame_count, const ImageFeatures &image, double td);
+    void removeBackShiftDepth(const Mat3 &marg_R, const Vec3 &marg_P, const Mat3 &new_R, const Vec3 &new_P);  // :271-310
+    void removeBack();                  // :312-325
+    void removeFront(int frame_count);  // :327-345
+    void removeFailures();              // :158-167 (a no-op in LF-VIO: setDepth never sets solve_flag = 2)
     int getFeatureCount();
     std::vector<double> getDepthVector();
     void setDepth(const std::vector<double> &x);
@@ -75,6 +88,15 @@ class Estimator {
     int flushIMU();
     // IntegrationBase::repropagate (integration_base.h:39-53) for frame j with new linearisation biases
     int repropagate(int j, const Vec3 &ba, const Vec3 &bg);
+    // estimator.cpp:122-219 without the initialisation (initialStructure): while solver_flag ==
+    // INITIAL the window only fills and slides; the caller switches to NON_LINEAR once the states are initialised.
+    enum SolverFlag { INITIAL = 0, NON_LINEAR = 1 };
+    void processImage(const ImageFeatures &image, double header_stamp);
+    void solveOdometry();      // :475-486
+    bool failureDetection();   // :628-675
+    void slideWindow();        // :1011-1105
+    void slideWindowNew();     // :1107-1112
+    void slideWindowOld();     // :1114-1131
     void optimization();    // estimator.cpp:676-1009
     void vector2double();   // :488-530
     void double2vector();   // :532-626
@@ -88,6 +110,12 @@ class Estimator {
     double td = 0;
     std::vector<IntegrationBase *> pre_integrations;  // [0 .. WINDOW_SIZE], entry j connects frames j-1 and j
     int frame_count = 0;
+    SolverFlag solver_flag = INITIAL;
+    std::vector<double> Headers;       // header.stamp.toSec() per window slot
+    std::vector<Vec3> key_poses;
+    Mat3 back_R0{}, last_R{};
+    Vec3 back_P0{}, last_P{};
+    int sum_of_back = 0, sum_of_front = 0;
     bool first_imu = false;
     Vec3 acc_0{}, gyr_0{};
     std::vector<std::vector<double>> dt_buf;                                   // estimator.h:96-98
@@ -115,7 +143,7 @@ class Estimator {
     void buildFactors();
     // per-frame interval bookkeeping of processIMU / flushIMU
     struct Interval {
-        bool open = false, dirty = false;
+        bool open = false, dirty = false, predict = false;  // predict: Ps/Vs/Rs[j] still to be propagated by flushIMU
         Vec3 acc_start{}, gyr_start{}, ba{}, bg{}, P{}, V{};
         Mat3 R{};
     };

@@ -233,11 +233,11 @@ class VioLoop:
         prob, used = self._problem()
         summ, prior = self.ops.optimize_full(prob, B.MARGIN_OLD)
         self.pose[:], self.sb[:], self.ex[:], self.td = prob.pose, prob.sb, prob.ex, float(prob.td[0])
-        self._failed = set()
-        for ft, lam in zip(used, prob.feat):  # FeatureManager::setDepth (feature_manager.cpp:145-159): solve_flag 2 if < 0
+        # FeatureManager::setDepth (feature_manager.cpp:138-156).  LF-VIO sets solve_flag = 1 in BOTH branches, so
+        # removeFailures (:158-167) never erases anything: a negative depth simply fails the `estimated_depth > 0` test
+        # of the next triangulate() and is re-triangulated.
+        for ft, lam in zip(used, prob.feat):
             ft.depth = 1.0 / lam
-            if ft.depth < 0:
-                self._failed.add(ft.fid)
         self.prior = prior
         self.iterations.append(int(summ.iterations))
 
@@ -262,7 +262,7 @@ class VioLoop:
             dep = float(np.linalg.norm(pts_j))
             ft.depth = dep if dep > 0 else 5.0
             keep.append(ft)
-        self.features = [ft for ft in keep if ft.fid not in self._failed]  # removeFailures (solve_flag == 2)
+        self.features = keep  # (removeFailures is a no-op in LF-VIO, see _optimize)
 
     # -- one camera frame ------------------------------------------------------------------------------------
     def step(self):

@@ -164,3 +164,65 @@ def test_estimator_process_imu_and_triangulate_mirrors(lfvio_mod, gpu, host):
     rc = host.lfvio_host_triangulate(arrs[0].ctypes.data, arrs[1].ctypes.data, len(d["Ps"]), arrs[2].ctypes.data, arrs[3].ctypes.data,
                                      arrs[4].ctypes.data, arrs[5].ctypes.data, arrs[6].ctypes.data, 120, got_d.ctypes.data)
     assert rc == 0 and np.array_equal(got_d, want_d) and (got_d > 0).sum() > 40
+
+
+def test_estimator_class_closed_loop_matches_python_orchestration(lfvio_mod, gpu, host):
+    """The C++ host mirror run as an estimator core — processIMU, processImage (addFeatureCheckParallax, triangulate,
+    optimization, slideWindow / removeBackShiftDepth) — over the synthetic world of lfvio.violoop, against the Python
+    restatement of the same control flow with the same device numeric steps.  MIN_PARALLAX = 0 makes every frame a
+    keyframe, which is what the Python loop assumes; td is fixed (the world cuts IMU intervals at the stamps)."""
+    from lfvio import violoop
+
+    world = violoop.World(seed=4, n_frames=30)
+    win = lfvio_mod.Window(10, 1000, 16384, device=gpu)
+    dopts = lfvio_mod.solver_default_opts()
+    dopts.row, dopts.estimate_td = 960, 0
+    py = violoop.VioLoop(world, violoop.device_ops(lfvio_mod, win, gpu), dopts)
+    py.td = 0.0
+    for f in py.features:  # (bootstrap observations were stamped with the constructor's td)
+        f.obs = [(o[0], o[1], 0.0, o[3]) for o in f.obs]
+    boot_pose, boot_sb = py.pose.copy(), py.sb.copy()
+    py.run()
+
+    F = 11
+    vp = lambda a: np.ascontiguousarray(a, np.float64).ctypes.data_as(C.c_void_p)
+    host.lfvio_host_estimator_create.restype = C.c_void_p
+    host.lfvio_host_estimator_create.argtypes = [C.c_int, C.c_int, C.c_int]
+    host.lfvio_host_estimator_destroy.argtypes = [C.c_void_p]
+    host.lfvio_host_estimator_set_params.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    host.lfvio_host_estimator_process_imu.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int]
+    host.lfvio_host_estimator_set_states.argtypes = [C.c_void_p] + [C.c_void_p] * 3 + [C.c_int]
+    host.lfvio_host_estimator_process_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+    host.lfvio_host_estimator_get.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    est = host.lfvio_host_estimator_create(10, 1000, gpu)
+    assert est, lfvio_mod.lib.lfvio_last_error()
+    keep = [np.ascontiguousarray(x, np.float64) for x in (world.noise, world.G, world.tic, world.ric, boot_sb[0, 3:6], boot_sb[0, 6:9])]
+    assert host.lfvio_host_estimator_set_params(est, vp(keep[0]), vp(keep[1]), vp(keep[2]), vp(keep[3]), 0.0, 0.0, 0, vp(keep[4]), vp(keep[5])) == 0
+    P, R, V = np.zeros((F, 3)), np.zeros((F, 9)), np.zeros((F, 3))
+    ba, bg, td, info = np.zeros((F, 3)), np.zeros((F, 3)), np.zeros(1), np.zeros(8, np.int32)
+    worst = 0.0
+    for k in range(world.n_frames):
+        if k > 0:
+            a0, g0, dt, acc, gyr = world.imu[k]
+            arrs = [np.ascontiguousarray(x, np.float64) for x in (a0, g0, dt, acc, gyr)]
+            assert host.lfvio_host_estimator_process_imu(est, *[vp(a) for a in arrs], len(dt)) == 0
+        if k == F - 1:
+            Rb = np.array([violoop._quat_to_rot(boot_pose[f, 3:]).ravel() for f in range(F)])
+            assert host.lfvio_host_estimator_set_states(est, vp(boot_pose[:, :3].copy()), vp(Rb), vp(boot_sb[:, :3].copy()), 1) == 0, \
+                lfvio_mod.lib.lfvio_last_error()
+        obs = world.frames[k]
+        ids = np.array(list(obs.keys()), np.int32)
+        feat = np.array([[*b, 0.0, row, *vel] for (b, vel, row) in obs.values()])
+        rc = host.lfvio_host_estimator_process_image(est, ids.ctypes.data_as(C.c_void_p), vp(feat), len(ids), float(world.times[k]))
+        assert rc == 0, lfvio_mod.lib.lfvio_last_error()
+        host.lfvio_host_estimator_get(est, vp(P), vp(R), vp(V), vp(ba), vp(bg), vp(td), info.ctypes.data_as(C.c_void_p))
+        if k >= F - 1:
+            assert info[0] == 0 and info[4] == 0 and info[2] > 0          # keyframe, no failure, the solver ran
+            worst = max(worst, np.abs(P[F - 1] - py.estimates[k][0]).max())
+    host.lfvio_host_estimator_destroy(est)
+    win.close()
+    assert info[5] == world.n_frames - (F - 1) and info[6] == 0            # one MARGIN_OLD slide per frame
+    assert worst < 1e-4, worst
+    ate = violoop.ate_rmse(np.array([py.estimates[k][0] for k in sorted(py.estimates)]),
+                           np.array([world.truth(k)[0] for k in sorted(py.estimates)]))
+    print(f"C++ estimator closed loop: max |p_cpp - p_python| = {worst:.3e} m, ATE {ate:.4f} m")
