@@ -392,7 +392,26 @@ __global__ void __launch_bounds__(BT) set_mask_select_kernel(TrackArrays in, Tra
         s_ok[k] = base_mask[(size_t)py * mask_pitch + px] == 255;
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
+    if (n > 512) {
+        // many tracks (3840x2880 / 2000 features): the whole CTA tests a candidate against the kept list
+        int nk = 0;
+        for (int k = 0; k < n; k++) {
+            if (!s_ok[k]) continue;  // (uniform)
+            const int px = s_px[k], py = s_py[k];
+            int hit = 0;
+            for (int j = threadIdx.x; j < nk; j += BT) {
+                const int q = kept[j];
+                const int dx = abs(px - s_px[q]), dy = abs(py - s_py[q]);
+                if (dy <= min_dist && dx <= half_width[dy]) hit = 1;
+            }
+            if (!__syncthreads_or(hit)) {  // (uniform)
+                if (threadIdx.x == 0) kept[nk] = k;
+                nk++;
+                __syncthreads();  // the new entry is read by everybody in the next round
+            }
+        }
+        if (threadIdx.x == 0) s_nkept = nk;
+    } else if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         int nk = 0;
         for (int k = 0; k < n; k++) {
