@@ -2,16 +2,26 @@
 """bench.py — VIO frames/sec (track + optimize, 10-keyframe window) on B200, next to the CPU path.
 
 One "step" = one camera frame through the hot path BASELINE.json's north_star names:
-  front end  FeatureTracker::readImage (CLAHE -> pyramidal LK -> border filter -> setMask -> Shi-Tomasi -> lift)
-  back end   Estimator::optimization   (8 dogleg iterations on an 11-frame window, DENSE_SCHUR semantics)
+  front end  FeatureTracker::readImage (CLAHE -> pyramidal LK -> border filter -> rejectWithF -> setMask -> Shi-Tomasi -> lift)
+  back end   Estimator::optimization   (8 dogleg iterations on an 11-frame window with the steady-state marginalisation
+             prior, DENSE_SCHUR semantics, then the MARGIN_OLD prior for the next frame)
 Workload (config.workload): BASELINE.json configs[1] shape — synthetic 1280x960 panoramic frames @15 Hz published
 at 10 Hz, 150 features, 200 Hz IMU, 10-keyframe window, estimate_td = 1.  One independent stream per GPU (weak
 scaling, no data-path collective; NCCL only reduces the timing counters).
 
-JSON keys follow the driver contract: value (inputs resident in HBM), e2e (host buffers through the C-ABI, H2D/D2H
-inside the timed region), roofline (dominant kernel, live CUDA-event durations), cpu_baseline, clocks, gpu_launches.
+JSON keys follow the driver contract:
+  value        frames/s with the inputs resident in HBM; the two halves run on their own CUDA streams, enqueued by two
+               host threads (the reference's two nodes); timed with CUDA events on those streams, max over ranks
+  e2e          the same metric through the blocking C-ABI calls with HOST buffers (pinned frame H2D, problem upload,
+               results D2H inside the timed region), two host threads; node_ms_per_frame / single_thread_ms_per_frame
+  roofline     dominant stage by live CUDA-event time; achieved = algorithmic bytes / average launch time; traffic from
+               the committed ncu capture (profiles/r1_traffic.json); per_stage lists every stage with a byte count
+  cpu_baseline bounded sample of the CPU arm on this box's cores (N = 1 only)
+  ate          closed-loop sliding-window run of both arms on one synthetic world (the second half of the metric)
+  clocks, gpu_launches, host_enqueue_ms_per_step
 `--impl reference` times the reference's CPU path (cv2 with the reference's arguments + the fp64 C++ oracle of the
 back end; the reference itself — ROS/OpenCV-C++/Ceres/Eigen — cannot be built in this image).
+`--config` selects BASELINE configs 3 / 4 (parity-test sizes; their lines are kept under profiles/).
 """
 from __future__ import annotations
 

@@ -5,6 +5,10 @@
 
 #include "common.cuh"
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 namespace lfvio {
 
 static thread_local char g_err[1024] = "";
@@ -17,6 +21,25 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void clear_error() { g_err[0] = 0; }
+int ensure_dyn_smem(const void *kernel, int bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void *, unsigned long long>> seen;  // kernel -> bit per device
+    int dev = 0;
+    LFVIO_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    unsigned long long *mask = nullptr;
+    for (auto &p : seen)
+        if (p.first == kernel) mask = &p.second;
+    if (!mask) {
+        seen.emplace_back(kernel, 0ull);
+        mask = &seen.back().second;
+    }
+    if ((*mask >> (dev & 63)) & 1ull) return LFVIO_OK;
+    LFVIO_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    *mask |= 1ull << (dev & 63);
+    return LFVIO_OK;
+}
+
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 int sm_count(int device) {

@@ -74,6 +74,10 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
 }
 #endif
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) property of a kernel: set it once per
+// (kernel, device).  Handles on several devices may live in one process (one host thread per stream).
+int ensure_dyn_smem(const void *kernel, int bytes);
+
 // B200: 148 SMs.  Queried once per device and cached.
 int sm_count(int device);
 

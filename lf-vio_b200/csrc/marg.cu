@@ -490,9 +490,11 @@ __global__ void __launch_bounds__(MF_THREADS) marg_finish_kernel(DevProblem P, c
     // first windows, whose prior is rank deficient elsewhere) the fully pivoted factorisation below runs on the intact A'.
     bool fast_ok = false;
     const int nblk_f = (n + NB - 1) / NB, c0_f = (nblk_f - 1) * NB, nl_f = n - c0_f;
-    if (plan.use_smem && n + 1 <= (int)blockDim.x - 32 && nblk_f >= 2 && nl_f >= 6) {
+    if (n + 1 <= (int)blockDim.x - 32 && nblk_f >= 2 && nl_f >= 6) {
         const int PW = chol_panel_pitch(n);
-        double *s_panel = Ts;  // T is dead: A' and b' are formed
+        // panel / rhs / pivots: in the region of the staged T (dead: A' and b' are formed), or — when the matrices live in
+        // the global workspace (large windows) — in the small dynamic shared-memory block the launcher provides for them
+        double *s_panel = plan.use_smem ? Ts : smem;
         double *s_y = s_panel + (size_t)NB * PW;
         double *s_invd = s_y + ((n + 1) & ~1);
         __shared__ __align__(16) double s_U[2 * NB * NB];
@@ -609,21 +611,16 @@ int launch_marginalize(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1
     const int per_item = max_obs * 40 + max_obs * 2 + max_obs * 6 + 16 + max_obs;
     size_t smem = sizeof(double) * (size_t)per_item;
     smem = std::max(smem, sizeof(int) * (size_t)(15 * kMaxFrames + 8));
-    static bool a1 = false, a2 = false;
-    if (!a1) {
-        LFVIO_CUDA_TRY(cudaFuncSetAttribute(marg_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        a1 = true;
-    }
+    LFVIO_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(marg_accumulate_kernel), 96 * 1024));
     marg_accumulate_kernel<<<n_item_cta + MARG_PRIOR_CTAS, MA_WARPS * 32, smem, s>>>(P, e0, e1, ctl, plan, mb.T, mb.T + (size_t)dim * dim,
                                                                       n_item_cta, max_obs);
     LFVIO_LAUNCH_CHECK();
     const size_t ws = sizeof(double) * marg_finish_workspace_doubles(plan.m_p, plan.n);
     plan.use_smem = ws <= 200 * 1024 ? 1 : 0;
-    if (!a2) {
-        LFVIO_CUDA_TRY(cudaFuncSetAttribute(marg_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        a2 = true;
-    }
-    marg_finish_kernel<<<1, MF_THREADS, plan.use_smem ? ws : 0, s>>>(P, x0, x1, ctl, plan, mb.T, mb.T + (size_t)dim * dim, mb.work,
+    LFVIO_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(marg_finish_kernel), 200 * 1024));
+    const size_t chol_bytes = sizeof(double) * ((size_t)NB * chol_panel_pitch(plan.n) + (size_t)((plan.n + 1) & ~1) +
+                                                (size_t)((plan.n + NB - 1) / NB) * NB + 2);
+    marg_finish_kernel<<<1, MF_THREADS, plan.use_smem ? ws : chol_bytes, s>>>(P, x0, x1, ctl, plan, mb.T, mb.T + (size_t)dim * dim, mb.work,
                                                                      mb.J0, mb.r0, mb.x0);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;

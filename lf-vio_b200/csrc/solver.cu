@@ -320,11 +320,7 @@ int launch_accumulate(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1,
     const int n_lm_cta = items;
     size_t smem = sizeof(double) * (size_t)acc_per_warp_doubles(max_obs);
     smem = std::max(smem, sizeof(int) * (size_t)(15 * kMaxFrames + 8));
-    static bool attr_set = false;
-    if (!attr_set) {
-        LFVIO_CUDA_TRY(cudaFuncSetAttribute(accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-    }
+    LFVIO_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(accumulate_kernel), 96 * 1024));
     LFVIO_CUDA_TRY(launch_pdl(accumulate_kernel, dim3(n_lm_cta + PRIOR_CTAS), dim3(ACC_WARPS * 32), smem, s, P, e0, e1, w,
                               (const SolverCtl *)ctl, n_lm_cta, max_obs));
     LFVIO_LAUNCH_CHECK();

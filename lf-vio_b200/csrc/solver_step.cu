@@ -540,11 +540,7 @@ int launch_step(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const
     const size_t packed = sizeof(double) * ((size_t)D * (D + 1) / 2);
     const size_t limit = 220 * 1024;
     const int use_smem = (base + packed <= limit) ? 1 : 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        LFVIO_CUDA_TRY(cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
-        attr_set = true;
-    }
+    LFVIO_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(chol_kernel), (int)limit));
     LFVIO_CUDA_TRY(launch_pdl(chol_kernel, dim3(1), dim3(CHOL_THREADS), base + (use_smem ? packed : 0), s, P, w, x0, x1, ctl, use_smem, fused));
     LFVIO_LAUNCH_CHECK();
     if (!fused) {

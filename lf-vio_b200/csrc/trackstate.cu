@@ -536,11 +536,7 @@ int launch_set_mask_select(const TrackArrays &in, const TrackArrays &out, int *n
     const int max_ranges = cap / 8 + 8;
     const size_t smem = sizeof(long long) * 2 * (size_t)cap + sizeof(int) * (2 * (size_t)cap + 6 * (size_t)max_ranges + 4 * (size_t)cap);
     LFVIO_REQUIRE(smem <= 200 * 1024, "setMask: too many tracks for the shared-memory sort (max_cnt <= ~5000)");
-    static bool attr_set = false;
-    if (!attr_set) {
-        LFVIO_CUDA_TRY(cudaFuncSetAttribute(set_mask_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+    LFVIO_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(set_mask_select_kernel), 200 * 1024));
     set_mask_select_kernel<<<1, BT, smem, s>>>(in, out, n_dev, cap, base_mask, mask_pitch, half_width, min_dist, max_ranges);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
