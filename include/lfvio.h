@@ -329,6 +329,71 @@ int lfvio_triangulate(const double *Ps, const double *Rs, int n_frames, const do
                       const int *start_frame, const int *obs_first, const double *obs_pts, int n_features,
                       double init_depth, double *depth, int device);
 
+/* ==========================================================================================
+ * Estimator initialisation: the numeric steps of Estimator::initialStructure
+ * (vins_estimator/src/estimator.cpp:221-376) and visualInitialAlign (:378-455).  Host buffers, synchronous.
+ * Rotation matrices are row-major, quaternions are (w, x, y, z) as Eigen prints them.
+ * ========================================================================================== */
+#define LFVIO_INIT_MAX_FRAMES 128   /* frames in all_image_frame accepted by lfvio_linear_alignment          */
+#define LFVIO_SFM_MAX_FRAMES 24     /* WINDOW_SIZE + 1 accepted by the SfM entries (shared-memory bound)     */
+#define LFVIO_SFM_MAX_BA_ITER 50    /* Ceres default max_num_iterations                                      */
+
+/* solveGyroscopeBias (initial/initial_aligment.cpp:3-29) without the repropagation (:31-37; the caller does it
+ * with lfvio_preintegrate).  R: n_frames x 9 = ImageFrame::R of every frame of all_image_frame in time order;
+ * delta_q (n_frames-1) x 4 and J_rg (n_frames-1) x 9 = pre_integration->delta_q and
+ * jacobian.block<3,3>(O_R, O_BG) of frames 1.. .  delta_bg: 3.                                              */
+int lfvio_solve_gyro_bias(const double *R, const double *delta_q, const double *J_rg, int n_frames, double *delta_bg,
+                          int device);
+/* LinearAlignment + RefineGravity (initial/initial_aligment.cpp:56-205).  T: n_frames x 3 = ImageFrame::T;
+ * delta_p / delta_v: (n_frames-1) x 3, sum_dt: n_frames-1, of frames 1.. ; tic = TIC[0]; g_norm = G.norm().
+ * Outputs: *ok = the function's return value; g (3) = refined gravity in the frame of R/T; x: caller provides
+ * 3 n_frames + 4 doubles; on success the first 3 n_frames + 3 hold [v_0 .. v_{n-1} (body frame) | dg (2) | s]
+ * with s already divided by 100 (:199-200); when the first solve is rejected (:186-194) x holds that solve's
+ * 3 n_frames + 4 unknowns and g its gravity.                                                                 */
+int lfvio_linear_alignment(const double *R, const double *T, const double *delta_p, const double *delta_v,
+                           const double *sum_dt, int n_frames, const double *tic, double g_norm, double *g, double *x,
+                           int *ok, int device);
+/* MotionEstimator::solveRelativeRT (initial/solve_5pts.cpp:538-575): spherical 8-point RANSAC
+ * (myfindFundamentalMat :266-335, injected random source seed/frame as in lfvio_reject_with_f) and recoverPose
+ * (:392-536).  corres: n x 6 = [bearing in the older frame | bearing in the newest frame].  rotation (9) /
+ * translation (3) = R^T, -R^T t of the pose recoverPose selects — the reference passes its outputs by value
+ * (:556-569) and returns uninitialised memory; this is the evident intent (stated deviation).
+ * The function's boolean is (*inlier_cnt > 12); below 15 correspondences nothing is computed and
+ * *inlier_cnt = 0.  E_out (9, may be NULL): the refit essential matrix.                                      */
+int lfvio_solve_relative_rt(const double *corres, int n, unsigned long long seed, unsigned frame, double *rotation,
+                            double *translation, int *inlier_cnt, double *E_out, int device);
+/* PnpSolver::compute_pose with set_internal_parameters(0, 0, 1, 1) (pnp_solver.cpp:275-338; call sites
+ * initial_sfm.cpp:55-69, estimator.cpp:343-357), batched: problem p uses correspondences
+ * [first[p], first[p+1]) of pws (world points) / us (bearings), one thread block each.  R: n_problems x 9,
+ * T: n_problems x 3 with p_cam = R p_w + T, err (may be NULL): the function's return value.                  */
+int lfvio_epnp(const double *pws, const double *us, const int *first, int n_problems, double *R, double *T, double *err,
+               int device);
+
+typedef struct lfvio_sfm_summary {
+    int ok;             /* GlobalSFM::construct's return value                                               */
+    int fail_stage;     /* 0 none, 1 solveFrameByPnP (< 10 points, initial_sfm.cpp:50-55), 2 BA not converged */
+    int fail_frame;     /* frame of a PnP failure                                                            */
+    int ba_iterations, ba_successful, ba_converged;
+    double ba_final_cost;
+    double ba_costs[LFVIO_SFM_MAX_BA_ITER + 1]; /* cost at the start and after every successful step         */
+} lfvio_sfm_summary;
+
+/* GlobalSFM::construct (initial/initial_sfm.cpp:127-316).  Feature j has the observations
+ * obs_first[j] .. obs_first[j+1] (SFMFeature::observation: frame index obs_frame[o], ascending, and bearing
+ * obs_pts[3 o ..]).  l / relative_R / relative_T: from relativePose.  Outputs: q (frame_num x 4) and
+ * T (frame_num x 3) = w_R_cam / camera position in the frame of camera l; points (n_features x 3, may be NULL)
+ * and state (n_features, may be NULL) = SFMFeature::position / state (sfm_tracked_points).  run_ba = 0 skips the
+ * full BA (:230-297, debugging / parity hook).  The BA is Ceres' Levenberg-Marquardt with DENSE_SCHUR restated;
+ * its 0.2 s wall-clock limit (:279) is replaced by the default 50-iteration limit.                            */
+int lfvio_global_sfm(int frame_num, int l, const double *relative_R, const double *relative_T, const int *obs_first,
+                     const int *obs_frame, const double *obs_pts, int n_features, int run_ba, double *q, double *T,
+                     double *points, unsigned char *state, lfvio_sfm_summary *summary, int device);
+/* The full BA alone (parity hook): c_rot (frame_num x 4, cam_R_w) / c_trans (frame_num x 3) / points are
+ * updated in place; rotation l and translations l, frame_num-1 stay constant (:243-251).                     */
+int lfvio_sfm_bundle_adjust(int frame_num, int l, const int *obs_first, const int *obs_frame, const double *obs_pts,
+                            int n_features, const unsigned char *state, double *c_rot, double *c_trans, double *points,
+                            lfvio_sfm_summary *summary, int device);
+
 /* ------------------------------------------------------------------------------------------
  * Live per-stage device timing (CUDA events recorded on the handle's own stream around each kernel
  * group).  Replaces the reference's TicToc prints (feature_tracker.cpp:106,141,153,170,175;

@@ -108,6 +108,9 @@ struct RansacScratch {
 // status[i] = 1 for the tracks rejectWithF keeps (all ones below 8 tracks).  seed/frame: injected random source.
 int launch_reject_with_f(const OcamDev &cam, const float2 *cur, const float2 *forw, const int *n_dev, int n_upper, int cap,
                          unsigned long long seed, unsigned frame, const RansacScratch &rs, uint8_t *status, cudaStream_t s);
+// the RANSAC alone on bearings already in rs.b1 / rs.b2 (estimator-side copy of the same code, solve_5pts.cpp:266-335)
+int launch_ransac_bearings(const int *n_dev, int n_upper, int cap, unsigned long long seed, unsigned frame, const RansacScratch &rs,
+                           uint8_t *status, cudaStream_t s);
 // setMask (feature_tracker.cpp:46-83): sort (libstdc++ introsort order), greedy keep, reorder.
 // half_width: circle_spans(min_dist) table (min_dist+1 ints), base_mask: the annulus.
 int launch_set_mask_select(const TrackArrays &in, const TrackArrays &out, int *n_dev, int cap,

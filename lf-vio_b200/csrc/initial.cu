@@ -1,0 +1,866 @@
+// K17-K22 — the estimator initialisation on device: everything Estimator::initialStructure
+// (vins_estimator/src/estimator.cpp:221-376) and visualInitialAlign (:378-455) compute, behind stage-level C-ABI entries.
+//
+//   gyro_bias_kernel        solveGyroscopeBias            initial/initial_aligment.cpp:3-29      one warp, lane per IMU interval
+//   alignment_kernel        LinearAlignment+RefineGravity initial/initial_aligment.cpp:56-205    one CTA: pair blocks scattered with
+//                                                          fp64 atomics, in-place Cholesky of the (3n+4)^2 normal equations, the four
+//                                                          gravity refinements without leaving the kernel
+//   recover_pose_kernel     recoverPose                   initial/solve_5pts.cpp:392-536         4 candidates x n cheirality tests
+//   sfm_*_kernel            GlobalSFM::construct          initial/initial_sfm.cpp:127-316        the whole chain (triangulate / PnP per
+//                                                          frame / full BA) is ENQUEUED on one stream, state and failure flag live on
+//                                                          the device, one synchronisation at the end
+//   epnp_kernel             PnpSolver::compute_pose       pnp_solver.cpp:275-338                 one CTA per frame (all non-keyframes of
+//                                                          estimator.cpp:320-357 in one launch)
+//   sfm_ba_kernel           ceres::Solve of :230-297      Ceres 1.12 LM + DENSE_SCHUR restated   one CTA, reduced camera system in
+//                                                          shared memory (see ba_core.cuh)
+// The small dense cores are the __host__ __device__ functions of init_math.cuh / ba_core.cuh (also compiled for the host by
+// the test shim, CPU-checked against oracle/initial.py); this file adds the parallel reductions, the atomics and the control.
+// These run once per start-up / restart, on tens of frames and a few hundred features: they are latency-sized, not
+// bandwidth-sized — the point of having them on the device is that initialisation needs no CPU numerics.
+#include <vector>
+
+#include "ba_core.cuh"
+#include "frontend.cuh"
+
+namespace lfvio {
+
+namespace {
+
+constexpr int NT = 256;      // threads of the single-CTA kernels
+constexpr int BA_NT = 512;
+
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    ~DBuf() {
+        if (p) cudaFree(p);
+    }
+    int put(const T *h, size_t n) {
+        LFVIO_CUDA_TRY(cudaMalloc(&p, sizeof(T) * (n ? n : 1)));
+        if (h && n) LFVIO_CUDA_TRY(cudaMemcpy(p, h, sizeof(T) * n, cudaMemcpyHostToDevice));
+        else LFVIO_CUDA_TRY(cudaMemset(p, 0, sizeof(T) * (n ? n : 1)));
+        return LFVIO_OK;
+    }
+    int get(T *h, size_t n) const {
+        LFVIO_CUDA_TRY(cudaMemcpy(h, p, sizeof(T) * n, cudaMemcpyDeviceToHost));
+        return LFVIO_OK;
+    }
+};
+
+// sum of K values over the CTA; every thread receives the totals.  red: K * (blockDim / 32) doubles of shared memory.
+template <int K>
+__device__ void block_sum(double *v, double *red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = warp_sum(v[k]);
+    __syncthreads();  // red may still be read from a previous call
+    if (lane == 0)
+        for (int k = 0; k < K; k++) red[k * nw + w] = v[k];
+    __syncthreads();
+    for (int k = 0; k < K; k++) {
+        double s = 0;
+        for (int i = 0; i < nw; i++) s += red[k * nw + i];
+        v[k] = s;
+    }
+}
+__device__ double block_max(double v, double *red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double s = red[0];
+    for (int i = 1; i < nw; i++) s = fmax(s, red[i]);
+    return s;
+}
+
+// In-place Cholesky (lower triangle, row-major, leading dimension ld) of an n x n matrix in shared or global memory by the
+// whole CTA, right-looking; *ok (shared) is cleared on a non-positive pivot.  Then solve A x = b in place in b.
+__device__ void cta_cholesky_solve(double *A, int ld, int n, double *b, int *ok) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int j = 0; j < n; j++) {
+        if (tid == 0) {
+            const double d = A[j * ld + j];
+            if (!(d > 0.0)) *ok = 0;
+            else A[j * ld + j] = sqrt(d);
+        }
+        __syncthreads();
+        if (!*ok) return;
+        const double inv = 1.0 / A[j * ld + j];
+        for (int i = j + 1 + tid; i < n; i += nt) A[i * ld + j] *= inv;
+        __syncthreads();
+        const int m = n - j - 1;
+        for (int idx = tid; idx < m * m; idx += nt) {
+            const int ii = idx / m, kk = idx - ii * m;
+            if (kk <= ii) A[(j + 1 + ii) * ld + j + 1 + kk] -= A[(j + 1 + ii) * ld + j] * A[(j + 1 + kk) * ld + j];
+        }
+        __syncthreads();
+    }
+    for (int j = 0; j < n; j++) {  // L y = b
+        if (tid == 0) b[j] /= A[j * ld + j];
+        __syncthreads();
+        const double yj = b[j];
+        for (int i = j + 1 + tid; i < n; i += nt) b[i] -= A[i * ld + j] * yj;
+        __syncthreads();
+    }
+    for (int j = n - 1; j >= 0; j--) {  // L^T x = y
+        if (tid == 0) b[j] /= A[j * ld + j];
+        __syncthreads();
+        const double xj = b[j];
+        for (int i = tid; i < j; i += nt) b[i] -= A[j * ld + i] * xj;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// solveGyroscopeBias
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void gyro_bias_kernel(const double *Rs, const double *dq, const double *Jrg, int n, double *delta_bg) {
+    const int lane = threadIdx.x;
+    double acc[12];
+    for (int k = 0; k < 12; k++) acc[k] = 0;
+    for (int i = lane; i < n - 1; i += 32) {
+        double a[9], b[3];
+        im::gyro_bias_pair(Rs + 9 * i, Rs + 9 * (i + 1), dq + 4 * i, Jrg + 9 * i, a, b);
+        for (int k = 0; k < 9; k++) acc[k] += a[k];
+        for (int k = 0; k < 3; k++) acc[9 + k] += b[k];
+    }
+    for (int k = 0; k < 12; k++) acc[k] = warp_sum(acc[k]);
+    if (lane == 0) {  // A.ldlt().solve(b) of a 3 x 3 system
+        double inv[9];
+        im::inv3(acc, inv);
+        im::mat3_vec(inv, acc + 9, delta_bg);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LinearAlignment + RefineGravity
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) alignment_kernel(const double *Rs, const double *Ts, const double *dp, const double *dv,
+                                                        const double *dts, int n, double t0, double t1, double t2, double g_norm,
+                                                        double *A, double *bvec, double *g_out, double *x_out, int *ok_out) {
+    __shared__ double s_gcols[9], s_gfixed[3], s_tic[3], s_g0[3];
+    __shared__ int s_ok, s_stop;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_tic[0] = t0, s_tic[1] = t1, s_tic[2] = t2;
+        for (int i = 0; i < 9; i++) s_gcols[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        s_gfixed[0] = s_gfixed[1] = s_gfixed[2] = 0.0;
+        s_ok = 1, s_stop = 0;
+    }
+    __syncthreads();
+    // pass 0 = LinearAlignment (k = 3), passes 1..4 = RefineGravity (k = 2)
+    for (int pass = 0; pass < 5; pass++) {
+        const int k = pass == 0 ? 3 : 2, kk = k + 1, ns = 3 * n + kk;
+        for (int i = tid; i < ns * ns; i += NT) A[i] = 0.0;
+        for (int i = tid; i < ns; i += NT) bvec[i] = 0.0;
+        __syncthreads();
+        for (int i = tid; i < n - 1; i += NT) {
+            double tA[60], tb[6];
+            im::alignment_pair(Rs + 9 * i, Rs + 9 * (i + 1), Ts + 3 * i, Ts + 3 * (i + 1), dp + 3 * i, dv + 3 * i, dts[i], s_tic, s_gcols, k,
+                               s_gfixed, tA, tb);
+            const int w = 6 + kk;
+            for (int a = 0; a < w; a++) {
+                const int ga = a < 6 ? 3 * i + a : ns - kk + (a - 6);
+                double rb = 0;
+                for (int r = 0; r < 6; r++) rb += tA[10 * r + a] * tb[r];
+                atomicAdd(&bvec[ga], rb * 1000.0);
+                for (int c = 0; c <= a; c++) {  // lower triangle only (the Cholesky reads nothing else)
+                    const int gc = c < 6 ? 3 * i + c : ns - kk + (c - 6);
+                    double s = 0;
+                    for (int r = 0; r < 6; r++) s += tA[10 * r + a] * tA[10 * r + c];
+                    atomicAdd(&A[ga * ns + gc], s * 1000.0);
+                }
+            }
+        }
+        __syncthreads();
+        cta_cholesky_solve(A, ns, ns, bvec, &s_ok);
+        __syncthreads();
+        if (tid == 0) {
+            if (!s_ok) s_stop = 1;
+            else if (pass == 0) {
+                const double s = bvec[ns - 1] / 100.0;
+                const double g[3] = {bvec[ns - 4], bvec[ns - 3], bvec[ns - 2]};
+                const double gn = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+                if (fabs(gn - g_norm) > 1.0 || s < 0) {  // initial_aligment.cpp:186-194
+                    s_ok = 0, s_stop = 1;
+                    for (int q = 0; q < 3; q++) g_out[q] = g[q];
+                } else {
+                    for (int q = 0; q < 3; q++) s_g0[q] = g[q] / gn * g_norm;  // RefineGravity :58
+                }
+            } else {
+                const double dg[2] = {bvec[ns - 3], bvec[ns - 2]};  // x.segment<2>(n_state - 3)
+                double g[3];
+                for (int q = 0; q < 3; q++) g[q] = s_g0[q] + s_gcols[2 * q] * dg[0] + s_gcols[2 * q + 1] * dg[1];
+                const double gn = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+                for (int q = 0; q < 3; q++) s_g0[q] = g[q] / gn * g_norm;
+            }
+            if (!s_stop && pass < 4) {  // next RefineGravity pass linearises at the current g0
+                im::tangent_basis(s_g0, s_gcols);
+                for (int q = 0; q < 3; q++) s_gfixed[q] = s_g0[q];
+            }
+        }
+        __syncthreads();
+        if (s_stop || pass == 4) {
+            for (int i = tid; i < ns; i += NT) x_out[i] = bvec[i];
+            break;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_ok) {
+            const int ns = 3 * n + 3;
+            const double s = x_out[ns - 1] / 100.0;  // :199-200
+            x_out[ns - 1] = s;
+            for (int q = 0; q < 3; q++) g_out[q] = s_g0[q];
+            if (s < 0.0) s_ok = 0;
+        }
+        *ok_out = s_ok;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// recoverPose + the (repaired) tail of solveRelativeRT
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) recover_pose_kernel(const double *E, const double3 *b1, const double3 *b2, int n, double *rotation,
+                                                           double *translation, int *inlier_cnt) {
+    __shared__ double s_R[2][9], s_t[2][3];
+    __shared__ int s_cnt[4];
+    if (threadIdx.x == 0) {
+        im::decompose_essential(E, s_R[0], s_R[1], s_t[0]);
+        for (int k = 0; k < 3; k++) s_t[1][k] = -s_t[0][k];
+        for (int k = 0; k < 4; k++) s_cnt[k] = 0;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 4 * n; idx += NT) {
+        const int c = idx / n, i = idx - c * n;
+        const double p[3] = {b1[i].x, b1[i].y, b1[i].z}, q[3] = {b2[i].x, b2[i].y, b2[i].z};
+        if (im::cheirality(s_R[c & 1], s_t[c >> 1], p, q)) atomicAdd(&s_cnt[c], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int g1 = s_cnt[0], g2 = s_cnt[1], g3 = s_cnt[2], g4 = s_cnt[3];
+        int k;
+        if (g1 >= g2 && g1 >= g3 && g1 >= g4) k = 0;
+        else if (g2 >= g1 && g2 >= g3 && g2 >= g4) k = 1;
+        else if (g3 >= g1 && g3 >= g2 && g3 >= g4) k = 2;
+        else k = 3;
+        const double *R = s_R[k & 1], *t = s_t[k >> 1];
+        double Rt_t[3];
+        im::mat3_tvec(R, t, Rt_t);
+        for (int r = 0; r < 3; r++) {
+            for (int c = 0; c < 3; c++) rotation[3 * r + c] = R[3 * c + r];  // Rotation = R^T
+            translation[r] = -Rt_t[r];                                        // Translation = -R^T t
+        }
+        *inlier_cnt = s_cnt[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// EPnP by one CTA
+// ---------------------------------------------------------------------------------------------------------------
+struct EpnpShared {
+    double mean[3], cws[12], CCi[9], MtM[144], V[144], ccs[12], pc0[3], R[9], T[3], bestR[9], bestT[3];
+    double sgn, best;
+    im::EpnpCore core;
+    double red[16 * (NT / 32)];
+};
+
+// pws, us: n x 3 (global); alphas: n x 4 global scratch.  All threads of the CTA call this; thread 0 ends up with the
+// result in sh.bestR / sh.bestT / sh.best (visible to all after the final barrier).
+__device__ void epnp_block(int n, const double *pws, const double *us, double *alphas, EpnpShared &sh) {
+    const int tid = threadIdx.x;
+    double v[9];
+    v[0] = v[1] = v[2] = 0;
+    for (int i = tid; i < n; i += NT)
+        for (int k = 0; k < 3; k++) v[k] += pws[3 * i + k];
+    block_sum<3>(v, sh.red);
+    if (tid == 0)
+        for (int k = 0; k < 3; k++) sh.mean[k] = v[k] / n;
+    __syncthreads();
+    for (int k = 0; k < 9; k++) v[k] = 0;
+    for (int i = tid; i < n; i += NT)
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) v[3 * a + b] += (pws[3 * i + a] - sh.mean[a]) * (pws[3 * i + b] - sh.mean[b]);
+    block_sum<9>(v, sh.red);
+    if (tid == 0) {
+        im::epnp_control_points(n, sh.mean, v, sh.cws);
+        im::epnp_cc_inv(sh.cws, sh.CCi);
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) im::epnp_alphas(sh.cws, sh.CCi, pws + 3 * i, alphas + 4 * i);
+    __syncthreads();
+    if (tid < 144) {
+        const int r = tid / 12, c = tid - 12 * r;
+        double acc = 0;
+        for (int i = 0; i < n; i++) acc += im::epnp_mtm_entry(alphas + 4 * i, us + 3 * i, r, c);
+        sh.MtM[tid] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) im::epnp_core(sh.MtM, sh.cws, &sh.core, sh.V);
+    __syncthreads();
+    for (int which = 0; which < 3; which++) {
+        if (tid == 0) {
+            im::epnp_ccs(&sh.core, which, sh.ccs);
+            double z = 0;  // solve_for_sign (:244-252) looks at correspondence 0 only
+            for (int j = 0; j < 4; j++) z += alphas[j] * sh.ccs[3 * j + 2];
+            const double s0 = us[2] > 0 ? 1.0 : -1.0;
+            sh.sgn = ((z < 0.0 && s0 > 0) || (z > 0.0 && s0 < 0)) ? -1.0 : 1.0;
+        }
+        __syncthreads();
+        v[0] = v[1] = v[2] = 0;
+        for (int i = tid; i < n; i += NT)
+            for (int k = 0; k < 3; k++) {
+                double s = 0;
+                for (int j = 0; j < 4; j++) s += alphas[4 * i + j] * sh.ccs[3 * j + k];
+                v[k] += sh.sgn * s;
+            }
+        block_sum<3>(v, sh.red);
+        if (tid == 0)
+            for (int k = 0; k < 3; k++) sh.pc0[k] = v[k] / n;
+        __syncthreads();
+        for (int k = 0; k < 9; k++) v[k] = 0;
+        for (int i = tid; i < n; i += NT) {
+            double pc[3];
+            for (int k = 0; k < 3; k++) {
+                double s = 0;
+                for (int j = 0; j < 4; j++) s += alphas[4 * i + j] * sh.ccs[3 * j + k];
+                pc[k] = sh.sgn * s - sh.pc0[k];
+            }
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) v[3 * a + b] += pc[a] * (pws[3 * i + b] - sh.mean[b]);
+        }
+        block_sum<9>(v, sh.red);
+        if (tid == 0) im::epnp_rt_from_w(v, sh.pc0, sh.mean, sh.R, sh.T);
+        __syncthreads();
+        double err = 0;
+        for (int i = tid; i < n; i += NT) {
+            double p[3];
+            im::mat3_vec(sh.R, pws + 3 * i, p);
+            for (int k = 0; k < 3; k++) {
+                const double d = us[3 * i + k] - (p[k] + sh.T[k]);
+                err += d * d;
+            }
+        }
+        block_sum<1>(&err, sh.red);
+        if (tid == 0) {
+            err /= n;
+            if (which == 0 || err < sh.best) {  // compute_pose :318-337
+                sh.best = err;
+                for (int k = 0; k < 9; k++) sh.bestR[k] = sh.R[k];
+                for (int k = 0; k < 3; k++) sh.bestT[k] = sh.T[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// one CTA per problem: correspondences [first[p], first[p+1])
+__global__ void __launch_bounds__(NT) epnp_kernel(const double *pws, const double *us, const int *first, double *alphas, double *R,
+                                                   double *T, double *err) {
+    __shared__ EpnpShared sh;
+    const int p = blockIdx.x, o = first[p], n = first[p + 1] - o;
+    if (n < 4) {
+        if (threadIdx.x == 0) err[p] = -1.0;
+        return;
+    }
+    epnp_block(n, pws + 3 * (size_t)o, us + 3 * (size_t)o, alphas + 4 * (size_t)o, sh);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 9; k++) R[9 * p + k] = sh.bestR[k];
+        for (int k = 0; k < 3; k++) T[3 * p + k] = sh.bestT[k];
+        err[p] = sh.best;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GlobalSFM::construct
+// ---------------------------------------------------------------------------------------------------------------
+struct SfmDev {
+    int F, L, l;
+    const int *obs_first, *obs_frame;
+    const double *obs_pts;
+    unsigned char *state;
+    double *points;      // L x 3
+    double *cR, *cT;     // F x 9, F x 3: c_Rotation / c_Translation (camera <- world of frame l)
+    double *cq;          // F x 4: c_Quat (w, x, y, z), the BA's rotation blocks
+    int *fail;           // [0] stage (0 ok, 1 PnP, 2 BA), [1] frame
+};
+
+__global__ void sfm_init_kernel(SfmDev d, const double *relative_R, const double *relative_T) {
+    if (threadIdx.x != 0) return;
+    const int last = d.F - 1;
+    for (int k = 0; k < 9; k++) d.cR[9 * d.l + k] = (k % 4 == 0) ? 1.0 : 0.0;   // q[l] = identity, T[l] = 0 (:136-140)
+    for (int k = 0; k < 3; k++) d.cT[3 * d.l + k] = 0.0;
+    d.cq[4 * d.l] = 1.0, d.cq[4 * d.l + 1] = d.cq[4 * d.l + 2] = d.cq[4 * d.l + 3] = 0.0;
+    double q[4], qi[4], t[3];
+    im::rot_to_quat(relative_R, q);                                              // q[last] = q[l] * Quaterniond(relative_R)
+    const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    qi[0] = q[0] / n2, qi[1] = -q[1] / n2, qi[2] = -q[2] / n2, qi[3] = -q[3] / n2;  // c_Quat[last] = q[last].inverse()
+    im::quat_to_rot(qi, d.cR + 9 * last);
+    im::mat3_vec(d.cR + 9 * last, relative_T, t);
+    for (int k = 0; k < 3; k++) d.cT[3 * last + k] = -t[k], d.cq[4 * last + k] = qi[k];
+    d.cq[4 * last + 3] = qi[3];
+}
+
+__device__ __forceinline__ void sfm_pose(const SfmDev &d, int f, double *P) {
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) P[4 * r + c] = d.cR[9 * f + 3 * r + c];
+        P[4 * r + 3] = d.cT[3 * f + r];
+    }
+}
+
+// triangulateTwoFrames (:74-114) for f0 >= 0; the "all other points" loop (:207-228) for f0 < 0
+__global__ void sfm_triangulate_kernel(SfmDev d, int f0, int f1) {
+    if (d.fail[0]) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= d.L || d.state[j]) return;
+    const int a = d.obs_first[j], b = d.obs_first[j + 1];
+    int o0 = -1, o1 = -1;
+    if (f0 >= 0) {
+        for (int o = a; o < b; o++) {
+            if (d.obs_frame[o] == f0) o0 = o;
+            if (d.obs_frame[o] == f1) o1 = o;
+        }
+        if (o0 < 0 || o1 < 0) return;
+    } else {
+        if (b - a < 2) return;
+        o0 = a, o1 = b - 1;
+    }
+    double P0[12], P1[12], X[3];
+    sfm_pose(d, d.obs_frame[o0], P0);
+    sfm_pose(d, d.obs_frame[o1], P1);
+    im::triangulate_point(P0, P1, d.obs_pts + 3 * o0, d.obs_pts + 3 * o1, X);
+    for (int k = 0; k < 3; k++) d.points[3 * j + k] = X[k];
+    d.state[j] = 1;
+}
+
+// solveFrameByPnP (:25-72): gather the triangulated features seen in frame i (in feature order: the sign fix of the EPnP
+// looks at the first one), EPnP, write the pose of frame i.
+__global__ void __launch_bounds__(NT) sfm_pnp_kernel(SfmDev d, int i, double *pw_list, double *us_list, double *alphas) {
+    __shared__ EpnpShared sh;
+    __shared__ int s_cnt[NT + 1];
+    if (d.fail[0]) return;
+    const int tid = threadIdx.x;
+    const int chunk = (d.L + NT - 1) / NT, j0 = tid * chunk, j1 = min(d.L, j0 + chunk);
+    int cnt = 0;
+    for (int j = j0; j < j1; j++) {
+        if (!d.state[j]) continue;
+        for (int o = d.obs_first[j]; o < d.obs_first[j + 1]; o++)
+            if (d.obs_frame[o] == i) {
+                cnt++;
+                break;
+            }
+    }
+    s_cnt[tid + 1] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        s_cnt[0] = 0;
+        for (int t = 0; t < NT; t++) s_cnt[t + 1] += s_cnt[t];
+    }
+    __syncthreads();
+    int pos = s_cnt[tid];
+    const int n = s_cnt[NT];
+    for (int j = j0; j < j1; j++) {
+        if (!d.state[j]) continue;
+        for (int o = d.obs_first[j]; o < d.obs_first[j + 1]; o++)
+            if (d.obs_frame[o] == i) {
+                for (int k = 0; k < 3; k++) {
+                    pw_list[3 * pos + k] = d.points[3 * j + k];
+                    us_list[3 * pos + k] = d.obs_pts[3 * o + k];
+                }
+                pos++;
+                break;
+            }
+    }
+    __syncthreads();
+    if (n < 10) {  // :50-55 (below 15 the reference only prints a warning)
+        if (tid == 0) d.fail[0] = 1, d.fail[1] = i;
+        return;
+    }
+    epnp_block(n, pw_list, us_list, alphas, sh);
+    if (tid == 0) {
+        for (int k = 0; k < 9; k++) d.cR[9 * i + k] = sh.bestR[k];
+        for (int k = 0; k < 3; k++) d.cT[3 * i + k] = sh.bestT[k];
+        im::rot_to_quat(sh.bestR, d.cq + 4 * i);  // c_Quat[i] = c_Rotation[i]
+    }
+}
+
+struct AtomicAdd {
+    __device__ void operator()(double *p, double v) const { atomicAdd(p, v); }
+};
+
+// Dynamic shared memory: S (D x D) | gc (D) | scale_c (D) | dxc (D) | cq (4F) | ct (3F) | cand_q (4F) | cand_t (3F) | red
+__global__ void __launch_bounds__(BA_NT) sfm_ba_kernel(SfmDev d, double *ct_io /* F x 3 */, double *V, double *gp, double *sp, double *Vinv,
+                                                       double *cand, im::BaCtl *ctl_out) {
+    extern __shared__ double smem[];
+    __shared__ im::BaCtl c;
+    __shared__ int s_go, s_accept;
+    if (d.fail[0]) return;
+    const int tid = threadIdx.x, F = d.F, L = d.L, D = 6 * F;
+    double *S = smem, *gc = S + D * D, *scale_c = gc + D, *dxc = scale_c + D, *cq = dxc + D, *ct = cq + 4 * F, *cand_q = ct + 3 * F,
+           *cand_t = cand_q + 4 * F, *red = cand_t + 3 * F;
+    const im::BaProblem P{F, L, d.l, d.obs_first, d.obs_frame, d.obs_pts, d.state};
+    for (int k = tid; k < 4 * F; k += BA_NT) cq[k] = d.cq[k];
+    for (int k = tid; k < 3 * F; k += BA_NT) ct[k] = ct_io[k];
+    for (int k = tid; k < D; k += BA_NT) scale_c[k] = 1.0;
+    if (tid == 0) im::ba_init(&c);
+    bool first = true;
+    const AtomicAdd add;
+    __syncthreads();
+    while (true) {
+        for (int k = tid; k < D * D + D; k += BA_NT) S[k] = 0.0;  // S and gc are contiguous
+        __syncthreads();
+        double v[3] = {0, 0, 0}, gmax = 0;
+        for (int j = tid; j < L; j += BA_NT)
+            if (d.state[j]) v[0] += im::ba_point_linearize(P, cq, ct, d.points, j, S, gc, V + 9 * j, gp + 3 * j, &gmax, add);
+        block_sum<1>(v, red);
+        for (int k = tid; k < D; k += BA_NT) gmax = fmax(gmax, fabs(gc[k]));  // (block_sum's barriers made gc complete)
+        gmax = block_max(gmax, red);
+        if (tid == 0) {
+            c.cost = v[0], c.gmax = gmax;
+            s_go = im::ba_begin_iteration(&c) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_go) break;
+        if (first) {
+            for (int k = tid; k < D; k += BA_NT) scale_c[k] = im::ba_jacobi_scale(S[k * D + k]);
+            for (int j = tid; j < L; j += BA_NT)
+                if (d.state[j])
+                    for (int a = 0; a < 3; a++) sp[3 * j + a] = im::ba_jacobi_scale(V[9 * j + 4 * a]);
+            first = false;
+            __syncthreads();
+        }
+        for (int k = tid; k < D * D; k += BA_NT) {
+            const int a = k / D, b = k - a * D;
+            S[k] *= scale_c[a] * scale_c[b];
+        }
+        for (int k = tid; k < D; k += BA_NT) gc[k] *= scale_c[k];
+        __syncthreads();
+        const double radius = c.radius;
+        for (int k = tid; k < D; k += BA_NT) S[k * D + k] = S[k * D + k] == 0.0 ? 1.0 : S[k * D + k] + im::ba_lm_diag(S[k * D + k], radius);
+        __syncthreads();
+        for (int j = tid; j < L; j += BA_NT)
+            if (d.state[j]) im::ba_point_schur(P, cq, ct, d.points, j, V + 9 * j, gp + 3 * j, scale_c, sp + 3 * j, radius, S, gc, Vinv + 9 * j, add);
+        __syncthreads();
+        for (int k = tid; k < D; k += BA_NT) dxc[k] = gc[k];
+        if (tid == 0) c.chol_ok = 1;
+        __syncthreads();
+        cta_cholesky_solve(S, D, D, dxc, &c.chol_ok);
+        __syncthreads();
+        v[0] = v[1] = v[2] = 0;
+        double cand_cost = 0;
+        if (c.chol_ok) {
+            for (int k = tid; k < D; k += BA_NT) dxc[k] = -dxc[k];
+            __syncthreads();
+            for (int j = tid; j < L; j += BA_NT)
+                if (d.state[j])
+                    im::ba_point_backsub(P, cq, ct, d.points, j, gp + 3 * j, scale_c, sp + 3 * j, Vinv + 9 * j, dxc, cand, &v[0], &v[1], &v[2]);
+            if (tid < F) im::ba_cam_candidate(P, cq, ct, tid, scale_c, dxc, cand_q, cand_t, &v[1], &v[2]);
+            block_sum<3>(v, red);  // (its barriers also publish cand / cand_q / cand_t)
+            for (int j = tid; j < L; j += BA_NT)
+                if (d.state[j]) cand_cost += im::ba_point_cost(P, cand_q, cand_t, cand, j);
+            block_sum<1>(&cand_cost, red);
+        }
+        if (tid == 0) {
+            c.model_change = v[0], c.step2 = v[1], c.xnorm2 = v[2], c.cand_cost = cand_cost;
+            s_accept = im::ba_decide(&c);
+        }
+        __syncthreads();
+        if (s_accept) {
+            for (int j = tid; j < L; j += BA_NT)
+                if (d.state[j])
+                    for (int a = 0; a < 3; a++) d.points[3 * j + a] = cand[3 * j + a];
+            for (int k = tid; k < 4 * F; k += BA_NT) cq[k] = cand_q[k];
+            for (int k = tid; k < 3 * F; k += BA_NT) ct[k] = cand_t[k];
+        }
+        __syncthreads();
+        if (c.done) break;
+    }
+    for (int k = tid; k < 4 * F; k += BA_NT) d.cq[k] = cq[k];
+    for (int k = tid; k < 3 * F; k += BA_NT) ct_io[k] = ct[k];
+    if (tid == 0) {
+        *ctl_out = c;
+        // initial_sfm.cpp:283-294: "CONVERGENCE || final_cost < 5e-03", otherwise construct() fails
+        if (!(c.converged || c.cost < 5e-3) && d.fail[0] == 0) d.fail[0] = 2, d.fail[1] = -1;
+    }
+}
+
+// q[i] = c_Quat[i].inverse(), T[i] = -(q[i] * c_translation[i])  (:295-309)
+__global__ void sfm_finish_kernel(SfmDev d, const double *ct, double *q_out, double *T_out) {
+    const int i = threadIdx.x;
+    if (i >= d.F) return;
+    const double *c = d.cq + 4 * i;
+    const double n2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2] + c[3] * c[3];
+    const double q[4] = {c[0] / n2, -c[1] / n2, -c[2] / n2, -c[3] / n2};
+    double R[9], t[3];
+    im::quat_to_rot(q, R);
+    im::mat3_vec(R, ct + 3 * i, t);
+    for (int k = 0; k < 4; k++) q_out[4 * i + k] = q[k];
+    for (int k = 0; k < 3; k++) T_out[3 * i + k] = -t[k];
+}
+
+size_t ba_smem_bytes(int F) {
+    const int D = 6 * F;
+    return sizeof(double) * ((size_t)D * D + 3 * D + 14 * F + 16 * (BA_NT / 32));
+}
+
+void fill_summary(const im::BaCtl &c, lfvio_sfm_summary *s) {
+    s->ba_iterations = c.iter;
+    s->ba_successful = c.n_success;
+    s->ba_converged = c.converged;
+    s->ba_final_cost = c.cost;
+    for (int k = 0; k <= LFVIO_SFM_MAX_BA_ITER; k++) s->ba_costs[k] = k <= c.n_success ? c.costs[k] : 0.0;
+}
+
+int check_tracks(const int *obs_first, const int *obs_frame, int n_features, int frame_num) {
+    LFVIO_REQUIRE(obs_first[0] == 0, "sfm: obs_first[0] must be 0");
+    for (int j = 0; j < n_features; j++) {
+        LFVIO_REQUIRE(obs_first[j + 1] >= obs_first[j], "sfm: obs_first must be non-decreasing");
+        for (int o = obs_first[j]; o < obs_first[j + 1]; o++) {
+            LFVIO_REQUIRE(obs_frame[o] >= 0 && obs_frame[o] < frame_num, "sfm: observation frame outside the window");
+            LFVIO_REQUIRE(o == obs_first[j] || obs_frame[o] > obs_frame[o - 1], "sfm: observations of a feature must be in ascending frame order");
+        }
+    }
+    return LFVIO_OK;
+}
+
+}  // namespace
+
+}  // namespace lfvio
+
+using namespace lfvio;
+
+extern "C" int lfvio_solve_gyro_bias(const double *R, const double *delta_q, const double *J_rg, int n_frames, double *delta_bg,
+                                     int device) {
+    clear_error();
+    LFVIO_REQUIRE(R && delta_q && J_rg && delta_bg && n_frames >= 2, "lfvio_solve_gyro_bias: bad arguments");
+    LFVIO_CUDA_TRY(cudaSetDevice(device));
+    DBuf<double> dR, dq, dJ, out;
+    LFVIO_TRY(dR.put(R, 9 * (size_t)n_frames));
+    LFVIO_TRY(dq.put(delta_q, 4 * (size_t)(n_frames - 1)));
+    LFVIO_TRY(dJ.put(J_rg, 9 * (size_t)(n_frames - 1)));
+    LFVIO_TRY(out.put(nullptr, 3));
+    gyro_bias_kernel<<<1, 32>>>(dR.p, dq.p, dJ.p, n_frames, out.p);
+    LFVIO_LAUNCH_CHECK();
+    return out.get(delta_bg, 3);
+}
+
+extern "C" int lfvio_linear_alignment(const double *R, const double *T, const double *delta_p, const double *delta_v,
+                                      const double *sum_dt, int n_frames, const double *tic, double g_norm, double *g, double *x,
+                                      int *ok, int device) {
+    clear_error();
+    LFVIO_REQUIRE(R && T && delta_p && delta_v && sum_dt && tic && g && x && ok, "lfvio_linear_alignment: null argument");
+    LFVIO_REQUIRE(n_frames >= 2 && n_frames <= LFVIO_INIT_MAX_FRAMES, "lfvio_linear_alignment: 2 <= n_frames <= LFVIO_INIT_MAX_FRAMES");
+    LFVIO_CUDA_TRY(cudaSetDevice(device));
+    const int ns = 3 * n_frames + 4;
+    DBuf<double> dR, dT, dp, dv, dt, A, b, dg, dx;
+    DBuf<int> dok;
+    LFVIO_TRY(dR.put(R, 9 * (size_t)n_frames));
+    LFVIO_TRY(dT.put(T, 3 * (size_t)n_frames));
+    LFVIO_TRY(dp.put(delta_p, 3 * (size_t)(n_frames - 1)));
+    LFVIO_TRY(dv.put(delta_v, 3 * (size_t)(n_frames - 1)));
+    LFVIO_TRY(dt.put(sum_dt, (size_t)(n_frames - 1)));
+    LFVIO_TRY(A.put(nullptr, (size_t)ns * ns));
+    LFVIO_TRY(b.put(nullptr, ns));
+    LFVIO_TRY(dg.put(nullptr, 3));
+    LFVIO_TRY(dx.put(nullptr, ns));
+    LFVIO_TRY(dok.put(nullptr, 1));
+    alignment_kernel<<<1, NT>>>(dR.p, dT.p, dp.p, dv.p, dt.p, n_frames, tic[0], tic[1], tic[2], g_norm, A.p, b.p, dg.p, dx.p, dok.p);
+    LFVIO_LAUNCH_CHECK();
+    LFVIO_TRY(dg.get(g, 3));
+    LFVIO_TRY(dx.get(x, ns));
+    return dok.get(ok, 1);
+}
+
+extern "C" int lfvio_solve_relative_rt(const double *corres, int n, unsigned long long seed, unsigned frame, double *rotation,
+                                       double *translation, int *inlier_cnt, double *E_out, int device) {
+    clear_error();
+    LFVIO_REQUIRE(n >= 0 && rotation && translation && inlier_cnt && (n == 0 || corres), "lfvio_solve_relative_rt: bad arguments");
+    *inlier_cnt = 0;
+    if (n < 15) return LFVIO_OK;  // solve_5pts.cpp:540: below 15 correspondences the reference returns false untouched
+    LFVIO_CUDA_TRY(cudaSetDevice(device));
+    std::vector<double> h1(3 * (size_t)n), h2(3 * (size_t)n);
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) h1[3 * i + k] = corres[6 * i + k], h2[3 * i + k] = corres[6 * i + 3 + k];
+    DBuf<double> b1, b2, E, Eb, R, T;
+    DBuf<float> score;
+    DBuf<uint8_t> flags, st;
+    DBuf<int> nd, best, cnt;
+    LFVIO_TRY(b1.put(h1.data(), h1.size()));
+    LFVIO_TRY(b2.put(h2.data(), h2.size()));
+    LFVIO_TRY(E.put(nullptr, 900));
+    LFVIO_TRY(Eb.put(nullptr, 9));
+    LFVIO_TRY(R.put(nullptr, 9));
+    LFVIO_TRY(T.put(nullptr, 3));
+    LFVIO_TRY(score.put(nullptr, 100));
+    LFVIO_TRY(flags.put(nullptr, 100 * (size_t)n));
+    LFVIO_TRY(st.put(nullptr, n));
+    LFVIO_TRY(nd.put(&n, 1));
+    LFVIO_TRY(best.put(nullptr, 1));
+    LFVIO_TRY(cnt.put(nullptr, 1));
+    const RansacScratch rs{reinterpret_cast<double3 *>(b1.p), reinterpret_cast<double3 *>(b2.p), E.p, score.p, flags.p, Eb.p, best.p};
+    LFVIO_TRY(launch_ransac_bearings(nd.p, n, n, seed, frame, rs, st.p, 0));
+    recover_pose_kernel<<<1, NT>>>(Eb.p, rs.b1, rs.b2, n, R.p, T.p, cnt.p);
+    LFVIO_LAUNCH_CHECK();
+    LFVIO_TRY(R.get(rotation, 9));
+    LFVIO_TRY(T.get(translation, 3));
+    LFVIO_TRY(cnt.get(inlier_cnt, 1));
+    if (E_out) LFVIO_TRY(Eb.get(E_out, 9));
+    return LFVIO_OK;
+}
+
+extern "C" int lfvio_epnp(const double *pws, const double *us, const int *first, int n_problems, double *R, double *T, double *err,
+                          int device) {
+    clear_error();
+    LFVIO_REQUIRE(n_problems >= 0 && (n_problems == 0 || (pws && us && first && R && T)), "lfvio_epnp: bad arguments");
+    if (n_problems == 0) return LFVIO_OK;
+    LFVIO_REQUIRE(first[0] == 0, "lfvio_epnp: first[0] must be 0");
+    for (int p = 0; p < n_problems; p++) LFVIO_REQUIRE(first[p + 1] - first[p] >= 4, "lfvio_epnp: a problem needs at least 4 correspondences");
+    const size_t n = first[n_problems];
+    LFVIO_CUDA_TRY(cudaSetDevice(device));
+    DBuf<double> dpw, dus, al, dR, dT, de;
+    DBuf<int> df;
+    LFVIO_TRY(dpw.put(pws, 3 * n));
+    LFVIO_TRY(dus.put(us, 3 * n));
+    LFVIO_TRY(al.put(nullptr, 4 * n));
+    LFVIO_TRY(df.put(first, (size_t)n_problems + 1));
+    LFVIO_TRY(dR.put(nullptr, 9 * (size_t)n_problems));
+    LFVIO_TRY(dT.put(nullptr, 3 * (size_t)n_problems));
+    LFVIO_TRY(de.put(nullptr, n_problems));
+    epnp_kernel<<<n_problems, NT>>>(dpw.p, dus.p, df.p, al.p, dR.p, dT.p, de.p);
+    LFVIO_LAUNCH_CHECK();
+    LFVIO_TRY(dR.get(R, 9 * (size_t)n_problems));
+    LFVIO_TRY(dT.get(T, 3 * (size_t)n_problems));
+    if (err) LFVIO_TRY(de.get(err, n_problems));
+    return LFVIO_OK;
+}
+
+namespace {
+
+struct SfmBuffers {
+    DBuf<int> of, ofr, fail;
+    DBuf<double> pts_obs, points, cR, cT, cq, V, gp, sp, Vinv, cand, pw_list, us_list, alphas, relR, relT, q_out, T_out;
+    DBuf<unsigned char> state;
+    DBuf<im::BaCtl> ctl;
+    SfmDev dev{};
+    int setup(int F, int l, const int *obs_first, const int *obs_frame, const double *obs_pts, int L) {
+        const size_t n_obs = obs_first[L];
+        LFVIO_TRY(of.put(obs_first, (size_t)L + 1));
+        LFVIO_TRY(ofr.put(obs_frame, n_obs));
+        LFVIO_TRY(pts_obs.put(obs_pts, 3 * n_obs));
+        LFVIO_TRY(fail.put(nullptr, 2));
+        LFVIO_TRY(points.put(nullptr, 3 * (size_t)L));
+        LFVIO_TRY(state.put(nullptr, L));
+        LFVIO_TRY(cR.put(nullptr, 9 * (size_t)F));
+        LFVIO_TRY(cT.put(nullptr, 3 * (size_t)F));
+        LFVIO_TRY(cq.put(nullptr, 4 * (size_t)F));
+        LFVIO_TRY(V.put(nullptr, 9 * (size_t)L));
+        LFVIO_TRY(gp.put(nullptr, 3 * (size_t)L));
+        LFVIO_TRY(sp.put(nullptr, 3 * (size_t)L));
+        LFVIO_TRY(Vinv.put(nullptr, 9 * (size_t)L));
+        LFVIO_TRY(cand.put(nullptr, 3 * (size_t)L));
+        LFVIO_TRY(pw_list.put(nullptr, 3 * (size_t)L));
+        LFVIO_TRY(us_list.put(nullptr, 3 * (size_t)L));
+        LFVIO_TRY(alphas.put(nullptr, 4 * (size_t)L));
+        LFVIO_TRY(q_out.put(nullptr, 4 * (size_t)F));
+        LFVIO_TRY(T_out.put(nullptr, 3 * (size_t)F));
+        LFVIO_TRY(ctl.put(nullptr, 1));
+        dev = SfmDev{F, L, l, of.p, ofr.p, pts_obs.p, state.p, points.p, cR.p, cT.p, cq.p, fail.p};
+        return LFVIO_OK;
+    }
+    int run_ba(int F) {
+        const size_t smem = ba_smem_bytes(F);
+        LFVIO_TRY(ensure_dyn_smem((const void *)sfm_ba_kernel, (int)ba_smem_bytes(LFVIO_SFM_MAX_FRAMES)));
+        sfm_ba_kernel<<<1, BA_NT, smem>>>(dev, cT.p, V.p, gp.p, sp.p, Vinv.p, cand.p, ctl.p);
+        LFVIO_LAUNCH_CHECK();
+        return LFVIO_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" int lfvio_sfm_bundle_adjust(int frame_num, int l, const int *obs_first, const int *obs_frame, const double *obs_pts,
+                                       int n_features, const unsigned char *state, double *c_rot, double *c_trans, double *points,
+                                       lfvio_sfm_summary *summary, int device) {
+    clear_error();
+    LFVIO_REQUIRE(obs_first && obs_frame && obs_pts && state && c_rot && c_trans && points && summary, "lfvio_sfm_bundle_adjust: null argument");
+    LFVIO_REQUIRE(frame_num >= 2 && frame_num <= LFVIO_SFM_MAX_FRAMES && l >= 0 && l < frame_num && n_features > 0,
+                  "lfvio_sfm_bundle_adjust: bad sizes");
+    LFVIO_TRY(check_tracks(obs_first, obs_frame, n_features, frame_num));
+    LFVIO_CUDA_TRY(cudaSetDevice(device));
+    SfmBuffers B;
+    LFVIO_TRY(B.setup(frame_num, l, obs_first, obs_frame, obs_pts, n_features));
+    LFVIO_CUDA_TRY(cudaMemcpy(B.state.p, state, n_features, cudaMemcpyHostToDevice));
+    LFVIO_CUDA_TRY(cudaMemcpy(B.points.p, points, sizeof(double) * 3 * n_features, cudaMemcpyHostToDevice));
+    LFVIO_CUDA_TRY(cudaMemcpy(B.cq.p, c_rot, sizeof(double) * 4 * frame_num, cudaMemcpyHostToDevice));
+    LFVIO_CUDA_TRY(cudaMemcpy(B.cT.p, c_trans, sizeof(double) * 3 * frame_num, cudaMemcpyHostToDevice));
+    LFVIO_TRY(B.run_ba(frame_num));
+    im::BaCtl c;
+    LFVIO_TRY(B.ctl.get(&c, 1));
+    LFVIO_TRY(B.cq.get(c_rot, 4 * (size_t)frame_num));
+    LFVIO_TRY(B.cT.get(c_trans, 3 * (size_t)frame_num));
+    LFVIO_TRY(B.points.get(points, 3 * (size_t)n_features));
+    int fail[2];
+    LFVIO_TRY(B.fail.get(fail, 2));
+    summary->ok = fail[0] == 0, summary->fail_stage = fail[0], summary->fail_frame = fail[1];
+    fill_summary(c, summary);
+    return LFVIO_OK;
+}
+
+extern "C" int lfvio_global_sfm(int frame_num, int l, const double *relative_R, const double *relative_T, const int *obs_first,
+                                const int *obs_frame, const double *obs_pts, int n_features, int run_ba, double *q, double *T,
+                                double *points, unsigned char *state, lfvio_sfm_summary *summary, int device) {
+    clear_error();
+    LFVIO_REQUIRE(relative_R && relative_T && obs_first && obs_frame && obs_pts && q && T && summary, "lfvio_global_sfm: null argument");
+    LFVIO_REQUIRE(frame_num >= 2 && frame_num <= LFVIO_SFM_MAX_FRAMES && l >= 0 && l < frame_num - 1 && n_features > 0,
+                  "lfvio_global_sfm: bad sizes");
+    LFVIO_TRY(check_tracks(obs_first, obs_frame, n_features, frame_num));
+    LFVIO_CUDA_TRY(cudaSetDevice(device));
+    SfmBuffers B;
+    const int F = frame_num, L = n_features, last = F - 1;
+    LFVIO_TRY(B.setup(F, l, obs_first, obs_frame, obs_pts, L));
+    LFVIO_TRY(B.relR.put(relative_R, 9));
+    LFVIO_TRY(B.relT.put(relative_T, 3));
+    const SfmDev &d = B.dev;
+    const int tg = cdiv(L, 128);
+    sfm_init_kernel<<<1, 32>>>(d, B.relR.p, B.relT.p);
+    LFVIO_LAUNCH_CHECK();
+    auto tri = [&](int f0, int f1) -> int {
+        sfm_triangulate_kernel<<<tg, 128>>>(d, f0, f1);
+        LFVIO_LAUNCH_CHECK();
+        return LFVIO_OK;
+    };
+    auto pnp = [&](int i) -> int {
+        sfm_pnp_kernel<<<1, NT>>>(d, i, B.pw_list.p, B.us_list.p, B.alphas.p);
+        LFVIO_LAUNCH_CHECK();
+        return LFVIO_OK;
+    };
+    for (int i = l; i < last; i++) {  // initial_sfm.cpp:167-185
+        if (i > l) LFVIO_TRY(pnp(i));
+        LFVIO_TRY(tri(i, last));
+    }
+    for (int i = l + 1; i < last; i++) LFVIO_TRY(tri(l, i));  // :186-188
+    for (int i = l - 1; i >= 0; i--) {                         // :191-206
+        LFVIO_TRY(pnp(i));
+        LFVIO_TRY(tri(i, l));
+    }
+    LFVIO_TRY(tri(-1, -1));                                    // :207-228
+    if (run_ba) LFVIO_TRY(B.run_ba(F));
+    sfm_finish_kernel<<<1, 64>>>(d, B.cT.p, B.q_out.p, B.T_out.p);
+    LFVIO_LAUNCH_CHECK();
+    int fail[2];
+    LFVIO_TRY(B.fail.get(fail, 2));  // (synchronises)
+    im::BaCtl c;
+    LFVIO_TRY(B.ctl.get(&c, 1));
+    summary->ok = fail[0] == 0, summary->fail_stage = fail[0], summary->fail_frame = fail[1];
+    if (!run_ba || fail[0] == 1) {
+        im::ba_init(&c);
+        c.converged = run_ba ? 0 : 1;
+    }
+    fill_summary(c, summary);
+    LFVIO_TRY(B.q_out.get(q, 4 * (size_t)F));
+    LFVIO_TRY(B.T_out.get(T, 3 * (size_t)F));
+    if (points) LFVIO_TRY(B.points.get(points, 3 * (size_t)L));
+    if (state) LFVIO_TRY(B.state.get(state, L));
+    return LFVIO_OK;
+}

@@ -421,4 +421,18 @@ int launch_reject_with_f(const OcamDev &cam, const float2 *cur, const float2 *fo
     return LFVIO_OK;
 }
 
+// myfindFundamentalMat on bearings that are already on the device (MotionEstimator::myfindFundamentalMat,
+// vins_estimator/src/initial/solve_5pts.cpp:266-335 — the same code as the tracker's copy): hypotheses, scores, refit.
+int launch_ransac_bearings(const int *n_dev, int n_upper, int cap, unsigned long long seed, unsigned frame, const RansacScratch &rs,
+                           uint8_t *status, cudaStream_t s) {
+    if (n_upper <= 0) return LFVIO_OK;
+    ransac_hypothesis_kernel<<<cdiv(kHyp, kWarpsPerCta), kWarpsPerCta * 32, 0, s>>>(rs.b1, rs.b2, n_dev, cap, seed, frame, rs.E);
+    LFVIO_LAUNCH_CHECK();
+    ransac_score_kernel<<<kHyp, kScoreThreads, 0, s>>>(rs.b1, rs.b2, n_dev, cap, rs.E, rs.score, rs.flags);
+    LFVIO_LAUNCH_CHECK();
+    ransac_refit_kernel<<<1, kRefitThreads, 0, s>>>(rs.b1, rs.b2, n_dev, cap, rs.score, rs.flags, rs.E_best, rs.best, status);
+    LFVIO_LAUNCH_CHECK();
+    return LFVIO_OK;
+}
+
 }  // namespace lfvio

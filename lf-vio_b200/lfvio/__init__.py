@@ -364,3 +364,35 @@ def preintegrate(intervals, dt, acc, gyr, noise, g, device: int = 0):
 
 def triangulate(Ps, Rs, tic, ric, start_frame, obs_first, obs_pts, depth, init_depth: float = 5.0, device: int = 0):
     return prestep.triangulate(lib, check, Ps, Rs, tic, ric, start_frame, obs_first, obs_pts, depth, init_depth, device)
+
+
+# ------------------------------------------------------------------------------------------------
+# estimator initialisation (initial.py): gyro bias, gravity/scale alignment, relative pose, EPnP, global SfM
+# ------------------------------------------------------------------------------------------------
+from . import initial  # noqa: E402
+
+initial.bind(lib)
+
+
+def solve_gyro_bias(Rs, delta_q, J_rg, device: int = 0):
+    return initial.solve_gyro_bias(lib, check, Rs, delta_q, J_rg, device)
+
+
+def linear_alignment(Rs, Ts, delta_p, delta_v, sum_dt, tic, g_norm, device: int = 0):
+    return initial.linear_alignment(lib, check, Rs, Ts, delta_p, delta_v, sum_dt, tic, g_norm, device)
+
+
+def solve_relative_rt(corres, seed, frame, device: int = 0):
+    return initial.solve_relative_rt(lib, check, corres, seed, frame, device)
+
+
+def epnp(problems, device: int = 0):
+    return initial.epnp(lib, check, problems, device)
+
+
+def global_sfm(frame_num, l, relative_R, relative_T, obs_first, obs_frame, obs_pts, ba=True, device: int = 0):
+    return initial.global_sfm(lib, check, frame_num, l, relative_R, relative_T, obs_first, obs_frame, obs_pts, ba, device)
+
+
+def sfm_bundle_adjust(c_rot, c_trans, points, state, obs_first, obs_frame, obs_pts, l, device: int = 0):
+    return initial.bundle_adjust(lib, check, c_rot, c_trans, points, state, obs_first, obs_frame, obs_pts, l, device)
