@@ -11,7 +11,7 @@ int ESTIMATE_TD = 1, ESTIMATE_EXTRINSIC = 1, NUM_ITERATIONS = 8, EST_ROW = 960;
 double TR = 0.0, TD = -0.008, FOCAL_LENGTH = 160.0, MIN_PARALLAX = 10.0 / 160.0;
 Vec3 G{0.0, 0.0, 9.81007};
 
-namespace {
+namespace detail {
 
 Mat3 matmul(const Mat3 &a, const Mat3 &b) {
     Mat3 r{};
@@ -64,7 +64,8 @@ Mat3 quat_to_rot(double w, double x, double y, double z, bool normalize) {
     return {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
 }
 
-}  // namespace
+}  // namespace detail
+using namespace detail;
 
 Vec3 R2ypr(const Mat3 &R) {
     const Vec3 n{R[0], R[3], R[6]}, o{R[1], R[4], R[7]}, a{R[2], R[5], R[8]};
@@ -268,6 +269,15 @@ void Estimator::processIMU(double dt, const Vec3 &linear_acceleration, const Vec
         linear_acceleration_buf[j].push_back(linear_acceleration);
         angular_velocity_buf[j].push_back(angular_velocity);
         iv.dirty = true;
+        if (m_tmp_valid) {  // tmp_pre_integration->push_back (estimator.cpp:103)
+            if (m_tmp.dt.empty()) {  // (acc_0 / gyr_0 are still the values its constructor saw, unless the caller overrode them)
+                m_tmp.acc_start = acc_0;
+                m_tmp.gyr_start = gyr_0;
+            }
+            m_tmp.dt.push_back(dt);
+            m_tmp.acc.push_back(linear_acceleration);
+            m_tmp.gyr.push_back(angular_velocity);
+        }
     }
     acc_0 = linear_acceleration;
     gyr_0 = angular_velocity;
@@ -330,12 +340,44 @@ void Estimator::processImage(const ImageFeatures &image, double header_stamp) {
     marginalization_flag = f_manager.addFeatureCheckParallax(frame_count, image, td) ? MARGIN_OLD : MARGIN_SECOND_NEW;
     if ((int)Headers.size() <= WINDOW_SIZE) Headers.resize(WINDOW_SIZE + 1, 0.0);
     Headers[frame_count] = header_stamp;
+    {  // estimator.cpp:136-140: the frame joins all_image_frame with the pre-integration since the previous image
+        ImageFrame imageframe = std::move(m_tmp);
+        imageframe.points = image;
+        imageframe.t = header_stamp;
+        imageframe.is_key_frame = false;
+        imageframe.has_pre = m_tmp_valid;
+        all_image_frame[header_stamp] = std::move(imageframe);
+        m_tmp = ImageFrame{};
+        m_tmp.acc_start = acc_0;
+        m_tmp.gyr_start = gyr_0;
+        m_tmp.ba = Bas[frame_count];
+        m_tmp.bg = Bgs[frame_count];
+        m_tmp_valid = true;
+    }
     if (solver_flag == INITIAL) {
-        // initialStructure() is not part of this mirror: the window fills, then slides until the caller has initialised
-        // the states and set solver_flag = NON_LINEAR (the reference does the same while its initialisation fails, :177-178)
+        // With run_initial_structure == false the window fills, then slides until the caller has initialised the states and
+        // set solver_flag = NON_LINEAR (what the reference does while its initialisation fails, :177-178).
         if (frame_count == WINDOW_SIZE) {
-            if (flushIMU() != LFVIO_OK) return;
-            slideWindow();
+            bool result = false;
+            if (run_initial_structure && ESTIMATE_EXTRINSIC != 2 && (header_stamp - initial_timestamp) > 0.1) {
+                result = initialStructure();
+                initial_timestamp = header_stamp;
+            }
+            if (result) {
+                solver_flag = NON_LINEAR;
+                if (stop_after_initial_structure) return;  // parity hook: expose the states initialStructure leaves
+                solveOdometry();
+                if (last_status != LFVIO_OK) return;
+                slideWindow();
+                f_manager.removeFailures();
+                last_R = Rs[WINDOW_SIZE];
+                last_P = Ps[WINDOW_SIZE];
+                last_R0 = Rs[0];
+                last_P0 = Ps[0];
+            } else {
+                if (flushIMU() != LFVIO_OK) return;
+                slideWindow();
+            }
         } else {
             frame_count++;
         }
@@ -377,9 +419,12 @@ bool Estimator::failureDetection() {
 
 void Estimator::slideWindow() {
     if (marginalization_flag == MARGIN_OLD) {
+        const double t_0 = Headers.empty() ? 0.0 : Headers[0];
         back_R0 = Rs[0];
         back_P0 = Ps[0];
         if (frame_count == WINDOW_SIZE) {
+            // estimator.cpp:1051-1066 (`true || solver_flag == INITIAL`): frames up to the old frame 0 leave all_image_frame
+            all_image_frame.erase(all_image_frame.begin(), all_image_frame.upper_bound(t_0));
             for (int i = 0; i < WINDOW_SIZE; i++) {
                 std::swap(Rs[i], Rs[i + 1]);
                 std::swap(m_pre[i], m_pre[i + 1]);
@@ -827,6 +872,28 @@ extern "C" int lfvio_host_estimator_set_states(void *h, const double *P, const d
     e->last_P0 = e->Ps[0];
     e->last_R0 = e->Rs[0];
     if (nonlinear) e->solver_flag = Estimator::NON_LINEAR;
+    return LFVIO_OK;
+}
+
+// switch the mirror to the reference's own start-up: processImage() runs initialStructure() once the window is full
+extern "C" int lfvio_host_estimator_enable_initialization(void *h, unsigned long long ransac_seed, int stop_after) {
+    auto *e = static_cast<lfvio_host::Estimator *>(h);
+    e->run_initial_structure = true;
+    e->stop_after_initial_structure = stop_after != 0;
+    e->ransac_seed = ransac_seed;
+    return LFVIO_OK;
+}
+// info: [0] solver_flag, [1] init_attempts, [2] init_fail_stage, [3] sfm ok, [4] BA iterations, [5] all_image_frame.size();
+// g: the aligned gravity
+extern "C" int lfvio_host_estimator_init_info(void *h, int *info, double *g) {
+    auto *e = static_cast<lfvio_host::Estimator *>(h);
+    info[0] = (int)e->solver_flag;
+    info[1] = (int)e->init_attempts;
+    info[2] = e->init_fail_stage;
+    info[3] = e->sfm_summary.ok;
+    info[4] = e->sfm_summary.ba_iterations;
+    info[5] = (int)e->all_image_frame.size();
+    for (int k = 0; k < 3; k++) g[k] = e->g[k];
     return LFVIO_OK;
 }
 

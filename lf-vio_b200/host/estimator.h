@@ -5,8 +5,8 @@
 //                                                       lfvio_window_marginalize -> last_marginalization_*)
 //   vector2double()/double2vector()  estimator.cpp:488-530 / :532-626 (incl. the yaw / position gauge re-anchoring)
 //   FeatureManager::getFeatureCount/getDepthVector/setDepth   feature_manager.cpp:36-43,145-197
-// Everything else of Estimator (processIMU/processImage, initialisation, slideWindow, failure detection) is outside
-// SURVEY.md §8 (rows marked "next") and is not mirrored yet.  WINDOW_SIZE and NUM_OF_F are runtime values here
+// processIMU / processImage / slideWindow / failureDetection and the initialisation (initialStructure, host/initial.cpp)
+// are the SURVEY.md §8(f) "next" rows, mirrored as well.  WINDOW_SIZE and NUM_OF_F are runtime values here
 // (compile-time constants in the reference, vins_estimator/src/parameters.h:12-13).
 #pragma once
 #include <array>
@@ -59,6 +59,9 @@ class FeatureManager {
     // feature_manager.cpp:199-253 — every untriangulated eligible track in ONE lfvio_triangulate call.
     // Returns the C-ABI status (the reference returns void).
     int triangulate(const std::vector<Vec3> &Ps, const std::vector<Mat3> &Rs, const Vec3 tic[], const Mat3 ric[], int device = 0);
+    // feature_manager.cpp:118-143: bearings of the features seen in both frames
+    std::vector<std::pair<Vec3, Vec3>> getCorresponding(int frame_count_l, int frame_count_r);
+    void clearDepth();  // clearDepth(dep = -1) as visualInitialAlign uses it (estimator.cpp:400-403, feature_manager.cpp:169-180)
     double init_depth = 5.0;  // INIT_DEPTH (parameters.cpp:116)
 };
 
@@ -70,6 +73,21 @@ struct MarginalizationInfo {  // what the reference keeps between frames (margin
     std::vector<int> block_id, block_idx;
     std::vector<double> x0, J0, r0;
     bool valid() const { return n > 0; }
+};
+
+// initial/initial_alignment.h:13-30.  pre_integration is kept as its IMU samples + linearisation point (so that
+// IntegrationBase::repropagate is one batched lfvio_preintegrate call over all frames) and the resulting record.
+struct ImageFrame {
+    ImageFeatures points;
+    double t = 0;
+    Mat3 R{};
+    Vec3 T{};
+    bool is_key_frame = false;
+    bool has_pre = false;  // pre_integration != nullptr
+    Vec3 acc_start{}, gyr_start{}, ba{}, bg{};
+    std::vector<double> dt;
+    std::vector<Vec3> acc, gyr;
+    IntegrationBase pre{};
 };
 
 class Estimator {
@@ -92,6 +110,21 @@ class Estimator {
     // INITIAL the window only fills and slides; the caller switches to NON_LINEAR once the states are initialised.
     enum SolverFlag { INITIAL = 0, NON_LINEAR = 1 };
     void processImage(const ImageFeatures &image, double header_stamp);
+    // estimator.cpp:221-376 / :378-455 / :457-484: the numeric steps run on the device through lfvio_solve_relative_rt,
+    // lfvio_global_sfm, lfvio_epnp (all non-keyframes in one call), lfvio_solve_gyro_bias, lfvio_preintegrate (the
+    // repropagations, batched) and lfvio_linear_alignment.
+    bool initialStructure();
+    bool visualInitialAlign();
+    bool relativePose(Mat3 &relative_R, Vec3 &relative_T, int &l);
+    bool run_initial_structure = false;  // false: the pre-initialisation behaviour of this mirror (the caller sets the states)
+    bool stop_after_initial_structure = false;  // test hook: return from processImage right after a successful initialStructure
+    std::map<double, ImageFrame> all_image_frame;
+    double initial_timestamp = 0;
+    Vec3 g{};
+    unsigned long long ransac_seed = 1;  // injected random source of the 8-point RANSAC (see lfvio_reject_with_f)
+    unsigned init_attempts = 0;
+    lfvio_sfm_summary sfm_summary{};
+    int init_fail_stage = 0;  // 0 ok, 1 relativePose, 2 GlobalSFM, 3 PnP of a non-keyframe, 4 alignment (debug)
     void solveOdometry();      // :475-486
     bool failureDetection();   // :628-675
     void slideWindow();        // :1011-1105
@@ -150,7 +183,18 @@ class Estimator {
     std::vector<Interval> m_iv;
     std::vector<lfvio_imu_factor> m_pre;  // storage behind pre_integrations[] filled by flushIMU
     int integrate(int j, bool propagate);
+    ImageFrame m_tmp;          // tmp_pre_integration (estimator.cpp:101-104, 138-140)
+    bool m_tmp_valid = false;
+    int integrateImageFrames(bool all, const Vec3 *new_bg);
 };
+
+namespace detail {  // 3 x 3 helpers shared by estimator.cpp and initial.cpp
+Mat3 matmul(const Mat3 &a, const Mat3 &b);
+Vec3 matvec(const Mat3 &a, const Vec3 &v);
+Mat3 transpose(const Mat3 &a);
+std::array<double, 4> rot_to_quat(const Mat3 &m);  // (x, y, z, w)
+Mat3 quat_to_rot(double w, double x, double y, double z, bool normalize);
+}  // namespace detail
 
 // Utility::R2ypr / ypr2R (utility/utility.h:66-104), degrees
 Vec3 R2ypr(const Mat3 &R);

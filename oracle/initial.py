@@ -546,3 +546,83 @@ def global_sfm(frame_num, l, relative_R, relative_T, obs_first, obs_frame, obs_p
     q = np.array([np.array([c[0], -c[1], -c[2], -c[3]]) / (c @ c) for c in c_rot])   # :295-303
     T = np.array([-(_qrot(q[i]) @ c_trans[i]) for i in range(frame_num)])             # :304-309
     return dict(ok=True, q=q, T=T, points=points, state=state, ba=summ, pre_ba=pre)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Estimator::initialStructure / visualInitialAlign (all frames key frames)
+# ------------------------------------------------------------------------------------------------------------------
+def _R2ypr_yaw_deg(Rm):  # Utility::R2ypr(R).x() (utility/utility.h:66-81)
+    return np.degrees(np.arctan2(Rm[1, 0], Rm[0, 0]))
+
+
+def _yaw_rot(deg):  # Utility::ypr2R({yaw, 0, 0})
+    a = np.radians(deg)
+    return np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+
+
+def g2R(g):
+    """utility/utility.cpp:3-12 (Quaterniond::FromTwoVectors(g.normalized(), e_z))."""
+    v0 = g / np.linalg.norm(g)
+    v1 = np.array([0.0, 0, 1])
+    c = v1 @ v0
+    axis = np.cross(v0, v1)
+    s = np.sqrt((1 + c) * 2)
+    R0 = _qrot(np.array([s * 0.5, *(axis / s)]))
+    return _yaw_rot(-_R2ypr_yaw_deg(R0)) @ R0
+
+
+def relative_pose(corres_fn, window_size, seed, attempt):
+    """Estimator::relativePose (estimator.cpp:457-484); corres_fn(i, j) -> (n, 6)."""
+    for i in range(window_size):
+        c = corres_fn(i, window_size)
+        if len(c) <= 20:
+            continue
+        par = np.mean(np.linalg.norm(c[:, :2] / c[:, 2:3] - c[:, 3:5] / c[:, 5:6], axis=1))
+        if not par * 160 > 30:
+            continue
+        ok, Rm, T, cnt, _ = solve_relative_rt(c, seed, attempt * 64 + i)
+        if ok:
+            return True, Rm, T, i
+    return False, None, None, -1
+
+
+def initial_structure(F, obs_first, obs_frame, obs_pts, corres_fn, reintegrate, ric, tic, g_norm, bgs0, seed, attempt=1,
+                      init_depth=5.0):
+    """Estimator::initialStructure + visualInitialAlign (estimator.cpp:221-455) for a window in which every frame of
+    all_image_frame is a key frame.  reintegrate(bg) -> list of IntegrationOracle of the F-1 intervals linearised at
+    (ba = 0, bg).  Returns None on failure, else dict(Ps, Rs, Vs, Bgs, g, depth (per feature, -1 where untouched), l, s)."""
+    from . import prestep as OP
+
+    ok, rel_R, rel_T, l = relative_pose(corres_fn, F - 1, seed, attempt)
+    if not ok:
+        return None
+    sfm = global_sfm(F, l, rel_R, rel_T, obs_first, obs_frame, obs_pts)
+    if not sfm["ok"]:
+        return None
+    fR = np.array([_qrot(sfm["q"][i]) @ ric.T for i in range(F)])      # frame.R = Q[i] * RIC^T  (:301)
+    fT = sfm["T"].copy()
+    pre = reintegrate(np.asarray(bgs0, float))
+    dbg = solve_gyroscope_bias(fR, [p.delta_q for p in pre], [p.jacobian[3:6, 12:15] for p in pre])
+    Bgs = np.asarray(bgs0, float) + dbg
+    pre = reintegrate(Bgs)
+    ok, g, x = linear_alignment(fR, fT, [p.delta_p for p in pre], [p.delta_v for p in pre], [p.sum_dt for p in pre], tic, g_norm)
+    if not ok:
+        return None
+    Ps, Rs = fT.copy(), fR.copy()
+    L = len(obs_first) - 1
+    start = np.array([obs_frame[obs_first[j]] for j in range(L)])
+    depth = np.full(L, -1.0)
+    depth = OP.triangulate(Ps, Rs, np.zeros(3), ric, start, obs_first, obs_pts, depth, init_depth)   # TIC_TMP = 0 (:405-410)
+    s = x[-1]
+    base = s * Ps[0] - Rs[0] @ tic
+    Ps = np.array([s * Ps[i] - Rs[i] @ tic - base for i in range(F)])
+    Vs = np.array([Rs[k] @ x[3 * k:3 * k + 3] for k in range(F)])
+    elig = np.array([(obs_first[j + 1] - obs_first[j] >= 2) and (start[j] < F - 1 - 2) for j in range(L)])
+    depth = np.where(elig, depth * s, depth)
+    R0 = g2R(g)
+    R0 = _yaw_rot(-_R2ypr_yaw_deg(R0 @ Rs[0])) @ R0
+    g = R0 @ g
+    Ps = Ps @ R0.T
+    Rs = np.array([R0 @ Rs[i] for i in range(F)])
+    Vs = Vs @ R0.T
+    return dict(Ps=Ps, Rs=Rs, Vs=Vs, Bgs=Bgs, g=g, depth=depth, l=l, s=s)

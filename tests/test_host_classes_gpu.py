@@ -277,3 +277,106 @@ def test_estimator_class_non_keyframe_path(lfvio_mod, gpu, host):
     # frames 0..8 of the window never move on and one ever longer IMU interval bridges to the newest frame: the
     # error grows (0.14 -> 0.37 m here) but stays bounded; the point of the test is the code path, not accuracy
     assert max(errs) < 1.0, errs
+
+
+def _bind_estimator(host):
+    host.lfvio_host_estimator_create.restype = C.c_void_p
+    host.lfvio_host_estimator_create.argtypes = [C.c_int, C.c_int, C.c_int]
+    host.lfvio_host_estimator_destroy.argtypes = [C.c_void_p]
+    host.lfvio_host_estimator_set_params.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    host.lfvio_host_estimator_process_imu.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int]
+    host.lfvio_host_estimator_process_image.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+    host.lfvio_host_estimator_get.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+    host.lfvio_host_estimator_enable_initialization.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
+    host.lfvio_host_estimator_init_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+
+
+def _feed(host, est, world, k, vp):
+    if k > 0:
+        a0, g0, dt, acc, gyr = world.imu[k]
+        arrs = [np.ascontiguousarray(x, np.float64) for x in (a0, g0, dt, acc, gyr)]
+        assert host.lfvio_host_estimator_process_imu(est, *[vp(a) for a in arrs], len(dt)) == 0
+    obs = world.frames[k]
+    ids = np.array(list(obs.keys()), np.int32)
+    feat = np.array([[*b, 0.0, row, *vel] for (b, vel, row) in obs.values()])
+    return host.lfvio_host_estimator_process_image(est, ids.ctypes.data_as(C.c_void_p), vp(feat), len(ids), float(world.times[k]))
+
+
+@pytest.mark.parametrize("seed,noise", [(1, 0.0), (2, 0.05), (4, 0.1)])
+def test_estimator_class_initial_structure_matches_oracle(lfvio_mod, gpu, host, seed, noise):
+    """Estimator::initialStructure + visualInitialAlign of the C++ mirror (device numeric steps) against the numpy
+    restatement of the same chain (oracle/initial.py): relative pose, global SfM + BA, gyroscope bias, gravity / scale
+    alignment, state rescaling and gravity alignment.  Every frame is a key frame (MIN_PARALLAX = 0)."""
+    from initial_data import InitScenario
+    from oracle import initial as OI
+
+    F = 11
+    sc = InitScenario(seed=seed, F=F, pixel_noise=noise)
+    world = sc.world
+    ref = OI.initial_structure(F, sc.obs_first, sc.obs_frame, sc.obs_pts, sc.corres, lambda bg: sc.preintegrations(bg=bg), sc.ric,
+                               sc.tic, sc.g_norm, np.zeros(3), seed=5)
+    assert ref is not None
+    vp = lambda a: np.ascontiguousarray(a, np.float64).ctypes.data_as(C.c_void_p)
+    _bind_estimator(host)
+    est = host.lfvio_host_estimator_create(10, 1000, gpu)
+    assert est, lfvio_mod.lib.lfvio_last_error()
+    keep = [np.ascontiguousarray(x, np.float64) for x in (world.noise, world.G, world.tic, world.ric, np.zeros(3), np.zeros(3))]
+    assert host.lfvio_host_estimator_set_params(est, vp(keep[0]), vp(keep[1]), vp(keep[2]), vp(keep[3]), 0.0, 0.0, 0, vp(keep[4]), vp(keep[5])) == 0
+    assert host.lfvio_host_estimator_enable_initialization(est, 5, 1) == 0
+    for k in range(F):
+        assert _feed(host, est, world, k, vp) == 0, lfvio_mod.lib.lfvio_last_error()
+    P, R, V = np.zeros((F, 3)), np.zeros((F, 9)), np.zeros((F, 3))
+    ba, bg, td, info, ii, g = np.zeros((F, 3)), np.zeros((F, 3)), np.zeros(1), np.zeros(8, np.int32), np.zeros(8, np.int32), np.zeros(3)
+    host.lfvio_host_estimator_get(est, vp(P), vp(R), vp(V), vp(ba), vp(bg), vp(td), info.ctypes.data_as(C.c_void_p))
+    host.lfvio_host_estimator_init_info(est, ii.ctypes.data_as(C.c_void_p), vp(g))
+    host.lfvio_host_estimator_destroy(est)
+    assert ii[0] == 1 and ii[1] == 1 and ii[2] == 0 and ii[3] == 1, ii    # NON_LINEAR after the first attempt
+    tol = 1e-6 if noise == 0.0 else 1e-4
+    assert np.allclose(g, ref["g"], atol=tol) and np.allclose(bg, ref["Bgs"], atol=tol)
+    assert np.allclose(P, ref["Ps"], atol=tol) and np.allclose(R.reshape(F, 3, 3), ref["Rs"], atol=tol)
+    assert np.allclose(V, ref["Vs"], atol=10 * tol)
+    # and against the ground truth (frame 0 at the origin with zero yaw)
+    Rz = OI._yaw_rot(-OI._R2ypr_yaw_deg(sc.Rb[0]))
+    assert np.abs(P - (sc.P - sc.P[0]) @ Rz.T).max() < 0.02
+    assert np.abs(V - sc.V @ Rz.T).max() < 0.05
+    print(f"initialStructure seed {seed}: max |P - oracle| = {np.abs(P - ref['Ps']).max():.2e}, max |P - truth| = "
+          f"{np.abs(P - (sc.P - sc.P[0]) @ Rz.T).max():.4f} m, scale {ref['s']:.4f}")
+
+
+def test_estimator_class_closed_loop_from_cold_start(lfvio_mod, gpu, host):
+    """No injected initial state: the C++ mirror initialises itself (initialStructure) when the window is full, then runs
+    the sliding-window optimisation; the trajectory is compared with the ground truth after a rigid alignment (ATE)."""
+    from lfvio import synthwin, violoop
+
+    E = synthwin.ESTIMATOR
+    old_td = E["td"]
+    E["td"] = 0.0
+    try:
+        world = violoop.World(seed=2, n_frames=40, pixel_noise=0.1)
+    finally:
+        E["td"] = old_td
+    F = 11
+    vp = lambda a: np.ascontiguousarray(a, np.float64).ctypes.data_as(C.c_void_p)
+    _bind_estimator(host)
+    est = host.lfvio_host_estimator_create(10, 1000, gpu)
+    assert est, lfvio_mod.lib.lfvio_last_error()
+    keep = [np.ascontiguousarray(x, np.float64) for x in (world.noise, world.G, world.tic, world.ric, np.zeros(3), np.zeros(3))]
+    assert host.lfvio_host_estimator_set_params(est, vp(keep[0]), vp(keep[1]), vp(keep[2]), vp(keep[3]), 0.0, 0.0, 0, vp(keep[4]), vp(keep[5])) == 0
+    assert host.lfvio_host_estimator_enable_initialization(est, 9, 0) == 0
+    P, R, V = np.zeros((F, 3)), np.zeros((F, 9)), np.zeros((F, 3))
+    ba, bg, td, info, ii, g = np.zeros((F, 3)), np.zeros((F, 3)), np.zeros(1), np.zeros(8, np.int32), np.zeros(8, np.int32), np.zeros(3)
+    est_pos, true_pos = [], []
+    for k in range(world.n_frames):
+        assert _feed(host, est, world, k, vp) == 0, lfvio_mod.lib.lfvio_last_error()
+        host.lfvio_host_estimator_get(est, vp(P), vp(R), vp(V), vp(ba), vp(bg), vp(td), info.ctypes.data_as(C.c_void_p))
+        host.lfvio_host_estimator_init_info(est, ii.ctypes.data_as(C.c_void_p), vp(g))
+        if k >= F - 1:
+            assert ii[0] == 1 and ii[1] == 1, (k, ii)                     # initialised at the first full window
+            assert info[4] == 0                                            # no failure detected
+            est_pos.append(P[F - 1].copy())                                # (after the slide the newest state sits in the last slot)
+            true_pos.append(world.truth(k)[0])
+    host.lfvio_host_estimator_destroy(est)
+    assert abs(g[2] - 9.81007) < 1e-3 and np.abs(g[:2]).max() < 1e-6      # gravity aligned with z
+    ate = violoop.ate_rmse(np.array(est_pos), np.array(true_pos))
+    print(f"cold start: ATE over {len(est_pos)} frames = {ate:.4f} m")
+    assert ate < 0.05, ate
