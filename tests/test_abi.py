@@ -46,3 +46,18 @@ def test_product_never_imports_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|#include\s+\".*oracle/", src, flags=re.M):
                     bad.append(os.path.join(dp, fn))
     assert not bad, bad
+
+
+def test_tum_writer_format():
+    """The trajectory line of pubOdometry (vins_estimator/src/utility/visualization.cpp:173-179): fixed notation, 12
+    decimals, "stamp px py pz qx qy qz qw" — pure host code, no GPU."""
+    import numpy as np
+
+    host = ctypes.CDLL(os.path.join(ROOT, "lf-vio_b200", "liblfvio_host.so"))
+    host.lfvio_host_tum_line.argtypes = [ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+    buf = ctypes.create_string_buffer(512)
+    p, q = np.array([1.5, -2.25, 3.0]), np.array([0.1, 0.2, 0.3, 0.9])
+    n = host.lfvio_host_tum_line(1403636579.5, p.ctypes.data, q.ctypes.data, buf, 512)
+    line = buf.value.decode()
+    assert n == len(line) and line.endswith("\n")
+    assert line == "1403636579.500000000000 1.500000000000 -2.250000000000 3.000000000000 0.100000000000 0.200000000000 0.300000000000 0.900000000000\n"
