@@ -358,9 +358,9 @@ LFVIO_HD void epnp_gauss_newton(const double *L, const double *rho, double *b) {
     }
 }
 
-// MtM: 12 x 12 (destroyed), cws: 4 x 3.
-LFVIO_HD void epnp_core(double *MtM, const double *cws, EpnpCore *out, double *V /* 144 scratch */) {
-    jacobi_sym(12, MtM, V);
+// After the eigen-decomposition of M^T M (MtM: its diagonal holds the eigenvalues, V: eigenvectors as columns): Ut, the
+// three beta initialisations and their Gauss-Newton refinements.  cws: 4 x 3.
+LFVIO_HD void epnp_core_after_eig(const double *MtM, const double *V, const double *cws, EpnpCore *out) {
     int ord[12];
     for (int i = 0; i < 12; i++) ord[i] = i;
     for (int a = 0; a < 11; a++)
@@ -454,6 +454,11 @@ LFVIO_HD void epnp_core(double *MtM, const double *cws, EpnpCore *out, double *V
         b[3] = 0.0;
     }
     for (int k = 0; k < 3; k++) epnp_gauss_newton(L, rho, out->betas[k]);
+}
+// MtM: 12 x 12 (destroyed), V: 144 scratch.  Serial form (host shim); the kernels run the Jacobi sweeps on a warp.
+LFVIO_HD void epnp_core(double *MtM, const double *cws, EpnpCore *out, double *V) {
+    jacobi_sym(12, MtM, V);
+    epnp_core_after_eig(MtM, V, cws, out);
 }
 // compute_ccs (:232-243): ccs 4 x 3
 LFVIO_HD void epnp_ccs(const EpnpCore *core, int which, double *ccs) {

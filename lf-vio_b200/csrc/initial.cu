@@ -112,6 +112,51 @@ __device__ void cta_cholesky_solve(double *A, int ld, int n, double *b, int *ok)
     }
 }
 
+// im::jacobi_sym on one warp (all 32 lanes call; n <= 32; A, V in shared memory): the same rotation sequence and formulas,
+// with the n independent element updates of each half-rotation spread over the lanes.
+__device__ void jacobi_sym_warp(int n, double *A, double *V) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < n * n; i += 32) V[i] = (i / n == i % n) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 40; sweep++) {
+        double off = 0, dia = 0;
+        if (lane < n) {
+            dia = fabs(A[lane * n + lane]);
+            for (int j = lane + 1; j < n; j++) off += fabs(A[lane * n + j]);
+        }
+        off = warp_sum(off);
+        dia = warp_sum(dia);
+        if (off <= 1e-300 || off <= 1e-18 * dia) break;
+        for (int p = 0; p < n - 1; p++)
+            for (int q = p + 1; q < n; q++) {
+                const double apq = A[p * n + q];
+                if (apq == 0.0) continue;  // (uniform: every lane reads the same element)
+                const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                __syncwarp();
+                if (lane < n) {  // A <- A J and V <- V J: row `lane`
+                    const int k = lane;
+                    const double akp = A[k * n + p], akq = A[k * n + q];
+                    A[k * n + p] = c * akp - s * akq;
+                    A[k * n + q] = s * akp + c * akq;
+                    const double vkp = V[k * n + p], vkq = V[k * n + q];
+                    V[k * n + p] = c * vkp - s * vkq;
+                    V[k * n + q] = s * vkp + c * vkq;
+                }
+                __syncwarp();
+                if (lane < n) {  // A <- J^T A: column `lane`
+                    const int k = lane;
+                    const double apk = A[p * n + k], aqk = A[q * n + k];
+                    A[p * n + k] = c * apk - s * aqk;
+                    A[q * n + k] = s * apk + c * aqk;
+                }
+                __syncwarp();
+            }
+    }
+    __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // solveGyroscopeBias
 // ---------------------------------------------------------------------------------------------------------------
@@ -297,7 +342,10 @@ __device__ void epnp_block(int n, const double *pws, const double *us, double *a
         sh.MtM[tid] = acc;
     }
     __syncthreads();
-    if (tid == 0) im::epnp_core(sh.MtM, sh.cws, &sh.core, sh.V);
+    if (tid < 32) {
+        jacobi_sym_warp(12, sh.MtM, sh.V);
+        if (tid == 0) im::epnp_core_after_eig(sh.MtM, sh.V, sh.cws, &sh.core);
+    }
     __syncthreads();
     for (int which = 0; which < 3; which++) {
         if (tid == 0) {

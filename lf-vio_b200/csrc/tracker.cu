@@ -442,9 +442,23 @@ extern "C" int lfvio_tracker_read_image(lfvio_tracker *t, const uint8_t *img, in
     LFVIO_REQUIRE(t && img && stride >= t->cfg.cols, "lfvio_tracker_read_image: bad arguments");
     LFVIO_CUDA_TRY(cudaSetDevice(t->device));
     const int rows = t->cfg.rows, cols = t->cfg.cols;
-    // stage through pinned memory so the H2D copy is a true async DMA on the tracker's stream
-    for (int y = 0; y < rows; y++) memcpy(t->h_img.p + (size_t)y * cols, img + (size_t)y * stride, cols);
-    LFVIO_CUDA_TRY(cudaMemcpy2DAsync(t->raw.p, t->pitch, t->h_img.p, cols, cols, rows, cudaMemcpyHostToDevice, t->stream));
+    // The call is blocking (download() synchronises), so a caller buffer that is already page-locked (cudaHostAlloc /
+    // cudaHostRegister — e.g. a ROS image transport that pins its pool) can be the DMA source directly.  Pageable memory is
+    // staged through the handle's pinned buffer in row bands, so that the host copy of band i+1 overlaps the DMA of band i.
+    cudaPointerAttributes attr{};
+    const bool pinned = cudaPointerGetAttributes(&attr, img) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) (void)cudaGetLastError();  // (older drivers report unregistered memory as an error)
+    if (pinned) {
+        LFVIO_CUDA_TRY(cudaMemcpy2DAsync(t->raw.p, t->pitch, img, stride, cols, rows, cudaMemcpyHostToDevice, t->stream));
+    } else {
+        constexpr int kBands = 4;
+        for (int b = 0; b < kBands; b++) {
+            const int y0 = (int)((long long)rows * b / kBands), y1 = (int)((long long)rows * (b + 1) / kBands);
+            for (int y = y0; y < y1; y++) memcpy(t->h_img.p + (size_t)y * cols, img + (size_t)y * stride, cols);
+            LFVIO_CUDA_TRY(cudaMemcpy2DAsync(t->raw.p + (size_t)y0 * t->pitch, t->pitch, t->h_img.p + (size_t)y0 * cols, cols, cols, y1 - y0,
+                                             cudaMemcpyHostToDevice, t->stream));
+        }
+    }
     LFVIO_TRY(enqueue_frame(t, t->raw.p, t->pitch, cur_time, pub_this_frame, false));
     return download(t);
 }

@@ -169,3 +169,16 @@ def test_global_sfm_pnp_failure(lfvio_mod, gpu, sc):
     got = lfvio_mod.global_sfm(11, 0, Rr, Tr, of, sc.obs_frame[:of[-1]], sc.obs_pts[:of[-1]])
     assert not ref["ok"] and not got["ok"]
     assert got["summary"].fail_stage == 1 and got["summary"].fail_frame == ref["frame"]
+
+
+def test_global_sfm_config4_window(lfvio_mod, gpu):
+    """A 21-frame window (BASELINE config 4's WINDOW_SIZE = 20: reduced camera system 126 x 126 in shared memory)."""
+    s, l = InitScenario(seed=3, F=21, pixel_noise=0.05), 12
+    ok, Rr, Tr, cnt, _ = OI.solve_relative_rt(s.corres(l, 20), 11, 0)
+    assert ok
+    ref = OI.global_sfm(21, l, Rr, Tr, s.obs_first, s.obs_frame, s.obs_pts)
+    got = lfvio_mod.global_sfm(21, l, Rr, Tr, s.obs_first, s.obs_frame, s.obs_pts)
+    assert ref["ok"] and got["ok"] and np.array_equal(got["state"], ref["state"])
+    assert got["summary"].ba_iterations == ref["ba"]["iterations"]
+    assert np.allclose(got["summary"].costs(), ref["ba"]["costs"], rtol=1e-5, atol=1e-15)
+    assert np.allclose(got["q"], ref["q"], atol=1e-6) and np.allclose(got["T"], ref["T"], atol=1e-6)
