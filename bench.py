@@ -238,6 +238,7 @@ def initialisation_leg(lfvio, device):
     lfvio.global_sfm(11, l, Rr, Tr, sc.obs_first, sc.obs_frame, sc.obs_pts, device=device)
     dev["global_sfm"], sfm = timed(lambda: lfvio.global_sfm(11, l, Rr, Tr, sc.obs_first, sc.obs_frame, sc.obs_pts, device=device), 5)
     cpu["global_sfm"], sfm_o = timed(lambda: OI.global_sfm(11, l, Rr_o, Tr_o, sc.obs_first, sc.obs_frame, sc.obs_pts), 1)
+    chain_ms, _ = timed(lambda: lfvio.global_sfm(11, l, Rr, Tr, sc.obs_first, sc.obs_frame, sc.obs_pts, ba=False, device=device), 5)
     fR = np.array([OI._qrot(sfm_o["q"][i]) @ sc.ric.T for i in range(11)])
     pre = sc.preintegrations()
     args = (fR, sfm_o["T"], [p.delta_p for p in pre], [p.delta_v for p in pre], [p.sum_dt for p in pre], sc.tic, sc.g_norm)
@@ -247,6 +248,7 @@ def initialisation_leg(lfvio, device):
     dev["total"], cpu["total"] = sum(dev.values()), sum(cpu.values())
     return {"scenario": "11-frame start-up window, %d tracks / %d observations, 0.05 px bearing noise" % (len(sc.ids), len(sc.obs_frame)),
             "device_ms": dev, "cpu_port_ms": cpu, "ba_iterations": int(sfm["summary"].ba_iterations),
+            "global_sfm_without_ba_device_ms": chain_ms,
             "agreement": {"relative_R": float(np.abs(Rr - Rr_o).max()), "sfm_T": float(np.abs(sfm["T"] - sfm_o["T"]).max()),
                           "scale": [float(x[-1]), float(x_o[-1])], "gravity": float(np.abs(g - g_o).max())},
             "note": "one-shot work at start-up / restart; stage-level entries allocate their device scratch per call"}

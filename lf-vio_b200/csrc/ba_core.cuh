@@ -7,9 +7,12 @@
 // translations l, F-1 (initial_sfm.cpp:243-251).  The points are the Schur-eliminated blocks; the reduced camera system
 // is D = 6 F wide (constant / unobserved columns get an identity row).
 //
-// This header holds the per-point work items and the trust-region decision as __host__ __device__ functions with the
-// accumulation primitive passed in (atomicAdd on shared/global memory in sfm_ba_kernel, a plain += in the host test shim
-// tests/native/init_math_shim.cpp), so the same arithmetic and control flow are checked on the CPU against oracle/initial.py.
+// This header holds the per-observation arithmetic (ba_obs, ba_w, the LM diagonal, Jacobi scaling), the camera / point
+// updates and the trust-region decision as __host__ __device__ functions, plus a scatter formulation of the Schur
+// elimination per point (ba_point_linearize / _schur / _backsub, accumulation primitive passed in) that the host test shim
+// tests/native/init_math_shim.cpp runs serially, so the arithmetic and the control flow are checked on the CPU against
+// oracle/initial.py.  sfm_ba_kernel uses the same helpers and decisions but GATHERS the reduced system per entry (no
+// atomics, every Jacobian evaluated once per iteration); the two formulations differ in summation order only.
 #pragma once
 #include "init_math.cuh"
 

@@ -533,13 +533,19 @@ __global__ void __launch_bounds__(NT) sfm_pnp_kernel(SfmDev d, int i, double *pw
     }
 }
 
-struct AtomicAdd {
-    __device__ void operator()(double *p, double v) const { atomicAdd(p, v); }
-};
+// Per-observation record kept between the phases of one LM iteration (L2 resident): r (3) | Jc (18, masked) | Jp (9) |
+// W = Jc_s^T Jp_s (18) | Y = W Vinv (18)
+constexpr int kObsRec = 66;
+constexpr int OB_R = 0, OB_JC = 3, OB_JP = 21, OB_W = 30, OB_Y = 48;
 
+// The LM loop of ba_core.cuh by one CTA.  Same per-observation arithmetic and the same trust-region decisions as the
+// CPU-checked work items there (ba_obs, ba_w, ba_lm_diag, ba_jacobi_scale, ba_cam_candidate, ba_point_cost, ba_begin_iteration,
+// ba_decide); the reduced camera system is GATHERED, not scattered: a thread owns an entry of S and sums over the points seen
+// in both of its frames through the table tab[j][f] (observation of point j in frame f, or -1), so there are no atomics and
+// every Jacobian is evaluated once per iteration.
 // Dynamic shared memory: S (D x D) | gc (D) | scale_c (D) | dxc (D) | cq (4F) | ct (3F) | cand_q (4F) | cand_t (3F) | red
 __global__ void __launch_bounds__(BA_NT) sfm_ba_kernel(SfmDev d, double *ct_io /* F x 3 */, double *V, double *gp, double *sp, double *Vinv,
-                                                       double *cand, im::BaCtl *ctl_out) {
+                                                       double *cand, double *obs_rec, int *tab, im::BaCtl *ctl_out) {
     extern __shared__ double smem[];
     __shared__ im::BaCtl c;
     __shared__ int s_go, s_accept;
@@ -551,18 +557,58 @@ __global__ void __launch_bounds__(BA_NT) sfm_ba_kernel(SfmDev d, double *ct_io /
     for (int k = tid; k < 4 * F; k += BA_NT) cq[k] = d.cq[k];
     for (int k = tid; k < 3 * F; k += BA_NT) ct[k] = ct_io[k];
     for (int k = tid; k < D; k += BA_NT) scale_c[k] = 1.0;
+    for (int k = tid; k < L * F; k += BA_NT) tab[k] = -1;
     if (tid == 0) im::ba_init(&c);
+    __syncthreads();
+    for (int j = tid; j < L; j += BA_NT)
+        if (d.state[j])
+            for (int o = d.obs_first[j]; o < d.obs_first[j + 1]; o++) tab[j * F + d.obs_frame[o]] = o;
     bool first = true;
-    const AtomicAdd add;
     __syncthreads();
     while (true) {
-        for (int k = tid; k < D * D + D; k += BA_NT) S[k] = 0.0;  // S and gc are contiguous
-        __syncthreads();
+        // ---- phase 1 (thread per point): residuals and Jacobians of its observations, V, g_p, cost ----
         double v[3] = {0, 0, 0}, gmax = 0;
-        for (int j = tid; j < L; j += BA_NT)
-            if (d.state[j]) v[0] += im::ba_point_linearize(P, cq, ct, d.points, j, S, gc, V + 9 * j, gp + 3 * j, &gmax, add);
-        block_sum<1>(v, red);
-        for (int k = tid; k < D; k += BA_NT) gmax = fmax(gmax, fabs(gc[k]));  // (block_sum's barriers made gc complete)
+        for (int j = tid; j < L; j += BA_NT) {
+            if (!d.state[j]) continue;
+            double Vj[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, gpj[3] = {0, 0, 0};
+            for (int o = d.obs_first[j]; o < d.obs_first[j + 1]; o++) {
+                double r[3], Jc[18], Jp[9];
+                im::ba_obs(P, cq, ct, d.points + 3 * j, o, r, Jc, Jp);
+                double *rec = obs_rec + (size_t)kObsRec * o;
+                for (int k = 0; k < 3; k++) rec[OB_R + k] = r[k];
+                for (int k = 0; k < 18; k++) rec[OB_JC + k] = Jc[k];
+                for (int k = 0; k < 9; k++) rec[OB_JP + k] = Jp[k];
+                v[0] += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+                for (int a = 0; a < 3; a++) {
+                    for (int b = 0; b < 3; b++) Vj[3 * a + b] += Jp[a] * Jp[b] + Jp[3 + a] * Jp[3 + b] + Jp[6 + a] * Jp[6 + b];
+                    gpj[a] += Jp[a] * r[0] + Jp[3 + a] * r[1] + Jp[6 + a] * r[2];
+                }
+            }
+            for (int k = 0; k < 9; k++) V[9 * j + k] = Vj[k];
+            for (int a = 0; a < 3; a++) {
+                gp[3 * j + a] = gpj[a];
+                gmax = fmax(gmax, fabs(gpj[a]));
+            }
+        }
+        block_sum<1>(v, red);  // (its barriers publish obs_rec / V / gp)
+        // ---- U (diagonal blocks of S) and g_c gathered per entry over the observations of the frame ----
+        for (int k = tid; k < D * D; k += BA_NT) S[k] = 0.0;
+        __syncthreads();
+        for (int e = tid; e < 42 * F; e += BA_NT) {
+            const int f = e / 42, q = e - 42 * f, a = q < 36 ? q / 6 : q - 36, b = q < 36 ? q % 6 : -1;
+            double acc = 0;
+            for (int j = 0; j < L; j++) {
+                const int o = tab[j * F + f];
+                if (o < 0) continue;
+                const double *rec = obs_rec + (size_t)kObsRec * o;
+                if (b >= 0) acc += rec[OB_JC + a] * rec[OB_JC + b] + rec[OB_JC + 6 + a] * rec[OB_JC + 6 + b] + rec[OB_JC + 12 + a] * rec[OB_JC + 12 + b];
+                else acc += rec[OB_JC + a] * rec[OB_R] + rec[OB_JC + 6 + a] * rec[OB_R + 1] + rec[OB_JC + 12 + a] * rec[OB_R + 2];
+            }
+            if (b >= 0) S[(6 * f + a) * D + 6 * f + b] = acc;
+            else gc[6 * f + a] = acc;
+        }
+        __syncthreads();
+        for (int k = tid; k < D; k += BA_NT) gmax = fmax(gmax, fabs(gc[k]));
         gmax = block_max(gmax, red);
         if (tid == 0) {
             c.cost = v[0], c.gmax = gmax;
@@ -578,19 +624,65 @@ __global__ void __launch_bounds__(BA_NT) sfm_ba_kernel(SfmDev d, double *ct_io /
             first = false;
             __syncthreads();
         }
-        for (int k = tid; k < D * D; k += BA_NT) {
-            const int a = k / D, b = k - a * D;
-            S[k] *= scale_c[a] * scale_c[b];
-        }
-        for (int k = tid; k < D; k += BA_NT) gc[k] *= scale_c[k];
-        __syncthreads();
         const double radius = c.radius;
-        for (int k = tid; k < D; k += BA_NT) S[k * D + k] = S[k * D + k] == 0.0 ? 1.0 : S[k * D + k] + im::ba_lm_diag(S[k * D + k], radius);
+        // ---- phase 2 (thread per point): scaled, damped V -> Vinv; W and Y of its observations ----
+        for (int j = tid; j < L; j += BA_NT) {
+            if (!d.state[j]) continue;
+            const double *spj = sp + 3 * j;
+            double Vs[9], Vi[9];
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) Vs[3 * a + b] = spj[a] * spj[b] * V[9 * j + 3 * a + b];
+            for (int a = 0; a < 3; a++) Vs[4 * a] += im::ba_lm_diag(Vs[4 * a], radius);
+            im::inv3(Vs, Vi);
+            for (int k = 0; k < 9; k++) Vinv[9 * j + k] = Vi[k];
+            for (int o = d.obs_first[j]; o < d.obs_first[j + 1]; o++) {
+                double *rec = obs_rec + (size_t)kObsRec * o;
+                double W[18];
+                im::ba_w(rec + OB_JC, rec + OB_JP, scale_c + 6 * d.obs_frame[o], spj, W);
+                for (int a = 0; a < 6; a++)
+                    for (int b = 0; b < 3; b++) {
+                        rec[OB_W + 3 * a + b] = W[3 * a + b];
+                        rec[OB_Y + 3 * a + b] = W[3 * a] * Vi[b] + W[3 * a + 1] * Vi[3 + b] + W[3 * a + 2] * Vi[6 + b];
+                    }
+            }
+        }
         __syncthreads();
-        for (int j = tid; j < L; j += BA_NT)
-            if (d.state[j]) im::ba_point_schur(P, cq, ct, d.points, j, V + 9 * j, gp + 3 * j, scale_c, sp + 3 * j, radius, S, gc, Vinv + 9 * j, add);
-        __syncthreads();
-        for (int k = tid; k < D; k += BA_NT) dxc[k] = gc[k];
+        // ---- phase 3 (thread per entry of the lower block triangle): S = U_s + D^2 - sum_j Y W^T, rhs = g_c,s - sum_j Y g_p,s ----
+        const int n_blk = F * (F + 1) / 2;
+        for (int e = tid; e < 36 * n_blk; e += BA_NT) {
+            const int blk = e / 36, q = e - 36 * blk, b = q / 6, a = q - 6 * b;  // entry (6 f2 + b, 6 f1 + a), f2 >= f1
+            int f2 = 0, rem = blk;
+            while (rem > f2) rem -= f2 + 1, f2++;
+            const int f1 = rem;
+            double acc = 0;
+            for (int j = 0; j < L; j++) {
+                const int o1 = tab[j * F + f1];
+                if (o1 < 0) continue;
+                const int o2 = f1 == f2 ? o1 : tab[j * F + f2];
+                if (o2 < 0) continue;
+                const double *y = obs_rec + (size_t)kObsRec * o1 + OB_Y + 3 * a, *w = obs_rec + (size_t)kObsRec * o2 + OB_W + 3 * b;
+                acc += y[0] * w[0] + y[1] * w[1] + y[2] * w[2];
+            }
+            const int row = 6 * f2 + b, col = 6 * f1 + a;
+            double u = 0;
+            if (f1 == f2) {
+                u = scale_c[row] * scale_c[col] * S[row * D + col];
+                if (row == col) u = (u == 0.0) ? 1.0 : u + im::ba_lm_diag(u, radius);  // constant / unobserved column: identity row
+            }
+            if (f1 == f2 && row < col) continue;  // upper part of a diagonal block: the Cholesky reads the lower triangle only
+            S[row * D + col] = u - acc;           // (each thread reads and writes only its own entry of S)
+        }
+        for (int e = tid; e < D; e += BA_NT) {
+            const int f = e / 6, a = e - 6 * f;
+            double acc = 0;
+            for (int j = 0; j < L; j++) {
+                const int o = tab[j * F + f];
+                if (o < 0) continue;
+                const double *y = obs_rec + (size_t)kObsRec * o + OB_Y + 3 * a;
+                acc += y[0] * sp[3 * j] * gp[3 * j] + y[1] * sp[3 * j + 1] * gp[3 * j + 1] + y[2] * sp[3 * j + 2] * gp[3 * j + 2];
+            }
+            dxc[e] = scale_c[e] * gc[e] - acc;
+        }
         if (tid == 0) c.chol_ok = 1;
         __syncthreads();
         cta_cholesky_solve(S, D, D, dxc, &c.chol_ok);
@@ -600,9 +692,36 @@ __global__ void __launch_bounds__(BA_NT) sfm_ba_kernel(SfmDev d, double *ct_io /
         if (c.chol_ok) {
             for (int k = tid; k < D; k += BA_NT) dxc[k] = -dxc[k];
             __syncthreads();
-            for (int j = tid; j < L; j += BA_NT)
-                if (d.state[j])
-                    im::ba_point_backsub(P, cq, ct, d.points, j, gp + 3 * j, scale_c, sp + 3 * j, Vinv + 9 * j, dxc, cand, &v[0], &v[1], &v[2]);
+            // ---- phase 5 (thread per point): back-substitution, candidate, model cost change ----
+            for (int j = tid; j < L; j += BA_NT) {
+                if (!d.state[j]) continue;
+                const double *spj = sp + 3 * j, *Vi = Vinv + 9 * j;
+                double wdx[3] = {0, 0, 0};
+                for (int o = d.obs_first[j]; o < d.obs_first[j + 1]; o++) {
+                    const double *W = obs_rec + (size_t)kObsRec * o + OB_W, *dx = dxc + 6 * d.obs_frame[o];
+                    for (int b = 0; b < 3; b++)
+                        for (int a = 0; a < 6; a++) wdx[b] += W[3 * a + b] * dx[a];
+                }
+                double rhs[3], dxp[3];
+                for (int a = 0; a < 3; a++) rhs[a] = spj[a] * gp[3 * j + a] + wdx[a];
+                for (int a = 0; a < 3; a++) dxp[a] = -(Vi[3 * a] * rhs[0] + Vi[3 * a + 1] * rhs[1] + Vi[3 * a + 2] * rhs[2]);
+                for (int o = d.obs_first[j]; o < d.obs_first[j + 1]; o++) {
+                    const int f = d.obs_frame[o];
+                    const double *rec = obs_rec + (size_t)kObsRec * o;
+                    for (int i = 0; i < 3; i++) {
+                        double m = 0;
+                        for (int a = 0; a < 6; a++) m += rec[OB_JC + 6 * i + a] * scale_c[6 * f + a] * dxc[6 * f + a];
+                        for (int a = 0; a < 3; a++) m += rec[OB_JP + 3 * i + a] * spj[a] * dxp[a];
+                        v[0] += -(m * (rec[OB_R + i] + m / 2.0));
+                    }
+                }
+                for (int a = 0; a < 3; a++) {
+                    const double dd = spj[a] * dxp[a];
+                    cand[3 * j + a] = d.points[3 * j + a] + dd;
+                    v[1] += dd * dd;
+                    v[2] += d.points[3 * j + a] * d.points[3 * j + a];
+                }
+            }
             if (tid < F) im::ba_cam_candidate(P, cq, ct, tid, scale_c, dxc, cand_q, cand_t, &v[1], &v[2]);
             block_sum<3>(v, red);  // (its barriers also publish cand / cand_q / cand_t)
             for (int j = tid; j < L; j += BA_NT)
@@ -786,40 +905,54 @@ extern "C" int lfvio_epnp(const double *pws, const double *us, const int *first,
 namespace {
 
 struct SfmBuffers {
-    DBuf<int> of, ofr, fail;
-    DBuf<double> pts_obs, points, cR, cT, cq, V, gp, sp, Vinv, cand, pw_list, us_list, alphas, relR, relT, q_out, T_out;
-    DBuf<unsigned char> state;
-    DBuf<im::BaCtl> ctl;
+    // one device allocation for everything (a cudaMalloc / cudaFree pair costs more than most of the kernels here)
+    DBuf<unsigned char> arena;
+    template <class T>
+    struct Ref {
+        T *p = nullptr;
+        size_t n = 0;
+        int get(T *h, size_t count) const {
+            LFVIO_CUDA_TRY(cudaMemcpy(h, p, sizeof(T) * count, cudaMemcpyDeviceToHost));
+            return LFVIO_OK;
+        }
+        int put(const T *h, size_t count) {
+            LFVIO_CUDA_TRY(cudaMemcpy(p, h, sizeof(T) * count, cudaMemcpyHostToDevice));
+            return LFVIO_OK;
+        }
+    };
+    Ref<int> of, ofr, fail;
+    Ref<double> pts_obs, points, cR, cT, cq, V, gp, sp, Vinv, cand, pw_list, us_list, alphas, relR, relT, q_out, T_out, obs_rec;
+    Ref<int> tab;
+    Ref<unsigned char> state;
+    Ref<im::BaCtl> ctl;
     SfmDev dev{};
     int setup(int F, int l, const int *obs_first, const int *obs_frame, const double *obs_pts, int L) {
         const size_t n_obs = obs_first[L];
+        size_t total = 0;
+        auto plan = [&](auto &r, size_t n) {
+            r.n = n;
+            r.p = reinterpret_cast<decltype(r.p)>(total);  // offset for now
+            total += (sizeof(*r.p) * (n ? n : 1) + 255) / 256 * 256;
+        };
+        plan(of, (size_t)L + 1), plan(ofr, n_obs), plan(pts_obs, 3 * n_obs), plan(fail, 2), plan(points, 3 * (size_t)L), plan(state, L);
+        plan(cR, 9 * (size_t)F), plan(cT, 3 * (size_t)F), plan(cq, 4 * (size_t)F), plan(V, 9 * (size_t)L), plan(gp, 3 * (size_t)L);
+        plan(sp, 3 * (size_t)L), plan(Vinv, 9 * (size_t)L), plan(cand, 3 * (size_t)L), plan(pw_list, 3 * (size_t)L), plan(us_list, 3 * (size_t)L);
+        plan(alphas, 4 * (size_t)L), plan(relR, 9), plan(relT, 3), plan(q_out, 4 * (size_t)F), plan(T_out, 3 * (size_t)F), plan(ctl, 1);
+        plan(obs_rec, (size_t)kObsRec * n_obs), plan(tab, (size_t)L * F);
+        LFVIO_TRY(arena.put(nullptr, total));  // (zero-filled)
+        auto fix = [&](auto &r) { r.p = reinterpret_cast<decltype(r.p)>(arena.p + reinterpret_cast<size_t>(r.p)); };
+        fix(of), fix(ofr), fix(pts_obs), fix(fail), fix(points), fix(state), fix(cR), fix(cT), fix(cq), fix(V), fix(gp), fix(sp), fix(Vinv);
+        fix(cand), fix(pw_list), fix(us_list), fix(alphas), fix(relR), fix(relT), fix(q_out), fix(T_out), fix(ctl), fix(obs_rec), fix(tab);
         LFVIO_TRY(of.put(obs_first, (size_t)L + 1));
         LFVIO_TRY(ofr.put(obs_frame, n_obs));
         LFVIO_TRY(pts_obs.put(obs_pts, 3 * n_obs));
-        LFVIO_TRY(fail.put(nullptr, 2));
-        LFVIO_TRY(points.put(nullptr, 3 * (size_t)L));
-        LFVIO_TRY(state.put(nullptr, L));
-        LFVIO_TRY(cR.put(nullptr, 9 * (size_t)F));
-        LFVIO_TRY(cT.put(nullptr, 3 * (size_t)F));
-        LFVIO_TRY(cq.put(nullptr, 4 * (size_t)F));
-        LFVIO_TRY(V.put(nullptr, 9 * (size_t)L));
-        LFVIO_TRY(gp.put(nullptr, 3 * (size_t)L));
-        LFVIO_TRY(sp.put(nullptr, 3 * (size_t)L));
-        LFVIO_TRY(Vinv.put(nullptr, 9 * (size_t)L));
-        LFVIO_TRY(cand.put(nullptr, 3 * (size_t)L));
-        LFVIO_TRY(pw_list.put(nullptr, 3 * (size_t)L));
-        LFVIO_TRY(us_list.put(nullptr, 3 * (size_t)L));
-        LFVIO_TRY(alphas.put(nullptr, 4 * (size_t)L));
-        LFVIO_TRY(q_out.put(nullptr, 4 * (size_t)F));
-        LFVIO_TRY(T_out.put(nullptr, 3 * (size_t)F));
-        LFVIO_TRY(ctl.put(nullptr, 1));
         dev = SfmDev{F, L, l, of.p, ofr.p, pts_obs.p, state.p, points.p, cR.p, cT.p, cq.p, fail.p};
         return LFVIO_OK;
     }
     int run_ba(int F) {
         const size_t smem = ba_smem_bytes(F);
         LFVIO_TRY(ensure_dyn_smem((const void *)sfm_ba_kernel, (int)ba_smem_bytes(LFVIO_SFM_MAX_FRAMES)));
-        sfm_ba_kernel<<<1, BA_NT, smem>>>(dev, cT.p, V.p, gp.p, sp.p, Vinv.p, cand.p, ctl.p);
+        sfm_ba_kernel<<<1, BA_NT, smem>>>(dev, cT.p, V.p, gp.p, sp.p, Vinv.p, cand.p, obs_rec.p, tab.p, ctl.p);
         LFVIO_LAUNCH_CHECK();
         return LFVIO_OK;
     }
