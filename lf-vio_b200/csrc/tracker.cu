@@ -168,7 +168,7 @@ struct lfvio_tracker {
     CornerStore corners;
     // host side
     PinBuf<uint8_t> h_img;
-    PinBuf<int> h_n;       // [0]=n, [1]=n_id
+    PinBuf<int> h_n;       // [0]=n, [1]=n_id, [2..3]=corner candidate counter / overflow flag
     PinBuf<float> h_pts, h_bearing, h_vel;
     PinBuf<int> h_ids, h_cnt;
     int n_host = 0, n_upper = 0, n_id_host = 0;
@@ -221,7 +221,7 @@ int tracker_init(lfvio_tracker *t, const lfvio_tracker_cfg *cfg, int device) {
     LFVIO_TRY(t->vel_out.alloc(3 * (size_t)t->cap));
     LFVIO_TRY(t->corners.alloc(rows, cols, cfg->min_dist));
     LFVIO_TRY(t->h_img.alloc((size_t)cols * rows));
-    LFVIO_TRY(t->h_n.alloc(2));
+    LFVIO_TRY(t->h_n.alloc(4));
     LFVIO_TRY(t->h_pts.alloc(2 * (size_t)t->cap));
     LFVIO_TRY(t->h_bearing.alloc(3 * (size_t)t->cap));
     LFVIO_TRY(t->h_vel.alloc(3 * (size_t)t->cap));
@@ -353,14 +353,16 @@ int download(lfvio_tracker *t) {
         LFVIO_CUDA_TRY(cudaMemcpyAsync(t->h_bearing.p, t->bearing_out.p, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, s));
         LFVIO_CUDA_TRY(cudaMemcpyAsync(t->h_vel.p, t->vel_out.p, sizeof(float) * 3 * m, cudaMemcpyDeviceToHost, s));
     }
+    t->h_n.p[2] = t->h_n.p[3] = 0;
+    if (t->corners.cs.counters)  // rides along with the other copies: no second round trip after the synchronisation
+        LFVIO_CUDA_TRY(cudaMemcpyAsync(t->h_n.p + 2, t->corners.cs.counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     LFVIO_CUDA_TRY(cudaStreamSynchronize(s));
     t->n_host = std::min(t->h_n.p[0], t->cap);
     t->n_id_host = t->h_n.p[1];
     t->n_upper = t->n_host;
     t->mirror_fresh = true;
     if (t->corners.cs.counters) {
-        int flags[2] = {0, 0};
-        LFVIO_CUDA_TRY(cudaMemcpy(flags, t->corners.cs.counters, sizeof(flags), cudaMemcpyDeviceToHost));
+        const int *flags = t->h_n.p + 2;
         if (flags[1]) {
             set_error("corner candidate buffer overflow (%d candidates > capacity %d)", flags[0], t->corners.cs.cand_cap);
             return LFVIO_ERR_CAPACITY;

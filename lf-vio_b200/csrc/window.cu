@@ -62,6 +62,7 @@ struct lfvio_window {
     DBuf<SolverCtl> ctl;
     SolverCtl *h_ctl = nullptr;  // pinned
     double *h_x = nullptr;       // pinned
+    int *h_status = nullptr;     // pinned (tail of h_x): imu_prepare status words
     DBuf<int> status;
     DevProblem P;
     EvalBuf e[2];
@@ -70,7 +71,7 @@ struct lfvio_window {
     MargPlan plan[2];        // [LFVIO_MARGIN_OLD], [LFVIO_MARGIN_SECOND_NEW], rebuilt at every upload
     bool plan_valid[2] = {false, false};
     DBuf<int> lm_list[2];
-    DBuf<double> margT, marg_work, marg_J0, marg_r0, marg_x0;
+    DBuf<double> margT, marg_work, marg_out;  // marg_out: [J0 n^2 | r0 n | x0] packed for the plan's n, so that one D2H copy returns the prior
     double *h_marg = nullptr;  // pinned: [J0 nmax^2 | r0 nmax | x0 9*blocks]
     int *h_lm[2] = {nullptr, nullptr};  // pinned staging of lm_list
     int last_marg_flag = -1;
@@ -154,7 +155,8 @@ int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_pro
     s.proj_colj = s.lm_coli + L;
     LFVIO_TRY(w->ctl.alloc(1));
     LFVIO_CUDA_TRY(cudaMallocHost(&w->h_ctl, sizeof(SolverCtl)));
-    LFVIO_CUDA_TRY(cudaMallocHost(&w->h_x, sizeof(double) * lay.size()));
+    LFVIO_CUDA_TRY(cudaMallocHost(&w->h_x, sizeof(double) * (lay.size() + 2)));
+    w->h_status = reinterpret_cast<int *>(w->h_x + lay.size());
     LFVIO_TRY(w->status.alloc(4));
     {
         const size_t dim = (size_t)w->nmax + 15;
@@ -164,9 +166,7 @@ int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_pro
         }
         LFVIO_TRY(w->margT.alloc(dim * dim + dim));
         LFVIO_TRY(w->marg_work.alloc(marg_finish_workspace_doubles(15, w->nmax)));
-        LFVIO_TRY(w->marg_J0.alloc((size_t)w->nmax * w->nmax));
-        LFVIO_TRY(w->marg_r0.alloc(w->nmax));
-        LFVIO_TRY(w->marg_x0.alloc(9 * (size_t)kMaxPriorBlocks));
+        LFVIO_TRY(w->marg_out.alloc((size_t)w->nmax * w->nmax + w->nmax + 9 * (size_t)kMaxPriorBlocks));
         LFVIO_CUDA_TRY(cudaMallocHost(&w->h_marg, sizeof(double) * ((size_t)w->nmax * w->nmax + w->nmax + 9 * kMaxPriorBlocks)));
     }
     return LFVIO_OK;
@@ -253,9 +253,14 @@ int build_marg_plan(lfvio_window *w, int flag, const lfvio_factor_list *fl, cons
     return LFVIO_OK;
 }
 
+static MargBuffers marg_buffers(lfvio_window *w, int n) {
+    double *base = w->marg_out.p;
+    return MargBuffers{w->margT.p, w->marg_work.p, base, base + (size_t)n * n, base + (size_t)n * n + n};
+}
+
 int enqueue_marginalize(lfvio_window *w, int flag, bool after_solve) {
     if (!w->plan_valid[flag]) return LFVIO_OK;
-    MargBuffers mb{w->margT.p, w->marg_work.p, w->marg_J0.p, w->marg_r0.p, w->marg_x0.p};
+    MargBuffers mb = marg_buffers(w, w->plan[flag].n);
     w->prof.begin(WS_MARGINALIZE, w->stream);
     LFVIO_TRY(launch_marginalize(w->P, w->e[0], w->e[1], w->x[0].p, w->x[1].p, after_solve ? w->ctl.p : nullptr, w->plan[flag], mb,
                                  w->stream));
@@ -265,7 +270,10 @@ int enqueue_marginalize(lfvio_window *w, int flag, bool after_solve) {
 }
 
 // Pack the problem into the pinned blob, enqueue the single H2D copy and fill the device-side descriptor.
-int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_list *fl, const lfvio_solver_opts *o) {
+// defer_plans: the caller builds the marginalisation plan it needs itself AFTER it has enqueued the solve, so that this
+// piece of host work (maps, a small H2D copy) overlaps the solve on the device instead of delaying its first kernel.
+int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_list *fl, const lfvio_solver_opts *o,
+           bool defer_plans = false) {
     LFVIO_REQUIRE(st && fl && o, "window: null argument");
     LFVIO_REQUIRE(st->n_frames == w->F, "window: n_frames != window_size + 1 of the handle");
     LFVIO_REQUIRE(st->n_landmarks >= 0 && st->n_landmarks <= w->Lmax, "window: too many landmarks for this handle");
@@ -354,8 +362,12 @@ int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_lis
     LFVIO_CUDA_TRY(cudaMemsetAsync(w->status.p, 0, sizeof(int) * 4, s));
     LFVIO_TRY(launch_imu_prepare(P, w->imu_sqrt_info.p, w->status.p, s));
     LFVIO_TRY(launch_prior_prepare(P, w->H0.p, s));
-    LFVIO_TRY(build_marg_plan(w, LFVIO_MARGIN_OLD, fl, o, L));
-    LFVIO_TRY(build_marg_plan(w, LFVIO_MARGIN_SECOND_NEW, fl, o, L));
+    if (defer_plans) {
+        w->plan_valid[0] = w->plan_valid[1] = false;
+    } else {
+        LFVIO_TRY(build_marg_plan(w, LFVIO_MARGIN_OLD, fl, o, L));
+        LFVIO_TRY(build_marg_plan(w, LFVIO_MARGIN_SECOND_NEW, fl, o, L));
+    }
     w->uploaded = true;
     return LFVIO_OK;
 }
@@ -474,8 +486,8 @@ int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum, 
     }
     LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_x, w->x_out.p, sizeof(double) * lay.size(), cudaMemcpyDeviceToHost, s));
     LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_ctl, w->ctl.p, sizeof(SolverCtl), cudaMemcpyDeviceToHost, s));
-    int status[4];
-    LFVIO_CUDA_TRY(cudaMemcpyAsync(status, w->status.p, sizeof(status), cudaMemcpyDeviceToHost, s));
+    int *status = w->h_status;  // pinned: a D2H copy into pageable memory would be staged synchronously
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(status, w->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     LFVIO_CUDA_TRY(cudaStreamSynchronize(s));
     if (st) {
         memcpy(st->para_Pose, w->h_x + lay.pose(0), sizeof(double) * 7 * lay.F);
@@ -590,13 +602,14 @@ extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *s
     LFVIO_REQUIRE(w && prior_out, "lfvio_window_optimize_full: null argument");
     LFVIO_REQUIRE(margin_flag == LFVIO_MARGIN_OLD || margin_flag == LFVIO_MARGIN_SECOND_NEW, "lfvio_window_optimize_full: bad margin_flag");
     LFVIO_CUDA_TRY(cudaSetDevice(w->device));
-    LFVIO_TRY(upload(w, state, factors, opts));
+    LFVIO_TRY(upload(w, state, factors, opts, /*defer_plans=*/true));
     LFVIO_TRY(enqueue_solve(w));
     cudaStream_t s = w->stream;
     const DevProblem &P = w->P;
     gauge_fix_kernel<<<cdiv(std::max(P.lay.size(), P.lay.F), 256), 256, 0, s>>>(P.lay, reinterpret_cast<const double *>(w->blob.p + w->off_x),
                                                                             w->x[0].p, w->x[1].p, w->ctl.p, w->x_out.p);
     LFVIO_LAUNCH_CHECK();
+    LFVIO_TRY(build_marg_plan(w, margin_flag, factors, opts, state->n_landmarks));  // host work under the running solve
     prior_out->n = 0;
     prior_out->n_blocks = 0;
     const bool do_marg = w->plan_valid[margin_flag];
@@ -607,15 +620,13 @@ extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *s
         LFVIO_REQUIRE(pl.n <= prior_out->cap_n && pl.n_keep <= prior_out->cap_blocks, "lfvio_window_optimize_full: output prior too small");
         // preMarginalize() at the re-anchored state: evaluate into buffer 0, then eliminate
         LFVIO_TRY(launch_evaluate(P, w->x_out.p, w->x_out.p, w->e[0], w->e[1], w->ctl.p, 2, 1, s));
-        MargBuffers mb{w->margT.p, w->marg_work.p, w->marg_J0.p, w->marg_r0.p, w->marg_x0.p};
+        MargBuffers mb = marg_buffers(w, pl.n);
         w->prof.begin(WS_MARGINALIZE, s);
         LFVIO_TRY(launch_marginalize(P, w->e[0], w->e[1], w->x_out.p, w->x_out.p, nullptr, w->plan[margin_flag], mb, s));
         w->prof.end(s);
         nn = (size_t)pl.n * pl.n;
         for (int b = 0; b < pl.n_keep; b++) x0_len += P.lay.block_gsize(pl.keep_id[b]);
-        LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg, w->marg_J0.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, s));
-        LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg + nn, w->marg_r0.p, sizeof(double) * pl.n, cudaMemcpyDeviceToHost, s));
-        LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg + nn + pl.n, w->marg_x0.p, sizeof(double) * x0_len, cudaMemcpyDeviceToHost, s));
+        LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg, w->marg_out.p, sizeof(double) * (nn + pl.n + x0_len), cudaMemcpyDeviceToHost, s));
     }
     LFVIO_TRY(download(w, state, summary, false));
     if (do_marg && getenv("LFVIO_DEBUG_STEP")) {
@@ -725,11 +736,9 @@ extern "C" int lfvio_window_marginalize(lfvio_window *w, const lfvio_window_stat
     const size_t nn = (size_t)pl.n * pl.n;
     int x0_len = 0;
     for (int b = 0; b < pl.n_keep; b++) x0_len += P.lay.block_gsize(pl.keep_id[b]);
-    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg, w->marg_J0.p, sizeof(double) * nn, cudaMemcpyDeviceToHost, s));
-    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg + nn, w->marg_r0.p, sizeof(double) * pl.n, cudaMemcpyDeviceToHost, s));
-    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg + nn + pl.n, w->marg_x0.p, sizeof(double) * x0_len, cudaMemcpyDeviceToHost, s));
-    int status[4];
-    LFVIO_CUDA_TRY(cudaMemcpyAsync(status, w->status.p, sizeof(status), cudaMemcpyDeviceToHost, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg, w->marg_out.p, sizeof(double) * (nn + pl.n + x0_len), cudaMemcpyDeviceToHost, s));
+    int *status = w->h_status;  // pinned: a D2H copy into pageable memory would be staged synchronously
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(status, w->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
     LFVIO_CUDA_TRY(cudaStreamSynchronize(s));
     if (status[0]) {
         set_error("IMU covariance of a pre-integration is singular / not positive definite");

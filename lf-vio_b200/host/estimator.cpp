@@ -386,7 +386,12 @@ void Estimator::processImage(const ImageFeatures &image, double header_stamp) {
     solveOdometry();
     if (last_status != LFVIO_OK) return;
     if (failureDetection()) {
-        failure_occur = true;  // the reference reboots here (clearState + setParameter); left to the caller
+        failure_occur = true;
+        if (run_initial_structure) {  // estimator.cpp:196-204: system reboot; the window refills and initialStructure() runs again
+            clearState();              // (this also clears failure_occur, as in the reference)
+            setParameter();
+            reboot_count++;
+        }  // otherwise (states injected by the caller) the reboot is the caller's: failure_occur stays set
         return;
     }
     slideWindow();
@@ -396,6 +401,39 @@ void Estimator::processImage(const ImageFeatures &image, double header_stamp) {
     last_P = Ps[WINDOW_SIZE];
     last_R0 = Rs[0];
     last_P0 = Ps[0];
+}
+
+void Estimator::setParameter() {
+    tic[0] = TIC0;
+    ric[0] = RIC0;
+    td = TD;
+}
+
+void Estimator::clearState() {
+    const Mat3 I{1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = 0; i <= WINDOW_SIZE; i++) {
+        Rs[i] = I;
+        Ps[i] = Vs[i] = Bas[i] = Bgs[i] = Vec3{0, 0, 0};
+        dt_buf[i].clear();
+        linear_acceleration_buf[i].clear();
+        angular_velocity_buf[i].clear();
+        pre_integrations[i] = nullptr;
+        m_iv[i] = Interval{};
+    }
+    tic[0] = Vec3{0, 0, 0};
+    ric[0] = I;
+    solver_flag = INITIAL;
+    first_imu = false;
+    sum_of_back = sum_of_front = 0;
+    frame_count = 0;
+    initial_timestamp = 0;
+    all_image_frame.clear();
+    td = TD;
+    m_tmp = ImageFrame{};
+    m_tmp_valid = false;
+    last_marginalization_info = MarginalizationInfo{};
+    f_manager.clearState();
+    failure_occur = false;
 }
 
 void Estimator::solveOdometry() {
@@ -828,9 +866,10 @@ extern "C" int lfvio_host_estimator_set_params(void *h, const double *noise4, co
     auto *e = static_cast<Estimator *>(h);
     e->imu_noise = lfvio_imu_noise{noise4[0], noise4[1], noise4[2], noise4[3]};
     G = Vec3{g3[0], g3[1], g3[2]};
-    e->tic[0] = Vec3{tic3[0], tic3[1], tic3[2]};
-    for (int k = 0; k < 9; k++) e->ric[0][k] = ric9[k];
-    e->td = td;
+    e->TIC0 = Vec3{tic3[0], tic3[1], tic3[2]};
+    for (int k = 0; k < 9; k++) e->RIC0[k] = ric9[k];
+    TD = td;
+    e->setParameter();
     MIN_PARALLAX = min_parallax;
     ESTIMATE_TD = estimate_td;
     for (int i = 0; i <= e->WINDOW_SIZE; i++) {
@@ -883,7 +922,8 @@ extern "C" int lfvio_host_estimator_enable_initialization(void *h, unsigned long
     e->ransac_seed = ransac_seed;
     return LFVIO_OK;
 }
-// info: [0] solver_flag, [1] init_attempts, [2] init_fail_stage, [3] sfm ok, [4] BA iterations, [5] all_image_frame.size();
+// info: [0] solver_flag, [1] init_attempts, [2] init_fail_stage, [3] sfm ok, [4] BA iterations, [5] all_image_frame.size(),
+// [6] reboot_count;
 // g: the aligned gravity
 extern "C" int lfvio_host_estimator_init_info(void *h, int *info, double *g) {
     auto *e = static_cast<lfvio_host::Estimator *>(h);
@@ -893,8 +933,16 @@ extern "C" int lfvio_host_estimator_init_info(void *h, int *info, double *g) {
     info[3] = e->sfm_summary.ok;
     info[4] = e->sfm_summary.ba_iterations;
     info[5] = (int)e->all_image_frame.size();
+    info[6] = e->reboot_count;
     for (int k = 0; k < 3; k++) g[k] = e->g[k];
     return LFVIO_OK;
+}
+
+// test hook: move last_P so that the next processImage() trips failureDetection() (|P - last_P| > 5 m, estimator.cpp:645-650)
+extern "C" int lfvio_host_estimator_poke_last_p(void *h, double dx) {
+    auto *e = static_cast<lfvio_host::Estimator *>(h);
+    e->last_P[0] += dx;
+    return e->reboot_count;
 }
 
 extern "C" int lfvio_host_estimator_process_image(void *h, const int *ids, const double *feat8, int n, double stamp) {

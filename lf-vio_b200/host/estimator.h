@@ -110,6 +110,13 @@ class Estimator {
     // INITIAL the window only fills and slides; the caller switches to NON_LINEAR once the states are initialised.
     enum SolverFlag { INITIAL = 0, NON_LINEAR = 1 };
     void processImage(const ImageFeatures &image, double header_stamp);
+    // estimator.cpp:10-21 / :23-84.  TIC / RIC / TD are globals of parameters.cpp in the reference; the mirror keeps the
+    // configured extrinsics per instance (TIC0 / RIC0) and TD as the global it is there.
+    void setParameter();
+    void clearState();
+    Vec3 TIC0{0, 0, 0};
+    Mat3 RIC0{1, 0, 0, 0, 1, 0, 0, 0, 1};
+    int reboot_count = 0;  // how often failureDetection() rebooted the estimator (estimator.cpp:196-204)
     // estimator.cpp:221-376 / :378-455 / :457-484: the numeric steps run on the device through lfvio_solve_relative_rt,
     // lfvio_global_sfm, lfvio_epnp (all non-keyframes in one call), lfvio_solve_gyro_bias, lfvio_preintegrate (the
     // repropagations, batched) and lfvio_linear_alignment.

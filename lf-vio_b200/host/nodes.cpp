@@ -133,8 +133,8 @@ void EstimatorNode::restart_callback(bool restart) {
     if (!restart) return;
     feature_buf.clear();
     imu_buf.clear();
-    // estimator.clearState(); estimator.setParameter();  -- the mirror has no global parameter file: the owner re-creates
-    // the EstimatorNode (same effect: every member back to its constructor value)
+    estimator.clearState();
+    estimator.setParameter();
     current_time = -1;
     last_imu_t = 0;
 }

@@ -50,7 +50,7 @@ class EstimatorNode {
     Estimator estimator;
     void imu_callback(const ImuMsg &imu_msg);            // estimator_node.cpp:136-162
     void feature_callback(const PointCloudMsg &msg);     // :164-176
-    void restart_callback(bool restart);                 // :178-198 (clearState + setParameter are the caller's: see .cpp)
+    void restart_callback(bool restart);                 // :178-198
     // process() (:210-343) for every complete measurement currently buffered; returns the number of images processed.
     int process();
     // pubOdometry (visualization.cpp:112-181): the odometry message of the newest frame and, when VINS_RESULT_PATH is set,

@@ -380,3 +380,48 @@ def test_estimator_class_closed_loop_from_cold_start(lfvio_mod, gpu, host):
     ate = violoop.ate_rmse(np.array(est_pos), np.array(true_pos))
     print(f"cold start: ATE over {len(est_pos)} frames = {ate:.4f} m")
     assert ate < 0.05, ate
+
+
+def test_estimator_class_failure_reboot_and_reinitialisation(lfvio_mod, gpu, host):
+    """The restart path (estimator.cpp:196-204): failureDetection() trips (here: last_P moved by 10 m), the
+    estimator reboots (clearState + setParameter), the window refills and initialStructure() runs a second time."""
+    from lfvio import synthwin, violoop
+
+    E = synthwin.ESTIMATOR
+    old_td = E["td"]
+    E["td"] = 0.0
+    try:
+        world = violoop.World(seed=4, n_frames=50, pixel_noise=0.1)
+    finally:
+        E["td"] = old_td
+    F = 11
+    vp = lambda a: np.ascontiguousarray(a, np.float64).ctypes.data_as(C.c_void_p)
+    _bind_estimator(host)
+    host.lfvio_host_estimator_poke_last_p.argtypes = [C.c_void_p, C.c_double]
+    est = host.lfvio_host_estimator_create(10, 1000, gpu)
+    assert est, lfvio_mod.lib.lfvio_last_error()
+    keep = [np.ascontiguousarray(x, np.float64) for x in (world.noise, world.G, world.tic, world.ric, np.zeros(3), np.zeros(3))]
+    assert host.lfvio_host_estimator_set_params(est, vp(keep[0]), vp(keep[1]), vp(keep[2]), vp(keep[3]), 0.0, 0.0, 0, vp(keep[4]), vp(keep[5])) == 0
+    assert host.lfvio_host_estimator_enable_initialization(est, 9, 0) == 0
+    P, R, V = np.zeros((F, 3)), np.zeros((F, 9)), np.zeros((F, 3))
+    ba, bg, td, info, ii, g = np.zeros((F, 3)), np.zeros((F, 3)), np.zeros(1), np.zeros(8, np.int32), np.zeros(8, np.int32), np.zeros(3)
+    flags, est_pos, true_pos = [], [], []
+    k_fail = 20
+    for k in range(world.n_frames):
+        if k == k_fail:
+            host.lfvio_host_estimator_poke_last_p(est, 10.0)
+        assert _feed(host, est, world, k, vp) == 0, lfvio_mod.lib.lfvio_last_error()
+        host.lfvio_host_estimator_get(est, vp(P), vp(R), vp(V), vp(ba), vp(bg), vp(td), info.ctypes.data_as(C.c_void_p))
+        host.lfvio_host_estimator_init_info(est, ii.ctypes.data_as(C.c_void_p), vp(g))
+        flags.append((int(ii[0]), int(ii[6]), int(info[3])))
+        if k >= k_fail + F and ii[0] == 1:
+            est_pos.append(P[F - 1].copy())
+            true_pos.append(world.truth(k)[0])
+    host.lfvio_host_estimator_destroy(est)
+    assert all(f[0] == 1 and f[1] == 0 for f in flags[F - 1:k_fail])          # running, no reboot yet
+    assert flags[k_fail] == (0, 1, 0)                                         # rebooted: INITIAL, frame_count 0
+    assert all(f[0] == 0 for f in flags[k_fail:k_fail + F])                   # the window refills (frames k_fail+1 .. k_fail+F)
+    assert flags[k_fail + F][0] == 1 and ii[1] == 2 and ii[6] == 1            # second initialisation at the first full window
+    ate = violoop.ate_rmse(np.array(est_pos), np.array(true_pos))
+    print(f"reboot at frame {k_fail}: re-initialised at frame {k_fail + F}, ATE of the {len(est_pos)} frames after it = {ate:.4f} m")
+    assert len(est_pos) == world.n_frames - (k_fail + F) and ate < 0.05, ate
