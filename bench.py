@@ -251,7 +251,7 @@ def initialisation_leg(lfvio, device):
             "global_sfm_without_ba_device_ms": chain_ms,
             "agreement": {"relative_R": float(np.abs(Rr - Rr_o).max()), "sfm_T": float(np.abs(sfm["T"] - sfm_o["T"]).max()),
                           "scale": [float(x[-1]), float(x_o[-1])], "gravity": float(np.abs(g - g_o).max())},
-            "note": "one-shot work at start-up / restart; stage-level entries allocate their device scratch per call"}
+            "note": "one-shot work at start-up / restart; the SfM entries reuse a per-process device scratch, the other stage-level entries allocate theirs per call"}
 
 
 def main():

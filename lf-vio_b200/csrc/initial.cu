@@ -17,6 +17,7 @@
 // the test shim, CPU-checked against oracle/initial.py); this file adds the parallel reductions, the atomics and the control.
 // These run once per start-up / restart, on tens of frames and a few hundred features: they are latency-sized, not
 // bandwidth-sized — the point of having them on the device is that initialisation needs no CPU numerics.
+#include <mutex>
 #include <vector>
 
 #include "ba_core.cuh"
@@ -904,9 +905,40 @@ extern "C" int lfvio_epnp(const double *pws, const double *us, const int *first,
 
 namespace {
 
+// Device scratch of the SfM entries: one grow-only allocation per device, kept for the life of the process and handed to one
+// call at a time (a cudaMalloc / cudaFree pair costs more than most of the kernels here, and cudaFree synchronises the device).
+struct SfmScratch {
+    std::mutex mu;
+    unsigned char *p[64] = {};
+    size_t cap[64] = {};
+};
+SfmScratch &sfm_scratch() {
+    static SfmScratch s;
+    return s;
+}
+
 struct SfmBuffers {
-    // one device allocation for everything (a cudaMalloc / cudaFree pair costs more than most of the kernels here)
-    DBuf<unsigned char> arena;
+    std::unique_lock<std::mutex> lock;
+    struct {
+        unsigned char *p = nullptr;
+    } arena;
+    int acquire(size_t bytes) {
+        int dev = 0;
+        LFVIO_CUDA_TRY(cudaGetDevice(&dev));
+        SfmScratch &sc = sfm_scratch();
+        lock = std::unique_lock<std::mutex>(sc.mu);
+        dev &= 63;
+        if (sc.cap[dev] < bytes) {
+            if (sc.p[dev]) LFVIO_CUDA_TRY(cudaFree(sc.p[dev]));
+            sc.p[dev] = nullptr, sc.cap[dev] = 0;
+            const size_t want = (bytes + (bytes >> 2) + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
+            LFVIO_CUDA_TRY(cudaMalloc(&sc.p[dev], want));
+            sc.cap[dev] = want;
+        }
+        arena.p = sc.p[dev];
+        LFVIO_CUDA_TRY(cudaMemsetAsync(arena.p, 0, bytes, 0));
+        return LFVIO_OK;
+    }
     template <class T>
     struct Ref {
         T *p = nullptr;
@@ -939,7 +971,7 @@ struct SfmBuffers {
         plan(sp, 3 * (size_t)L), plan(Vinv, 9 * (size_t)L), plan(cand, 3 * (size_t)L), plan(pw_list, 3 * (size_t)L), plan(us_list, 3 * (size_t)L);
         plan(alphas, 4 * (size_t)L), plan(relR, 9), plan(relT, 3), plan(q_out, 4 * (size_t)F), plan(T_out, 3 * (size_t)F), plan(ctl, 1);
         plan(obs_rec, (size_t)kObsRec * n_obs), plan(tab, (size_t)L * F);
-        LFVIO_TRY(arena.put(nullptr, total));  // (zero-filled)
+        LFVIO_TRY(acquire(total));  // (zero-filled)
         auto fix = [&](auto &r) { r.p = reinterpret_cast<decltype(r.p)>(arena.p + reinterpret_cast<size_t>(r.p)); };
         fix(of), fix(ofr), fix(pts_obs), fix(fail), fix(points), fix(state), fix(cR), fix(cT), fix(cq), fix(V), fix(gp), fix(sp), fix(Vinv);
         fix(cand), fix(pw_list), fix(us_list), fix(alphas), fix(relR), fix(relT), fix(q_out), fix(T_out), fix(ctl), fix(obs_rec), fix(tab);
