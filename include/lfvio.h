@@ -362,6 +362,19 @@ int lfvio_linear_alignment(const double *R, const double *T, const double *delta
  * *inlier_cnt = 0.  E_out (9, may be NULL): the refit essential matrix.                                      */
 int lfvio_solve_relative_rt(const double *corres, int n, unsigned long long seed, unsigned frame, double *rotation,
                             double *translation, int *inlier_cnt, double *E_out, int device);
+/* InitialEXRotation::solveRelativeR (initial/initial_ex_rotation.cpp:220-289; ESTIMATE_EXTRINSIC == 2 only): the same
+ * RANSAC (:89-150), the two rotations of the essential matrix made proper (the reference decomposes -E when the first
+ * candidate is a reflection, :268-272), the four testTriangulation ratios (:291-318) and `ratio1 > ratio2 ? R1 : R2`,
+ * transposed (:283-287).  rotation (9): identity below 9 correspondences (:222, :288).                        */
+int lfvio_solve_relative_r(const double *corres, int n, unsigned long long seed, unsigned frame, double *rotation,
+                           int device);
+/* The linear system of InitialEXRotation::CalibrationExRotation (initial/initial_ex_rotation.cpp:20-60) for the n
+ * rotation pairs collected so far: Rc (camera, from lfvio_solve_relative_r), Rimu (delta_q of the pre-integration),
+ * Rc_g (ric^-1 Rimu ric with the ric of the time the pair was added), each n x 9.  ric (9): the new estimate;
+ * sv (4): singular values, descending — the function returns true when frame_count >= WINDOW_SIZE and
+ * sv[2] > 0.25 (:62-68).                                                                                    */
+int lfvio_calibrate_ex_rotation(const double *Rc, const double *Rimu, const double *Rc_g, int n, double *ric, double *sv,
+                                int device);
 /* PnpSolver::compute_pose with set_internal_parameters(0, 0, 1, 1) (pnp_solver.cpp:275-338; call sites
  * initial_sfm.cpp:55-69, estimator.cpp:343-357), batched: problem p uses correspondences
  * [first[p], first[p+1]) of pws (world points) / us (bearings), one thread block each.  R: n_problems x 9,

@@ -535,6 +535,54 @@ LFVIO_HD void gyro_bias_pair(const double *Ri, const double *Rj, const double *d
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// extrinsic rotation calibration (InitialEXRotation::CalibrationExRotation, initial/initial_ex_rotation.cpp:13-68)
+// ------------------------------------------------------------------------------------------------------------
+// Rc / Rimu / Rc_g: N x 9 row-major rotation matrices of the pairs i = 1 .. N; A: 4N x 4 work space.  ric: the estimated
+// camera-to-IMU rotation (row-major), sv: the four singular values of the stacked system, descending.
+LFVIO_HD void ex_rotation_solve(int N, const double *Rc, const double *Rimu, const double *Rc_g, double *A, double *ric, double *sv) {
+    for (int i = 0; i < N; i++) {
+        double r1[4], r2[4], ri[4], d[4];
+        rot_to_quat(Rc + 9 * i, r1);
+        rot_to_quat(Rc_g + 9 * i, r2);
+        rot_to_quat(Rimu + 9 * i, ri);
+        const double r2c[4] = {r2[0], -r2[1], -r2[2], -r2[3]};
+        quat_mul(r1, r2c, d);  // Eigen::Quaternion::angularDistance
+        const double ang = 180.0 / 3.14159265358979323846 * 2.0 * atan2(sqrt(d[1] * d[1] + d[2] * d[2] + d[3] * d[3]), fabs(d[0]));
+        const double huber = ang > 5.0 ? 5.0 / ang : 1.0;
+        // L (left-multiplication matrix of Rc, :35-41) - R (right-multiplication matrix of Rimu, :43-50), coefficients (x, y, z, w)
+        const double lw = r1[0], lx = r1[1], ly = r1[2], lz = r1[3], rw = ri[0], rx = ri[1], ry = ri[2], rz = ri[3];
+        const double Lm[16] = {lw, -lz, ly, lx, lz, lw, -lx, ly, -ly, lx, lw, lz, -lx, -ly, -lz, lw};
+        const double Rm[16] = {rw, rz, -ry, rx, -rz, rw, rx, ry, ry, -rx, rw, rz, -rx, -ry, -rz, rw};
+        for (int k = 0; k < 16; k++) A[16 * i + k] = huber * (Lm[k] - Rm[k]);
+    }
+    double V[16];
+    onesided_jacobi(4 * N, 4, A, V);
+    double nn[4];
+    int ord[4] = {0, 1, 2, 3};
+    for (int c = 0; c < 4; c++) {
+        double t = 0;
+        for (int r = 0; r < 4 * N; r++) t += A[4 * r + c] * A[4 * r + c];
+        nn[c] = sqrt(t);
+    }
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3 - a; b++)
+            if (nn[ord[b]] < nn[ord[b + 1]]) {
+                const int t = ord[b];
+                ord[b] = ord[b + 1];
+                ord[b + 1] = t;
+            }
+    for (int c = 0; c < 4; c++) sv[c] = nn[ord[c]];
+    const int o = ord[3];  // svd.matrixV().col(3); Quaterniond(Vector4d) reads (x, y, z, w)
+    const double x[4] = {V[o], V[4 + o], V[8 + o], V[12 + o]};
+    const double n = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+    const double q[4] = {x[3] / n, x[0] / n, x[1] / n, x[2] / n};
+    double R[9];
+    quat_to_rot(q, R);
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) ric[3 * r + c] = R[3 * c + r];  // toRotationMatrix().inverse()
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // bundle adjustment residual
 // ------------------------------------------------------------------------------------------------------------
 // r = n(R(q) p + t) - obs; Jr (rotation, local: ceres::QuaternionParameterization, x_plus = [cos|d|, sin|d| d/|d|] (x) x),

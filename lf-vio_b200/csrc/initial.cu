@@ -268,8 +268,11 @@ __global__ void __launch_bounds__(NT) alignment_kernel(const double *Rs, const d
 // ---------------------------------------------------------------------------------------------------------------
 // recoverPose + the (repaired) tail of solveRelativeRT
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) recover_pose_kernel(const double *E, const double3 *b1, const double3 *b2, int n, double *rotation,
-                                                           double *translation, int *inlier_cnt) {
+// mode 0: recoverPose + the tail of solveRelativeRT.  mode 1: InitialEXRotation::solveRelativeR (initial_ex_rotation.cpp:
+// 220-289): the same four cheirality counts (testTriangulation :291-318), rotation chosen by `ratio1 > ratio2 ? R1 : R2`
+// where the reference's R1 (built with the transposed W, :312-317) is decompose_essential's R2; output = its transpose.
+__global__ void __launch_bounds__(NT) recover_pose_kernel(const double *E, const double3 *b1, const double3 *b2, int n, int mode,
+                                                           double *rotation, double *translation, int *inlier_cnt) {
     __shared__ double s_R[2][9], s_t[2][3];
     __shared__ int s_cnt[4];
     if (threadIdx.x == 0) {
@@ -286,6 +289,14 @@ __global__ void __launch_bounds__(NT) recover_pose_kernel(const double *E, const
     __syncthreads();
     if (threadIdx.x == 0) {
         const int g1 = s_cnt[0], g2 = s_cnt[1], g3 = s_cnt[2], g4 = s_cnt[3];
+        if (mode == 1) {
+            const int ratio1 = max(g2, g4), ratio2 = max(g1, g3);  // counts of the reference's R1 (= s_R[1]) and R2 (= s_R[0])
+            const double *R = ratio1 > ratio2 ? s_R[1] : s_R[0];
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) rotation[3 * r + c] = R[3 * c + r];
+            *inlier_cnt = max(ratio1, ratio2);
+            return;
+        }
         int k;
         if (g1 >= g2 && g1 >= g3 && g1 >= g4) k = 0;
         else if (g2 >= g1 && g2 >= g3 && g2 >= g4) k = 1;
@@ -840,12 +851,8 @@ extern "C" int lfvio_linear_alignment(const double *R, const double *T, const do
     return dok.get(ok, 1);
 }
 
-extern "C" int lfvio_solve_relative_rt(const double *corres, int n, unsigned long long seed, unsigned frame, double *rotation,
-                                       double *translation, int *inlier_cnt, double *E_out, int device) {
-    clear_error();
-    LFVIO_REQUIRE(n >= 0 && rotation && translation && inlier_cnt && (n == 0 || corres), "lfvio_solve_relative_rt: bad arguments");
-    *inlier_cnt = 0;
-    if (n < 15) return LFVIO_OK;  // solve_5pts.cpp:540: below 15 correspondences the reference returns false untouched
+static int relative_pose_impl(const double *corres, int n, unsigned long long seed, unsigned frame, int mode, double *rotation,
+                              double *translation, int *inlier_cnt, double *E_out, int device) {
     LFVIO_CUDA_TRY(cudaSetDevice(device));
     std::vector<double> h1(3 * (size_t)n), h2(3 * (size_t)n);
     for (int i = 0; i < n; i++)
@@ -868,13 +875,59 @@ extern "C" int lfvio_solve_relative_rt(const double *corres, int n, unsigned lon
     LFVIO_TRY(cnt.put(nullptr, 1));
     const RansacScratch rs{reinterpret_cast<double3 *>(b1.p), reinterpret_cast<double3 *>(b2.p), E.p, score.p, flags.p, Eb.p, best.p};
     LFVIO_TRY(launch_ransac_bearings(nd.p, n, n, seed, frame, rs, st.p, 0));
-    recover_pose_kernel<<<1, NT>>>(Eb.p, rs.b1, rs.b2, n, R.p, T.p, cnt.p);
+    recover_pose_kernel<<<1, NT>>>(Eb.p, rs.b1, rs.b2, n, mode, R.p, T.p, cnt.p);
     LFVIO_LAUNCH_CHECK();
     LFVIO_TRY(R.get(rotation, 9));
-    LFVIO_TRY(T.get(translation, 3));
-    LFVIO_TRY(cnt.get(inlier_cnt, 1));
+    if (translation) LFVIO_TRY(T.get(translation, 3));
+    if (inlier_cnt) LFVIO_TRY(cnt.get(inlier_cnt, 1));
     if (E_out) LFVIO_TRY(Eb.get(E_out, 9));
     return LFVIO_OK;
+}
+
+extern "C" int lfvio_solve_relative_rt(const double *corres, int n, unsigned long long seed, unsigned frame, double *rotation,
+                                       double *translation, int *inlier_cnt, double *E_out, int device) {
+    clear_error();
+    LFVIO_REQUIRE(n >= 0 && rotation && translation && inlier_cnt && (n == 0 || corres), "lfvio_solve_relative_rt: bad arguments");
+    *inlier_cnt = 0;
+    if (n < 15) return LFVIO_OK;  // solve_5pts.cpp:540: below 15 correspondences the reference returns false untouched
+    return relative_pose_impl(corres, n, seed, frame, 0, rotation, translation, inlier_cnt, E_out, device);
+}
+
+extern "C" int lfvio_solve_relative_r(const double *corres, int n, unsigned long long seed, unsigned frame, double *rotation,
+                                      int device) {
+    clear_error();
+    LFVIO_REQUIRE(n >= 0 && rotation && (n == 0 || corres), "lfvio_solve_relative_r: bad arguments");
+    if (n < 9) {  // initial_ex_rotation.cpp:222, :288: identity below 9 correspondences
+        for (int k = 0; k < 9; k++) rotation[k] = (k % 4 == 0) ? 1.0 : 0.0;
+        return LFVIO_OK;
+    }
+    return relative_pose_impl(corres, n, seed, frame, 1, rotation, nullptr, nullptr, nullptr, device);
+}
+
+namespace lfvio {
+namespace {
+__global__ void ex_rotation_kernel(int N, const double *Rc, const double *Rimu, const double *Rc_g, double *A, double *ric, double *sv) {
+    if (threadIdx.x == 0) im::ex_rotation_solve(N, Rc, Rimu, Rc_g, A, ric, sv);
+}
+}  // namespace
+}  // namespace lfvio
+
+extern "C" int lfvio_calibrate_ex_rotation(const double *Rc, const double *Rimu, const double *Rc_g, int n, double *ric, double *sv,
+                                           int device) {
+    clear_error();
+    LFVIO_REQUIRE(Rc && Rimu && Rc_g && ric && sv && n >= 1 && n <= 4096, "lfvio_calibrate_ex_rotation: bad arguments");
+    LFVIO_CUDA_TRY(cudaSetDevice(device));
+    DBuf<double> dRc, dRi, dRg, dA, dric, dsv;
+    LFVIO_TRY(dRc.put(Rc, 9 * (size_t)n));
+    LFVIO_TRY(dRi.put(Rimu, 9 * (size_t)n));
+    LFVIO_TRY(dRg.put(Rc_g, 9 * (size_t)n));
+    LFVIO_TRY(dA.put(nullptr, 16 * (size_t)n));
+    LFVIO_TRY(dric.put(nullptr, 9));
+    LFVIO_TRY(dsv.put(nullptr, 4));
+    ex_rotation_kernel<<<1, 32>>>(n, dRc.p, dRi.p, dRg.p, dA.p, dric.p, dsv.p);
+    LFVIO_LAUNCH_CHECK();
+    LFVIO_TRY(dric.get(ric, 9));
+    return dsv.get(sv, 4);
 }
 
 extern "C" int lfvio_epnp(const double *pws, const double *us, const int *first, int n_problems, double *R, double *T, double *err,

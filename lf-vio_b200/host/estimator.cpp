@@ -354,6 +354,25 @@ void Estimator::processImage(const ImageFeatures &image, double header_stamp) {
         m_tmp.bg = Bgs[frame_count];
         m_tmp_valid = true;
     }
+    if (ESTIMATE_EXTRINSIC == 2 && frame_count != 0) {  // estimator.cpp:142-159: calibrate the extrinsic rotation online
+        if (flushIMU() != LFVIO_OK) return;
+        if (pre_integrations[frame_count]) {
+            const auto corres = f_manager.getCorresponding(frame_count - 1, frame_count);
+            const double *dq = pre_integrations[frame_count]->delta_q;
+            Mat3 calib_ric{};
+            initial_ex_rotation.window_size = WINDOW_SIZE;
+            initial_ex_rotation.device = m_device;
+            if (initial_ex_rotation.CalibrationExRotation(corres, {dq[0], dq[1], dq[2], dq[3]}, calib_ric)) {
+                ric[0] = calib_ric;
+                RIC0 = calib_ric;
+                ESTIMATE_EXTRINSIC = 1;
+            }
+            if (initial_ex_rotation.status != LFVIO_OK) {
+                last_status = initial_ex_rotation.status;
+                return;
+            }
+        }
+    }
     if (solver_flag == INITIAL) {
         // With run_initial_structure == false the window fills, then slides until the caller has initialised the states and
         // set solver_flag = NON_LINEAR (what the reference does while its initialisation fails, :177-178).

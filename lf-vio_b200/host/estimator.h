@@ -90,6 +90,24 @@ struct ImageFrame {
     IntegrationBase pre{};
 };
 
+// initial/initial_ex_rotation.h:16-45 — online calibration of the camera-IMU rotation (ESTIMATE_EXTRINSIC == 2)
+class InitialEXRotation {
+  public:
+    InitialEXRotation() { ric = Mat3{1, 0, 0, 0, 1, 0, 0, 0, 1}; }
+    // initial_ex_rotation.cpp:13-68.  delta_q_imu (w, x, y, z).  The two numeric steps are lfvio_solve_relative_r and
+    // lfvio_calibrate_ex_rotation; status: last C-ABI status.
+    bool CalibrationExRotation(const std::vector<std::pair<Vec3, Vec3>> &corres, const std::array<double, 4> &delta_q_imu,
+                               Mat3 &calib_ric_result);
+    int window_size = 10, device = 0, status = 0;
+    unsigned long long ransac_seed = 1;
+    double sv[4] = {0, 0, 0, 0};  // singular values of the last solve (ric_cov = sv[1..3])
+
+  private:
+    int frame_count = 0;
+    std::vector<double> Rc, Rimu, Rc_g;  // 9 doubles per pair (the identity pushed by the reference's constructor is never read)
+    Mat3 ric;
+};
+
 class Estimator {
   public:
     enum MarginalizationFlag { MARGIN_OLD = 0, MARGIN_SECOND_NEW = 1 };
@@ -123,6 +141,7 @@ class Estimator {
     bool initialStructure();
     bool visualInitialAlign();
     bool relativePose(Mat3 &relative_R, Vec3 &relative_T, int &l);
+    InitialEXRotation initial_ex_rotation;
     bool run_initial_structure = false;  // false: the pre-initialisation behaviour of this mirror (the caller sets the states)
     bool stop_after_initial_structure = false;  // test hook: return from processImage right after a successful initialStructure
     std::map<double, ImageFrame> all_image_frame;

@@ -104,6 +104,32 @@ int Estimator::integrateImageFrames(bool all, const Vec3 *new_bg) {
     return LFVIO_OK;
 }
 
+bool InitialEXRotation::CalibrationExRotation(const std::vector<std::pair<Vec3, Vec3>> &corres, const std::array<double, 4> &dq,
+                                              Mat3 &calib_ric_result) {
+    frame_count++;
+    std::vector<double> flat;
+    flat.reserve(6 * corres.size());
+    for (const auto &c : corres) {
+        flat.insert(flat.end(), c.first.begin(), c.first.end());
+        flat.insert(flat.end(), c.second.begin(), c.second.end());
+    }
+    Mat3 rc{};
+    status = lfvio_solve_relative_r(flat.data(), (int)corres.size(), ransac_seed, (unsigned)frame_count, rc.data(), device);
+    if (status != LFVIO_OK) return false;
+    const Mat3 ri = quat_to_rot(dq[0], dq[1], dq[2], dq[3], false);
+    const Mat3 rg = matmul(matmul(transpose(ric), ri), ric);  // ric.inverse() * delta_q_imu * ric
+    Rc.insert(Rc.end(), rc.begin(), rc.end());
+    Rimu.insert(Rimu.end(), ri.begin(), ri.end());
+    Rc_g.insert(Rc_g.end(), rg.begin(), rg.end());
+    status = lfvio_calibrate_ex_rotation(Rc.data(), Rimu.data(), Rc_g.data(), frame_count, ric.data(), sv, device);
+    if (status != LFVIO_OK) return false;
+    if (frame_count >= window_size && sv[2] > 0.25) {  // ric_cov(1) > 0.25 (:62-68)
+        calib_ric_result = ric;
+        return true;
+    }
+    return false;
+}
+
 bool Estimator::relativePose(Mat3 &relative_R, Vec3 &relative_T, int &l) {
     for (int i = 0; i < WINDOW_SIZE; i++) {  // estimator.cpp:459-483
         const auto corres = f_manager.getCorresponding(i, WINDOW_SIZE);
@@ -313,3 +339,28 @@ bool Estimator::visualInitialAlign() {
 }
 
 }  // namespace lfvio_host
+
+// ---- C entry points for the Python tests ---------------------------------------------------------------------------
+extern "C" void *lfvio_host_ex_rotation_create(int window_size, unsigned long long seed, int device) {
+    auto *e = new lfvio_host::InitialEXRotation();
+    e->window_size = window_size;
+    e->ransac_seed = seed;
+    e->device = device;
+    return e;
+}
+extern "C" void lfvio_host_ex_rotation_destroy(void *h) { delete static_cast<lfvio_host::InitialEXRotation *>(h); }
+// corres: n x 6, dq: (w, x, y, z); ric_out (9) receives calib_ric_result when the function returns true (1); sv_out (4)
+extern "C" int lfvio_host_ex_rotation_step(void *h, const double *corres, int n, const double *dq, double *ric_out, double *sv_out) {
+    using namespace lfvio_host;
+    auto *e = static_cast<InitialEXRotation *>(h);
+    std::vector<std::pair<Vec3, Vec3>> c;
+    for (int i = 0; i < n; i++)
+        c.emplace_back(Vec3{corres[6 * i], corres[6 * i + 1], corres[6 * i + 2]}, Vec3{corres[6 * i + 3], corres[6 * i + 4], corres[6 * i + 5]});
+    Mat3 out{};
+    const bool ok = e->CalibrationExRotation(c, {dq[0], dq[1], dq[2], dq[3]}, out);
+    if (e->status != LFVIO_OK) return -1;
+    for (int k = 0; k < 4; k++) sv_out[k] = e->sv[k];
+    if (ok)
+        for (int k = 0; k < 9; k++) ric_out[k] = out[k];
+    return ok ? 1 : 0;
+}

@@ -396,3 +396,11 @@ def global_sfm(frame_num, l, relative_R, relative_T, obs_first, obs_frame, obs_p
 
 def sfm_bundle_adjust(c_rot, c_trans, points, state, obs_first, obs_frame, obs_pts, l, device: int = 0):
     return initial.bundle_adjust(lib, check, c_rot, c_trans, points, state, obs_first, obs_frame, obs_pts, l, device)
+
+
+def solve_relative_r(corres, seed, frame, device: int = 0):
+    return initial.solve_relative_r(lib, check, corres, seed, frame, device)
+
+
+def calibrate_ex_rotation(Rc, Rimu, Rc_g, device: int = 0):
+    return initial.calibrate_ex_rotation(lib, check, Rc, Rimu, Rc_g, device)

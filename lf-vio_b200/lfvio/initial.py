@@ -26,6 +26,8 @@ def bind(lib):
     lib.lfvio_linear_alignment.argtypes = [_dp, _dp, _dp, _dp, _dp, C.c_int, _dp, C.c_double, _dp, _dp, _ip, C.c_int]
     lib.lfvio_solve_relative_rt.argtypes = [_dp, C.c_int, C.c_uint64, C.c_uint, _dp, _dp, _ip, _dp, C.c_int]
     lib.lfvio_epnp.argtypes = [_dp, _dp, _ip, C.c_int, _dp, _dp, _dp, C.c_int]
+    lib.lfvio_solve_relative_r.argtypes = [_dp, C.c_int, C.c_uint64, C.c_uint, _dp, C.c_int]
+    lib.lfvio_calibrate_ex_rotation.argtypes = [_dp, _dp, _dp, C.c_int, _dp, _dp, C.c_int]
     lib.lfvio_global_sfm.argtypes = [C.c_int, C.c_int, _dp, _dp, _ip, _ip, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _u8p,
                                      C.POINTER(SfmSummary), C.c_int]
     lib.lfvio_sfm_bundle_adjust.argtypes = [C.c_int, C.c_int, _ip, _ip, _dp, C.c_int, _u8p, _dp, _dp, _dp, C.POINTER(SfmSummary),
@@ -101,3 +103,18 @@ def bundle_adjust(lib, check, c_rot, c_trans, points, state, obs_first, obs_fram
     check(lib.lfvio_sfm_bundle_adjust(len(c_rot), l, _p(of, C.c_int), _p(ofr, C.c_int), _p(pts), len(st), _p(st, C.c_ubyte), _p(c_rot),
                                       _p(c_trans), _p(points), C.byref(s), device), "lfvio_sfm_bundle_adjust")
     return s
+
+
+def solve_relative_r(lib, check, corres, seed, frame, device=0):
+    c = _d(corres, (-1, 6))
+    Rm = np.zeros((3, 3))
+    check(lib.lfvio_solve_relative_r(_p(c), len(c), int(seed), int(frame), _p(Rm), device), "lfvio_solve_relative_r")
+    return Rm
+
+
+def calibrate_ex_rotation(lib, check, Rc, Rimu, Rc_g, device=0):
+    """-> (ric, singular values (4,))"""
+    Rc, Ri, Rg = _d(Rc, (-1, 9)), _d(Rimu, (-1, 9)), _d(Rc_g, (-1, 9))
+    ric, sv = np.zeros((3, 3)), np.zeros(4)
+    check(lib.lfvio_calibrate_ex_rotation(_p(Rc), _p(Ri), _p(Rg), len(Rc), _p(ric), _p(sv), device), "lfvio_calibrate_ex_rotation")
+    return ric, sv

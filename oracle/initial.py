@@ -626,3 +626,76 @@ def initial_structure(F, obs_first, obs_frame, obs_pts, corres_fn, reintegrate, 
     Rs = np.array([R0 @ Rs[i] for i in range(F)])
     Vs = Vs @ R0.T
     return dict(Ps=Ps, Rs=Rs, Vs=Vs, Bgs=Bgs, g=g, depth=depth, l=l, s=s)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# InitialEXRotation (ESTIMATE_EXTRINSIC == 2): extrinsic rotation from camera / IMU rotation pairs
+# ------------------------------------------------------------------------------------------------------------------
+def solve_relative_r(corres, seed, frame):
+    """InitialEXRotation::solveRelativeR (initial/initial_ex_rotation.cpp:220-289).  The reference decomposes E with cv::SVD
+    and, when the first candidate is a reflection, decomposes -E instead (:268-272); both candidates are then proper
+    rotations.  Restated with the candidates made proper directly (decompose_essential); the reference's "R1" is built with
+    the transposed W (:312-317), i.e. it is decompose_essential's R2 — which only matters for the tie of `ratio1 > ratio2`."""
+    corres = np.asarray(corres, float).reshape(-1, 6)
+    if len(corres) < 9:
+        return np.eye(3)
+    b1, b2 = corres[:, :3], corres[:, 3:]
+    E = R8.find_fundamental(b1, b2, seed, frame)[0]
+    Ra, Rb, t = decompose_essential(E)              # reference order: R1 = Rb, R2 = Ra
+    n = len(corres)
+    ratio1 = max(cheirality_count(Rb, t, b1, b2), cheirality_count(Rb, -t, b1, b2)) / n    # testTriangulation :291-318
+    ratio2 = max(cheirality_count(Ra, t, b1, b2), cheirality_count(Ra, -t, b1, b2)) / n
+    ans = Rb if ratio1 > ratio2 else Ra
+    return ans.T                                    # ans_R_eigen(j, i) = ans_R_cv(i, j)  (:283-287)
+
+
+def _angular_distance(qa, qb):
+    """Eigen::Quaternion::angularDistance, (w, x, y, z)."""
+    d = _qmul(qa, np.array([qb[0], -qb[1], -qb[2], -qb[3]]))
+    return 2.0 * np.arctan2(np.linalg.norm(d[1:]), abs(d[0]))
+
+
+def ex_rotation_solve(Rc, Rimu, Rc_g):
+    """The linear system of CalibrationExRotation (initial_ex_rotation.cpp:20-60) for the pairs i = 1 .. N (arrays without the
+    identity the constructor pushes).  Returns (ric, singular values (4,))."""
+    N = len(Rc)
+    A = np.zeros((4 * N, 4))
+    for i in range(N):
+        r1, r2 = rot_to_quat(Rc[i]), rot_to_quat(Rc_g[i])
+        ang = 180.0 / np.pi * _angular_distance(r1, r2)
+        huber = 5.0 / ang if ang > 5.0 else 1.0
+        w, q = r1[0], r1[1:]
+        Lm = np.zeros((4, 4))
+        Lm[:3, :3] = w * np.eye(3) + np.array([[0, -q[2], q[1]], [q[2], 0, -q[0]], [-q[1], q[0], 0]])
+        Lm[:3, 3], Lm[3, :3], Lm[3, 3] = q, -q, w
+        rq = rot_to_quat(Rimu[i])
+        w, q = rq[0], rq[1:]
+        Rm = np.zeros((4, 4))
+        Rm[:3, :3] = w * np.eye(3) - np.array([[0, -q[2], q[1]], [q[2], 0, -q[0]], [-q[1], q[0], 0]])
+        Rm[:3, 3], Rm[3, :3], Rm[3, 3] = q, -q, w
+        A[4 * i:4 * i + 4] = huber * (Lm - Rm)
+    _, sv, Vt = np.linalg.svd(A)
+    x = Vt[3]                                       # matrixV().col(3); Quaterniond(Vector4d) reads (x, y, z, w)
+    ric = _qrot(np.array([x[3], x[0], x[1], x[2]]) / np.linalg.norm(x)).T   # toRotationMatrix().inverse()
+    sv4 = np.zeros(4)
+    sv4[:len(sv)] = sv
+    return ric, sv4
+
+
+class InitialEXRotationOracle:
+    """InitialEXRotation (initial_ex_rotation.h:16-45, .cpp:4-68)."""
+
+    def __init__(self, window_size=10):
+        self.frame_count, self.window_size = 0, window_size
+        self.Rc, self.Rimu, self.Rc_g = [], [], []
+        self.ric = np.eye(3)
+
+    def calibrate(self, corres, delta_q_imu, seed):
+        """delta_q_imu (w, x, y, z).  Returns (ok, ric)."""
+        self.frame_count += 1
+        self.Rc.append(solve_relative_r(corres, seed, self.frame_count))
+        Ri = _qrot(np.asarray(delta_q_imu, float))
+        self.Rimu.append(Ri)
+        self.Rc_g.append(self.ric.T @ Ri @ self.ric)            # ric.inverse() * delta_q_imu * ric
+        self.ric, sv = ex_rotation_solve(self.Rc, self.Rimu, self.Rc_g)
+        return bool(self.frame_count >= self.window_size and sv[2] > 0.25), self.ric

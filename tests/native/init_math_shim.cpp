@@ -142,6 +142,10 @@ void shim_ba_residual_jac(const double *q, const double *t, const double *p, con
 }
 void shim_quat_plus(const double *q, const double *d, double *o) { quat_plus(q, d, o); }
 void shim_svd3(const double *M, double *U, double *s, double *V) { svd3(M, U, s, V); }
+void shim_ex_rotation_solve(int N, const double *Rc, const double *Rimu, const double *Rc_g, double *ric, double *sv) {
+    std::vector<double> A(16 * (size_t)N);
+    ex_rotation_solve(N, Rc, Rimu, Rc_g, A.data(), ric, sv);
+}
 
 // The LM loop of sfm_ba_kernel, serial: same per-point work items and decisions (ba_core.cuh), plain += instead of atomics
 // and a serial Cholesky.  Returns the number of iterations.

@@ -144,3 +144,21 @@ def test_ba_residual_jacobian(shim):
             assert np.allclose(fd, Jt[:, k], atol=1e-5)
             fd = (OI._ba_residual_jac(q, t, p + d, obs, False)[0] - ro) / eps
             assert np.allclose(fd, Jp[:, k], atol=1e-5)
+
+
+def test_ex_rotation_solve(shim):
+    """CalibrationExRotation's stacked system (initial_ex_rotation.cpp:20-60): device core vs numpy, and the known answer."""
+    sc = InitScenario(seed=1, F=14)
+    pre = sc.preintegrations(bg=sc.world.bg)
+    Rc = np.ascontiguousarray([sc.Rc[k - 1].T @ sc.Rc[k] for k in range(1, 14)])          # exact camera rotations
+    Rimu = np.ascontiguousarray([OI._qrot(np.asarray(p.delta_q)) for p in pre])
+    ric_guess = np.eye(3)
+    Rc_g = np.ascontiguousarray([ric_guess.T @ Rimu[i] @ ric_guess for i in range(13)])
+    for N in (1, 5, 13):
+        ric, sv = np.zeros((3, 3)), np.zeros(4)
+        shim.shim_ex_rotation_solve(N, _p(Rc), _p(Rimu), _p(Rc_g), _p(ric), _p(sv))
+        ric_o, sv_o = OI.ex_rotation_solve(Rc[:N], Rimu[:N], Rc_g[:N])
+        assert np.allclose(sv, sv_o, rtol=1e-9, atol=1e-12)
+        if N > 1:
+            assert np.allclose(ric, ric_o, atol=1e-7)
+    assert np.abs(ric - sc.ric).max() < 0.02                                               # gyro noise / bias limited
