@@ -105,3 +105,24 @@ def test_initial_structure_end_to_end(sc):
     assert np.abs(r["Vs"] - sc.V @ Rz.T).max() < 0.05
     assert np.allclose(r["g"], [0, 0, sc.g_norm], atol=1e-9)
     assert abs(OI._R2ypr_yaw_deg(r["Rs"][0])) < 1e-9                   # yaw of frame 0 removed
+
+
+def test_extrinsic_rotation_calibration_recovers_ric():
+    """InitialEXRotation restatement on a rotation-rich synthetic stream: succeeds exactly when frame_count reaches
+    WINDOW_SIZE (the singular-value test is already satisfied by then) and returns the true camera-IMU rotation."""
+    from exrot_data import make_stream
+
+    ric_true, stream = make_stream(seed=0)
+    ex = OI.InitialEXRotationOracle(10)
+    oks = []
+    for c, dq in stream:
+        ok, ric = ex.calibrate(c, dq, 3)
+        oks.append(ok)
+    assert oks == [False] * 9 + [True] * (len(stream) - 9)
+    assert np.abs(ric - ric_true).max() < 5e-3
+    # the camera rotation of one pair, against the construction
+    c, dq = stream[4]
+    Rc = OI.solve_relative_r(c, 3, 5)
+    Rimu = _qrot(np.asarray(dq))
+    assert np.abs(ric_true @ Rc @ ric_true.T - Rimu).max() < 5e-3          # R_imu = ric R_c ric^T up to the injected gyro error
+    assert np.array_equal(OI.solve_relative_r(c[:8], 3, 5), np.eye(3))     # below 9 correspondences: identity
