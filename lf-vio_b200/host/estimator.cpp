@@ -999,3 +999,55 @@ extern "C" int lfvio_host_estimator_get(void *h, double *P, double *R, double *V
     info[6] = e->sum_of_front;
     return LFVIO_OK;
 }
+
+// ---- FeatureManager alone (pure host bookkeeping: usable and testable without a CUDA device) ------------------------------
+extern "C" void *lfvio_host_fm_create(int window_size, double min_parallax) {
+    auto *f = new lfvio_host::FeatureManager();
+    f->window_size = window_size;
+    lfvio_host::MIN_PARALLAX = min_parallax;
+    return f;
+}
+extern "C" void lfvio_host_fm_destroy(void *h) { delete static_cast<lfvio_host::FeatureManager *>(h); }
+// ids (n) / bearings (n x 3): one image; returns addFeatureCheckParallax (1 = key frame)
+extern "C" int lfvio_host_fm_add(void *h, int frame_count, const int *ids, const double *bearings, int n, double td) {
+    using namespace lfvio_host;
+    ImageFeatures image;
+    for (int i = 0; i < n; i++)
+        image[ids[i]].emplace_back(0, std::array<double, 8>{bearings[3 * i], bearings[3 * i + 1], bearings[3 * i + 2], 0, 0, 0, 0, 0});
+    return static_cast<FeatureManager *>(h)->addFeatureCheckParallax(frame_count, image, td) ? 1 : 0;
+}
+extern "C" int lfvio_host_fm_corresponding(void *h, int l, int r, double *out, int cap) {
+    const auto c = static_cast<lfvio_host::FeatureManager *>(h)->getCorresponding(l, r);
+    const int n = (int)c.size() < cap ? (int)c.size() : cap;
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) out[6 * i + k] = c[i].first[k], out[6 * i + 3 + k] = c[i].second[k];
+    return (int)c.size();
+}
+// op: 0 removeBack, 1 removeFront(arg), 2 removeBackShiftDepth(pose: marg_R 9 | marg_P 3 | new_R 9 | new_P 3)
+extern "C" void lfvio_host_fm_slide(void *h, int op, int arg, const double *pose) {
+    using namespace lfvio_host;
+    auto *f = static_cast<FeatureManager *>(h);
+    if (op == 0) f->removeBack();
+    else if (op == 1) f->removeFront(arg);
+    else {
+        Mat3 mR{}, nR{};
+        for (int k = 0; k < 9; k++) mR[k] = pose[k], nR[k] = pose[12 + k];
+        f->removeBackShiftDepth(mR, Vec3{pose[9], pose[10], pose[11]}, nR, Vec3{pose[21], pose[22], pose[23]});
+    }
+}
+// snapshot: per feature [id, start_frame, n_obs] (ints) and estimated_depth; set_depth != NULL first assigns estimated_depth in
+// list order.  Returns the number of features (getFeatureCount() in *count_out).
+extern "C" int lfvio_host_fm_snapshot(void *h, int *meta, double *depth, int cap, const double *set_depth, int *count_out) {
+    auto *f = static_cast<lfvio_host::FeatureManager *>(h);
+    int i = 0;
+    for (auto &it : f->feature) {
+        if (set_depth) it.estimated_depth = set_depth[i];
+        if (i < cap) {
+            meta[3 * i] = it.feature_id, meta[3 * i + 1] = it.start_frame, meta[3 * i + 2] = (int)it.feature_per_frame.size();
+            depth[i] = it.estimated_depth;
+        }
+        i++;
+    }
+    if (count_out) *count_out = f->getFeatureCount();
+    return i;
+}
