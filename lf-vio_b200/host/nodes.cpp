@@ -225,9 +225,12 @@ void EstimatorNode::pubOdometry(double stamp) {
 }  // namespace lfvio_host
 
 // ---- C entry points for the Python tests ---------------------------------------------------------------------------
+// device < 0: build the node without a device window (its creation fails and is tolerated) — for CPU-only tests of the
+// host-side message synchronisation; such a node must not be fed more than WINDOW_SIZE images (the first device call
+// happens when the window is full).
 extern "C" void *lfvio_host_estimator_node_create(int window_size, int max_features, int device, const char *result_path) {
     auto *n = new lfvio_host::EstimatorNode(window_size, max_features, device);
-    if (n->estimator.last_status != LFVIO_OK) {
+    if (n->estimator.last_status != LFVIO_OK && device >= 0) {
         delete n;
         return nullptr;
     }
@@ -302,3 +305,22 @@ extern "C" int lfvio_host_tracker_node_configure(void *h, const lfvio_ocam *cam,
     n->trackerData[0].setCamera(std::make_shared<camodocal::OCAMCamera>(*cam), *cam);
     return LFVIO_OK;
 }
+
+// the IMU samples buffered for window slot j (dt_buf / linear_acceleration_buf / angular_velocity_buf, estimator.h:96-98);
+// returns their number.  info (may be NULL): [frame_count, sum_of_wait, imu_buf.size(), feature_buf.size()]
+extern "C" int lfvio_host_estimator_node_imu_buf(void *h, int j, double *dt, double *acc, double *gyr, int cap, int *info) {
+    auto *n = static_cast<lfvio_host::EstimatorNode *>(h);
+    const auto &e = n->estimator;
+    if (info) {
+        info[0] = e.frame_count, info[1] = n->sum_of_wait, info[2] = (int)n->imu_buf.size(), info[3] = (int)n->feature_buf.size();
+    }
+    if (j < 0 || j > e.WINDOW_SIZE) return -1;
+    const int m = (int)e.dt_buf[j].size();
+    for (int i = 0; i < m && i < cap; i++) {
+        dt[i] = e.dt_buf[j][i];
+        for (int k = 0; k < 3; k++) acc[3 * i + k] = e.linear_acceleration_buf[j][i][k], gyr[3 * i + k] = e.angular_velocity_buf[j][i][k];
+    }
+    return m;
+}
+extern "C" void lfvio_host_estimator_node_set_td(void *h, double td) { static_cast<lfvio_host::EstimatorNode *>(h)->estimator.td = td; }
+extern "C" void lfvio_host_estimator_node_restart(void *h) { static_cast<lfvio_host::EstimatorNode *>(h)->restart_callback(true); }
