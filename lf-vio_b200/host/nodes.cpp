@@ -324,3 +324,6 @@ extern "C" int lfvio_host_estimator_node_imu_buf(void *h, int j, double *dt, dou
 }
 extern "C" void lfvio_host_estimator_node_set_td(void *h, double td) { static_cast<lfvio_host::EstimatorNode *>(h)->estimator.td = td; }
 extern "C" void lfvio_host_estimator_node_restart(void *h) { static_cast<lfvio_host::EstimatorNode *>(h)->restart_callback(true); }
+// FREQ alone (parameters.cpp), for CPU-only tests of the node's frequency control: without a camera the tracker has no
+// device handle, readImage returns at once and the node publishes empty messages on the frames it would publish on
+extern "C" void lfvio_host_tracker_node_set_freq(int freq) { lfvio_host::FREQ = freq; }

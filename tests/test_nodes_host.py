@@ -89,3 +89,57 @@ def test_measurement_synchronisation(host, td):
     *_, info = _slot(host, node, 0)
     assert info[0] == 0 and info[2] == 0 and info[3] == 0
     host.lfvio_host_estimator_node_destroy(node)
+
+
+def _freq_control_reference(stamps, freq):
+    """feature_tracker_node.cpp:27-62, 110-112, 173-178 restated: per image -1 (nothing published), -2 (stream restart) or 0
+    (a message is published; it is empty here because there is no device)."""
+    first_flag, first_time, last_time, pub_count, init_pub = True, 0.0, 0.0, 1, False
+    out = []
+    for t in stamps:
+        if first_flag:
+            first_flag, first_time, last_time = False, t, t
+            out.append(-1)
+            continue
+        if t - last_time > 1.0 or t < last_time:
+            first_flag, last_time, pub_count = True, 0.0, 1
+            out.append(-2)
+            continue
+        last_time = t
+        r = 1.0 * pub_count / (t - first_time)
+        pub = np.floor(r + 0.5) <= freq                       # C round(): half away from zero (r > 0)
+        if pub and abs(r - freq) < 0.01 * freq:
+            first_time, pub_count = t, 0
+        if not pub:
+            out.append(-1)
+            continue
+        pub_count += 1
+        out.append(0 if init_pub else -1)
+        init_pub = True
+    return out
+
+
+@pytest.mark.parametrize("rate,freq", [(15.0, 10), (30.0, 10), (20.0, 20), (10.0, 30)])
+def test_tracker_node_frequency_control(host, rate, freq):
+    host.lfvio_host_tracker_node_create.restype = C.c_void_p
+    host.lfvio_host_tracker_node_destroy.argtypes = [C.c_void_p]
+    host.lfvio_host_tracker_node_image.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int]
+    host.lfvio_host_tracker_node_set_freq.argtypes = [C.c_int]
+    host.lfvio_host_tracker_node_set_freq(freq)
+    node = host.lfvio_host_tracker_node_create()
+    stamps = [200.0 + k / rate for k in range(60)]
+    stamps += [stamps[-1] + 1.5 + k / rate for k in range(25)]            # a gap of more than a second: restart
+    stamps += [stamps[-1] - 0.3] + [stamps[-1] - 0.3 + (k + 1) / rate for k in range(25)]   # time goes backwards: restart
+    img = np.zeros((4, 4), np.uint8)
+    out = np.zeros((8, 9), np.float32)
+    got = [host.lfvio_host_tracker_node_image(node, img.ctypes.data, 4, 4, 4, t, out.ctypes.data, 8) for t in stamps]
+    host.lfvio_host_tracker_node_destroy(node)
+    want = _freq_control_reference(stamps, freq)
+    assert got == want
+    assert want.count(-2) == 2
+    published = want.count(0)
+    if rate > freq:                                                       # throttled to about FREQ messages per second
+        span = 60 / rate + 25 / rate + 26 / rate
+        assert abs(published / span - freq) < 0.25 * freq
+    else:                                                                 # slower camera than FREQ: every frame goes out
+        assert published >= len(stamps) - 2 * 3 - 2
