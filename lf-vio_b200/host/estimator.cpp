@@ -1051,3 +1051,35 @@ extern "C" int lfvio_host_fm_snapshot(void *h, int *meta, double *depth, int cap
     if (count_out) *count_out = f->getFeatureCount();
     return i;
 }
+
+// ---- vector2double / double2vector alone (pure host math: the gauge re-anchoring of estimator.cpp:532-583) -----------------
+// P, R (row-major), V, Ba, Bg: the F = window_size + 1 states before the solve; pose7 (x y z qx qy qz qw) / sb9: the optimised
+// parameter arrays as ceres leaves them; ex7.  On return P / R / V / Ba / Bg hold what double2vector() writes, pose7_rt / sb9_rt
+// what the following vector2double() packs again.  Needs no device (the estimator is built without a device window).
+extern "C" int lfvio_host_double2vector(int window_size, double *P, double *R, double *V, double *Ba, double *Bg, const double *pose7,
+                                        const double *sb9, const double *ex7, double *pose7_rt, double *sb9_rt) {
+    using namespace lfvio_host;
+    Estimator e(window_size, 16, -1);  // (window creation fails without a device and is not needed here)
+    const int F = window_size + 1;
+    for (int i = 0; i < F; i++) {
+        e.Ps[i] = Vec3{P[3 * i], P[3 * i + 1], P[3 * i + 2]};
+        e.Vs[i] = Vec3{V[3 * i], V[3 * i + 1], V[3 * i + 2]};
+        e.Bas[i] = Vec3{Ba[3 * i], Ba[3 * i + 1], Ba[3 * i + 2]};
+        e.Bgs[i] = Vec3{Bg[3 * i], Bg[3 * i + 1], Bg[3 * i + 2]};
+        for (int k = 0; k < 9; k++) e.Rs[i][k] = R[9 * i + k];
+    }
+    for (int k = 0; k < 7 * F; k++) e.para_Pose[k] = pose7[k];
+    for (int k = 0; k < 9 * F; k++) e.para_SpeedBias[k] = sb9[k];
+    for (int k = 0; k < 7; k++) e.para_Ex_Pose[0][k] = ex7[k];
+    e.double2vector();
+    for (int i = 0; i < F; i++)
+        for (int k = 0; k < 3; k++) {
+            P[3 * i + k] = e.Ps[i][k], V[3 * i + k] = e.Vs[i][k], Ba[3 * i + k] = e.Bas[i][k], Bg[3 * i + k] = e.Bgs[i][k];
+        }
+    for (int i = 0; i < F; i++)
+        for (int k = 0; k < 9; k++) R[9 * i + k] = e.Rs[i][k];
+    e.vector2double();
+    for (int k = 0; k < 7 * F; k++) pose7_rt[k] = e.para_Pose[k];
+    for (int k = 0; k < 9 * F; k++) sb9_rt[k] = e.para_SpeedBias[k];
+    return 0;
+}
