@@ -162,3 +162,28 @@ def test_ex_rotation_solve(shim):
         if N > 1:
             assert np.allclose(ric, ric_o, atol=1e-7)
     assert np.abs(ric - sc.ric).max() < 0.02                                               # gyro noise / bias limited
+
+
+def test_cores_terminate_on_degenerate_input(shim):
+    """The fixed-size cores must come back (possibly with non-finite numbers, as Eigen would) on degenerate input — they run
+    inside single-CTA kernels where a non-terminating loop would hang the device: coplanar world points (singular
+    control-point basis), a bearing on the image plane's horizon (division by z = 0), an all-zero essential matrix."""
+    rng = np.random.default_rng(0)
+    pw = np.ascontiguousarray(np.hstack([rng.uniform(-1, 1, (20, 2)), np.zeros((20, 1))]))        # coplanar
+    pc = pw + [0, 0, 4.0]
+    us = np.ascontiguousarray(pc / np.linalg.norm(pc, axis=1, keepdims=True))
+    R, T = np.zeros((3, 3)), np.zeros(3)
+    shim.shim_epnp(_p(pw), _p(us), 20, _p(R), _p(T))
+    us2 = us.copy()
+    us2[3] = [1.0, 0.0, 0.0]                                                                       # z = 0
+    shim.shim_epnp(_p(np.ascontiguousarray(pw + rng.normal(0, 0.3, pw.shape))), _p(us2), 20, _p(R), _p(T))
+    E = np.zeros((3, 3))
+    b = np.ascontiguousarray(us)
+    Rr, t, counts = np.zeros((3, 3)), np.zeros(3), np.zeros(4, np.int32)
+    shim.shim_recover_pose(_p(E), _p(b), _p(b), 20, _p(Rr), _p(t), counts.ctypes.data_as(C.POINTER(C.c_int)))
+    X = np.zeros(3)
+    P0 = np.ascontiguousarray(np.hstack([np.eye(3), np.zeros((3, 1))]))
+    shim.shim_triangulate_point(_p(P0), _p(P0), _p(b[0]), _p(b[0]), _p(X))                         # zero baseline
+    U, s, V = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
+    shim.shim_svd3(_p(np.zeros((3, 3))), _p(U), _p(s), _p(V))
+    assert np.all(s == 0)
