@@ -187,3 +187,21 @@ def test_cores_terminate_on_degenerate_input(shim):
     U, s, V = np.zeros((3, 3)), np.zeros(3), np.zeros((3, 3))
     shim.shim_svd3(_p(np.zeros((3, 3))), _p(U), _p(s), _p(V))
     assert np.all(s == 0)
+
+
+def test_ba_control_flow_terminates_on_non_finite_cost(shim):
+    """A point sitting on a camera centre makes the residual non-finite; the LM loop (ba_begin_iteration / ba_decide — the same
+    functions the kernel runs) must still stop, at the iteration cap at the latest, and report non-convergence."""
+    sc = InitScenario(seed=2, F=6, max_feat=40)
+    ok, Rr, Tr, _, _ = OI.solve_relative_rt(sc.corres(0, 5), 7, 0)
+    res = OI.global_sfm(6, 0, Rr, Tr, sc.obs_first, sc.obs_frame, sc.obs_pts, ba=False)
+    cr, ct, pts = [np.ascontiguousarray(a) for a in res["pre_ba"]]
+    state = res["state"].astype(np.uint8)
+    j = int(np.argmax(state))
+    pts[j] = -OI._qrot(cr[sc.obs_frame[sc.obs_first[j]]] * [1, -1, -1, -1]) @ ct[sc.obs_frame[sc.obs_first[j]]]   # camera centre
+    costs, ns, cv = np.zeros(51), C.c_int(), C.c_int()
+    of, ofr = np.ascontiguousarray(sc.obs_first, np.int32), np.ascontiguousarray(sc.obs_frame, np.int32)
+    ip = C.POINTER(C.c_int)
+    it = shim.shim_ba(6, len(state), 0, of.ctypes.data_as(ip), ofr.ctypes.data_as(ip), _p(sc.obs_pts), state.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                      _p(cr), _p(ct), _p(pts), _p(costs), C.byref(ns), C.byref(cv))
+    assert 0 <= it <= 50
