@@ -10,7 +10,9 @@
 // Build (from the repo root, after `make -C lf-vio_b200`):
 //   g++ -O2 -std=c++17 -Iinclude -Ilf-vio_b200/host examples/vio_from_files.cpp -Llf-vio_b200 -llfvio_host -llfvio
 //       -Wl,-rpath,$PWD/lf-vio_b200 -o vio_from_files            (one command line)
-// Run on a machine with a B200:  ./vio_from_files imu.txt features.txt result_tum.txt [td] [ransac_seed]
+// Run on a machine with a B200:  ./vio_from_files imu.txt features.txt result_tum.txt [calib.txt] [td] [ransac_seed]
+//   calib.txt (optional, whitespace separated): ric (9, row-major: camera -> IMU rotation) tic (3) acc_n gyr_n acc_w gyr_w g_norm
+// tools/make_example_stream.py writes a matching set of files from the synthetic world used by the tests.
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -23,9 +25,10 @@
 using namespace lfvio_host;
 
 static void usage() {
-    std::puts("usage: vio_from_files imu.txt features.txt result_tum.txt [td] [ransac_seed]\n"
+    std::puts("usage: vio_from_files imu.txt features.txt result_tum.txt [calib.txt] [td] [ransac_seed]\n"
               "  imu.txt:      stamp ax ay az gx gy gz\n"
               "  features.txt: blocks \"F stamp n\" + n lines \"id x y z u v vx vy vz\"\n"
+              "  calib.txt:    ric (9, row-major) tic (3) acc_n gyr_n acc_w gyr_w g_norm\n"
               "  writes \"stamp px py pz qx qy qz qw\" per optimised frame (TUM)");
 }
 
@@ -49,10 +52,23 @@ int main(int argc, char **argv) {
         return 1;
     }
     node.VINS_RESULT_PATH = argv[3];
-    if (argc > 4) TD = std::atof(argv[4]);
-    node.estimator.setParameter();            // tic / ric / td from TIC0 / RIC0 / TD (set them from your calibration first)
+    if (argc > 4) {  // readParameters(): extrinsicRotation / extrinsicTranslation / acc_n .. g_norm of the reference's YAML
+        std::ifstream cal(argv[4]);
+        double v[17];
+        for (double &x : v)
+            if (!(cal >> x)) {
+                std::fprintf(stderr, "calib.txt needs 17 numbers: ric (9) tic (3) acc_n gyr_n acc_w gyr_w g_norm\n");
+                return 2;
+            }
+        for (int k = 0; k < 9; k++) node.estimator.RIC0[k] = v[k];
+        node.estimator.TIC0 = Vec3{v[9], v[10], v[11]};
+        node.estimator.imu_noise = lfvio_imu_noise{v[12], v[13], v[14], v[15]};
+        G = Vec3{0.0, 0.0, v[16]};
+    }
+    if (argc > 5) TD = std::atof(argv[5]);
+    node.estimator.setParameter();            // tic / ric / td from TIC0 / RIC0 / TD
     node.estimator.run_initial_structure = true;
-    if (argc > 5) node.estimator.ransac_seed = std::strtoull(argv[5], nullptr, 10);
+    if (argc > 6) node.estimator.ransac_seed = std::strtoull(argv[6], nullptr, 10);
 
     // merge the two streams by time stamp, as the ROS callbacks would arrive
     ImuMsg im;
