@@ -45,7 +45,8 @@ __device__ void eval_projection(const lfvio_proj_factor &f, const double *x, con
     const D3 b2 = cross3(a, b1);
     D3 pts_i_td = pts_i, pts_j_td = pts_j;
     if (o.estimate_td) {
-        const double row_i = f.row_i - (double)(o.row / 2), row_j = f.row_j - (double)(o.row / 2);
+        // ROW is a double in the reference (vins_estimator/src/parameters.h:39): ROW / 2 is a floating division
+        const double row_i = f.row_i - (double)o.row / 2, row_j = f.row_j - (double)o.row / 2;
         pts_i_td = pts_i - (td - f.td_i + o.tr / o.row * row_i) * vel_i;
         pts_j_td = pts_j - (td - f.td_j + o.tr / o.row * row_j) * vel_j;
     }

@@ -184,7 +184,8 @@ __global__ void gyro_bias_kernel(const double *Rs, const double *dq, const doubl
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NT) alignment_kernel(const double *Rs, const double *Ts, const double *dp, const double *dv,
                                                         const double *dts, int n, double t0, double t1, double t2, double g_norm,
-                                                        double *A, double *bvec, double *g_out, double *x_out, int *ok_out) {
+                                                        double *A, double *bvec, double *Aacc, double *bacc, double *g_out,
+                                                        double *x_out, int *ok_out) {
     __shared__ double s_gcols[9], s_gfixed[3], s_tic[3], s_g0[3];
     __shared__ int s_ok, s_stop;
     const int tid = threadIdx.x;
@@ -198,8 +199,13 @@ __global__ void __launch_bounds__(NT) alignment_kernel(const double *Rs, const d
     // pass 0 = LinearAlignment (k = 3), passes 1..4 = RefineGravity (k = 2)
     for (int pass = 0; pass < 5; pass++) {
         const int k = pass == 0 ? 3 : 2, kk = k + 1, ns = 3 * n + kk;
-        for (int i = tid; i < ns * ns; i += NT) A[i] = 0.0;
-        for (int i = tid; i < ns; i += NT) bvec[i] = 0.0;
+        // Aacc / bacc are the reference's A and b: LinearAlignment zeroes its own (:137-140); RefineGravity zeroes them ONCE
+        // before its four passes (:62-65), so every later pass adds its blocks to the already scaled sum and scales again
+        // (A = A * 1000 inside the loop, :119-120) — the first linearisation dominates the later solves. Kept as is.
+        if (pass <= 1) {
+            for (int i = tid; i < ns * ns; i += NT) Aacc[i] = 0.0;
+            for (int i = tid; i < ns; i += NT) bacc[i] = 0.0;
+        }
         __syncthreads();
         for (int i = tid; i < n - 1; i += NT) {
             double tA[60], tb[6];
@@ -210,15 +216,18 @@ __global__ void __launch_bounds__(NT) alignment_kernel(const double *Rs, const d
                 const int ga = a < 6 ? 3 * i + a : ns - kk + (a - 6);
                 double rb = 0;
                 for (int r = 0; r < 6; r++) rb += tA[10 * r + a] * tb[r];
-                atomicAdd(&bvec[ga], rb * 1000.0);
+                atomicAdd(&bacc[ga], rb);
                 for (int c = 0; c <= a; c++) {  // lower triangle only (the Cholesky reads nothing else)
                     const int gc = c < 6 ? 3 * i + c : ns - kk + (c - 6);
                     double s = 0;
                     for (int r = 0; r < 6; r++) s += tA[10 * r + a] * tA[10 * r + c];
-                    atomicAdd(&A[ga * ns + gc], s * 1000.0);
+                    atomicAdd(&Aacc[ga * ns + gc], s);
                 }
             }
         }
+        __syncthreads();
+        for (int i = tid; i < ns * ns; i += NT) A[i] = Aacc[i] = Aacc[i] * 1000.0;  // the factorisation below works in place on A
+        for (int i = tid; i < ns; i += NT) bvec[i] = bacc[i] = bacc[i] * 1000.0;
         __syncthreads();
         cta_cholesky_solve(A, ns, ns, bvec, &s_ok);
         __syncthreads();
@@ -832,7 +841,7 @@ extern "C" int lfvio_linear_alignment(const double *R, const double *T, const do
     LFVIO_REQUIRE(n_frames >= 2 && n_frames <= LFVIO_INIT_MAX_FRAMES, "lfvio_linear_alignment: 2 <= n_frames <= LFVIO_INIT_MAX_FRAMES");
     LFVIO_CUDA_TRY(cudaSetDevice(device));
     const int ns = 3 * n_frames + 4;
-    DBuf<double> dR, dT, dp, dv, dt, A, b, dg, dx;
+    DBuf<double> dR, dT, dp, dv, dt, A, b, Aacc, bacc, dg, dx;
     DBuf<int> dok;
     LFVIO_TRY(dR.put(R, 9 * (size_t)n_frames));
     LFVIO_TRY(dT.put(T, 3 * (size_t)n_frames));
@@ -841,10 +850,12 @@ extern "C" int lfvio_linear_alignment(const double *R, const double *T, const do
     LFVIO_TRY(dt.put(sum_dt, (size_t)(n_frames - 1)));
     LFVIO_TRY(A.put(nullptr, (size_t)ns * ns));
     LFVIO_TRY(b.put(nullptr, ns));
+    LFVIO_TRY(Aacc.put(nullptr, (size_t)ns * ns));
+    LFVIO_TRY(bacc.put(nullptr, ns));
     LFVIO_TRY(dg.put(nullptr, 3));
     LFVIO_TRY(dx.put(nullptr, ns));
     LFVIO_TRY(dok.put(nullptr, 1));
-    alignment_kernel<<<1, NT>>>(dR.p, dT.p, dp.p, dv.p, dt.p, n_frames, tic[0], tic[1], tic[2], g_norm, A.p, b.p, dg.p, dx.p, dok.p);
+    alignment_kernel<<<1, NT>>>(dR.p, dT.p, dp.p, dv.p, dt.p, n_frames, tic[0], tic[1], tic[2], g_norm, A.p, b.p, Aacc.p, bacc.p, dg.p, dx.p, dok.p);
     LFVIO_LAUNCH_CHECK();
     LFVIO_TRY(dg.get(g, 3));
     LFVIO_TRY(dx.get(x, ns));

@@ -56,7 +56,8 @@ void eval_projection(const lfvio_proj_factor &f, const double *pose_i, const dou
     const V3 b2 = cross(a, b1);
     V3 pts_i_td = pts_i, pts_j_td = pts_j;
     if (o.estimate_td) {
-        const double row_i = f.row_i - o.row / 2, row_j = f.row_j - o.row / 2;  // integer ROW / 2
+        // ROW is a double in the reference (parameters.h:39, projection_td_factor.cpp:20-21): floating division
+        const double row_i = f.row_i - (double)o.row / 2, row_j = f.row_j - (double)o.row / 2;
         pts_i_td = pts_i - (td - f.td_i + o.tr / o.row * row_i) * vel_i;
         pts_j_td = pts_j - (td - f.td_j + o.tr / o.row * row_j) * vel_j;
     }

@@ -81,12 +81,14 @@ def tangent_basis(g0):
     return np.stack([b, np.cross(a, b)], axis=1)
 
 
-def _alignment_system(Rs, Ts, dp, dv, dts, tic, g_cols, g_fixed):
+def _alignment_system(Rs, Ts, dp, dv, dts, tic, g_cols, g_fixed, A=None, b=None):
     """The normal equations shared by LinearAlignment (:132-180, g_cols = I3, g_fixed = 0) and one RefineGravity pass
-    (:73-123, g_cols = lxly, g_fixed = g0)."""
+    (:73-123, g_cols = lxly, g_fixed = g0).  A / b: accumulate on top of these (RefineGravity zeroes them ONCE, before its
+    four passes, :62-65) and scale the sum by 1000 (:119-120)."""
     n, k = len(Rs), g_cols.shape[1]
     ns = 3 * n + k + 1
-    A, b = np.zeros((ns, ns)), np.zeros(ns)
+    if A is None:
+        A, b = np.zeros((ns, ns)), np.zeros(ns)
     for i in range(n - 1):
         dt = dts[i]
         Ri_T = Rs[i].T
@@ -114,9 +116,13 @@ def refine_gravity(Rs, Ts, dp, dv, dts, tic, g, g_norm):
     """initial_aligment.cpp:56-130.  Returns (g, x) with x of size 3n + 2 + 1."""
     g0 = g / np.linalg.norm(g) * g_norm
     x = None
+    A = b = None
     for _ in range(4):
+        # The reference does NOT reset A and b between the passes: pass k solves 1000 (A_{k-1} + new_k), so the first
+        # linearisation dominates every later solve by three orders of magnitude per pass (kept as is; pinned against the
+        # reference's own code by tests/test_oracle_ref.py).
         lxly = tangent_basis(g0)
-        A, b = _alignment_system(Rs, Ts, dp, dv, dts, tic, lxly, g0)
+        A, b = _alignment_system(Rs, Ts, dp, dv, dts, tic, lxly, g0, A, b)
         x = np.linalg.solve(A, b)
         dg = x[-3:-1]
         g0 = g0 + lxly @ dg
