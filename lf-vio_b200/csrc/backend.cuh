@@ -59,6 +59,18 @@ struct DevProblem {
     const double *imu_sqrt_info;  // n_imu x 225
     const int *lm_first;          // L + 1: landmark l owns proj factors [lm_first[l], lm_first[l+1])
     DevPrior prior;
+    // The kernels read this struct from DEVICE memory (self_dev), so that a launch carries no per-frame value and the
+    // whole launch sequence of a solve can be replayed from a CUDA graph.  Launch geometry comes from the g_* fields:
+    // the counts rounded up to coarse buckets (host side, window.cu: upload), stable from frame to frame; CTAs beyond the
+    // true counts exit.
+    const DevProblem *self_dev;
+    int g_nbp;    // CTAs of 128 projection factors (evaluate_kernel, colnorm_kernel)
+    int g_L;      // landmark items (accumulate_kernel)
+    int g_imu;    // IMU items = F - 1
+    int cap_L;    // landmark capacity of the handle (sizes of the per-solve clears)
+    int cap_n;    // prior capacity of the handle (15 F + 7)
+    int nd_ok;    // the speed-bias blocks sb_1 .. sb_{F-1} are coupled only through the IMU chain (no prior on them):
+                  // the step kernel may eliminate them by nested dissection (chol_nd.cuh)
 };
 
 // residuals + local, loss-corrected Jacobians of every factor at one state

@@ -40,7 +40,12 @@ int ensure_dyn_smem(const void *kernel, int bytes) {
     return LFVIO_OK;
 }
 
-void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+static thread_local uint64_t tl_launches = 0;
+void count_launch(int n) {
+    g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed);
+    tl_launches += (uint64_t)n;
+}
+uint64_t thread_launch_count() { return tl_launches; }
 
 int sm_count(int device) {
     static int cached[64] = {0};

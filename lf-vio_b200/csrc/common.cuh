@@ -1,5 +1,6 @@
 // Shared host/device helpers for the lfvio CUDA library (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -15,6 +16,8 @@ void set_error(const char *fmt, ...);
 void clear_error();
 // process-wide kernel launch counter (lfvio_launch_count)
 void count_launch(int n = 1);
+// launches counted on the calling thread (delta around a stream capture = kernels inside the captured graph)
+uint64_t thread_launch_count();
 
 #define LFVIO_CUDA_TRY(expr)                                                              \
     do {                                                                                  \
@@ -54,6 +57,26 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // the stream is still running; pdl_prologue() at the top of BOTH kernels (a) lets the successor's CTAs become resident
 // right away and (b) blocks until the predecessor has completed and its writes are visible.  For chains of short,
 // strictly dependent kernels (the trust-region loop) this removes the launch/scheduling gap between them.
+// Optional per-CTA timeline (make EXTRA=-DLFVIO_CTA_PROFILE): globaltimer stamps of up to 4 points per CTA of the last launch.
+#ifdef LFVIO_CTA_PROFILE
+#define CTA_PROF_DECL(name) static __device__ long long name[4096][4]
+#define CTA_PROF(name, i)                                                                              \
+    do {                                                                                               \
+        if (threadIdx.x == 0 && blockIdx.x < 4096) {                                                   \
+            unsigned long long t_;                                                                     \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                      \
+            name[blockIdx.x][i] = (long long)t_;                                                       \
+        }                                                                                              \
+    } while (0)
+#define CTA_PROF_READER(fn, name)                                                                      \
+    extern "C" int fn(long long *out, int n_cta) {                                                     \
+        return cudaMemcpyFromSymbol(out, name, sizeof(long long) * 4 * (size_t)n_cta) == cudaSuccess ? 0 : -1; \
+    }
+#else
+#define CTA_PROF_DECL(name)
+#define CTA_PROF(name, i)
+#define CTA_PROF_READER(fn, name)
+#endif
 __device__ __forceinline__ void pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -69,7 +92,11 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = (s == nullptr) ? 0 : 1;  // stage-level entry points run on the default stream: plain launch there
+    // Off by default (LFVIO_PDL=1 turns it on): measured on a B200, a dependent grid that was launched early keeps the OTHER
+    // stream's kernels from being scheduled (tracker stream 0.27 -> 0.76 ms/frame next to the solver chain) and, with the
+    // chain replayed from a CUDA graph, gains the chain itself only 1.6 % (profiles/r2_streams.md).
+    static const bool pdl = [] { const char *e = getenv("LFVIO_PDL"); return e && e[0] == '1'; }();
+    cfg.numAttrs = (s == nullptr || !pdl) ? 0 : 1;  // stage-level entry points run on the default stream: plain launch there
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 #endif

@@ -331,8 +331,10 @@ __device__ void accept_logic(SolverCtl *ctl, const lfvio_solver_opts &o) {
 
 // mode 0: evaluate the current state unconditionally (initial point).  mode 1: evaluate the candidate if one
 // is pending, then run accept_logic in the last CTA.  mode 2: plain evaluation of buffer 0 (debug entry point).
-__global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(DevProblem P, const double *x0, const double *x1, EvalBuf e0,
-                                                              EvalBuf e1, SolverCtl *ctl, int mode, int robust, int nbp) {
+CTA_PROF_DECL(g_eval_prof);
+__global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(const DevProblem *__restrict__ Pd, const double *x0, const double *x1, EvalBuf e0,
+                                                              EvalBuf e1, SolverCtl *ctl, int mode, int robust, int nbp, int n_imu_cta) {
+    const DevProblem &P = *Pd;
     __shared__ double s_Jr[15][30];
     __shared__ double s_raw[16];
     __shared__ double s_res[16];
@@ -341,7 +343,9 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(DevProblem P, cons
     __shared__ double s_red[EV_THREADS / 32];
     __shared__ int s_last;
     const int tid = threadIdx.x;
+    CTA_PROF(g_eval_prof, 0);
     pdl_prologue();
+    CTA_PROF(g_eval_prof, 1);
     bool active = true;
     int target = 0;
     if (mode == 0) {
@@ -368,9 +372,11 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(DevProblem P, cons
                 for (int q = 0; q < EV_THREADS / 32; q++) t += s_red[q];
                 atomicAdd(cost_acc, t);
             }
-        } else if (b < nbp + P.n_imu) {
+        } else if (b < nbp + n_imu_cta) {
             const int k = b - nbp;
-            if (P.imu[k].sum_dt <= 10.0) {  // estimator.cpp:720-721
+            if (k >= P.n_imu) {
+                // (launch geometry is sized for F - 1 IMU factors; fewer are present)
+            } else if (P.imu[k].sum_dt <= 10.0) {  // estimator.cpp:720-721
                 double c = 0;
                 eval_imu_cta(P.imu[k], P.imu_sqrt_info + 225 * (size_t)k, x, P.lay, P.o, e.ri + 15 * (size_t)k,
                              e.Ji + 450 * (size_t)k, &c, s_Jr, s_raw, s_sq, s_res);
@@ -388,6 +394,7 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(DevProblem P, cons
     if (mode == 2) return;
     // ---- last CTA done: bookkeeping ----
     __syncthreads();
+    CTA_PROF(g_eval_prof, 2);
     if (tid == 0) {
         __threadfence();
         const unsigned t = atomicAdd(&ctl->ticket, 1u);
@@ -407,14 +414,16 @@ __global__ void __launch_bounds__(EV_THREADS) evaluate_kernel(DevProblem P, cons
             accept_logic(ctl, P.o);
         }
     }
+    CTA_PROF(g_eval_prof, 3);
 }
 
 // Eigen::LLT<Matrix15d>(covariance.inverse()).matrixL().transpose()  (imu_factor.h:64), once per solve.
 // One warp per factor on a shared-memory 15 x 30 augmented matrix: Gauss-Jordan with partial pivoting (same pivot
 // rule and operation order as the oracle's invert()), then Cholesky of the inverse.
-__global__ void __launch_bounds__(32) imu_prepare_kernel(const lfvio_imu_factor *imu, int n_imu, double *out, int *status) {
+__global__ void __launch_bounds__(32) imu_prepare_kernel(const DevProblem *__restrict__ Pd, double *out, int *status) {
+    const lfvio_imu_factor *imu = Pd->imu;
     const int k = blockIdx.x, lane = threadIdx.x;
-    if (k >= n_imu) return;
+    if (k >= Pd->n_imu) return;
     __shared__ double w[15][31];
     __shared__ double Lm[15][16];
     if (imu[k].sum_dt > 10.0) {  // inactive factor: leave zeros
@@ -496,7 +505,9 @@ __global__ void __launch_bounds__(32) imu_prepare_kernel(const lfvio_imu_factor 
 }
 
 // H0 = J0^T J0 of the prior (constant during a solve).
-__global__ void prior_prepare_kernel(const double *J0, int n, double *H0) {
+__global__ void prior_prepare_kernel(const DevProblem *__restrict__ Pd, double *H0) {
+    const double *J0 = Pd->prior.J0;
+    const int n = Pd->prior.n;
     const int a = blockIdx.x, b = threadIdx.x + blockIdx.y * blockDim.x;
     if (a >= n || b >= n) return;
     double s = 0;
@@ -505,27 +516,26 @@ __global__ void prior_prepare_kernel(const double *J0, int n, double *H0) {
 }
 
 }  // namespace
+CTA_PROF_READER(lfvio_debug_eval_prof, g_eval_prof)
 
 int launch_imu_prepare(const DevProblem &P, double *imu_sqrt_info, int *status, cudaStream_t s) {
-    if (P.n_imu == 0) return LFVIO_OK;
-    imu_prepare_kernel<<<P.n_imu, 32, 0, s>>>(P.imu, P.n_imu, imu_sqrt_info, status);
+    imu_prepare_kernel<<<std::max(P.g_imu, 1), 32, 0, s>>>(P.self_dev, imu_sqrt_info, status);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }
 
 int launch_prior_prepare(const DevProblem &P, double *H0, cudaStream_t s) {
-    if (P.prior.n == 0) return LFVIO_OK;
-    prior_prepare_kernel<<<dim3(P.prior.n, cdiv(P.prior.n, 128)), 128, 0, s>>>(P.prior.J0, P.prior.n, H0);
+    prior_prepare_kernel<<<dim3(std::max(P.cap_n, 1), cdiv(std::max(P.cap_n, 1), 128)), 128, 0, s>>>(P.self_dev, H0);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }
 
 int launch_evaluate(const DevProblem &P, const double *x0, const double *x1, const EvalBuf &e0, const EvalBuf &e1,
                     SolverCtl *ctl, int mode, int robust, cudaStream_t s) {
-    const int nbp = cdiv(P.n_proj, EV_THREADS);
-    const int grid = nbp + P.n_imu + (P.prior.n > 0 ? 1 : 0);
-    if (grid == 0) return LFVIO_OK;
-    LFVIO_CUDA_TRY(launch_pdl(evaluate_kernel, dim3(grid), dim3(EV_THREADS), 0, s, P, x0, x1, e0, e1, ctl, mode, robust, nbp));
+    const int nbp = P.g_nbp;  // >= cdiv(P.n_proj, EV_THREADS)
+    const int grid = nbp + P.g_imu + 1;
+    LFVIO_CUDA_TRY(launch_pdl(evaluate_kernel, dim3(grid), dim3(EV_THREADS), 0, s, P.self_dev, x0, x1, e0, e1, ctl, mode, robust, nbp,
+                              P.g_imu));
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

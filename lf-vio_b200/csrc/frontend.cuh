@@ -107,7 +107,8 @@ struct RansacScratch {
 };
 // status[i] = 1 for the tracks rejectWithF keeps (all ones below 8 tracks).  seed/frame: injected random source.
 int launch_reject_with_f(const OcamDev &cam, const float2 *cur, const float2 *forw, const int *n_dev, int n_upper, int cap,
-                         unsigned long long seed, unsigned frame, const RansacScratch &rs, uint8_t *status, cudaStream_t s);
+                         unsigned long long seed, unsigned frame, const RansacScratch &rs, uint8_t *status, cudaStream_t s,
+                         const unsigned *frame_dev = nullptr /* device word overriding `frame` (graph replay) */);
 // the RANSAC alone on bearings already in rs.b1 / rs.b2 (estimator-side copy of the same code, solve_5pts.cpp:266-335)
 int launch_ransac_bearings(const int *n_dev, int n_upper, int cap, unsigned long long seed, unsigned frame, const RansacScratch &rs,
                            uint8_t *status, cudaStream_t s);
@@ -126,7 +127,8 @@ int launch_fill_circle(uint8_t *img, int rows, int cols, int pitch, int cx, int 
 // undistortedPoints (feature_tracker.cpp:441-504): lift + normalise in f64, cast to f32, velocity.
 int launch_undistort(const OcamDev &cam, const float2 *pts, const int *ids, float *bearing_prev_inout,
                      uint8_t *prev_valid_inout, float *bearing_out, float *vel_out, const int *n_dev, int cap,
-                     double dt, const int *have_prev_in, int *have_prev_out, cudaStream_t s);
+                     double dt, const int *have_prev_in, int *have_prev_out, cudaStream_t s,
+                     const double *dt_dev = nullptr /* device double overriding `dt` (graph replay) */);
 // updateID loop (feature_tracker.cpp:388-398, feature_tracker_node.cpp:103-111).
 int launch_update_ids(int *ids, const int *n_dev, int cap, int *n_id_dev, cudaStream_t s);
 

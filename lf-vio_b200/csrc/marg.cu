@@ -46,10 +46,14 @@ __device__ __forceinline__ void add_sym(double *T, int ld, int a, int b, double 
     if (a != b) atomicAdd(&T[(size_t)b * ld + a], v);
 }
 
-__global__ void __launch_bounds__(MA_WARPS * 32) marg_accumulate_kernel(DevProblem P, EvalBuf e0, EvalBuf e1,
-                                                                       const SolverCtl *ctl, MargPlan plan, double *T,
-                                                                       double *bvec, int n_item_cta, int max_obs) {
+__global__ void __launch_bounds__(MA_WARPS * 32) marg_accumulate_kernel(const DevProblem *__restrict__ Pd, EvalBuf e0, EvalBuf e1,
+                                                                       const SolverCtl *ctl, const MargPlan *__restrict__ planp,
+                                                                       double *T, int n_item_cta, int max_obs) {
     extern __shared__ double smem[];
+    const DevProblem &P = *Pd;
+    const MargPlan &plan = *planp;
+    if (plan.n <= 0) return;  // nothing to marginalise this frame (the launch is part of a replayed graph)
+    double *bvec = T + (size_t)plan.dim * plan.dim;
     const EvalBuf &e = (ctl && ctl->cur) ? e1 : e0;
     const StateLayout lay = P.lay;
     const int ld = plan.dim;
@@ -377,11 +381,16 @@ __device__ void pivoted_cholesky(double *A, double *b, int n, double tol, double
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(MF_THREADS) marg_finish_kernel(DevProblem P, const double *x0, const double *x1,
-                                                                const SolverCtl *ctl, MargPlan plan, const double *T,
-                                                                const double *bvec, double *work, double *J0_out,
-                                                                double *r0_out, double *x0_out) {
+__global__ void __launch_bounds__(MF_THREADS) marg_finish_kernel(const DevProblem *__restrict__ Pd, const double *x0, const double *x1,
+                                                                const SolverCtl *ctl, const MargPlan *__restrict__ planp,
+                                                                const double *T, double *work, double *out_base) {
     extern __shared__ double smem[];
+    const DevProblem &P = *Pd;
+    const MargPlan &plan = *planp;
+    if (plan.n <= 0) return;
+    // outputs packed for this plan's n, so that one D2H copy returns the prior: [J0 n x n | r0 n | x0]
+    const double *bvec = T + (size_t)plan.dim * plan.dim;
+    double *J0_out = out_base, *r0_out = out_base + (size_t)plan.n * plan.n, *x0_out = r0_out + plan.n;
     __shared__ double s_c[32], s_s[32], s_best[64];
     __shared__ int s_p[32], s_q[32], s_bidx[64], s_done[15 * kMaxFrames + 8];
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -601,27 +610,28 @@ size_t marg_finish_workspace_doubles(int m_p, int n) {
     return (size_t)3 * m_p * m_p + 2 * (size_t)n * n + 2 * (size_t)n + (size_t)n * m_p + std::max(chol, tdim) + 2;
 }
 
+// Launch geometry and shared-memory sizes come from the handle's capacities / the plan's item bucket, the plan itself is read
+// from device memory (plan.self_dev): the two launches are the same from frame to frame and can sit in a replayed graph.
+bool marg_workspace_in_smem(int cap_n) { return sizeof(double) * marg_finish_workspace_doubles(15, cap_n) <= 200 * 1024; }
+
 int launch_marginalize(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const double *x0, const double *x1,
                        const SolverCtl *ctl, MargPlan &plan, const MargBuffers &mb, cudaStream_t s) {
-    const int dim = plan.dim;
+    const int dim = P.cap_n + 15;
     LFVIO_CUDA_TRY(cudaMemsetAsync(mb.T, 0, sizeof(double) * ((size_t)dim * dim + dim), s));
     const int max_obs = std::max(P.lay.F - 1, 10);
-    const int items = plan.n_lm + 1;
-    const int n_item_cta = items;
+    const int n_item_cta = plan.g_items;  // >= plan.n_lm + 1
     const int per_item = max_obs * 40 + max_obs * 2 + max_obs * 6 + 16 + max_obs;
     size_t smem = sizeof(double) * (size_t)per_item;
     smem = std::max(smem, sizeof(int) * (size_t)(15 * kMaxFrames + 8));
     LFVIO_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(marg_accumulate_kernel), 96 * 1024));
-    marg_accumulate_kernel<<<n_item_cta + MARG_PRIOR_CTAS, MA_WARPS * 32, smem, s>>>(P, e0, e1, ctl, plan, mb.T, mb.T + (size_t)dim * dim,
-                                                                      n_item_cta, max_obs);
+    marg_accumulate_kernel<<<n_item_cta + MARG_PRIOR_CTAS, MA_WARPS * 32, smem, s>>>(P.self_dev, e0, e1, ctl, plan.self_dev, mb.T,
+                                                                                    n_item_cta, max_obs);
     LFVIO_LAUNCH_CHECK();
-    const size_t ws = sizeof(double) * marg_finish_workspace_doubles(plan.m_p, plan.n);
-    plan.use_smem = ws <= 200 * 1024 ? 1 : 0;
+    const size_t ws = sizeof(double) * marg_finish_workspace_doubles(15, plan.g_cap_n);  // plan.use_smem was set from the same bound
     LFVIO_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(marg_finish_kernel), 200 * 1024));
-    const size_t chol_bytes = sizeof(double) * ((size_t)NB * chol_panel_pitch(plan.n) + (size_t)((plan.n + 1) & ~1) +
-                                                (size_t)((plan.n + NB - 1) / NB) * NB + 2);
-    marg_finish_kernel<<<1, MF_THREADS, plan.use_smem ? ws : chol_bytes, s>>>(P, x0, x1, ctl, plan, mb.T, mb.T + (size_t)dim * dim, mb.work,
-                                                                     mb.J0, mb.r0, mb.x0);
+    const size_t chol_bytes = sizeof(double) * ((size_t)NB * chol_panel_pitch(plan.g_cap_n) + (size_t)((plan.g_cap_n + 1) & ~1) +
+                                                (size_t)((plan.g_cap_n + NB - 1) / NB) * NB + 2);
+    marg_finish_kernel<<<1, MF_THREADS, plan.use_smem ? ws : chol_bytes, s>>>(P.self_dev, x0, x1, ctl, plan.self_dev, mb.T, mb.work, mb.J0);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

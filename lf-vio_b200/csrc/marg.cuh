@@ -17,8 +17,13 @@ struct MargPlan {
     int n_keep;
     int keep_id[kMaxPriorBlocks];   // kept blocks in column order (ids BEFORE the addr_shift renaming)
     int keep_x0[kMaxPriorBlocks];   // offset of each kept block's data in x0_out
-    int use_smem;
+    int use_smem;                   // marg_finish_kernel's workspace fits in shared memory (decided on the handle's capacity)
+    int g_items;                    // launch geometry: n_lm + 1 rounded up to a bucket (stable from frame to frame)
+    int g_cap_n;                    // bound on n that sizes marg_finish_kernel's shared memory: 6 F + 10 (what the estimator's
+                                    // own priors reach) or, for a larger hand-made prior, 15 F + 7
+    const MargPlan *self_dev;       // device copy the kernels read
 };
+bool marg_workspace_in_smem(int cap_n);
 
 struct MargBuffers {
     double *T;     // dim*dim + dim (system + right-hand side)

@@ -164,9 +164,11 @@ __global__ void ransac_lift_kernel(OcamDev cam, const float2 *__restrict__ cur, 
 __global__ void __launch_bounds__(kWarpsPerCta * 32) ransac_hypothesis_kernel(const double3 *__restrict__ b1,
                                                                               const double3 *__restrict__ b2, const int *n_dev,
                                                                               int cap, unsigned long long seed, unsigned frame,
+                                                                              const unsigned *frame_dev,
                                                                               double *E_out /* kHyp x 9 */) {
     __shared__ double s_A[kWarpsPerCta][8][9];
     __shared__ int s_idx[kWarpsPerCta][8];
+    if (frame_dev) frame = *frame_dev;  // per-frame parameter block (the launch itself can then be replayed from a CUDA graph)
     const int n = min(*n_dev, cap);
     if (n < 8) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -408,11 +410,12 @@ __global__ void __launch_bounds__(kRefitThreads) ransac_refit_kernel(const doubl
 
 // ---------------------------------------------------------------------------------------------------------------
 int launch_reject_with_f(const OcamDev &cam, const float2 *cur, const float2 *forw, const int *n_dev, int n_upper, int cap,
-                         unsigned long long seed, unsigned frame, const RansacScratch &rs, uint8_t *status, cudaStream_t s) {
+                         unsigned long long seed, unsigned frame, const RansacScratch &rs, uint8_t *status, cudaStream_t s,
+                         const unsigned *frame_dev) {
     if (n_upper <= 0) return LFVIO_OK;
     ransac_lift_kernel<<<cdiv(n_upper, 128), 128, 0, s>>>(cam, cur, forw, n_dev, cap, rs.b1, rs.b2);
     LFVIO_LAUNCH_CHECK();
-    ransac_hypothesis_kernel<<<cdiv(kHyp, kWarpsPerCta), kWarpsPerCta * 32, 0, s>>>(rs.b1, rs.b2, n_dev, cap, seed, frame, rs.E);
+    ransac_hypothesis_kernel<<<cdiv(kHyp, kWarpsPerCta), kWarpsPerCta * 32, 0, s>>>(rs.b1, rs.b2, n_dev, cap, seed, frame, frame_dev, rs.E);
     LFVIO_LAUNCH_CHECK();
     ransac_score_kernel<<<kHyp, kScoreThreads, 0, s>>>(rs.b1, rs.b2, n_dev, cap, rs.E, rs.score, rs.flags);
     LFVIO_LAUNCH_CHECK();
@@ -426,7 +429,7 @@ int launch_reject_with_f(const OcamDev &cam, const float2 *cur, const float2 *fo
 int launch_ransac_bearings(const int *n_dev, int n_upper, int cap, unsigned long long seed, unsigned frame, const RansacScratch &rs,
                            uint8_t *status, cudaStream_t s) {
     if (n_upper <= 0) return LFVIO_OK;
-    ransac_hypothesis_kernel<<<cdiv(kHyp, kWarpsPerCta), kWarpsPerCta * 32, 0, s>>>(rs.b1, rs.b2, n_dev, cap, seed, frame, rs.E);
+    ransac_hypothesis_kernel<<<cdiv(kHyp, kWarpsPerCta), kWarpsPerCta * 32, 0, s>>>(rs.b1, rs.b2, n_dev, cap, seed, frame, nullptr, rs.E);
     LFVIO_LAUNCH_CHECK();
     ransac_score_kernel<<<kHyp, kScoreThreads, 0, s>>>(rs.b1, rs.b2, n_dev, cap, rs.E, rs.score, rs.flags);
     LFVIO_LAUNCH_CHECK();

@@ -26,11 +26,12 @@ namespace lfvio {
 
 namespace {
 
-constexpr int ACC_WARPS = 4;    // warps of one CTA; they split the rows of an item's local block
-constexpr int PRIOR_CTAS = 8;   // CTAs that share the prior's n x n block and its gradient
+constexpr int ACC_WARPS = 8;    // warps of one CTA; its threads share the pairs of an item's local block
+constexpr int PRIOR_CTAS = 16;  // CTAs that share the prior's n x n block and its gradient
 
 // ---- Jacobi scaling: scale = 1 / (1 + sqrt(sum_i J_ic^2)) at the initial point ---------------------
-__global__ void colnorm_kernel(DevProblem P, EvalBuf e, double *scale) {
+__global__ void colnorm_kernel(const DevProblem *__restrict__ Pd, EvalBuf e, double *scale) {
+    const DevProblem &P = *Pd;
     const StateLayout lay = P.lay;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int k = tid; k < P.n_proj; k += nth) {
@@ -55,7 +56,8 @@ __global__ void colnorm_kernel(DevProblem P, EvalBuf e, double *scale) {
         for (int q = tid; q < ls; q += nth) atomicAdd(&scale[c0 + q], p.H0[(size_t)(p.block_idx[b] + q) * (p.n + 1)]);
     }
 }
-__global__ void scale_finalize_kernel(double *scale, int n) {
+__global__ void scale_finalize_kernel(const DevProblem *__restrict__ Pd, double *scale) {
+    const int n = Pd->lay.D() + Pd->lay.L;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n) scale[c] = 1.0 / (1.0 + sqrt(scale[c]));
 }
@@ -63,13 +65,22 @@ __global__ void scale_finalize_kernel(double *scale, int n) {
 // ---- accumulate -----------------------------------------------------------------------------------
 __device__ __forceinline__ void add_upper(double *S, int D, int ga, int gb, double v) {
     if (v == 0.0) return;
+#ifdef LFVIO_ACC_NOATOMIC  // timing experiment only (wrong sums)
+    if (ga <= gb) S[(size_t)ga * D + gb] = v;
+    else S[(size_t)gb * D + ga] = v;
+    return;
+#endif
     if (ga <= gb) atomicAdd(&S[(size_t)ga * D + gb], v);
     else atomicAdd(&S[(size_t)gb * D + ga], v);
 }
 
-__global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P, EvalBuf e0, EvalBuf e1, SolverScratch w,
-                                                                   const SolverCtl *ctl, int n_lm_cta, int max_obs) {
+CTA_PROF_DECL(g_acc_prof);
+__global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(const DevProblem *__restrict__ Pd, EvalBuf e0, EvalBuf e1, SolverScratch w,
+                                                                   const SolverCtl *ctl, int n_lm_cta, int g_L, int max_obs) {
+    const DevProblem &P = *Pd;
+    CTA_PROF(g_acc_prof, 0);
     pdl_prologue();
+    CTA_PROF(g_acc_prof, 1);
     if (ctl->done != 0 || ctl->reuse != 0) return;
     extern __shared__ double smem[];
     const EvalBuf &e = ctl->cur ? e1 : e0;
@@ -175,35 +186,65 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
                 const double rr = g - wval(A) * g_l * inv_c;
                 if (rr != 0.0) atomicAdd(&w.rhs[gc], rr);
             }
-            // reduced-system contribution: every unordered local pair (A <= B) exactly once; the warps interleave the rows
-            for (int A = wid; A < n_l; A += ACC_WARPS) {
-                const int gA = gcol(A);
-                const double wA = wval(A);
-                for (int B = A + lane; B < n_l; B += 32) {
-                    double v = 0;
+            // reduced-system contribution: every unordered local pair (A <= B) exactly once.  The pairs are independent and
+            // cheap (a table look-up each way + at most two products): all threads of the CTA share them through a flat index
+            // — a landmark seen from 10 frames has 2701 pairs, and walking them row by row with four warps left the CTA
+            // latency-bound (18 us, measured); the shared 13 x 13 block J_s^T J_s is summed over the observations first.
+            double *sH = sWs + 16 + ((max_obs + 1) >> 1);           // 91: J_s^T J_s, packed upper
+            double *sWl = sH + 92;                                   // n_l: w of every local column
+            int *sG = reinterpret_cast<int *>(sWl + 13 + 6 * max_obs);  // n_l: global column of every local column
+            for (int q = tid; q < 91; q += ACC_WARPS * 32) {
+                int a = 0, rem = q;
+                while (rem >= 13 - a) {
+                    rem -= 13 - a;
+                    a++;
+                }
+                const int ca = shared_c(a), cb = shared_c(a + rem);
+                double v = 0;
+                for (int k = 0; k < K; k++) v += sJ[k * 40 + ca] * sJ[k * 40 + cb] + sJ[k * 40 + 20 + ca] * sJ[k * 40 + 20 + cb];
+                sH[q] = v;
+            }
+            for (int A = tid; A < n_l; A += ACC_WARPS * 32) {
+                sWl[A] = wval(A);
+                sG[A] = gcol(A);
+            }
+            __syncthreads();
+            // rows r and n_l - 1 - r of the upper triangle together have n_l + 1 entries: a rectangle of ceil(n_l / 2) such
+            // double rows covers the triangle without idle iterations
+            const int wrow = n_l + 1, nrow = (n_l + 1) >> 1, npair = nrow * wrow;
+            const float inv_w = 1.0f / (float)wrow;
+            for (int q = tid; q < npair; q += ACC_WARPS * 32) {
+                int r = (int)((float)q * inv_w);
+                r += (q - r * wrow >= wrow) - (q - r * wrow < 0);  // exact quotient (the float estimate is off by at most one)
+                const int c = q - r * wrow, r2 = n_l - 1 - r;
+                int A, B;
+                if (c < n_l - r) {
+                    A = r;
+                    B = r + c;
+                } else {
+                    if (r2 == r) continue;  // middle row of an odd n_l: already covered
+                    A = r2;
+                    B = r2 + (c - (n_l - r));
+                }
+                double v;
+                if (B < 13) {
+                    v = sH[A * 13 - ((A * (A - 1)) >> 1) + (B - A)];
+                } else {
+                    const int kb = (B - 13) / 6, cb = 6 + (B - 13) % 6;
                     if (A < 13) {
                         const int ca = shared_c(A);
-                        if (B < 13) {
-                            const int cb = shared_c(B);
-                            for (int k = 0; k < K; k++) v += sJ[k * 40 + ca] * sJ[k * 40 + cb] + sJ[k * 40 + 20 + ca] * sJ[k * 40 + 20 + cb];
-                        } else {
-                            const int k = (B - 13) / 6, cb = 6 + (B - 13) % 6;
-                            v = sJ[k * 40 + ca] * sJ[k * 40 + cb] + sJ[k * 40 + 20 + ca] * sJ[k * 40 + 20 + cb];
-                        }
+                        v = sJ[kb * 40 + ca] * sJ[kb * 40 + cb] + sJ[kb * 40 + 20 + ca] * sJ[kb * 40 + 20 + cb];
                     } else {
-                        const int ka = (A - 13) / 6, kb = (B - 13) / 6;
-                        if (ka == kb) {
-                            const int ca = 6 + (A - 13) % 6, cb = 6 + (B - 13) % 6;
-                            v = sJ[ka * 40 + ca] * sJ[ka * 40 + cb] + sJ[ka * 40 + 20 + ca] * sJ[ka * 40 + 20 + cb];
-                        }
+                        const int ka = (A - 13) / 6, ca = 6 + (A - 13) % 6;
+                        v = (ka == kb) ? sJ[ka * 40 + ca] * sJ[ka * 40 + cb] + sJ[ka * 40 + 20 + ca] * sJ[ka * 40 + 20 + cb] : 0.0;
                     }
-                    v -= wA * wval(B) * inv_c;
-                    add_upper(w.S, D, gA, gcol(B), v);
                 }
+                v -= sWl[A] * sWl[B] * inv_c;
+                add_upper(w.S, D, sG[A], sG[B], v);
             }
-        } else if (item < lay.L + P.n_imu) {
-            // ===== one IMU factor: dense 15 x 30 block =====
-            const int k = item - lay.L;
+        } else if (item >= g_L && item - g_L < P.n_imu) {
+            // ===== one IMU factor: dense 15 x 30 block =====  (items [lay.L, g_L) are launch padding)
+            const int k = item - g_L;
             if (P.imu[k].sum_dt > 10.0) return;
             const int fi = P.imu[k].frame_i;
             double *sI = sJ;  // 450 doubles fit (per_warp >= 49 * max_obs + 16 >= 450 is ensured by the launcher)
@@ -232,6 +273,7 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
                 }
             }
         }
+        CTA_PROF(g_acc_prof, 2);
         return;
     }
     // ===== prior CTAs: S += scale (J0^T J0) scale, gradient += scale J0^T r =====
@@ -261,10 +303,12 @@ __global__ void __launch_bounds__(ACC_WARPS * 32) accumulate_kernel(DevProblem P
         atomicAdd(&w.grad[pmap[a]], g);
         atomicAdd(&w.rhs[pmap[a]], g);
     }
+    CTA_PROF(g_acc_prof, 2);
 }
 
-__global__ void solver_init_kernel(SolverCtl *ctl, lfvio_solver_opts o) {
+__global__ void solver_init_kernel(SolverCtl *ctl, const DevProblem *__restrict__ Pd) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const lfvio_solver_opts &o = Pd->o;
     ctl->cur = 0;
     ctl->reuse = 0;
     ctl->done = 0;
@@ -291,24 +335,26 @@ __global__ void solver_init_kernel(SolverCtl *ctl, lfvio_solver_opts o) {
 }
 
 }  // namespace
+CTA_PROF_READER(lfvio_debug_acc_prof, g_acc_prof)
 
-int launch_solver_init(SolverCtl *ctl, const lfvio_solver_opts &o, cudaStream_t s) {
-    solver_init_kernel<<<1, 32, 0, s>>>(ctl, o);
+int launch_solver_init(SolverCtl *ctl, const DevProblem &P, cudaStream_t s) {
+    solver_init_kernel<<<1, 32, 0, s>>>(ctl, P.self_dev);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }
 
 int launch_jacobi_scale(const DevProblem &P, const EvalBuf &e0, const SolverScratch &w, cudaStream_t s) {
-    const int N = P.lay.D() + P.lay.L;
+    const int N = P.lay.D() + P.cap_L;  // capacity: the launch geometry does not follow the landmark count
     LFVIO_CUDA_TRY(cudaMemsetAsync(w.scale, 0, sizeof(double) * N, s));
-    colnorm_kernel<<<std::max(1, std::min(cdiv(P.n_proj, 128), 296)), 128, 0, s>>>(P, e0, w.scale);
+    colnorm_kernel<<<std::max(1, std::min(P.g_nbp, 296)), 128, 0, s>>>(P.self_dev, e0, w.scale);
     LFVIO_LAUNCH_CHECK();
-    scale_finalize_kernel<<<cdiv(N, 256), 256, 0, s>>>(w.scale, N);
+    scale_finalize_kernel<<<cdiv(N, 256), 256, 0, s>>>(P.self_dev, w.scale);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }
 
-static int acc_per_warp_doubles(int max_obs) { return max_obs * 40 + max_obs * 2 + max_obs * 6 + 16 + max_obs; }
+// sJ 40 K | sR 2 K | sW 6 K | sWs 16 | sFj K ints | sH 92 | sWl 13 + 6 K | sG 13 + 6 K ints
+static int acc_per_warp_doubles(int max_obs) { return max_obs * 40 + max_obs * 2 + max_obs * 6 + 16 + (max_obs + 1) / 2 + 92 + (13 + 6 * max_obs) + (13 + 6 * max_obs + 1) / 2 + 2; }
 
 int launch_accumulate(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const SolverScratch &w, SolverCtl *ctl,
                       cudaStream_t s, bool clear_done) {
@@ -316,13 +362,13 @@ int launch_accumulate(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1,
     // (step_zeroes_system), that kernel clears them as it consumes them; otherwise clear them here.
     if (!clear_done) LFVIO_CUDA_TRY(cudaMemsetAsync(w.S, 0, w.zero_bytes, s));
     int max_obs = std::max(P.lay.F - 1, 10);  // 49 * 10 + 16 = 506 doubles >= 465 needed by an IMU warp
-    const int items = P.lay.L + P.n_imu;
+    const int items = P.g_L + P.g_imu;  // landmark items padded to the bucket, then the IMU items
     const int n_lm_cta = items;
     size_t smem = sizeof(double) * (size_t)acc_per_warp_doubles(max_obs);
     smem = std::max(smem, sizeof(int) * (size_t)(15 * kMaxFrames + 8));
     LFVIO_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(accumulate_kernel), 96 * 1024));
-    LFVIO_CUDA_TRY(launch_pdl(accumulate_kernel, dim3(n_lm_cta + PRIOR_CTAS), dim3(ACC_WARPS * 32), smem, s, P, e0, e1, w,
-                              (const SolverCtl *)ctl, n_lm_cta, max_obs));
+    LFVIO_CUDA_TRY(launch_pdl(accumulate_kernel, dim3(n_lm_cta + PRIOR_CTAS), dim3(ACC_WARPS * 32), smem, s, P.self_dev, e0, e1, w,
+                              (const SolverCtl *)ctl, n_lm_cta, P.g_L, max_obs));
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

@@ -4,7 +4,9 @@
 // One handle == one camera == one CUDA stream.  All per-track state (positions, ids, track_cnt, previous
 // bearings) lives in HBM as SoA; counts stay on device so the whole frame is enqueued without a host
 // round trip; the host mirror is refreshed with one batch of small D2H copies at the end of the frame.
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "frontend.cuh"
@@ -174,6 +176,27 @@ struct lfvio_tracker {
     int n_host = 0, n_upper = 0, n_id_host = 0;
     bool mirror_fresh = true;
     double cur_time = 0, prev_time = 0;
+    // Per-frame scalars (dt of undistortedPoints, the frame counter of the injected RANSAC sampler) travel through a small
+    // device block so that the kernel launches of a frame carry no frame-dependent argument and the whole readImage can be
+    // replayed as ONE cudaGraphLaunch.  A frame's launch sequence depends only on (which track store is live, which
+    // pyramid slot is current, whether cur/forw of each store are swapped, frame parity, publish flag, ids on device):
+    // one executable graph per reachable combination, captured the first time it occurs.
+    struct FrameParams {
+        double dt;
+        unsigned frame, pad;
+    };
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        int a = 0, cur_slot = 0, kernels = 0;  // kernels: launches inside the graph (for lfvio_launch_count)
+        bool swapped[2] = {false, false};
+    };
+    DevBuf<FrameParams> fp_dev;
+    PinBuf<FrameParams> fp_host;  // ring: a slot is rewritten only kFpRing frames later
+    static constexpr int kFpRing = 256;
+    unsigned fp_next = 0;
+    bool use_graphs = true;
+    std::map<unsigned, GraphEntry> graphs;
+    long graph_launches = 0, graph_captures = 0;
 
     TrackArrays live() { return store[a].view(); }
     TrackArrays spare() { return store[a ^ 1].view(); }
@@ -213,6 +236,12 @@ int tracker_init(lfvio_tracker *t, const lfvio_tracker_cfg *cfg, int device) {
         LFVIO_TRY(t->rs_flags.alloc(100 * (size_t)t->cap));
         LFVIO_TRY(t->rs_best.alloc(1));
     }
+    LFVIO_TRY(t->fp_dev.alloc(1));
+    LFVIO_TRY(t->fp_host.alloc(lfvio_tracker::kFpRing));
+    {
+        const char *e = getenv("LFVIO_NO_GRAPH"), *e2 = getenv("LFVIO_NO_GRAPH_TRACKER");
+        t->use_graphs = !(e && e[0] == '1') && !(e2 && e2[0] == '1');
+    }
     LFVIO_TRY(t->n_dev.alloc(1));
     LFVIO_TRY(t->have_prev.alloc(2));
     LFVIO_TRY(t->n_id_dev.alloc(1));
@@ -249,8 +278,9 @@ int tracker_init(lfvio_tracker *t, const lfvio_tracker_cfg *cfg, int device) {
     return LFVIO_OK;
 }
 
-// Enqueue one readImage on t->stream.  src is device memory (u8, pitch src_pitch).
-int enqueue_frame(lfvio_tracker *t, const uint8_t *src, int src_pitch, double cur_time, int pub, bool ids_on_device) {
+// The launch sequence of one readImage on t->stream (directly, or into a stream capture).  src is device memory (u8, pitch
+// src_pitch).  dt and the RANSAC frame counter are read from t->fp_dev by the kernels.
+int frame_body(lfvio_tracker *t, const uint8_t *src, int src_pitch, double cur_time, int pub, bool ids_on_device) {
     const lfvio_tracker_cfg &c = t->cfg;
     cudaStream_t s = t->stream;
     t->cur_time = cur_time;
@@ -287,7 +317,7 @@ int enqueue_frame(lfvio_tracker *t, const uint8_t *src, int src_pitch, double cu
         if (c.ransac && t->n_upper > 0) {  // rejectWithF() :149, :329-386
             t->prof.begin(TS_RANSAC, s);
             LFVIO_TRY(launch_reject_with_f(t->cam, A.cur, A.forw, t->n_dev.p, t->n_upper, t->cap, c.ransac_seed, (unsigned)t->frames,
-                                           t->ransac(), t->status.p, s));
+                                           t->ransac(), t->status.p, s, &t->fp_dev.p->frame));
             LFVIO_TRY(launch_compact(A, B, t->status.p, t->n_dev.p, t->cap, 0, s));
             t->prof.end(s);
             t->a ^= 1;
@@ -322,12 +352,13 @@ int enqueue_frame(lfvio_tracker *t, const uint8_t *src, int src_pitch, double cu
     // prev_img = cur_img; cur_img = forw_img; cur_pts = forw_pts
     t->cur_slot = forw_slot;
     std::swap(t->store[t->a].cur.p, t->store[t->a].forw.p);
+    t->swapped_cf[t->a] = !t->swapped_cf[t->a];
     A = t->live();
     const int hp = (int)(t->frames & 1);
     t->prof.begin(TS_UNDISTORT, s);
         LFVIO_TRY(launch_undistort(t->cam, A.cur, A.ids, A.bearing, A.prev_valid, t->bearing_out.p, t->vel_out.p,
                                t->n_dev.p, t->n_upper, cur_time - t->prev_time, t->have_prev.p + hp,
-                               t->have_prev.p + (hp ^ 1), s));
+                               t->have_prev.p + (hp ^ 1), s, &t->fp_dev.p->dt));
         t->prof.end(s);
     t->prev_time = cur_time;
     t->frames++;
@@ -337,6 +368,66 @@ int enqueue_frame(lfvio_tracker *t, const uint8_t *src, int src_pitch, double cu
         t->prof.end(s);
     }
     t->mirror_fresh = false;
+    return LFVIO_OK;
+}
+
+// Enqueue one readImage on t->stream: stage the per-frame scalars, then either launch the frame's kernels one by one (first
+// frame, stage profiling on, LFVIO_NO_GRAPH=1) or replay the executable graph of the current pointer state.
+int enqueue_frame(lfvio_tracker *t, const uint8_t *src, int src_pitch, double cur_time, int pub, bool ids_on_device) {
+    cudaStream_t s = t->stream;
+    lfvio_tracker::FrameParams *hp = t->fp_host.p + (t->fp_next++ % lfvio_tracker::kFpRing);
+    hp->dt = cur_time - t->prev_time;
+    hp->frame = (unsigned)t->frames;
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(t->fp_dev.p, hp, sizeof(*hp), cudaMemcpyHostToDevice, s));
+    if (!t->use_graphs || t->prof.on || t->frames == 0) return frame_body(t, src, src_pitch, cur_time, pub, ids_on_device);
+    // grids sized by capacity, counts read on the device: the launch geometry is then the same for every frame
+    t->n_upper = t->cap;
+    if (src != t->raw.p)
+        LFVIO_CUDA_TRY(cudaMemcpy2DAsync(t->raw.p, t->pitch, src, src_pitch, t->cfg.cols, t->cfg.rows, cudaMemcpyDeviceToDevice, s));
+    const unsigned key = (unsigned)t->a | (unsigned)t->cur_slot << 1 | (unsigned)t->swapped_cf[0] << 2 | (unsigned)t->swapped_cf[1] << 3 |
+                         (unsigned)(t->frames & 1) << 4 | (unsigned)(pub != 0) << 5 | (unsigned)ids_on_device << 6;
+    auto it = t->graphs.find(key);
+    if (it == t->graphs.end()) {  // first occurrence of this state: plain launches (also loads the kernels outside any capture)
+        t->graphs.emplace(key, lfvio_tracker::GraphEntry());
+        return frame_body(t, t->raw.p, t->pitch, cur_time, pub, ids_on_device);
+    }
+    if (it->second.exec == nullptr) {
+        cudaGraph_t g = nullptr;
+        LFVIO_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const unsigned long long l0 = thread_launch_count();
+        const int st = frame_body(t, t->raw.p, t->pitch, cur_time, pub, ids_on_device);
+        const int n_kernels = (int)(thread_launch_count() - l0);
+        const cudaError_t ce = cudaStreamEndCapture(s, &g);
+        if (st != LFVIO_OK) {
+            if (g) cudaGraphDestroy(g);
+            return st;
+        }
+        LFVIO_CUDA_TRY(ce);
+        lfvio_tracker::GraphEntry e;
+        LFVIO_CUDA_TRY(cudaGraphInstantiate(&e.exec, g, 0));
+        cudaGraphDestroy(g);
+        e.a = t->a, e.cur_slot = t->cur_slot, e.swapped[0] = t->swapped_cf[0], e.swapped[1] = t->swapped_cf[1];
+        e.kernels = n_kernels;
+        it->second = e;
+        t->graph_captures++;
+    } else {
+        // the host-side bookkeeping frame_body would have done
+        const lfvio_tracker::GraphEntry &e = it->second;
+        for (int k = 0; k < 2; k++)
+            if (e.swapped[k] != t->swapped_cf[k]) {
+                std::swap(t->store[k].cur.p, t->store[k].forw.p);
+                t->swapped_cf[k] = e.swapped[k];
+            }
+        t->a = e.a;
+        t->cur_slot = e.cur_slot;
+        t->cur_time = cur_time;
+        t->prev_time = cur_time;
+        t->frames++;
+        t->mirror_fresh = false;
+        count_launch(e.kernels);
+    }
+    LFVIO_CUDA_TRY(cudaGraphLaunch(it->second.exec, s));
+    t->graph_launches++;
     return LFVIO_OK;
 }
 
@@ -433,6 +524,8 @@ extern "C" void lfvio_tracker_destroy(lfvio_tracker *t) {
     cudaSetDevice(t->device);
     if (t->stream) {
         cudaStreamSynchronize(t->stream);
+        for (auto &kv : t->graphs)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         cudaStreamDestroy(t->stream);
     }
     delete t;

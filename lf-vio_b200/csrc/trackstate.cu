@@ -472,7 +472,8 @@ __global__ void __launch_bounds__(256) undistort_kernel(OcamDev cam, const float
                                                         uint8_t *prev_valid, float *__restrict__ bearing_out,
                                                         float *__restrict__ vel_out, const int *__restrict__ n_dev, int cap,
                                                         double dt, const int *__restrict__ have_prev_in,
-                                                        int *__restrict__ have_prev_out) {
+                                                        int *__restrict__ have_prev_out, const double *__restrict__ dt_dev) {
+    if (dt_dev) dt = *dt_dev;
     const int n = min(*n_dev, cap);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int have_prev = *have_prev_in;  // !prev_un_pts_map_3d.empty()
@@ -562,10 +563,10 @@ int launch_fill_circle(uint8_t *img, int rows, int cols, int pitch, int cx, int 
 
 int launch_undistort(const OcamDev &cam, const float2 *pts, const int *ids, float *bearing_prev_inout,
                      uint8_t *prev_valid_inout, float *bearing_out, float *vel_out, const int *n_dev, int cap,
-                     double dt, const int *have_prev_in, int *have_prev_out, cudaStream_t s) {
+                     double dt, const int *have_prev_in, int *have_prev_out, cudaStream_t s, const double *dt_dev) {
     if (cap <= 0) cap = 1;  // still rotates the have_prev flag
     undistort_kernel<<<cdiv(cap, 256), 256, 0, s>>>(cam, pts, ids, bearing_prev_inout, prev_valid_inout, bearing_out,
-                                                    vel_out, n_dev, cap, dt, have_prev_in, have_prev_out);
+                                                    vel_out, n_dev, cap, dt, have_prev_in, have_prev_out, dt_dev);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

@@ -17,7 +17,7 @@
 #include "marg.cuh"
 
 namespace lfvio {
-int launch_solver_init(SolverCtl *ctl, const lfvio_solver_opts &o, cudaStream_t s);
+int launch_solver_init(SolverCtl *ctl, const DevProblem &P, cudaStream_t s);
 }  // namespace lfvio
 
 using namespace lfvio;
@@ -64,9 +64,22 @@ struct lfvio_window {
     double *h_x = nullptr;       // pinned
     int *h_status = nullptr;     // pinned (tail of h_x): imu_prepare status words
     DBuf<int> status;
-    DevProblem P;
+    DevProblem P;            // host mirror (launch geometry, sizes of the copies)
+    DBuf<DevProblem> P_dev;  // what the kernels read
+    DevProblem *h_P = nullptr;  // pinned staging of P
     EvalBuf e[2];
     bool uploaded = false;
+    // One executable graph per launch geometry (g_* buckets, step variant, marginalisation flag ...), captured the first
+    // time that geometry occurs: a solve is then one cudaGraphLaunch instead of ~35 launches.
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;
+        int kernels = 0;
+    };
+    std::map<unsigned long long, GraphEntry> graphs;
+    bool use_graphs = true;
+    long graph_launches = 0, graph_captures = 0;
+    DBuf<MargPlan> plan_dev[2];
+    MargPlan *h_plan = nullptr;  // pinned staging, 2 entries
     // marginalisation (K14)
     MargPlan plan[2];        // [LFVIO_MARGIN_OLD], [LFVIO_MARGIN_SECOND_NEW], rebuilt at every upload
     bool plan_valid[2] = {false, false};
@@ -77,6 +90,10 @@ struct lfvio_window {
     int last_marg_flag = -1;
 
     ~lfvio_window() {
+        for (auto &kv : graphs)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        if (h_P) cudaFreeHost(h_P);
+        if (h_plan) cudaFreeHost(h_plan);
         if (h_blob) cudaFreeHost(h_blob);
         if (h_ctl) cudaFreeHost(h_ctl);
         if (h_x) cudaFreeHost(h_x);
@@ -91,7 +108,12 @@ namespace {
 int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_proj, int device) {
     w->device = device;
     LFVIO_CUDA_TRY(cudaSetDevice(device));
-    LFVIO_CUDA_TRY(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    {   // highest priority: the solve is a chain of small dependent kernels; a CTA of it should never queue behind the
+        // image-sized grids of a tracker that shares the GPU
+        int lo = 0, hi = 0;
+        LFVIO_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        LFVIO_CUDA_TRY(cudaStreamCreateWithPriority(&w->stream, cudaStreamNonBlocking, hi));
+    }
     const int F = window_size + 1;
     w->F = F;
     w->Lmax = max_landmarks;
@@ -154,6 +176,14 @@ int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_pro
     s.lm_coli = reinterpret_cast<int *>(p);
     s.proj_colj = s.lm_coli + L;
     LFVIO_TRY(w->ctl.alloc(1));
+    LFVIO_TRY(w->P_dev.alloc(1));
+    LFVIO_CUDA_TRY(cudaMallocHost(&w->h_P, sizeof(DevProblem)));
+    LFVIO_CUDA_TRY(cudaMallocHost(&w->h_plan, 2 * sizeof(MargPlan)));
+    for (int k = 0; k < 2; k++) LFVIO_TRY(w->plan_dev[k].alloc(1));
+    {
+        const char *e = getenv("LFVIO_NO_GRAPH"), *e2 = getenv("LFVIO_NO_GRAPH_WINDOW");
+        w->use_graphs = !(e && e[0] == '1') && !(e2 && e2[0] == '1');
+    }
     LFVIO_CUDA_TRY(cudaMallocHost(&w->h_ctl, sizeof(SolverCtl)));
     LFVIO_CUDA_TRY(cudaMallocHost(&w->h_x, sizeof(double) * (lay.size() + 2)));
     w->h_status = reinterpret_cast<int *>(w->h_x + lay.size());
@@ -169,6 +199,20 @@ int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_pro
         LFVIO_TRY(w->marg_out.alloc((size_t)w->nmax * w->nmax + w->nmax + 9 * (size_t)kMaxPriorBlocks));
         LFVIO_CUDA_TRY(cudaMallocHost(&w->h_marg, sizeof(double) * ((size_t)w->nmax * w->nmax + w->nmax + 9 * kMaxPriorBlocks)));
     }
+    return LFVIO_OK;
+}
+
+// Launch geometry of the plan + its device copy (the kernels read the plan from device memory; an empty plan has n = 0 and
+// makes both marginalisation kernels return at once).
+int publish_plan(lfvio_window *w, int flag) {
+    MargPlan &pl = w->plan[flag];
+    const int cap_small = 6 * w->F + 10;  // 6 (F - 1) + 9 + 6 + 1: the largest prior the estimator itself produces
+    pl.g_cap_n = (pl.n <= cap_small && w->P.prior.n <= cap_small) ? cap_small : w->nmax;
+    pl.use_smem = marg_workspace_in_smem(pl.g_cap_n) ? 1 : 0;
+    pl.g_items = std::min(w->Lmax + 1, (pl.n_lm + 1 + 63) / 64 * 64);
+    pl.self_dev = w->plan_dev[flag].p;
+    w->h_plan[flag] = pl;
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->plan_dev[flag].p, &w->h_plan[flag], sizeof(MargPlan), cudaMemcpyHostToDevice, w->stream));
     return LFVIO_OK;
 }
 
@@ -218,11 +262,11 @@ int build_marg_plan(lfvio_window *w, int flag, const lfvio_factor_list *fl, cons
         bool found = false;
         if (have_prior)
             for (int b = 0; b < fl->prior->n_blocks; b++) found |= (fl->prior->block_id[b] == drop_id);
-        if (!found) return LFVIO_OK;  // nothing to do (estimator.cpp:942-943)
+        if (!found) return publish_plan(w, flag);  // nothing to do (estimator.cpp:942-943)
         pl.use_prior = 1;
         for (int b = 0; b < fl->prior->n_blocks; b++) touch(fl->prior->block_id[b], fl->prior->block_id[b] == drop_id);
     }
-    if (is_drop.empty()) return LFVIO_OK;
+    if (is_drop.empty()) return publish_plan(w, flag);
     int pos = 0;
     for (auto &kv : is_drop)
         if (kv.second) {
@@ -250,7 +294,7 @@ int build_marg_plan(lfvio_window *w, int flag, const lfvio_factor_list *fl, cons
         LFVIO_CUDA_TRY(cudaMemcpyAsync(w->lm_list[flag].p, w->h_lm[flag], sizeof(int) * lms.size(), cudaMemcpyHostToDevice, w->stream));
     }
     w->plan_valid[flag] = pl.n > 0;
-    return LFVIO_OK;
+    return publish_plan(w, flag);
 }
 
 static MargBuffers marg_buffers(lfvio_window *w, int n) {
@@ -258,22 +302,81 @@ static MargBuffers marg_buffers(lfvio_window *w, int n) {
     return MargBuffers{w->margT.p, w->marg_work.p, base, base + (size_t)n * n, base + (size_t)n * n + n};
 }
 
-int enqueue_marginalize(lfvio_window *w, int flag, bool after_solve) {
-    if (!w->plan_valid[flag]) return LFVIO_OK;
+// (an empty plan has n = 0 on the device and both kernels return at once: the launch sequence does not depend on it)
+int enqueue_marginalize(lfvio_window *w, int flag, bool after_solve, const double *x0 = nullptr, const double *x1 = nullptr) {
     MargBuffers mb = marg_buffers(w, w->plan[flag].n);
     w->prof.begin(WS_MARGINALIZE, w->stream);
-    LFVIO_TRY(launch_marginalize(w->P, w->e[0], w->e[1], w->x[0].p, w->x[1].p, after_solve ? w->ctl.p : nullptr, w->plan[flag], mb,
-                                 w->stream));
+    LFVIO_TRY(launch_marginalize(w->P, w->e[0], w->e[1], x0 ? x0 : w->x[0].p, x1 ? x1 : w->x[1].p, after_solve ? w->ctl.p : nullptr,
+                                 w->plan[flag], mb, w->stream));
     w->prof.end(w->stream);
-    w->last_marg_flag = flag;
     return LFVIO_OK;
+}
+
+// Run `body` (a launch sequence on w->stream whose arguments depend only on the handle and on `key`) as an executable
+// graph: captured the first time the key occurs, replayed afterwards.  Stage profiling and LFVIO_NO_GRAPH=1 launch directly.
+template <class Body>
+int run_graphed(lfvio_window *w, unsigned long long key, Body body) {
+    if (!w->use_graphs || w->prof.on) return body();
+    cudaStream_t s = w->stream;
+    auto it = w->graphs.find(key);
+    if (it == w->graphs.end()) {  // first occurrence: plain launches (also loads the kernels outside any capture)
+        w->graphs.emplace(key, lfvio_window::GraphEntry());
+        return body();
+    }
+    if (it->second.exec == nullptr) {
+        cudaGraph_t g = nullptr;
+        LFVIO_CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const unsigned long long l0 = thread_launch_count();
+        const int st = body();
+        const int n_kernels = (int)(thread_launch_count() - l0);
+        const cudaError_t ce = cudaStreamEndCapture(s, &g);
+        if (st != LFVIO_OK) {
+            if (g) cudaGraphDestroy(g);
+            return st;
+        }
+        LFVIO_CUDA_TRY(ce);
+        lfvio_window::GraphEntry e;
+        LFVIO_CUDA_TRY(cudaGraphInstantiate(&e.exec, g, 0));
+        cudaGraphDestroy(g);
+        e.kernels = n_kernels;
+        it->second = e;
+        w->graph_captures++;
+    } else {
+        count_launch(it->second.kernels);
+    }
+    LFVIO_CUDA_TRY(cudaGraphLaunch(it->second.exec, s));
+    w->graph_launches++;
+    return LFVIO_OK;
+}
+
+// everything a launch sequence of this handle depends on besides the handle itself
+unsigned long long geometry_key(const lfvio_window *w, int variant, int flag, bool with_plan) {
+    const DevProblem &P = w->P;
+    unsigned long long k = (unsigned long long)variant;
+    k = k * 4 + (unsigned)flag;
+    k = k * 1024 + (unsigned)P.g_nbp;
+    k = k * 65536 + (unsigned)P.g_L;
+    k = k * 128 + (unsigned)P.o.max_num_iterations;
+    k = k * 65536 + (with_plan ? (unsigned)w->plan[flag].g_items : 0u);
+    k = k * 2 + (with_plan ? (unsigned)(w->plan[flag].g_cap_n == w->nmax) : 0u);
+    return k;
 }
 
 // Pack the problem into the pinned blob, enqueue the single H2D copy and fill the device-side descriptor.
 // defer_plans: the caller builds the marginalisation plan it needs itself AFTER it has enqueued the solve, so that this
 // piece of host work (maps, a small H2D copy) overlaps the solve on the device instead of delaying its first kernel.
+// Per-upload constants of the solve: square-root information of the IMU factors, H0 = J0^T J0 of the prior.
+int enqueue_prepare(lfvio_window *w) {
+    cudaStream_t s = w->stream;
+    LFVIO_CUDA_TRY(cudaMemsetAsync(w->status.p, 0, sizeof(int) * 4, s));
+    LFVIO_TRY(launch_imu_prepare(w->P, w->imu_sqrt_info.p, w->status.p, s));
+    LFVIO_TRY(launch_prior_prepare(w->P, w->H0.p, s));
+    return LFVIO_OK;
+}
+
+// defer_prepare: the caller enqueues enqueue_prepare() itself (as part of a replayed graph).
 int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_list *fl, const lfvio_solver_opts *o,
-           bool defer_plans = false) {
+           bool defer_plans = false, bool defer_prepare = false) {
     LFVIO_REQUIRE(st && fl && o, "window: null argument");
     LFVIO_REQUIRE(st->n_frames == w->F, "window: n_frames != window_size + 1 of the handle");
     LFVIO_REQUIRE(st->n_landmarks >= 0 && st->n_landmarks <= w->Lmax, "window: too many landmarks for this handle");
@@ -340,6 +443,25 @@ int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_lis
         P.prior.r0 = reinterpret_cast<const double *>(w->blob.p + w->off_pr0);
         P.prior.H0 = w->H0.p;
     }
+    // launch geometry: counts rounded up to coarse buckets so that consecutive frames of a stream share one graph
+    P.self_dev = w->P_dev.p;
+    P.g_nbp = std::max(1, std::min(cdiv(w->Rmax, 128), (cdiv(fl->n_proj, 128) + 7) / 8 * 8));
+    P.g_L = std::max(1, std::min(w->Lmax, (L + 127) / 128 * 128));
+    P.g_imu = F - 1;
+    P.cap_L = w->Lmax;
+    P.cap_n = w->nmax;
+    P.nd_ok = 1;
+    for (int b = 0; b < P.prior.n_blocks; b++)
+        if ((P.prior.block_id[b] & 1) && P.prior.block_id[b] != 1 && P.prior.block_id[b] < 2 * F) P.nd_ok = 0;
+    {   // Nested dissection of the speed-bias chain (chol_nd.cuh) is OFF unless LFVIO_ND=1: measured on a B200 at F = 11 it
+        // does not pay — every level costs ~3 us of dependent fp64 / shared-memory latency (DFMA 23 cycles, LDS 30), 4 levels
+        // + the 82-column dense remainder come to 0.727 ms per solve against 0.700 ms for the skyline Cholesky
+        // (profiles/r2_summary.md).  It is kept because it is parity-tested and is the shorter chain for long windows.
+        static const bool nd_on = [] { const char *e = getenv("LFVIO_ND"); return e && e[0] == '1'; }();
+        if (!nd_on) P.nd_ok = 0;
+    }
+    *w->h_P = P;
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->P_dev.p, w->h_P, sizeof(DevProblem), cudaMemcpyHostToDevice, w->stream));
     double *hx = reinterpret_cast<double *>(hb + w->off_x);
     memcpy(hx + lay.pose(0), st->para_Pose, sizeof(double) * 7 * F);
     memcpy(hx + lay.sb(0), st->para_SpeedBias, sizeof(double) * 9 * F);
@@ -359,9 +481,7 @@ int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_lis
         LFVIO_TRY(copy(w->off_pr0, sizeof(double) * P.prior.n));
     }
     LFVIO_TRY(copy(w->off_x, sizeof(double) * lay.size()));
-    LFVIO_CUDA_TRY(cudaMemsetAsync(w->status.p, 0, sizeof(int) * 4, s));
-    LFVIO_TRY(launch_imu_prepare(P, w->imu_sqrt_info.p, w->status.p, s));
-    LFVIO_TRY(launch_prior_prepare(P, w->H0.p, s));
+    if (!defer_prepare) LFVIO_TRY(enqueue_prepare(w));
     if (defer_plans) {
         w->plan_valid[0] = w->plan_valid[1] = false;
     } else {
@@ -376,9 +496,9 @@ int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_lis
 int enqueue_solve(lfvio_window *w) {
     cudaStream_t s = w->stream;
     const DevProblem &P = w->P;
-    const size_t xbytes = sizeof(double) * P.lay.size();
+    const size_t xbytes = sizeof(double) * (size_t)StateLayout{w->F, w->Lmax}.size();  // capacity: same copy every frame
     w->prof.begin(WS_PREPARE, s);
-    LFVIO_TRY(launch_solver_init(w->ctl.p, P.o, s));
+    LFVIO_TRY(launch_solver_init(w->ctl.p, P, s));
     LFVIO_CUDA_TRY(cudaMemcpyAsync(w->x[0].p, w->blob.p + w->off_x, xbytes, cudaMemcpyDeviceToDevice, s));
     w->prof.end(s);
     w->prof.begin(WS_EVAL_INITIAL, s);
@@ -403,7 +523,9 @@ int enqueue_solve(lfvio_window *w) {
     return LFVIO_OK;
 }
 
-__global__ void select_state_kernel(const double *x0, const double *x1, const SolverCtl *ctl, double *out, int n) {
+__global__ void select_state_kernel(const DevProblem *__restrict__ Pd, const double *x0, const double *x1, const SolverCtl *ctl,
+                                    double *out) {
+    const int n = Pd->lay.size();
     const double *x = ctl->cur ? x1 : x0;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) out[q] = x[q];
 }
@@ -448,8 +570,9 @@ __device__ void dev_rot_to_quat(const DM3 &m, double *q /* x y z w */) {  // Eig
         q[k] = (m.m[k][i] + m.m[i][k]) * t;
     }
 }
-__global__ void gauge_fix_kernel(StateLayout lay, const double *x_init, const double *x0, const double *x1, const SolverCtl *ctl,
-                                 double *out) {
+__global__ void gauge_fix_kernel(const DevProblem *__restrict__ Pd, const double *x_init, const double *x0, const double *x1,
+                                 const SolverCtl *ctl, double *out) {
+    const StateLayout lay = Pd->lay;
     const double *x = ctl->cur ? x1 : x0;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int q = lay.ex() + tid; q < lay.size(); q += nth) out[q] = x[q];  // extrinsic, td, inverse depths: unchanged
@@ -481,7 +604,7 @@ int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum, 
     cudaStream_t s = w->stream;
     const StateLayout lay = w->P.lay;
     if (select_state) {
-        select_state_kernel<<<cdiv(lay.size(), 256), 256, 0, s>>>(w->x[0].p, w->x[1].p, w->ctl.p, w->x_out.p, lay.size());
+        select_state_kernel<<<cdiv(lay.size(), 256), 256, 0, s>>>(w->P.self_dev, w->x[0].p, w->x[1].p, w->ctl.p, w->x_out.p);
         LFVIO_LAUNCH_CHECK();
     }
     LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_x, w->x_out.p, sizeof(double) * lay.size(), cudaMemcpyDeviceToHost, s));
@@ -508,6 +631,9 @@ int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum, 
     if (getenv("LFVIO_DEBUG_STEP")) {
         static const char *names[6] = {"cauchy+xnorm", "copy+quadform", "cholesky", "tri-solve", "gn+backsub", "cand_tail"};
         for (int i = 0; i < 6; i++) fprintf(stderr, "step phase %-16s %8.2f us\n", names[i], (c.phase_clk[i + 1] - c.phase_clk[i]) / 1000.0);
+        static const char *nd_names[4] = {"nd level0 factor", "nd level0 panel", "nd level0 update", "nd other levels"};
+        for (int i = 0; i < 4; i++) fprintf(stderr, "  %-18s %8.2f us\n", nd_names[i], (c.phase_clk[9 + i] - c.phase_clk[8 + i]) / 1000.0);
+        fprintf(stderr, "  %-18s %8.2f us\n", "dense remainder", (c.phase_clk[3] - c.phase_clk[12]) / 1000.0);
     }
     if (sum) {
         memset(sum, 0, sizeof(*sum));
@@ -589,8 +715,11 @@ extern "C" int lfvio_window_optimize(lfvio_window *w, lfvio_window_state *state,
     clear_error();
     LFVIO_REQUIRE(w, "lfvio_window_optimize: null handle");
     LFVIO_CUDA_TRY(cudaSetDevice(w->device));
-    LFVIO_TRY(upload(w, state, factors, opts));
-    LFVIO_TRY(enqueue_solve(w));
+    LFVIO_TRY(upload(w, state, factors, opts, false, /*defer_prepare=*/true));
+    LFVIO_TRY(run_graphed(w, geometry_key(w, 1, 0, false), [&]() -> int {
+        LFVIO_TRY(enqueue_prepare(w));
+        return enqueue_solve(w);
+    }));
     return download(w, state, summary);
 }
 
@@ -602,13 +731,19 @@ extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *s
     LFVIO_REQUIRE(w && prior_out, "lfvio_window_optimize_full: null argument");
     LFVIO_REQUIRE(margin_flag == LFVIO_MARGIN_OLD || margin_flag == LFVIO_MARGIN_SECOND_NEW, "lfvio_window_optimize_full: bad margin_flag");
     LFVIO_CUDA_TRY(cudaSetDevice(w->device));
-    LFVIO_TRY(upload(w, state, factors, opts, /*defer_plans=*/true));
-    LFVIO_TRY(enqueue_solve(w));
+    LFVIO_TRY(upload(w, state, factors, opts, /*defer_plans=*/true, /*defer_prepare=*/true));
     cudaStream_t s = w->stream;
     const DevProblem &P = w->P;
-    gauge_fix_kernel<<<cdiv(std::max(P.lay.size(), P.lay.F), 256), 256, 0, s>>>(P.lay, reinterpret_cast<const double *>(w->blob.p + w->off_x),
-                                                                            w->x[0].p, w->x[1].p, w->ctl.p, w->x_out.p);
-    LFVIO_LAUNCH_CHECK();
+    const int size_cap = StateLayout{w->F, w->Lmax}.size();
+    // graph 1: per-upload constants, the solve, the gauge re-anchoring
+    LFVIO_TRY(run_graphed(w, geometry_key(w, 2, 0, false), [&]() -> int {
+        LFVIO_TRY(enqueue_prepare(w));
+        LFVIO_TRY(enqueue_solve(w));
+        gauge_fix_kernel<<<cdiv(std::max(size_cap, w->F), 256), 256, 0, s>>>(P.self_dev, reinterpret_cast<const double *>(w->blob.p + w->off_x),
+                                                                          w->x[0].p, w->x[1].p, w->ctl.p, w->x_out.p);
+        LFVIO_LAUNCH_CHECK();
+        return LFVIO_OK;
+    }));
     LFVIO_TRY(build_marg_plan(w, margin_flag, factors, opts, state->n_landmarks));  // host work under the running solve
     prior_out->n = 0;
     prior_out->n_blocks = 0;
@@ -618,12 +753,12 @@ extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *s
     int x0_len = 0;
     if (do_marg) {
         LFVIO_REQUIRE(pl.n <= prior_out->cap_n && pl.n_keep <= prior_out->cap_blocks, "lfvio_window_optimize_full: output prior too small");
-        // preMarginalize() at the re-anchored state: evaluate into buffer 0, then eliminate
-        LFVIO_TRY(launch_evaluate(P, w->x_out.p, w->x_out.p, w->e[0], w->e[1], w->ctl.p, 2, 1, s));
-        MargBuffers mb = marg_buffers(w, pl.n);
-        w->prof.begin(WS_MARGINALIZE, s);
-        LFVIO_TRY(launch_marginalize(P, w->e[0], w->e[1], w->x_out.p, w->x_out.p, nullptr, w->plan[margin_flag], mb, s));
-        w->prof.end(s);
+        // graph 2: preMarginalize() at the re-anchored state (evaluate into buffer 0), then eliminate
+        LFVIO_TRY(run_graphed(w, geometry_key(w, 3, margin_flag, true), [&]() -> int {
+            LFVIO_TRY(launch_evaluate(P, w->x_out.p, w->x_out.p, w->e[0], w->e[1], w->ctl.p, 2, 1, s));
+            return enqueue_marginalize(w, margin_flag, false, w->x_out.p, w->x_out.p);
+        }));
+        w->last_marg_flag = margin_flag;
         nn = (size_t)pl.n * pl.n;
         for (int b = 0; b < pl.n_keep; b++) x0_len += P.lay.block_gsize(pl.keep_id[b]);
         LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg, w->marg_out.p, sizeof(double) * (nn + pl.n + x0_len), cudaMemcpyDeviceToHost, s));
@@ -670,8 +805,12 @@ extern "C" int lfvio_window_optimize_dev(lfvio_window *w, int with_marginalize, 
     LFVIO_REQUIRE(w && w->uploaded, "lfvio_window_optimize_dev: call lfvio_window_upload first");
     LFVIO_CUDA_TRY(cudaSetDevice(w->device));
     LFVIO_REQUIRE(margin_flag == LFVIO_MARGIN_OLD || margin_flag == LFVIO_MARGIN_SECOND_NEW, "lfvio_window_optimize_dev: bad margin_flag");
-    LFVIO_TRY(enqueue_solve(w));
-    if (with_marginalize) LFVIO_TRY(enqueue_marginalize(w, margin_flag, true));
+    LFVIO_TRY(run_graphed(w, geometry_key(w, with_marginalize ? 5 : 4, margin_flag, with_marginalize != 0), [&]() -> int {
+        LFVIO_TRY(enqueue_solve(w));
+        if (with_marginalize) LFVIO_TRY(enqueue_marginalize(w, margin_flag, true));
+        return LFVIO_OK;
+    }));
+    if (with_marginalize) w->last_marg_flag = margin_flag;
     return LFVIO_OK;
 }
 
@@ -691,7 +830,7 @@ extern "C" int lfvio_window_evaluate(lfvio_window *w, const lfvio_window_state *
     LFVIO_TRY(upload(w, state, factors, opts));
     cudaStream_t s = w->stream;
     const DevProblem &P = w->P;
-    LFVIO_TRY(launch_solver_init(w->ctl.p, P.o, s));
+    LFVIO_TRY(launch_solver_init(w->ctl.p, P, s));
     LFVIO_CUDA_TRY(cudaMemcpyAsync(w->x[0].p, w->blob.p + w->off_x, sizeof(double) * P.lay.size(), cudaMemcpyDeviceToDevice, s));
     LFVIO_TRY(launch_evaluate(P, w->x[0].p, w->x[1].p, w->e[0], w->e[1], w->ctl.p, 2, robust, s));
     LFVIO_CUDA_TRY(cudaStreamSynchronize(s));
@@ -729,10 +868,11 @@ extern "C" int lfvio_window_marginalize(lfvio_window *w, const lfvio_window_stat
     const MargPlan &pl = w->plan[margin_flag];
     LFVIO_REQUIRE(pl.n <= out->cap_n && pl.n_keep <= out->cap_blocks, "lfvio_window_marginalize: output prior too small");
     // preMarginalize(): evaluate the dropped factors (with the loss correction) at the given state
-    LFVIO_TRY(launch_solver_init(w->ctl.p, P.o, s));
+    LFVIO_TRY(launch_solver_init(w->ctl.p, P, s));
     LFVIO_CUDA_TRY(cudaMemcpyAsync(w->x[0].p, w->blob.p + w->off_x, sizeof(double) * P.lay.size(), cudaMemcpyDeviceToDevice, s));
     LFVIO_TRY(launch_evaluate(P, w->x[0].p, w->x[1].p, w->e[0], w->e[1], w->ctl.p, 2, 1, s));
     LFVIO_TRY(enqueue_marginalize(w, margin_flag, false));
+    w->last_marg_flag = margin_flag;
     const size_t nn = (size_t)pl.n * pl.n;
     int x0_len = 0;
     for (int b = 0; b < pl.n_keep; b++) x0_len += P.lay.block_gsize(pl.keep_id[b]);
