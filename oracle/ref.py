@@ -243,3 +243,15 @@ class RefFeatureManager:
     def set_depth(self, x):
         x = np.ascontiguousarray(x, np.float64)
         self.L.ref_fm_set_depth(self.h, x.ctypes.data, len(x))
+
+
+def find_fundamental(b1, b2, seed: int, frame: int):
+    """myfindFundamentalMat (feature_tracker.cpp:266-327) with the injected random source -> (E 3x3, status)."""
+    b1 = np.ascontiguousarray(b1, np.float64).reshape(-1, 3)
+    b2 = np.ascontiguousarray(b2, np.float64).reshape(-1, 3)
+    n = len(b1)
+    status, E = np.zeros(n, np.uint8), np.zeros(9)
+    L = lib()
+    L.ref_find_fundamental.argtypes = [_dp, _dp, C.c_int, C.c_ulonglong, C.c_uint, C.c_void_p, _dp]
+    assert L.ref_find_fundamental(_p(b1), _p(b2), n, seed, frame, status.ctypes.data, _p(E)) == 0
+    return E.reshape(3, 3), status

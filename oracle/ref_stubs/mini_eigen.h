@@ -1207,8 +1207,12 @@ class SelfAdjointEigenSolver {
 template <class M>
 class JacobiSVD {
     typedef typename M::Scalar S;
-    Matrix<S, Dynamic, Dynamic> U, V;
+    mutable Matrix<S, Dynamic, Dynamic> left;  // singular vectors of the long side (completed lazily)
+    Matrix<S, Dynamic, Dynamic> Rt;            // singular vectors of the short side
     Matrix<S, Dynamic, 1> sv;
+    Index rank = 0;
+    bool want_full_left = false, is_wide = false;
+    mutable bool left_done = false;
 
     static void hestenes(Matrix<S, Dynamic, Dynamic> &a, Matrix<S, Dynamic, Dynamic> &v) {  // a: m x n, m >= n; columns orthogonalised in place
         const Index m = a.rows(), n = a.cols();
@@ -1223,7 +1227,7 @@ class JacobiSVD {
                         beta += a(k, q) * a(k, q);
                         gamma += a(k, p) * a(k, q);
                     }
-                    if (gamma == S(0) || std::abs(gamma) <= S(1e-17) * std::sqrt(alpha * beta)) continue;
+                    if (gamma == S(0) || std::abs(gamma) <= S(1.8e-15) * std::sqrt(alpha * beta)) continue;  // orthogonal to working precision
                     rotated = true;
                     const S zeta = (beta - alpha) / (S(2) * gamma);
                     const S t = (zeta >= 0 ? S(1) : S(-1)) / (std::abs(zeta) + std::sqrt(S(1) + zeta * zeta));
@@ -1290,9 +1294,10 @@ class JacobiSVD {
         std::stable_sort(ord.begin(), ord.end(), [&](Index x, Index y) { return nrm[(size_t)x] > nrm[(size_t)y]; });
         sv.resize(nn);
         const bool fullL = wide ? (opts & ComputeFullV) : (opts & ComputeFullU);
-        Matrix<S, Dynamic, Dynamic> left(mm, fullL ? mm : nn), right(nn, nn);
+        left.resize(mm, nn);
         left.setZero();
-        Index rank = 0;
+        Matrix<S, Dynamic, Dynamic> right(nn, nn);
+        rank = 0;
         const S tiny = nn ? nrm[(size_t)ord[0]] * S(1e-300) : S(0);
         for (Index j = 0; j < nn; j++) {
             const Index o = ord[(size_t)j];
@@ -1303,37 +1308,54 @@ class JacobiSVD {
                 rank = j + 1;
             }
         }
-        if (rank < left.cols()) {
-            if (left.cols() == mm)
-                complete(left, rank);
-            else {  // thin: still orthonormalise the null columns
-                Matrix<S, Dynamic, Dynamic> full(mm, mm);
-                full.setZero();
-                for (Index j = 0; j < rank; j++)
-                    for (Index k = 0; k < mm; k++) full(k, j) = left(k, j);
-                complete(full, rank);
-                for (Index j = rank; j < left.cols(); j++)
-                    for (Index k = 0; k < mm; k++) left(k, j) = full(k, j);
-            }
-        }
-        if (wide) {
-            U = right;
-            V = left;
-        } else {
-            U = left;
-            V = right;
-        }
+        // The long side's orthonormal completion (the m x m "full U" of a tall matrix) is only built when it is asked for:
+        // the reference requests ComputeFullU | ComputeFullV everywhere but reads matrixV() only (feature_tracker.cpp:202-206).
+        want_full_left = fullL;
+        left_done = false;
+        is_wide = wide;
+        Rt = right;
         return *this;
     }
-    const Matrix<S, Dynamic, Dynamic> &matrixU() const { return U; }
-    const Matrix<S, Dynamic, Dynamic> &matrixV() const { return V; }
+    void finish_left() const {
+        if (left_done) return;
+        const Index mm = left.rows(), nn = left.cols();
+        if (want_full_left || rank < nn) {
+            Matrix<S, Dynamic, Dynamic> full(mm, want_full_left ? mm : nn);
+            full.setZero();
+            for (Index j = 0; j < rank; j++)
+                for (Index k = 0; k < mm; k++) full(k, j) = left(k, j);
+            if (want_full_left) {
+                complete(full, rank);
+                left = full;
+            } else {
+                Matrix<S, Dynamic, Dynamic> sq(mm, mm);
+                sq.setZero();
+                for (Index j = 0; j < rank; j++)
+                    for (Index k = 0; k < mm; k++) sq(k, j) = left(k, j);
+                complete(sq, rank);
+                for (Index j = rank; j < nn; j++)
+                    for (Index k = 0; k < mm; k++) left(k, j) = sq(k, j);
+            }
+        }
+        left_done = true;
+    }
+    const Matrix<S, Dynamic, Dynamic> &matrixU() const {
+        if (is_wide) return Rt;
+        finish_left();
+        return left;
+    }
+    const Matrix<S, Dynamic, Dynamic> &matrixV() const {
+        if (!is_wide) return Rt;
+        finish_left();
+        return left;
+    }
     const Matrix<S, Dynamic, 1> &singularValues() const { return sv; }
     template <class D>
     Matrix<S, Dynamic, Dynamic> solve(const MatrixBase<D> &b) const {
-        Matrix<S, Dynamic, Dynamic> y = U.transpose() * b;
+        Matrix<S, Dynamic, Dynamic> y = matrixU().transpose() * b;
         for (Index i = 0; i < sv.size(); i++)
             for (Index j = 0; j < y.cols(); j++) y(i, j) = sv(i) > sv(0) * S(1e-15) ? y(i, j) / sv(i) : S(0);
-        return V * y.topRows(sv.size());
+        return matrixV().leftCols(sv.size()) * y.topRows(sv.size());
     }
 };
 template <class D>

@@ -89,6 +89,16 @@ def main():
     out["al_dt"] = np.array([p.sum_dt for p in pre])
     out["al_Jrg"] = np.array([np.array(p.jacobian).reshape(15, 15)[3:6, 12:15] for p in pre])
     out["al_bg"], out["al_g"], out["al_x"], out["al_ok"] = r0["bg"], r1["g"], r1["x"], np.array([int(r1["ok"])])
+    # rejectWithF's RANSAC (the reference's compute_E_21 / check_inliers / myfindFundamentalMat on the injected random source)
+    import lfvio
+    from oracle import ransac as R
+    from ransac_data import two_view
+
+    cur, forw, _ = two_view(lfvio.PAL_UP, lfvio.tracker_defaults(), 150, 12)
+    b1, b2 = R.lift_pair(lfvio.PAL_UP, cur, forw)
+    E, st = ref.find_fundamental(b1, b2, 5, 3)
+    out["rs_cur"], out["rs_forw"], out["rs_seed_frame"] = cur, forw, np.array([5, 3])
+    out["rs_status"], out["rs_E"] = st, E
     np.savez_compressed(os.path.join(HERE, "ref_backend.npz"), **out)
     print("wrote ref_backend.npz:", sum(v.nbytes for v in out.values()) // 1024, "KiB raw,", len(out), "arrays")
 

@@ -234,6 +234,23 @@ def test_triangulate():
     assert rel(got, want) < 1e-9
 
 
+@pytest.mark.parametrize("n,seed", [(150, 1), (60, 2), (9, 3), (8, 5), (400, 4)])
+def test_reject_with_f_ransac(n, seed):
+    """compute_E_21 / check_inliers / myfindFundamentalMat (feature_tracker.cpp:186-327) — the reference's own code, fed from the
+    injected random source — against oracle/ransac.py: same inlier decisions, same refit essential matrix up to sign."""
+    from oracle import ransac as R
+    from ransac_data import two_view
+
+    cam, cfg = lfvio.PAL_UP, lfvio.tracker_defaults()
+    cur, forw, _ = two_view(cam, cfg, n, seed)
+    b1, b2 = R.lift_pair(cam, cur, forw)
+    for frame in (0, 11):
+        Eo, so, _, _ = R.find_fundamental(b1, b2, 7 + seed, frame)
+        Er, sr = ref.find_fundamental(b1, b2, 7 + seed, frame)
+        assert np.array_equal(so, sr)
+        assert np.abs(Eo - np.sign((Eo * Er).sum()) * Er).max() < 1e-12
+
+
 @pytest.fixture(scope="module")
 def host():
     lib = C.CDLL(os.path.join(ROOT, "lf-vio_b200", "liblfvio_host.so"))

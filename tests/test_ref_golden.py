@@ -75,6 +75,16 @@ def test_oracle_alignment_equals_reference(g):
     assert ok == bool(g["al_ok"][0]) and np.abs(gv - g["al_g"]).max() < 1e-9 and np.abs(x - g["al_x"]).max() < 1e-8
 
 
+def test_oracle_ransac_equals_reference(g):
+    import lfvio
+    from oracle import ransac as R
+
+    b1, b2 = R.lift_pair(lfvio.PAL_UP, g["rs_cur"], g["rs_forw"])
+    E, st, _, _ = R.find_fundamental(b1, b2, int(g["rs_seed_frame"][0]), int(g["rs_seed_frame"][1]))
+    assert np.array_equal(st, g["rs_status"])
+    assert np.abs(E - np.sign((E * g["rs_E"]).sum()) * g["rs_E"]).max() < 1e-12
+
+
 # ------------------------------------------------------------------------------------------------ (b) the CUDA path
 @pytest.fixture(scope="module")
 def win(lfvio_mod, gpu):
@@ -108,6 +118,14 @@ def test_device_preintegration_equals_reference(lfvio_mod, gpu, g):
         assert np.abs(np.array(a.delta_v) - np.array(b.delta_v)).max() < 1e-13
         assert rel(np.array(a.jacobian), np.array(b.jacobian)) < 1e-11
         assert rel(np.array(a.covariance), np.array(b.covariance)) < 1e-11
+
+
+@pytest.mark.gpu
+def test_device_ransac_equals_reference(lfvio_mod, gpu, g):
+    """lfvio_reject_with_f (the tracker's rejectWithF kernels) on the stored point pairs: same status as the reference's code."""
+    st = lfvio_mod.reject_with_f(lfvio_mod.PAL_UP, g["rs_cur"], g["rs_forw"], int(g["rs_seed_frame"][0]), int(g["rs_seed_frame"][1]))
+    status = st[0] if isinstance(st, tuple) else st
+    assert np.array_equal(np.asarray(status).astype(np.uint8), g["rs_status"])
 
 
 @pytest.mark.gpu
