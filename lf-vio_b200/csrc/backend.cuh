@@ -69,8 +69,6 @@ struct DevProblem {
     int g_imu;    // IMU items = F - 1
     int cap_L;    // landmark capacity of the handle (sizes of the per-solve clears)
     int cap_n;    // prior capacity of the handle (15 F + 7)
-    int nd_ok;    // the speed-bias blocks sb_1 .. sb_{F-1} are coupled only through the IMU chain (no prior on them):
-                  // the step kernel may eliminate them by nested dissection (chol_nd.cuh)
 };
 
 // residuals + local, loss-corrected Jacobians of every factor at one state

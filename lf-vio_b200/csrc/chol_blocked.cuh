@@ -34,23 +34,28 @@ struct MatPacked {  // packed upper triangle, row-major (c >= r)
 
 // ---- look-ahead blocked Cholesky + fused forward substitution ---------------------------------------------------
 // S = U^T U on the upper triangle, 16-column block steps, one CTA.  Warp 0 is the "diagonal warp": while the other
-// warps (workers) apply block step k to the trailing matrix, warp 0 already solves the 16 panel columns of block k+1,
-// applies step k to diagonal block k+1 and factors it in registers — the serial pivot chain of block k+1 overlaps the
-// throughput-bound trailing update of block k.  The right-hand side rides along as one extra panel column, so the
+// warps (workers) apply block step k to the trailing matrix, warp 0 already forms the 16 panel columns of block k+1,
+// applies step k to diagonal block k+1 and factors it in registers (factor_diag_block_ldl, which also hands out U11^-T so
+// that no panel column is a substitution) — the serial pivot chain of block k+1 overlaps the trailing update of block k.  The right-hand side rides along as one extra panel column, so the
 // forward substitution U^T z = b costs nothing extra; solve_upper_back finishes with U y = z.
 // Barriers: id 1 = "diagonal block ready / trailing update done" (all threads), id 2 = "panel complete"
 // (workers wait, warp 0 only arrives).
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// one panel column: a <- U11^-T a by substitution with the factored diagonal block (broadcast reads of U, 1/pivot)
-__device__ __forceinline__ void panel_column_solve(double (&a)[NB], const double *U, const double *invd) {
+// one panel column through the explicit inverse of the diagonal block: a <- U11^-T a with U11^-T lower triangular in shared
+// memory (factor_diag_block_ldl) — 136 independent-ish FMAs instead of a 16-step substitution; in place, last row first
+__device__ __forceinline__ void panel_column_apply(double (&a)[NB], uint32_t pl) {
 #pragma unroll
-    for (int j = 0; j < NB; j++) {
-        const double u = a[j] * invd[j];
-        a[j] = u;
+    for (int t = NB - 1; t >= 0; t--) {
+        double e = 0, o = 0;
 #pragma unroll
-        for (int r = j + 1; r < NB; r++) a[r] = fma(-U[j * NB + r], u, a[r]);
+        for (int r = 0; r <= t; r += 2) {
+            const double2 l = lds2(pl + 8u * (t * NB + r));
+            e = fma(l.x, a[r], e);
+            if (r + 1 <= t) o = fma(l.y, a[r + 1], o);
+        }
+        a[t] = e + o;
     }
 }
 
@@ -89,7 +94,7 @@ struct WindowProfile {
 };
 
 template <class M, class Prof = DenseProfile>
-__device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, int PW, double *s_U /* 2 x NB x NB */,
+__device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, int PW, double *s_U /* 2 x NB x NB */, double *s_PL /* 2 x NB x NB */,
                                    double *s_invd /* nblk x NB */, double *s_y /* D: b in, z out */, int *s_okv /* nblk */, double *s_row /* 2 x NB */,
                                    Prof prof = Prof(), bool leave_last = false) {
     // leave_last: stop before the last diagonal block — on return it holds the fully updated (unfactored) Schur
@@ -97,8 +102,13 @@ __device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, in
     // (marg.cu: with diagonal pivoting, because that is where a gauge-deficient matrix shows its tiny pivots).
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
     const int nblk = (D + NB - 1) / NB;
-    const int nworkers = nt - 32, wtid = tid - 32;
-    const int nbar = nt;  // threads taking part in the named barriers
+    // Warps 4, 8, 12, .. share warp 0's scheduler (warp w runs on scheduler w % 4; fp64 issue is per scheduler: measured, the
+    // diagonal-block factorisation takes 1.8 k cycles alone and 3.3 k next to three busy warps there): they sit the whole
+    // factorisation out, so that the chain warp never waits for an issue slot or the fp64 pipe.
+    const bool idle = wid >= 4 && (wid & 3) == 0;
+    const int n_idle = ((nt >> 5) - 1) / 4;
+    const int nworkers = nt - 32 - 32 * n_idle, wtid = (wid - 1 - wid / 4) * 32 + lane;
+    const int nbar = nt - 32 * n_idle;  // threads taking part in the named barriers
     const int zc = PW - 1;           // panel column of the right-hand side
     SUB_T0();
     if (wid == 0) {  // factor diagonal block 0
@@ -108,35 +118,56 @@ __device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, in
             s_U[q] = (r < nb && c < nb && c >= r) ? S.at(r, c) : ((r == c) ? 1.0 : 0.0);
         }
         __syncwarp();
-        const bool ok = factor_diag_block_split(s_U, s_invd, s_row);
+        const bool ok = factor_diag_block_ldl(s_U, s_invd, s_PL, s_row);
         if (lane == 0) s_okv[0] = ok ? 1 : 0;
         for (int q = lane; q < NB * NB; q += 32) {
             const int r = q / NB, c = q % NB;
             if (c >= r && c < nb) S.at(r, c) = s_U[q];
         }
     }
-    bar_sync(1, nbar);
+    if (!idle) bar_sync(1, nbar);
 #ifdef LFVIO_CHOL_PROFILE
     sub_t = clock64();
 #endif
-    for (int blk = 0; blk < nblk; blk++) {
-        if (s_okv[blk] == 0) return false;
+    bool ok_all = true;
+    for (int blk = 0; blk < nblk && !idle; blk++) {
+        if (s_okv[blk] == 0) {
+            ok_all = false;
+            break;
+        }
         if (leave_last && blk == nblk - 1) break;
         const int j0 = blk * NB, nb = min(NB, D - j0);
         const int rest0 = j0 + nb, nrest = D - rest0, nb1 = min(NB, nrest);
-        const double *U = s_U + (blk & 1) * NB * NB, *invd = s_invd + blk * NB;
+        const uint32_t pl = smem_u32(s_PL + (blk & 1) * NB * NB);  // U11^-T of this block
         if (wid == 0) {
             // ---- diagonal warp: panel columns of block blk+1, then look ahead ----
             double *Un = s_U + ((blk + 1) & 1) * NB * NB;
-            if (lane < nb1) {
-                double a[NB];
+            {
+                // the 16 look-ahead columns through U11^-T: lane (h, c) forms rows h, h + 2, .. of column c (72 FMAs per lane)
+                const int c = lane & 15, h = lane >> 4;
+                if (c < nb1) {
+                    double a[NB];
 #pragma unroll
-                for (int r = 0; r < NB; r++) a[r] = (r < nb) ? S.at(j0 + r, rest0 + lane) : 0.0;
-                panel_column_solve(a, U, invd);
+                    for (int r = 0; r < NB; r++) a[r] = (r < nb) ? S.at(j0 + r, rest0 + c) : 0.0;
+                    double out[NB / 2];
 #pragma unroll
-                for (int r = 0; r < NB; r++) {
-                    if (r < nb) S.at(j0 + r, rest0 + lane) = a[r];
-                    s_panel[r * PW + lane] = a[r];
+                    for (int u = 0; u < NB / 2; u++) {
+                        const uint32_t prow = pl + 8u * ((2 * u + h) * NB);
+                        double e = 0, o = 0;
+#pragma unroll
+                        for (int r = 0; r <= 2 * u + 1; r += 2) {  // (entry 2u + 1 of row 2u is zero)
+                            const double2 l = lds2(prow + 8u * r);
+                            e = fma(l.x, a[r], e);
+                            o = fma(l.y, a[r + 1], o);
+                        }
+                        out[u] = e + o;
+                    }
+#pragma unroll
+                    for (int u = 0; u < NB / 2; u++) {
+                        const int t = 2 * u + h;
+                        if (t < nb) S.at(j0 + t, rest0 + c) = out[u];
+                        s_panel[t * PW + c] = out[u];
+                    }
                 }
             }
             __threadfence_block();
@@ -164,7 +195,7 @@ __device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, in
                 }
                 __syncwarp();
                 SUB_MARK(1);
-                const bool ok = (leave_last && blk + 1 == nblk - 1) ? true : factor_diag_block_split(Un, s_invd + (blk + 1) * NB, s_row);
+                const bool ok = (leave_last && blk + 1 == nblk - 1) ? true : factor_diag_block_ldl(Un, s_invd + (blk + 1) * NB, s_PL + ((blk + 1) & 1) * NB * NB, s_row);
                 if (lane == 0) s_okv[blk + 1] = ok ? 1 : 0;
                 for (int q = lane; q < NB * NB; q += 32) {
                     const int r = q / NB, cc = q % NB;
@@ -190,7 +221,7 @@ __device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, in
 #pragma unroll
                 for (int r = 0; r < NB; r++) a[r] = (r < nb) ? (is_rhs ? s_y[j0 + r] : S.at(j0 + r, rc)) : 0.0;
                 SUB_MARK(4);
-                panel_column_solve(a, U, invd);
+                panel_column_apply(a, pl);
                 SUB_MARK(5);
                 const int pc = is_rhs ? zc : c;
 #pragma unroll
@@ -254,7 +285,9 @@ __device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, in
         SUB_MARK(3);
     }
     SUB_FLUSH();
-    return true;
+    if (tid == 0) s_okv[nblk] = ok_all ? 1 : 0;  // (the idle warps never looked)
+    __syncthreads();
+    return s_okv[nblk] != 0;
 }
 
 // U y = z on the shared vector y (in/out), last block first: warp 0 back-substitutes the 16 x 16 diagonal block with

@@ -507,6 +507,7 @@ __global__ void __launch_bounds__(MF_THREADS) marg_finish_kernel(const DevProble
         double *s_y = s_panel + (size_t)NB * PW;
         double *s_invd = s_y + ((n + 1) & ~1);
         __shared__ __align__(16) double s_U[2 * NB * NB];
+        __shared__ __align__(16) double s_PL[2 * NB * NB];
         __shared__ __align__(16) double s_row[2 * NB];
         __shared__ int s_okv[kMaxFrames * 15 / NB + 4];
         __shared__ int s_perm[15 * kMaxFrames + 8];
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__(MF_THREADS) marg_finish_kernel(const DevProble
         }
         for (int i = tid; i < n; i += nt) s_y[i] = br[s_perm[i]];
         __syncthreads();
-        fast_ok = cholesky_lookahead(MatFull{R, n}, n, s_panel, PW, s_U, s_invd, s_y, s_okv, s_row, DenseProfile(), true);
+        fast_ok = cholesky_lookahead(MatFull{R, n}, n, s_panel, PW, s_U, s_PL, s_invd, s_y, s_okv, s_row, DenseProfile(), true);
         __syncthreads();
         if (fast_ok) {
             int bad = 0;

@@ -22,7 +22,6 @@
 #include "solver_common.cuh"
 #include "chol16.cuh"
 #include "chol_blocked.cuh"
-#include "chol_nd.cuh"
 
 namespace lfvio {
 
@@ -331,9 +330,9 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
     extern __shared__ double smem[];
     __shared__ double s_red[33];
     __shared__ __align__(16) double s_U[2 * NB * NB];
+    __shared__ __align__(16) double s_PL[2 * NB * NB];
     __shared__ __align__(16) double s_row[2 * NB];
     __shared__ int s_okv[kMaxFrames * 15 / NB + 4];
-    __shared__ int s_nd_off[52], s_nd_flag;
     const StateLayout lay = P.lay;
     const lfvio_solver_opts &o = P.o;
     const int D = lay.D(), L = lay.L, N = D + L;
@@ -348,8 +347,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
     double *s_y = s_panel + (size_t)NB * PW;       // D (padded to even)
     double *s_invd = s_y + ((D + 1) & ~1);         // nblk * NB reciprocal pivots
     double *s_a = s_invd + (size_t)nblk * NB;      // D (padded to even): Cauchy direction, reduced columns
-    double *s_nd = s_a + ((D + 1) & ~1);           // nested-dissection staging (chol_nd.cuh)
-    double *s_S = s_nd + ((nd_stage_doubles(lay.F) + 1) & ~1);  // packed upper triangle when use_smem
+    double *s_S = s_a + ((D + 1) & ~1);            // packed upper triangle when use_smem
     PHASE_MARK(0);
     const double mu = ctl->mu;
     double gg, jj_part = 0, gmax;
@@ -442,20 +440,8 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
     __syncthreads();
     if (ctl->done != 0) return;
     PHASE_MARK(2);
-    const bool nd = P.nd_ok != 0 && lay.F >= 3;
-    const int nd_off = SBW * (lay.F - 1), D2 = D - nd_off;  // [sb_0 | poses | ex | td]: the dense remainder
-    if (nd) {
-        // speed-bias blocks sb_{F-1} .. sb_1 by nested dissection (chain of 9 ceil(log2 F) pivots), then the dense remainder
-        if (use_smem) {
-            pd = nd_eliminate(Sp, lay.F, s_y, s_nd, s_nd_off, &s_nd_flag, ctl->phase_clk + 8);
-            if (pd) pd = cholesky_lookahead(MatSub<MatPacked>{Sp, nd_off}, D2, s_panel, PW, s_U, s_invd, s_y + nd_off, s_okv, s_row);
-        } else {
-            const MatFull Sg{w.S, D};
-            pd = nd_eliminate(Sg, lay.F, s_y, s_nd, s_nd_off, &s_nd_flag);
-            if (pd) pd = cholesky_lookahead(MatSub<MatFull>{Sg, nd_off}, D2, s_panel, PW, s_U, s_invd, s_y + nd_off, s_okv, s_row);
-        }
-    } else if (use_smem) pd = cholesky_lookahead(Sp, D, s_panel, PW, s_U, s_invd, s_y, s_okv, s_row, WindowProfile{lay.F});
-    else pd = cholesky_lookahead(MatFull{w.S, D}, D, s_panel, PW, s_U, s_invd, s_y, s_okv, s_row, WindowProfile{lay.F});
+    if (use_smem) pd = cholesky_lookahead(Sp, D, s_panel, PW, s_U, s_PL, s_invd, s_y, s_okv, s_row, WindowProfile{lay.F});
+    else pd = cholesky_lookahead(MatFull{w.S, D}, D, s_panel, PW, s_U, s_PL, s_invd, s_y, s_okv, s_row, WindowProfile{lay.F});
     if (!pd) {
         if (tid == 0) ctl->pad = 0;
         __syncthreads();
@@ -463,16 +449,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
         return;
     }
     PHASE_MARK(3);
-    if (nd) {
-        if (use_smem) {
-            solve_upper_back(MatSub<MatPacked>{Sp, nd_off}, D2, s_y + nd_off, s_invd);
-            nd_backsolve(Sp, lay.F, s_y);
-        } else {
-            const MatFull Sg{w.S, D};
-            solve_upper_back(MatSub<MatFull>{Sg, nd_off}, D2, s_y + nd_off, s_invd);
-            nd_backsolve(Sg, lay.F, s_y);
-        }
-    } else if (use_smem) solve_upper_back(Sp, D, s_y, s_invd);
+    if (use_smem) solve_upper_back(Sp, D, s_y, s_invd);
     else solve_upper_back(MatFull{w.S, D}, D, s_y, s_invd);
     PHASE_MARK(4);
     double gn2 = 0, gdot = 0;
@@ -547,10 +524,10 @@ void chol_profile_read(long long *out) { cudaMemcpyFromSymbol(out, g_sub, sizeof
 
 static size_t chol_base_bytes(int D) {
     const int F = (D - 7) / 15;
-    return sizeof(double) * ((size_t)NB * chol_panel_pitch(D) + 2 * (size_t)((D + 1) & ~1) + (size_t)cdiv(D, NB) * NB +
-                             (size_t)((nd_stage_doubles(F) + 1) & ~1));
+    (void)F;
+    return sizeof(double) * ((size_t)NB * chol_panel_pitch(D) + 2 * (size_t)((D + 1) & ~1) + (size_t)cdiv(D, NB) * NB);
 }
-static bool chol_in_smem(int D) { return chol_base_bytes(D) + sizeof(double) * ((size_t)D * (D + 1) / 2) <= 220 * 1024; }
+static bool chol_in_smem(int D) { return chol_base_bytes(D) + sizeof(double) * ((size_t)D * (D + 1) / 2) <= 218 * 1024; }
 
 // fused / self-clearing is decided on the landmark BUCKET (g_L), so that it does not flip from frame to frame
 bool step_zeroes_system(const DevProblem &P) { return P.g_L <= kFuseMaxL && chol_in_smem(P.lay.D()); }
@@ -564,12 +541,12 @@ int launch_step(const DevProblem &P, const EvalBuf &e0, const EvalBuf &e1, const
         LFVIO_CUDA_TRY(launch_pdl(pre_kernel, dim3(std::max(1, std::min(cdiv(work, PRE_THREADS), 148))), dim3(PRE_THREADS), 0, s, P.self_dev, e0, e1, w, ctl));
         LFVIO_LAUNCH_CHECK();
     }
-    LFVIO_REQUIRE(D + 1 <= CHOL_THREADS - 32, "window too large for the single-pass panel solve (15 F + 8 <= 480)");
+    LFVIO_REQUIRE(D + 1 <= CHOL_THREADS - 128, "window too large for the single-pass panel solve (15 F + 8 <= 384)");
     const int nblk = cdiv(D, NB);
     const size_t base = chol_base_bytes(D);
     (void)nblk;
     const size_t packed = sizeof(double) * ((size_t)D * (D + 1) / 2);
-    const size_t limit = 220 * 1024;
+    const size_t limit = 218 * 1024;
     const int use_smem = (base + packed <= limit) ? 1 : 0;
     LFVIO_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(chol_kernel), (int)limit));
     LFVIO_CUDA_TRY(launch_pdl(chol_kernel, dim3(1), dim3(CHOL_THREADS), base + (use_smem ? packed : 0), s, P.self_dev, w, x0, x1, ctl, use_smem, fused));

@@ -450,16 +450,6 @@ int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_lis
     P.g_imu = F - 1;
     P.cap_L = w->Lmax;
     P.cap_n = w->nmax;
-    P.nd_ok = 1;
-    for (int b = 0; b < P.prior.n_blocks; b++)
-        if ((P.prior.block_id[b] & 1) && P.prior.block_id[b] != 1 && P.prior.block_id[b] < 2 * F) P.nd_ok = 0;
-    {   // Nested dissection of the speed-bias chain (chol_nd.cuh) is OFF unless LFVIO_ND=1: measured on a B200 at F = 11 it
-        // does not pay — every level costs ~3 us of dependent fp64 / shared-memory latency (DFMA 23 cycles, LDS 30), 4 levels
-        // + the 82-column dense remainder come to 0.727 ms per solve against 0.700 ms for the skyline Cholesky
-        // (profiles/r2_summary.md).  It is kept because it is parity-tested and is the shorter chain for long windows.
-        static const bool nd_on = [] { const char *e = getenv("LFVIO_ND"); return e && e[0] == '1'; }();
-        if (!nd_on) P.nd_ok = 0;
-    }
     *w->h_P = P;
     LFVIO_CUDA_TRY(cudaMemcpyAsync(w->P_dev.p, w->h_P, sizeof(DevProblem), cudaMemcpyHostToDevice, w->stream));
     double *hx = reinterpret_cast<double *>(hb + w->off_x);
@@ -631,9 +621,6 @@ int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum, 
     if (getenv("LFVIO_DEBUG_STEP")) {
         static const char *names[6] = {"cauchy+xnorm", "copy+quadform", "cholesky", "tri-solve", "gn+backsub", "cand_tail"};
         for (int i = 0; i < 6; i++) fprintf(stderr, "step phase %-16s %8.2f us\n", names[i], (c.phase_clk[i + 1] - c.phase_clk[i]) / 1000.0);
-        static const char *nd_names[4] = {"nd level0 factor", "nd level0 panel", "nd level0 update", "nd other levels"};
-        for (int i = 0; i < 4; i++) fprintf(stderr, "  %-18s %8.2f us\n", nd_names[i], (c.phase_clk[9 + i] - c.phase_clk[8 + i]) / 1000.0);
-        fprintf(stderr, "  %-18s %8.2f us\n", "dense remainder", (c.phase_clk[3] - c.phase_clk[12]) / 1000.0);
     }
     if (sum) {
         memset(sum, 0, sizeof(*sum));
