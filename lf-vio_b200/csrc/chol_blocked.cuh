@@ -19,17 +19,32 @@ static __device__ long long g_sub[16];
 // row pitch of the shared panel: trailing columns rounded up to the 4-wide tiles, + one tile whose last column holds the rhs
 __host__ __device__ inline int chol_panel_pitch(int D) { return ((D + 3) & ~3) + 4; }
 
+// Element handles for the hot loops: a pointer walk down a column costs one add per row; for the shared-memory triangle the
+// handle is a 32-bit shared address (a generic pointer into shared memory costs an S2R + LEA per access to rebuild the
+// window base, the packed index five integer operations — measured: the workers spent half their time "loading 16 values").
 struct MatFull {
     double *p;
     int D;
     __device__ __forceinline__ double &at(int r, int c) const { return p[(size_t)r * D + c]; }
     __device__ __forceinline__ double *row(int r) const { return p + (size_t)r * D; }  // row(r)[c] == at(r, c)
+    typedef double *hnd;
+    __device__ __forceinline__ hnd h(int r, int c) const { return p + (size_t)r * D + c; }
+    __device__ __forceinline__ hnd down(hnd e, int r) const { return e + D; }  // (r, c) -> (r + 1, c)
+    static __device__ __forceinline__ hnd right(hnd e, int n) { return e + n; }
+    static __device__ __forceinline__ double ld(hnd e) { return *e; }
+    static __device__ __forceinline__ void st(hnd e, double v) { *e = v; }
 };
 struct MatPacked {  // packed upper triangle, row-major (c >= r)
     double *p;
     int D;
     __device__ __forceinline__ double &at(int r, int c) const { return p[r * D - ((r * (r - 1)) >> 1) + (c - r)]; }
     __device__ __forceinline__ double *row(int r) const { return p + (r * D - ((r * (r - 1)) >> 1) - r); }  // valid for c >= r
+    typedef uint32_t hnd;
+    __device__ __forceinline__ hnd h(int r, int c) const { return smem_u32(p) + 8u * (unsigned)(r * D - ((r * (r - 1)) >> 1) + (c - r)); }
+    __device__ __forceinline__ hnd down(hnd e, int r) const { return e + 8u * (unsigned)(D - r - 1); }
+    static __device__ __forceinline__ hnd right(hnd e, int n) { return e + 8u * (unsigned)n; }
+    static __device__ __forceinline__ double ld(hnd e) { return lds(e); }
+    static __device__ __forceinline__ void st(hnd e, double v) { sts(e, v); }
 };
 
 // ---- look-ahead blocked Cholesky + fused forward substitution ---------------------------------------------------
@@ -94,9 +109,10 @@ struct WindowProfile {
 };
 
 template <class M, class Prof = DenseProfile>
-__device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, int PW, double *s_U /* 2 x NB x NB */, double *s_PL /* 2 x NB x NB */,
+__device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, int PW, double *s_U /* 2 x NB x NB */, double *s_PL /* 2 (or, pl_all, nblk) x NB x NB */,
                                    double *s_invd /* nblk x NB */, double *s_y /* D: b in, z out */, int *s_okv /* nblk */, double *s_row /* 2 x NB */,
-                                   Prof prof = Prof(), bool leave_last = false) {
+                                   Prof prof = Prof(), bool leave_last = false, bool pl_all = false) {
+    // pl_all: keep U11^-T of every block (s_PL holds nblk of them) for solve_upper_back_inv; else two buffers alternate
     // leave_last: stop before the last diagonal block — on return it holds the fully updated (unfactored) Schur
     // complement of the leading blocks and s_y its updated right-hand side; the caller factors it its own way
     // (marg.cu: with diagonal pivoting, because that is where a gauge-deficient matrix shows its tiny pivots).
@@ -118,7 +134,7 @@ __device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, in
             s_U[q] = (r < nb && c < nb && c >= r) ? S.at(r, c) : ((r == c) ? 1.0 : 0.0);
         }
         __syncwarp();
-        const bool ok = factor_diag_block_ldl(s_U, s_invd, s_PL, s_row);
+        const bool ok = factor_diag_block_ldl(s_U, s_invd, s_PL, s_row);  // (block 0 -> buffer 0 either way)
         if (lane == 0) s_okv[0] = ok ? 1 : 0;
         for (int q = lane; q < NB * NB; q += 32) {
             const int r = q / NB, c = q % NB;
@@ -138,7 +154,7 @@ __device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, in
         if (leave_last && blk == nblk - 1) break;
         const int j0 = blk * NB, nb = min(NB, D - j0);
         const int rest0 = j0 + nb, nrest = D - rest0, nb1 = min(NB, nrest);
-        const uint32_t pl = smem_u32(s_PL + (blk & 1) * NB * NB);  // U11^-T of this block
+        const uint32_t pl = smem_u32(s_PL + (pl_all ? blk : (blk & 1)) * NB * NB);  // U11^-T of this block
         if (wid == 0) {
             // ---- diagonal warp: panel columns of block blk+1, then look ahead ----
             double *Un = s_U + ((blk + 1) & 1) * NB * NB;
@@ -148,7 +164,14 @@ __device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, in
                 if (c < nb1) {
                     double a[NB];
 #pragma unroll
-                    for (int r = 0; r < NB; r++) a[r] = (r < nb) ? S.at(j0 + r, rest0 + c) : 0.0;
+                    {
+                        typename M::hnd e = S.h(j0, rest0 + c);
+#pragma unroll
+                        for (int r = 0; r < NB; r++) {
+                            a[r] = (r < nb) ? M::ld(e) : 0.0;
+                            e = S.down(e, j0 + r);
+                        }
+                    }
                     double out[NB / 2];
 #pragma unroll
                     for (int u = 0; u < NB / 2; u++) {
@@ -162,10 +185,12 @@ __device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, in
                         }
                         out[u] = e + o;
                     }
+                    typename M::hnd e = S.h(j0 + h, rest0 + c);
 #pragma unroll
                     for (int u = 0; u < NB / 2; u++) {
                         const int t = 2 * u + h;
-                        if (t < nb) S.at(j0 + t, rest0 + c) = out[u];
+                        if (t < nb) M::st(e, out[u]);
+                        e = S.down(S.down(e, j0 + t), j0 + t + 1);
                         s_panel[t * PW + c] = out[u];
                     }
                 }
@@ -195,7 +220,7 @@ __device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, in
                 }
                 __syncwarp();
                 SUB_MARK(1);
-                const bool ok = (leave_last && blk + 1 == nblk - 1) ? true : factor_diag_block_ldl(Un, s_invd + (blk + 1) * NB, s_PL + ((blk + 1) & 1) * NB * NB, s_row);
+                const bool ok = (leave_last && blk + 1 == nblk - 1) ? true : factor_diag_block_ldl(Un, s_invd + (blk + 1) * NB, s_PL + (pl_all ? blk + 1 : ((blk + 1) & 1)) * NB * NB, s_row);
                 if (lane == 0) s_okv[blk + 1] = ok ? 1 : 0;
                 for (int q = lane; q < NB * NB; q += 32) {
                     const int r = q / NB, cc = q % NB;
@@ -219,17 +244,32 @@ __device__ bool cholesky_lookahead(M S, int D, double *s_panel /* NB x PW */, in
                 const int rc = ccol(c);
                 double a[NB];
 #pragma unroll
-                for (int r = 0; r < NB; r++) a[r] = (r < nb) ? (is_rhs ? s_y[j0 + r] : S.at(j0 + r, rc)) : 0.0;
+                for (int r = 0; r < NB; r++) a[r] = 0.0;
+                const typename M::hnd e0 = S.h(j0, is_rhs ? j0 : rc);
+                if (is_rhs) {
+#pragma unroll
+                    for (int r = 0; r < NB; r++)
+                        if (r < nb) a[r] = s_y[j0 + r];
+                } else {
+                    typename M::hnd e = e0;
+#pragma unroll
+                    for (int r = 0; r < NB; r++) {
+                        if (r < nb) a[r] = M::ld(e);
+                        e = S.down(e, j0 + r);
+                    }
+                }
                 SUB_MARK(4);
                 panel_column_apply(a, pl);
                 SUB_MARK(5);
                 const int pc = is_rhs ? zc : c;
+                typename M::hnd e = e0;
 #pragma unroll
                 for (int r = 0; r < NB; r++) {
                     if (r < nb) {
                         if (is_rhs) s_y[j0 + r] = a[r];
-                        else S.at(j0 + r, rc) = a[r];
+                        else M::st(e, a[r]);
                     }
+                    e = S.down(e, j0 + r);
                     s_panel[r * PW + pc] = a[r];
                 }
             }
@@ -318,6 +358,45 @@ __device__ void solve_upper_back(M S, int D, double *y, const double *s_invd) {
 #pragma unroll 4
             for (int t = 0; t < nb; t++) sacc = fma(S.at(i, j0 + t), y[j0 + t], sacc);
             y[i] -= sacc;
+        }
+        __syncthreads();
+    }
+}
+
+// The same with the explicit inverses U11^-T of all diagonal blocks (cholesky_lookahead with pl_all): the block solve is a
+// 16-term dot product per unknown (two half sums + one shuffle) instead of 16 dependent shuffle + FMA steps.
+template <class M>
+__device__ void solve_upper_back_inv(M S, int D, double *y, const double *s_PL) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int nblk = (D + NB - 1) / NB;
+    const uint32_t ya = smem_u32(y), pla = smem_u32(s_PL);
+    for (int blk = nblk - 1; blk >= 0; blk--) {
+        const int j0 = blk * NB, nb = min(NB, D - j0);
+        if (tid < 32) {
+            const int c = lane & 15, r0 = (lane >> 4) * 8;
+            const uint32_t pl = pla + 8u * (blk * NB * NB);
+            double e = 0, o = 0;
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                const int r = r0 + u;
+                const double z0 = (r < nb) ? lds(ya + 8u * (j0 + r)) : 0.0, z1 = (r + 1 < nb) ? lds(ya + 8u * (j0 + r + 1)) : 0.0;
+                e = fma(lds(pl + 8u * (r * NB + c)), z0, e);  // U^-1 = (U^-T)^T: column c of the stored rows (zero above the diagonal)
+                o = fma(lds(pl + 8u * ((r + 1) * NB + c)), z1, o);
+            }
+            double acc = e + o;
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (lane < nb) sts(ya + 8u * (j0 + lane), acc);
+        }
+        __syncthreads();
+        for (int i = tid; i < j0; i += nt) {
+            const typename M::hnd e = S.h(i, j0);
+            double s0 = 0, s1 = 0;
+#pragma unroll 4
+            for (int t = 0; t < NB; t += 2) {
+                if (t < nb) s0 = fma(M::ld(M::right(e, t)), lds(ya + 8u * (j0 + t)), s0);
+                if (t + 1 < nb) s1 = fma(M::ld(M::right(e, t + 1)), lds(ya + 8u * (j0 + t + 1)), s1);
+            }
+            sts(ya + 8u * i, lds(ya + 8u * i) - (s0 + s1));
         }
         __syncthreads();
     }

@@ -330,7 +330,6 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
     extern __shared__ double smem[];
     __shared__ double s_red[33];
     __shared__ __align__(16) double s_U[2 * NB * NB];
-    __shared__ __align__(16) double s_PL[2 * NB * NB];
     __shared__ __align__(16) double s_row[2 * NB];
     __shared__ int s_okv[kMaxFrames * 15 / NB + 4];
     const StateLayout lay = P.lay;
@@ -347,7 +346,8 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
     double *s_y = s_panel + (size_t)NB * PW;       // D (padded to even)
     double *s_invd = s_y + ((D + 1) & ~1);         // nblk * NB reciprocal pivots
     double *s_a = s_invd + (size_t)nblk * NB;      // D (padded to even): Cauchy direction, reduced columns
-    double *s_S = s_a + ((D + 1) & ~1);            // packed upper triangle when use_smem
+    double *s_PL = s_a + ((D + 1) & ~1);           // nblk x NB x NB: U11^-T of every diagonal block
+    double *s_S = s_PL + (size_t)nblk * NB * NB;   // packed upper triangle when use_smem
     PHASE_MARK(0);
     const double mu = ctl->mu;
     double gg, jj_part = 0, gmax;
@@ -405,24 +405,35 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
         s_y[c] = w.rhs[c];
         if (clear_sys) w.rhs[c] = 0.0;
     }
-    // copy (or regularise in place) and, when fused, a_p^T S a_p on the way: one warp per row, coalesced upper triangle
+    // copy (or regularise in place) and, when fused, a_p^T S a_p on the way: coalesced upper triangle, four rows per warp
+    // and pass with all their loads issued before the first use (a row at a time cost one L2 round trip per row: 11 per warp)
     const MatPacked Sp{s_S, D};
-    for (int r = wid; r < D; r += nwarp) {
-        double *src = w.S + (size_t)r * D;
-        double *dst = use_smem ? &Sp.at(r, r) - r : src;
-        const double ar = fused ? s_a[r] : 0.0;
-        for (int c0 = r + lane; c0 < D; c0 += 32 * 6) {
-            double v[6];
+    constexpr int RG = 4;
+    for (int rb = wid * RG; rb < D; rb += nwarp * RG) {
+        for (int cb = lane; rb + cb < D; cb += 32 * 6) {
+            double v[RG][6];
 #pragma unroll
-            for (int u = 0; u < 6; u++) v[u] = (c0 + 32 * u < D) ? src[c0 + 32 * u] : 0.0;
+            for (int rr = 0; rr < RG; rr++) {
+                const int r = rb + rr;
 #pragma unroll
-            for (int u = 0; u < 6; u++) {
-                const int c = c0 + 32 * u;
-                if (c >= D) continue;
-                if (fused) jj_part += ar * v[u] * s_a[c] * (c == r ? 1.0 : 2.0);
-                if (use_smem) dst[c] = v[u] + (r == c ? w.diagonal[c] * w.diagonal[c] * mu : 0.0);
-                if (clear_sys) src[c] = 0.0;
-                else if (r == c) dst[c] = v[u] + w.diagonal[c] * w.diagonal[c] * mu;
+                for (int u = 0; u < 6; u++) v[rr][u] = (r < D && r + cb + 32 * u < D) ? w.S[(size_t)r * D + r + cb + 32 * u] : 0.0;
+            }
+#pragma unroll
+            for (int rr = 0; rr < RG; rr++) {
+                const int r = rb + rr;
+                if (r >= D) break;
+                double *src = w.S + (size_t)r * D;
+                double *dst = use_smem ? &Sp.at(r, r) - r : src;
+                const double ar = fused ? s_a[r] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 6; u++) {
+                    const int c = r + cb + 32 * u;
+                    if (c >= D) continue;
+                    if (fused) jj_part += ar * v[rr][u] * s_a[c] * (c == r ? 1.0 : 2.0);
+                    if (use_smem) dst[c] = v[rr][u] + (r == c ? w.diagonal[c] * w.diagonal[c] * mu : 0.0);
+                    if (clear_sys) src[c] = 0.0;
+                    else if (r == c) dst[c] = v[rr][u] + w.diagonal[c] * w.diagonal[c] * mu;
+                }
             }
         }
     }
@@ -440,8 +451,8 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
     __syncthreads();
     if (ctl->done != 0) return;
     PHASE_MARK(2);
-    if (use_smem) pd = cholesky_lookahead(Sp, D, s_panel, PW, s_U, s_PL, s_invd, s_y, s_okv, s_row, WindowProfile{lay.F});
-    else pd = cholesky_lookahead(MatFull{w.S, D}, D, s_panel, PW, s_U, s_PL, s_invd, s_y, s_okv, s_row, WindowProfile{lay.F});
+    if (use_smem) pd = cholesky_lookahead(Sp, D, s_panel, PW, s_U, s_PL, s_invd, s_y, s_okv, s_row, WindowProfile{lay.F}, false, true);
+    else pd = cholesky_lookahead(MatFull{w.S, D}, D, s_panel, PW, s_U, s_PL, s_invd, s_y, s_okv, s_row, WindowProfile{lay.F}, false, true);
     if (!pd) {
         if (tid == 0) ctl->pad = 0;
         __syncthreads();
@@ -449,8 +460,8 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
         return;
     }
     PHASE_MARK(3);
-    if (use_smem) solve_upper_back(Sp, D, s_y, s_invd);
-    else solve_upper_back(MatFull{w.S, D}, D, s_y, s_invd);
+    if (use_smem) solve_upper_back_inv(Sp, D, s_y, s_PL);
+    else solve_upper_back_inv(MatFull{w.S, D}, D, s_y, s_PL);
     PHASE_MARK(4);
     double gn2 = 0, gdot = 0;
     int bad = 0;
@@ -525,7 +536,7 @@ void chol_profile_read(long long *out) { cudaMemcpyFromSymbol(out, g_sub, sizeof
 static size_t chol_base_bytes(int D) {
     const int F = (D - 7) / 15;
     (void)F;
-    return sizeof(double) * ((size_t)NB * chol_panel_pitch(D) + 2 * (size_t)((D + 1) & ~1) + (size_t)cdiv(D, NB) * NB);
+    return sizeof(double) * ((size_t)NB * chol_panel_pitch(D) + 2 * (size_t)((D + 1) & ~1) + (size_t)cdiv(D, NB) * (NB + NB * NB));
 }
 static bool chol_in_smem(int D) { return chol_base_bytes(D) + sizeof(double) * ((size_t)D * (D + 1) / 2) <= 218 * 1024; }
 
