@@ -170,7 +170,12 @@ def build_workload(cfg_name: str, rank: int, n_frames_pool: int):
 def make_window_problem(wl, opts, rank, optimize, marginalize):
     """Steady-state Estimator::optimization() input: projection + IMU factors AND the marginalisation prior left by the
     previous frame (n = 76 at F = 11), produced by `optimize` / `marginalize` of the arm that is being timed."""
-    return wl["synthwin"].make_window_with_prior(optimize, marginalize, seed=rank + 1, n_frames=wl["window_size"] + 1,
+    # Weak scaling = the SAME work on every GPU: every rank solves the window of seed 1 (the image streams differ per rank).
+    # Round 1 seeded the window with the rank: windows whose trust-region steps are all accepted factor the reduced system 8
+    # times, others re-use it after a rejected step, and the max over ranks then measured that lottery (step_kernel 51 us per
+    # launch on two ranks, 88 us on the other two — the whole of round 1's "0.65 scaling efficiency").
+    del rank
+    return wl["synthwin"].make_window_with_prior(optimize, marginalize, seed=1, n_frames=wl["window_size"] + 1,
                                                  n_landmarks=wl["n_landmarks"], feats_per_frame=wl["max_cnt"], opts=opts,
                                                  perturb=0.3)
 
@@ -464,6 +469,25 @@ def main():
 
     import threading
 
+    # One process per GPU, NUMA-local: bind this rank to the CPUs next to its GPU BEFORE the CUDA context and the pinned buffers
+    # exist (torchrun does not bind).  Recorded in the line as per_rank[..].cpu_affinity.
+    numa_note = "unbound"
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis else local_rank
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            numa_note = f"{min(cpus)}-{max(cpus)} ({len(cpus)} cpus)"
+    except Exception as e:  # no NVML / not permitted: run unbound
+        numa_note = f"unbound ({type(e).__name__})"
+
     import torch
 
     import lfvio
@@ -517,6 +541,29 @@ def main():
     if clocks:
         clocks.start()
         clocks.wait_ready()
+    # The path is a chain of latency-sized kernels on one or a few SMs: its speed follows the SM clock, and a GPU that has been
+    # idle sits at a low clock for the first tenths of a second of such a light load (measured at N = 4: two ranks ran their
+    # solver stream 1.5x slower than the other two with identical kernels and a 0.01 ms host enqueue).  So every rank first
+    # brings ITS clock up with a dense load, then does the W warm-up steps; the SM clock of every rank is read (NVML, one call)
+    # right after the timed region and reported in per_rank.
+    def sm_clock_mhz():
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device() if not os.environ.get("CUDA_VISIBLE_DEVICES") else
+                                                  int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[torch.cuda.current_device()]))
+            return float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            return float("nan")
+
+    spin = torch.randn(4096, 4096, device=dev, dtype=torch.bfloat16)
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 1.0:
+        for _ in range(20):
+            spin = (spin @ spin).clamp_(-1, 1)
+        torch.cuda.synchronize()
+    del spin
     for k in range(args.warmup):
         step_dev(k)
     tracker.sync()
@@ -553,6 +600,7 @@ def main():
         t.join()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
+    my_sm_mhz = sm_clock_mhz()
     if clocks:
         clocks.mark_end()
     launches = lfvio.lib.lfvio_launch_count() - launches0
@@ -647,7 +695,7 @@ def main():
 
     # per-rank record (every N): which rank is the slow one, and whether its host or its device was
     mine = torch.tensor([my_ms_total / args.steps, ms_tracker / args.steps, ms_window / args.steps, 1e3 * enq[0] / args.steps,
-                         1e3 * enq[1] / args.steps, my_e2e_ms / e2e_steps, e2e_node_ms["tracker"], e2e_node_ms["estimator"]],
+                         1e3 * enq[1] / args.steps, my_e2e_ms / e2e_steps, e2e_node_ms["tracker"], e2e_node_ms["estimator"], my_sm_mhz],
                         dtype=torch.float64, device=dev)
     if world > 1:
         allr = [torch.zeros_like(mine) for _ in range(world)]
@@ -655,8 +703,15 @@ def main():
     else:
         allr = [mine]
     keys = ("ms_per_step", "ms_tracker_stream", "ms_window_stream", "host_enqueue_ms_tracker", "host_enqueue_ms_window",
-            "e2e_ms_per_step", "e2e_tracker_node_ms", "e2e_estimator_node_ms")
+            "e2e_ms_per_step", "e2e_tracker_node_ms", "e2e_estimator_node_ms", "sm_mhz_after_timed_region")
     per_rank = [{k: round(float(v), 5) for k, v in zip(keys, r_.tolist())} for r_ in allr]
+    if world > 1:
+        notes = [None] * world
+        dist.all_gather_object(notes, numa_note)
+    else:
+        notes = [numa_note]
+    for pr_, nt_ in zip(per_rank, notes):
+        pr_["cpu_affinity"] = nt_
 
     # ---- per-kernel durations, live (CUDA events on the launching streams), same workload ---------------
     prof_steps = min(args.steps, 200)
@@ -678,6 +733,16 @@ def main():
     for i in range(nw):
         if w_cnt[i]:
             stages[lfvio.lib.lfvio_window_stage_name(i).decode()] = (w_ms[i] / prof_steps, w_ms[i] / w_cnt[i], w_cnt[i] / prof_steps)
+    # per-rank kernel times of the solver chain (us per launch): tells a slow rank's slow KERNELS from gaps between them
+    chain = ("step_kernel", "evaluate_kernel(candidate)", "accumulate_kernel", "marginalize", "lk_kernel")
+    mine_k = torch.tensor([1e3 * stages[k_][1] if k_ in stages else float("nan") for k_ in chain], dtype=torch.float64, device=dev)
+    if world > 1:
+        allk = [torch.zeros_like(mine_k) for _ in range(world)]
+        dist.all_gather(allk, mine_k)
+    else:
+        allk = [mine_k]
+    for pr_, kk_ in zip(per_rank, allk):
+        pr_["us_per_launch"] = {k_: round(float(v_), 2) for k_, v_ in zip(chain, kk_.tolist())}
     # algorithmic bytes per launch group (SURVEY.md §8d / DESIGN.md)
     n_lk = max(n_tracks, 1)
     D = 15 * (wsz + 1) + 7

@@ -385,6 +385,7 @@ __device__ void solve_upper_back_inv(M S, int D, double *y, const double *s_PL) 
             }
             double acc = e + o;
             acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            __syncwarp();  // every lane has read its z before any lane overwrites one
             if (lane < nb) sts(ya + 8u * (j0 + lane), acc);
         }
         __syncthreads();

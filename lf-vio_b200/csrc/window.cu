@@ -13,6 +13,8 @@
 
 #include <map>
 
+#include <time.h>
+
 #include "backend.cuh"
 #include "marg.cuh"
 
@@ -715,10 +717,18 @@ extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *s
                                           const lfvio_solver_opts *opts, int margin_flag, lfvio_solve_summary *summary,
                                           lfvio_prior *prior_out) {
     clear_error();
+    // LFVIO_DEBUG_HOST=1: where the host time of this call goes (averages printed every 200 calls)
+    static const bool dbg_host = getenv("LFVIO_DEBUG_HOST") != nullptr;
+    static double t_acc[6] = {0, 0, 0, 0, 0, 0};
+    static int t_calls = 0;
+    auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    double t_prev = dbg_host ? now_us() : 0.0;
+    auto lap = [&](int i) { if (dbg_host) { const double t = now_us(); t_acc[i] += t - t_prev; t_prev = t; } };
     LFVIO_REQUIRE(w && prior_out, "lfvio_window_optimize_full: null argument");
     LFVIO_REQUIRE(margin_flag == LFVIO_MARGIN_OLD || margin_flag == LFVIO_MARGIN_SECOND_NEW, "lfvio_window_optimize_full: bad margin_flag");
     LFVIO_CUDA_TRY(cudaSetDevice(w->device));
     LFVIO_TRY(upload(w, state, factors, opts, /*defer_plans=*/true, /*defer_prepare=*/true));
+    lap(0);
     cudaStream_t s = w->stream;
     const DevProblem &P = w->P;
     const int size_cap = StateLayout{w->F, w->Lmax}.size();
@@ -731,7 +741,9 @@ extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *s
         LFVIO_LAUNCH_CHECK();
         return LFVIO_OK;
     }));
+    lap(1);
     LFVIO_TRY(build_marg_plan(w, margin_flag, factors, opts, state->n_landmarks));  // host work under the running solve
+    lap(2);
     prior_out->n = 0;
     prior_out->n_blocks = 0;
     const bool do_marg = w->plan_valid[margin_flag];
@@ -750,7 +762,9 @@ extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *s
         for (int b = 0; b < pl.n_keep; b++) x0_len += P.lay.block_gsize(pl.keep_id[b]);
         LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg, w->marg_out.p, sizeof(double) * (nn + pl.n + x0_len), cudaMemcpyDeviceToHost, s));
     }
+    lap(3);
     LFVIO_TRY(download(w, state, summary, false));
+    lap(4);
     if (do_marg && getenv("LFVIO_DEBUG_STEP")) {
         long long mc[8];
         marg_profile_read(mc);
@@ -775,6 +789,12 @@ extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *s
         memcpy(prior_out->J0, w->h_marg, sizeof(double) * nn);
         memcpy(prior_out->r0, w->h_marg + nn, sizeof(double) * pl.n);
         memcpy(prior_out->x0, w->h_marg + nn + pl.n, sizeof(double) * x0_len);
+    }
+    lap(5);
+    if (dbg_host && ++t_calls % 200 == 0) {
+        static const char *nm[6] = {"upload (pack + enqueue H2D)", "enqueue graph 1 (solve)", "marginalisation plan (host)", "enqueue graph 2 + D2H",
+                                    "download (wait for the stream + copy out)", "prior copy out"};
+        for (int i = 0; i < 6; i++) fprintf(stderr, "optimize_full host %-44s %8.1f us\n", nm[i], t_acc[i] / t_calls);
     }
     return LFVIO_OK;
 }

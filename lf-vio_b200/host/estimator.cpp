@@ -422,6 +422,10 @@ void Estimator::processImage(const ImageFeatures &image, double header_stamp) {
     last_P0 = Ps[0];
 }
 
+void Estimator::pokeCovariance(int j) {
+    if (j >= 0 && j < (int)m_pre.size()) memset(m_pre[j].covariance, 0, sizeof(m_pre[j].covariance));
+}
+
 void Estimator::setParameter() {
     tic[0] = TIC0;
     ric[0] = RIC0;
@@ -674,7 +678,36 @@ void Estimator::optimization() {
     const int L = f_manager.getFeatureCount();
     lfvio_window_state st{WINDOW_SIZE + 1, L, para_Pose.data(), para_SpeedBias.data(), para_Ex_Pose[0], para_Feature.data(), para_Td[0]};
     lfvio_factor_list fl{(int)m_proj.size(), m_proj.data(), (int)m_imu.size(), m_imu.data(), lm.valid() ? &prior : nullptr};
+    // A failed solve is not fatal in the reference: ceres::Solve (estimator.cpp:825) leaves the parameter blocks at the last
+    // accepted state, optimization() goes on to the marginalisation, processImage() to failureDetection() / slideWindow().
+    // Same here for the numeric and capacity failures of the device solve; only CUDA / argument errors stop the estimator.
+    const auto pose0 = para_Pose;
+    const auto sb0 = para_SpeedBias;
+    const auto feat0 = para_Feature;
+    double ex0[7];
+    memcpy(ex0, para_Ex_Pose[0], sizeof(ex0));
+    const double td0 = para_Td[0][0];
     last_status = lfvio_window_optimize(m_window, &st, &fl, &o, &summary);  // ceres::Solve (estimator.cpp:825)
+    if (last_status == LFVIO_ERR_NUMERIC || last_status == LFVIO_ERR_CAPACITY) {
+        solve_failures++;
+        last_solve_failure = last_status;
+        last_status = LFVIO_OK;
+        bool finite = true;
+        for (double v : para_Pose) finite = finite && std::isfinite(v);
+        for (double v : para_SpeedBias) finite = finite && std::isfinite(v);
+        if (!finite || last_solve_failure == LFVIO_ERR_CAPACITY) {  // nothing usable came back: the state the solve started from
+            para_Pose = pose0;
+            para_SpeedBias = sb0;
+            memcpy(para_Ex_Pose[0], ex0, sizeof(ex0));
+            para_Feature = feat0;
+            para_Td[0][0] = td0;
+        }
+        if (last_solve_failure == LFVIO_ERR_CAPACITY) {  // the marginalisation would hit the same limit: go on without a prior
+            double2vector();
+            last_marginalization_info = MarginalizationInfo{};
+            return;
+        }
+    }
     if (last_status != LFVIO_OK) return;
     double2vector();
     // ---- next prior (estimator.cpp:833-1005): the dropped factors are evaluated at the re-anchored state ----
@@ -696,11 +729,22 @@ void Estimator::optimization() {
     out.cap_n = nmax;
     out.cap_blocks = bmax;
     last_status = lfvio_window_marginalize(m_window, &st, &fl, &o, marginalization_flag == MARGIN_OLD ? LFVIO_MARGIN_OLD : LFVIO_MARGIN_SECOND_NEW, &out);
+    if (last_status == LFVIO_ERR_NUMERIC || last_status == LFVIO_ERR_CAPACITY) {  // no usable prior: drop it (its block ids would be stale after the slide)
+        solve_failures++;
+        last_solve_failure = last_status;
+        last_status = LFVIO_OK;
+        last_marginalization_info = MarginalizationInfo{};
+        return;
+    }
     if (last_status != LFVIO_OK) return;
     if (out.n > 0) {  // MARGIN_SECOND_NEW without a matching prior leaves the old one in place (estimator.cpp:942-943)
         next.n = out.n;
         next.n_blocks = out.n_blocks;
         last_marginalization_info = std::move(next);
+    } else if (marginalization_flag == MARGIN_OLD) {
+        // the reference replaces the prior unconditionally (estimator.cpp:933-936); the window is about to shift, so a kept
+        // prior would name the wrong frames
+        last_marginalization_info = MarginalizationInfo{};
     }
 }
 
@@ -962,6 +1006,14 @@ extern "C" int lfvio_host_estimator_poke_last_p(void *h, double dx) {
     auto *e = static_cast<lfvio_host::Estimator *>(h);
     e->last_P[0] += dx;
     return e->reboot_count;
+}
+
+// test hook: make the covariance of pre_integrations[j] singular, so that the next solves fail numerically (LFVIO_ERR_NUMERIC)
+// until that interval has left the window; returns how many failed solves the estimator has survived so far
+extern "C" int lfvio_host_estimator_poke_covariance(void *h, int j) {
+    auto *e = static_cast<lfvio_host::Estimator *>(h);
+    e->pokeCovariance(j);
+    return e->solve_failures;
 }
 
 extern "C" int lfvio_host_estimator_process_image(void *h, const int *ids, const double *feat8, int n, double stamp) {

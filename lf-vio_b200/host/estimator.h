@@ -17,6 +17,20 @@
 
 #include "lfvio.h"
 
+#if !defined(LFVIO_HOST_NO_EIGEN) && defined(__has_include)
+#if __has_include(<Eigen/Dense>)
+#include <Eigen/Dense>
+#define LFVIO_HOST_HAVE_EIGEN 1
+#elif __has_include(<eigen3/Eigen/Dense>)
+#include <eigen3/Eigen/Dense>
+#define LFVIO_HOST_HAVE_EIGEN 1
+#endif
+#if __has_include(<std_msgs/Header.h>)
+#include <std_msgs/Header.h>
+#define LFVIO_HOST_HAVE_ROS_HEADER 1
+#endif
+#endif
+
 namespace lfvio_host {
 
 using Vec3 = std::array<double, 3>;
@@ -128,6 +142,19 @@ class Estimator {
     // INITIAL the window only fills and slides; the caller switches to NON_LINEAR once the states are initialised.
     enum SolverFlag { INITIAL = 0, NON_LINEAR = 1 };
     void processImage(const ImageFeatures &image, double header_stamp);
+#if defined(LFVIO_HOST_HAVE_EIGEN) && defined(LFVIO_HOST_HAVE_ROS_HEADER)
+    // the reference's own signature (estimator.h:35)
+    void processImage(const std::map<int, std::vector<std::pair<int, Eigen::Matrix<double, 8, 1>>>> &image, const std_msgs::Header &header) {
+        ImageFeatures f;
+        for (const auto &kv : image)
+            for (const auto &obs : kv.second) {
+                std::array<double, 8> a;
+                for (int k = 0; k < 8; k++) a[k] = obs.second(k);
+                f[kv.first].emplace_back(obs.first, a);
+            }
+        processImage(f, header.stamp.toSec());
+    }
+#endif
     // estimator.cpp:10-21 / :23-84.  TIC / RIC / TD are globals of parameters.cpp in the reference; the mirror keeps the
     // configured extrinsics per instance (TIC0 / RIC0) and TD as the global it is there.
     void setParameter();
@@ -135,6 +162,9 @@ class Estimator {
     Vec3 TIC0{0, 0, 0};
     Mat3 RIC0{1, 0, 0, 0, 1, 0, 0, 0, 1};
     int reboot_count = 0;  // how often failureDetection() rebooted the estimator (estimator.cpp:196-204)
+    void pokeCovariance(int j);  // test hook: make pre_integrations[j]'s covariance singular
+    int solve_failures = 0;      // solves / marginalisations that failed numerically or on capacity and were survived
+    int last_solve_failure = 0;  // status of the last such failure
     // estimator.cpp:221-376 / :378-455 / :457-484: the numeric steps run on the device through lfvio_solve_relative_rt,
     // lfvio_global_sfm, lfvio_epnp (all non-keyframes in one call), lfvio_solve_gyro_bias, lfvio_preintegrate (the
     // repropagations, batched) and lfvio_linear_alignment.

@@ -1,6 +1,8 @@
 // Implementation of the FeatureTracker / OCAMCamera host mirrors: pure plumbing over the C-ABI (no image math here).
 #include "feature_tracker.h"
 
+#include <cmath>
+
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -78,6 +80,19 @@ void OCAMCamera::liftProjective(const Vector2d &p, Vector3d &P) const {
 }
 void OCAMCamera::liftSphere(const Vector2d &p, Vector3d &P) const {
     lfvio_lift_projective(&mParameters, p.data(), P.data(), 1, 1, m_device);
+}
+void OCAMCamera::spaceToPlane(const Vector3d &P, Vector2d &p) const {
+    const double norm = std::sqrt(P[0] * P[0] + P[1] * P[1]);
+    const double theta = std::atan2(-P[2], norm);
+    double rho = 0.0, theta_i = 1.0;
+    for (int i = 0; i < 20; i++) {
+        rho += theta_i * mParameters.inv_poly[i];
+        theta_i *= theta;
+    }
+    const double invNorm = 1.0 / norm;
+    const double xn0 = P[0] * invNorm * rho, xn1 = P[1] * invNorm * rho;
+    p[0] = xn0 * mParameters.C + xn1 * mParameters.D + mParameters.cx;
+    p[1] = xn0 * mParameters.E + xn1 + mParameters.cy;
 }
 bool OCAMCamera::liftProjective(const std::vector<Vector2d> &p, std::vector<Vector3d> &P, bool normalize) const {
     P.resize(p.size());
@@ -250,4 +265,17 @@ extern "C" int lfvio_host_tracker_run(const lfvio_ocam *cam, const uint8_t *fram
     *n_out = m;
     *n_id_out = FeatureTracker::n_id;
     return m > 0 ? LFVIO_OK : LFVIO_ERR_CUDA;
+}
+
+// test hook (tests/test_signature_dropin.py): OCAMCamera::spaceToPlane of the host mirror, batched
+extern "C" int lfvio_host_ocam_space_to_plane(const lfvio_ocam *cam, const double *xyz, double *uv, int n) {
+    if (!cam || !xyz || !uv) return LFVIO_ERR_ARG;
+    lfvio_host::camodocal::OCAMCamera c(*cam);
+    for (int i = 0; i < n; i++) {
+        lfvio_host::Vector2d p;
+        c.spaceToPlane(lfvio_host::Vector3d{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, p);
+        uv[2 * i] = p[0];
+        uv[2 * i + 1] = p[1];
+    }
+    return LFVIO_OK;
 }

@@ -15,6 +15,25 @@
 
 #include "lfvio.h"
 
+// Where the reference's third-party types exist, the mirrors also carry the reference's own signatures (so that
+// feature_tracker_node.cpp / estimator_node.cpp call them unchanged): readImage(const cv::Mat &, double), fisheye_mask / cur_img
+// as cv::Mat, liftProjective / spaceToPlane on Eigen vectors.  -DLFVIO_HOST_NO_OPENCV / -DLFVIO_HOST_NO_EIGEN switch them off.
+#if !defined(LFVIO_HOST_NO_OPENCV) && defined(__has_include)
+#if __has_include(<opencv2/core.hpp>)
+#include <opencv2/core.hpp>
+#define LFVIO_HOST_HAVE_OPENCV 1
+#endif
+#endif
+#if !defined(LFVIO_HOST_NO_EIGEN) && defined(__has_include)
+#if __has_include(<Eigen/Dense>)
+#include <Eigen/Dense>
+#define LFVIO_HOST_HAVE_EIGEN 1
+#elif __has_include(<eigen3/Eigen/Dense>)
+#include <eigen3/Eigen/Dense>
+#define LFVIO_HOST_HAVE_EIGEN 1
+#endif
+#endif
+
 namespace lfvio_host {
 
 struct Point2f {
@@ -52,6 +71,25 @@ class Camera {
     virtual ~Camera() {}
     virtual void liftSphere(const Vector2d &p, Vector3d &P) const = 0;      // Camera.h:72
     virtual void liftProjective(const Vector2d &p, Vector3d &P) const = 0;  // Camera.h:76
+    virtual void spaceToPlane(const Vector3d &P, Vector2d &p) const = 0;    // Camera.h:80
+#ifdef LFVIO_HOST_HAVE_EIGEN
+    // the reference's own signatures (Camera.h:72-80)
+    void liftSphere(const Eigen::Vector2d &p, Eigen::Vector3d &P) const {
+        Vector3d o;
+        liftSphere(Vector2d{p[0], p[1]}, o);
+        P = Eigen::Vector3d(o[0], o[1], o[2]);
+    }
+    void liftProjective(const Eigen::Vector2d &p, Eigen::Vector3d &P) const {
+        Vector3d o;
+        liftProjective(Vector2d{p[0], p[1]}, o);
+        P = Eigen::Vector3d(o[0], o[1], o[2]);
+    }
+    void spaceToPlane(const Eigen::Vector3d &P, Eigen::Vector2d &p) const {
+        Vector2d o;
+        spaceToPlane(Vector3d{P[0], P[1], P[2]}, o);
+        p = Eigen::Vector2d(o[0], o[1]);
+    }
+#endif
     virtual int imageWidth() const = 0;
     virtual int imageHeight() const = 0;
 };
@@ -63,6 +101,10 @@ class OCAMCamera : public Camera {
     explicit OCAMCamera(const lfvio_ocam &params, int device = 0) : mParameters(params), m_device(device) {}
     void liftSphere(const Vector2d &p, Vector3d &P) const override;
     void liftProjective(const Vector2d &p, Vector3d &P) const override;
+    void spaceToPlane(const Vector3d &P, Vector2d &p) const override;  // ScaramuzzaCamera.cc:653-674 (host arithmetic, as in the reference)
+    using Camera::liftProjective;
+    using Camera::liftSphere;
+    using Camera::spaceToPlane;
     // batched forms (what the tracker uses): uv n x 2 -> xyz n x 3
     bool liftProjective(const std::vector<Vector2d> &p, std::vector<Vector3d> &P, bool normalize = false) const;
     int imageWidth() const override { return mParameters.image_width; }
@@ -87,6 +129,18 @@ class FeatureTracker {
     FeatureTracker &operator=(const FeatureTracker &) = delete;
 
     void readImage(const ImageView &_img, double _cur_time);        // feature_tracker.cpp:95-184
+#ifdef LFVIO_HOST_HAVE_OPENCV
+    // the reference's own signature (feature_tracker.h:39): a CV_8UC1 image, continuous or not
+    void readImage(const cv::Mat &_img, double _cur_time) { readImage(ImageView{_img.data, _img.rows, _img.cols, (int)_img.step}, _cur_time); }
+    // members the node reads (feature_tracker.h:56-57).  The annulus mask is rasterised on the device from CENTER_X/Y, MIN_R,
+    // MAX_R (what feature_tracker_node.cpp builds into fisheye_mask); both members are refreshed from the device on demand.
+    cv::Mat fisheye_mask, cur_img;
+    bool fetchMaskMat() {
+        if (!fetchMask()) return false;
+        fisheye_mask = cv::Mat(ROW, COL, CV_8UC1, mask.data());
+        return true;
+    }
+#endif
     bool updateID(unsigned int i);                                   // :388-398
     void readIntrinsicParameter(const std::string &calib_file);     // :400-404
     void setCamera(const camodocal::CameraPtr &cam, const lfvio_ocam &params);

@@ -425,3 +425,48 @@ def test_estimator_class_failure_reboot_and_reinitialisation(lfvio_mod, gpu, hos
     ate = violoop.ate_rmse(np.array(est_pos), np.array(true_pos))
     print(f"reboot at frame {k_fail}: re-initialised at frame {k_fail + F}, ATE of the {len(est_pos)} frames after it = {ate:.4f} m")
     assert len(est_pos) == world.n_frames - (k_fail + F) and ate < 0.05, ate
+
+
+def test_estimator_class_survives_a_failed_solve(lfvio_mod, gpu, host):
+    """A solve that fails numerically is not fatal (the reference's ceres::Solve leaves the state at the last accepted point
+    and processImage goes on to failureDetection / slideWindow, estimator.cpp:183-215): a pre-integration with a singular
+    covariance makes lfvio_window_optimize return LFVIO_ERR_NUMERIC for as long as it stays in the window; the window must keep
+    sliding (frame_count stays WINDOW_SIZE, tracks do not outgrow it) and the estimator must track again afterwards."""
+    from lfvio import synthwin, violoop
+
+    E = synthwin.ESTIMATOR
+    old_td = E["td"]
+    E["td"] = 0.0
+    try:
+        world = violoop.World(seed=4, n_frames=45, pixel_noise=0.1)
+    finally:
+        E["td"] = old_td
+    F = 11
+    vp = lambda a: np.ascontiguousarray(a, np.float64).ctypes.data_as(C.c_void_p)
+    _bind_estimator(host)
+    host.lfvio_host_estimator_poke_covariance.argtypes = [C.c_void_p, C.c_int]
+    est = host.lfvio_host_estimator_create(10, 1000, gpu)
+    assert est, lfvio_mod.lib.lfvio_last_error()
+    keep = [np.ascontiguousarray(x, np.float64) for x in (world.noise, world.G, world.tic, world.ric, np.zeros(3), np.zeros(3))]
+    assert host.lfvio_host_estimator_set_params(est, vp(keep[0]), vp(keep[1]), vp(keep[2]), vp(keep[3]), 0.0, 0.0, 0, vp(keep[4]), vp(keep[5])) == 0
+    assert host.lfvio_host_estimator_enable_initialization(est, 9, 0) == 0
+    P, R, V = np.zeros((F, 3)), np.zeros((F, 9)), np.zeros((F, 3))
+    ba, bg, td, info = np.zeros((F, 3)), np.zeros((F, 3)), np.zeros(1), np.zeros(8, np.int32)
+    k_poke, failures, est_pos, true_pos = 20, [], [], []
+    for k in range(world.n_frames):
+        if k == k_poke:
+            host.lfvio_host_estimator_poke_covariance(est, 3)
+        assert _feed(host, est, world, k, vp) == 0, lfvio_mod.lib.lfvio_last_error()   # never a fatal status
+        failures.append(host.lfvio_host_estimator_poke_covariance(est, -1))
+        host.lfvio_host_estimator_get(est, vp(P), vp(R), vp(V), vp(ba), vp(bg), vp(td), info.ctypes.data_as(C.c_void_p))
+        if k >= F - 1:
+            assert info[3] == F - 1, (k, info[3])                                          # the window kept sliding
+        if k >= k_poke + 8:
+            est_pos.append(P[F - 1].copy())
+            true_pos.append(world.truth(k)[0])
+    host.lfvio_host_estimator_destroy(est)
+    assert failures[k_poke - 1] == 0 and failures[k_poke] >= 1                             # the poisoned solve failed and was survived
+    assert failures[-1] == failures[k_poke + 6]                                            # and stopped failing once the interval left the window
+    ate = violoop.ate_rmse(np.array(est_pos), np.array(true_pos))
+    print(f"{failures[-1]} failed solves survived; ATE of the {len(est_pos)} frames afterwards = {ate:.4f} m")
+    assert np.isfinite(P).all() and ate < 0.5, ate
