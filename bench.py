@@ -543,9 +543,9 @@ def main():
         clocks.wait_ready()
     # The path is a chain of latency-sized kernels on one or a few SMs: its speed follows the SM clock, and a GPU that has been
     # idle sits at a low clock for the first tenths of a second of such a light load (measured at N = 4: two ranks ran their
-    # solver stream 1.5x slower than the other two with identical kernels and a 0.01 ms host enqueue).  So every rank first
-    # brings ITS clock up with a dense load, then does the W warm-up steps; the SM clock of every rank is read (NVML, one call)
-    # right after the timed region and reported in per_rank.
+    # solver stream 1.5x slower than the other two — which turned out to be the rank-seeded window, not the clock: all four read
+    # 1965 MHz).  Every rank still runs the path for half a second before the W warm-up steps, and the SM clock of every rank is
+    # read (NVML, one call) right after the timed region and reported in per_rank, so that a cold rank would show.
     def sm_clock_mhz():
         try:
             import pynvml
@@ -557,13 +557,13 @@ def main():
         except Exception:
             return float("nan")
 
-    spin = torch.randn(4096, 4096, device=dev, dtype=torch.bfloat16)
     t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 1.0:
-        for _ in range(20):
-            spin = (spin @ spin).clamp_(-1, 1)
-        torch.cuda.synchronize()
-    del spin
+    k_spin = 0
+    while time.perf_counter() - t_spin < 0.5:  # the path itself, half a second, before the W warm-up steps (own kernels only)
+        for _ in range(32):
+            step_dev(k_spin)
+            k_spin += 1
+        tracker.sync()
     for k in range(args.warmup):
         step_dev(k)
     tracker.sync()

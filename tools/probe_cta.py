@@ -13,7 +13,7 @@ for _ in range(5):
     win.optimize_dev(True, B.MARGIN_OLD)
 s = win.download(w.clone())
 L = lfvio.lib
-nbp = (w.n_proj + 127) // 128
+nbp = 2 * (((w.n_proj + 127) // 128 + 7) // 8 * 8)  # two threads per factor, CTA count bucketed to 8 (window.cu)
 for name, fn, ncta, groups in (("evaluate", L.lfvio_debug_eval_prof, nbp + w.n_imu + 1, [("proj", 0, nbp), ("imu", nbp, nbp + w.n_imu), ("prior", nbp + w.n_imu, nbp + w.n_imu + 1)]),
                                ("accumulate", L.lfvio_debug_acc_prof, w.L + w.n_imu + 8, [("landmark", 0, w.L), ("imu", w.L, w.L + w.n_imu), ("prior", w.L + w.n_imu, w.L + w.n_imu + 8)])):
     buf = np.zeros((ncta, 4), np.int64)
