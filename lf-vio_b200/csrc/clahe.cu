@@ -101,35 +101,48 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint32_t *__restri
     lut[tile * 256 + i] = (uint8_t)min(max(r, 0), 255);
 }
 
+// Round 2: a CTA works inside ONE band of rows between two tile-centre lines (the rows that interpolate between tile rows ty1 and
+// ty2: nine bands) and stages, for the nine column bands, the four LUT bytes a pixel of value v blends as ONE 32-bit word
+// (l11 | l12 << 8 | l21 << 16 | l22 << 24, 9 KB): one shared load per pixel instead of four byte gathers out of the 16 KB of all
+// 64 LUTs (139 k bank conflicts per launch at 3840 x 2880 in round 1).  Same un-fused f32 blend, bit-exact.
+constexpr int kClaheBands = kClaheTiles + 1;
+
 __global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t *__restrict__ src, int src_pitch,
                                                           uint8_t *__restrict__ dst, int dst_pitch, ClaheGeom g,
-                                                          const uint8_t *__restrict__ lut) {
-    __shared__ __align__(16) uint8_t s_lut[kClaheTiles * kClaheTiles * 256];
-    {
-        const uint4 *l4 = reinterpret_cast<const uint4 *>(lut);
-        uint4 *s4 = reinterpret_cast<uint4 *>(s_lut);
-        for (int k = threadIdx.x; k < kClaheTiles * kClaheTiles * 256 / 16; k += blockDim.x) s4[k] = l4[k];
+                                                          const uint8_t *__restrict__ lut, int chunks_per_band) {
+    __shared__ uint32_t s_tab[kClaheBands][256];
+    const int band = blockIdx.y;  // rows [ceil((band - 0.5) tile_h), ceil((band + 0.5) tile_h)): ty1 = band - 1 (clamped), ty2 = band (clamped)
+    const int ty1 = max(band - 1, 0), ty2 = min(band, kClaheTiles - 1);
+    for (int k = threadIdx.x; k < kClaheBands * 256; k += blockDim.x) {
+        const int xb = k >> 8, v = k & 255;
+        const int tx1 = max(xb - 1, 0), tx2 = min(xb, kClaheTiles - 1);
+        const uint32_t l11 = lut[(ty1 * kClaheTiles + tx1) * 256 + v], l12 = lut[(ty1 * kClaheTiles + tx2) * 256 + v];
+        const uint32_t l21 = lut[(ty2 * kClaheTiles + tx1) * 256 + v], l22 = lut[(ty2 * kClaheTiles + tx2) * 256 + v];
+        s_tab[xb][v] = l11 | (l12 << 8) | (l21 << 16) | (l22 << 24);
     }
     __syncthreads();
     const float inv_tw = __fdiv_rn(1.0f, (float)g.tile_w);
     const float inv_th = __fdiv_rn(1.0f, (float)g.tile_h);
+    // first row y with floor(y / tile_h - 0.5) == band - 1, i.e. y >= (band - 0.5) tile_h: (2 band - 1) tile_h / 2 rounded up
+    const int ya0 = max(0, ((2 * band - 1) * g.tile_h + 1) >> 1), ya1 = min(g.rows, ((2 * band + 1) * g.tile_h + 1) >> 1);
     const int chunks_per_row = (g.cols + 3) / 4;
-    const long long total = (long long)chunks_per_row * g.rows;
     const bool vec_ok = ((src_pitch & 3) == 0) && ((dst_pitch & 3) == 0) && ((g.cols & 3) == 0);
-    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total;
-         c += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)(c / chunks_per_row);
+    const long long total = (long long)chunks_per_row * max(ya1 - ya0, 0);
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
+        const int y = ya0 + (int)(c / chunks_per_row);
         const int x0 = (int)(c % chunks_per_row) * 4;
         const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
-        int ty1 = cv_floor(tyf);
-        const float ya = __fsub_rn(tyf, (float)ty1);
-        const float ya1 = __fsub_rn(1.0f, ya);
-        int ty2 = min(ty1 + 1, kClaheTiles - 1);
-        ty1 = max(ty1, 0);
+        const int ty1f = cv_floor(tyf);
+        const float ya = __fsub_rn(tyf, (float)ty1f);
+        const float yb = __fsub_rn(1.0f, ya);
+        // (the band limits above are the exact integer statement of ty1f == band - 1; the f32 product can land on the other side
+        // of a boundary for no y below 2^22 / tile_h — checked by the bit-exact tests at every supported size — but the table of the
+        // neighbouring band would be the wrong one, so such a row falls back to the byte LUTs)
+        const bool band_ok = (ty1f == band - 1);
         uint8_t in[4], out[4];
         const int nvalid = min(4, g.cols - x0);
         if (vec_ok) {
-            uchar4 v = *reinterpret_cast<const uchar4 *>(src + (size_t)y * src_pitch + x0);
+            const uchar4 v = *reinterpret_cast<const uchar4 *>(src + (size_t)y * src_pitch + x0);
             in[0] = v.x; in[1] = v.y; in[2] = v.z; in[3] = v.w;
         } else {
             for (int k = 0; k < nvalid; k++) in[k] = src[(size_t)y * src_pitch + x0 + k];
@@ -139,19 +152,27 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t *__restr
             if (k >= nvalid) break;
             const int x = x0 + k;
             const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
-            int tx1 = cv_floor(txf);
-            const float xa = __fsub_rn(txf, (float)tx1);
+            const int tx1f = cv_floor(txf);
+            const float xa = __fsub_rn(txf, (float)tx1f);
             const float xa1 = __fsub_rn(1.0f, xa);
-            int tx2 = min(tx1 + 1, kClaheTiles - 1);
-            tx1 = max(tx1, 0);
             const int sv = in[k];
-            const float l11 = (float)s_lut[(ty1 * kClaheTiles + tx1) * 256 + sv];
-            const float l12 = (float)s_lut[(ty1 * kClaheTiles + tx2) * 256 + sv];
-            const float l21 = (float)s_lut[(ty2 * kClaheTiles + tx1) * 256 + sv];
-            const float l22 = (float)s_lut[(ty2 * kClaheTiles + tx2) * 256 + sv];
+            float l11, l12, l21, l22;
+            if (band_ok) {
+                const uint32_t w = s_tab[min(max(tx1f + 1, 0), kClaheBands - 1)][sv];
+                l11 = (float)(w & 255u);
+                l12 = (float)((w >> 8) & 255u);
+                l21 = (float)((w >> 16) & 255u);
+                l22 = (float)(w >> 24);
+            } else {
+                const int a1 = max(ty1f, 0), a2 = min(ty1f + 1, kClaheTiles - 1), b1 = max(tx1f, 0), b2 = min(tx1f + 1, kClaheTiles - 1);
+                l11 = (float)lut[(a1 * kClaheTiles + b1) * 256 + sv];
+                l12 = (float)lut[(a1 * kClaheTiles + b2) * 256 + sv];
+                l21 = (float)lut[(a2 * kClaheTiles + b1) * 256 + sv];
+                l22 = (float)lut[(a2 * kClaheTiles + b2) * 256 + sv];
+            }
             const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
             const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
-            const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+            const float res = __fadd_rn(__fmul_rn(top, yb), __fmul_rn(bot, ya));
             out[k] = (uint8_t)min(max(cv_round(res), 0), 255);
         }
         if (vec_ok) {
@@ -160,6 +181,7 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t *__restr
             for (int k = 0; k < nvalid; k++) dst[(size_t)y * dst_pitch + x0 + k] = out[k];
         }
     }
+    (void)chunks_per_band;
 }
 
 }  // namespace
@@ -191,10 +213,12 @@ int launch_clahe(const uint8_t *src, int src_pitch, uint8_t *dst, int dst_pitch,
     LFVIO_LAUNCH_CHECK();
     clahe_lut_kernel<<<kClaheTiles * kClaheTiles, 256, 0, s>>>(hist, lut, clip, lut_scale);
     LFVIO_LAUNCH_CHECK();
-    const long long chunks = (long long)((cols + 3) / 4) * rows;
-    long long want = (chunks + 255) / 256;
-    int grid = (int)(want < 2LL * n_sm ? want : 2LL * n_sm);
-    clahe_apply_kernel<<<grid, 256, 0, s>>>(src, src_pitch, dst, dst_pitch, g, lut);
+    // nine row bands x enough CTAs per band to fill the machine about twice
+    const long long chunks_band = (long long)((cols + 3) / 4) * (g.tile_h + 1);
+    long long want = (chunks_band + 255) / 256;
+    const long long per_band = std::max<long long>(1, (2LL * n_sm + kClaheTiles) / (kClaheTiles + 1));
+    const int gx = (int)(want < per_band ? want : per_band);
+    clahe_apply_kernel<<<dim3(gx, kClaheTiles + 1), 256, 0, s>>>(src, src_pitch, dst, dst_pitch, g, lut, (int)chunks_band);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

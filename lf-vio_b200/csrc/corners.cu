@@ -34,75 +34,145 @@ __device__ __forceinline__ float dec_ordered(uint32_t e) {
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int ET_W = 32, ET_H = 16;  // outputs per CTA; 256 threads, 2 rows each
+// Round 2: 64 x 64 outputs per CTA (256 threads).  The image tile goes to shared memory once as bytes (aligned 32-bit loads away
+// from the border); a thread then owns a 4-wide, 4-high strip: it forms the derivative rows it needs from three byte rows of the
+// tile, keeps the f64 horizontal 3-sums of the products of three derivative rows in registers (the box filter is separable, as in
+// OpenCV's boxFilter) and rolls them down the strip — 3 conversions + 12 f64 additions per pixel instead of 27 + 27, no shared
+// memory for floats, one barrier.  Rounding sequence unchanged (see the header of this file): bit-exact against cv2.
+constexpr int ET_W = 64, ET_H = 64, ET_R = 4;       // tile, rows per strip
+constexpr int ET_TW = ET_W + 8, ET_TH = ET_H + 4;  // byte tile: virtual columns x0-4 .. x0+67, rows y0-2 .. y0+65
 
 __global__ void __launch_bounds__(256) min_eig_kernel(const uint8_t *__restrict__ img, int pitch,
                                                       const uint8_t *__restrict__ mask, int mask_pitch,
                                                       float *__restrict__ eig, int rows, int cols,
                                                       uint32_t *__restrict__ max_bits) {
-    __shared__ float s_I[ET_H + 4][ET_W + 4 + 1];
-    __shared__ float s_dx[ET_H + 2][ET_W + 2 + 1], s_dy[ET_H + 2][ET_W + 2 + 1];
+    __shared__ __align__(16) uint8_t s_I[ET_TH][ET_TW];
     __shared__ uint32_t s_max[8];
     const int x0 = blockIdx.x * ET_W, y0 = blockIdx.y * ET_H;
     const int tid = threadIdx.x;
-    // I tile at virtual coords [y0-2, y0+ET_H+2) x [x0-2, x0+ET_W+2), REFLECT_101
-    for (int k = tid; k < (ET_H + 4) * (ET_W + 4); k += 256) {
-        const int ty = k / (ET_W + 4), tx = k % (ET_W + 4);
-        const int y = reflect101(y0 - 2 + ty, rows), x = reflect101(x0 - 2 + tx, cols);
-        s_I[ty][tx] = (float)img[(size_t)y * pitch + x];
+    // ---- byte tile at virtual coordinates, REFLECT_101 ----
+    const bool interior = x0 >= 4 && x0 + ET_W + 4 <= cols && y0 >= 2 && y0 + ET_H + 2 <= rows && ((pitch & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(img) & 3) == 0);
+    if (interior) {
+        const uint8_t *base = img + (size_t)(y0 - 2) * pitch + (x0 - 4);
+        for (int k = tid; k < ET_TH * (ET_TW / 4); k += 256) {
+            const int ty = k / (ET_TW / 4), w = k % (ET_TW / 4);
+            *reinterpret_cast<uint32_t *>(&s_I[ty][4 * w]) = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)ty * pitch) + w);
+        }
+    } else {
+        for (int k = tid; k < ET_TH * ET_TW; k += 256) {
+            const int ty = k / ET_TW, tx = k % ET_TW;
+            const int y = reflect101(y0 - 2 + ty, rows), x = reflect101(x0 - 4 + tx, cols);
+            s_I[ty][tx] = img[(size_t)y * pitch + x];
+        }
     }
     __syncthreads();
     const float s = (float)(1.0 / (4 * 3 * 255.0));  // Sobel scale for u8, ksize 3, blockSize 3
     const float s2 = 2.0f * s;
-    // derivatives at virtual coords [y0-1, y0+ET_H+1) x [x0-1, x0+ET_W+1); positions outside the image take
-    // the value at the REFLECT_101 position (the box filter's border rule on the covariance images)
-    for (int k = tid; k < (ET_H + 2) * (ET_W + 2); k += 256) {
-        const int ty = k / (ET_W + 2), tx = k % (ET_W + 2);
-        int ry = reflect101(y0 - 1 + ty, rows) - (y0 - 2);  // tile-local index of the reflected centre
-        int rx = reflect101(x0 - 1 + tx, cols) - (x0 - 2);
-        ry = min(max(ry, 1), ET_H + 2);
-        rx = min(max(rx, 1), ET_W + 2);
-        const float a00 = s_I[ry - 1][rx - 1], a01 = s_I[ry - 1][rx], a02 = s_I[ry - 1][rx + 1];
-        const float a10 = s_I[ry][rx - 1], a11 = s_I[ry][rx], a12 = s_I[ry][rx + 1];
-        const float a20 = s_I[ry + 1][rx - 1], a21 = s_I[ry + 1][rx], a22 = s_I[ry + 1][rx + 1];
-        // dx: row filter [-1 0 1] (exact), column filter [s 2s s] as fma(S0+S2, s, S1*2s)
-        const float S0 = a02 - a00, S1 = a12 - a10, S2 = a22 - a20;
-        s_dx[ty][tx] = __fmaf_rn(__fadd_rn(S0, S2), s, __fmul_rn(S1, s2));
-        // dy: row filter [s 2s s] as fma(C, s, fma(B, 2s, A*s)), column filter [-1 0 1]
-        const float R0 = __fmaf_rn(a02, s, __fmaf_rn(a01, s2, __fmul_rn(a00, s)));
-        const float R2 = __fmaf_rn(a22, s, __fmaf_rn(a21, s2, __fmul_rn(a20, s)));
-        s_dy[ty][tx] = __fsub_rn(R2, R0);
-        (void)a11;
-    }
-    __syncthreads();
-    uint32_t local_max = 0;  // enc_ordered(-NaN..) minimum
-    const int lx = tid % ET_W;
+    const int X = x0 + 4 * (tid & 15), Y0 = y0 + ET_R * (tid >> 4);  // first output of this strip
+    uint32_t local_max = 0;                                          // enc_ordered(-NaN..) minimum
+    if (X < cols && Y0 < rows) {
+        // derivative row at VIRTUAL row vy, virtual columns X-1 .. X+4: a position outside the image takes the value at its
+        // REFLECT_101 position (the box filter's border rule on the covariance images)
+        auto deriv_row = [&](int vy, float (&gx)[6], float (&gy)[6]) {
+            const int t = reflect101(vy, rows) - (y0 - 2);  // tile row of the centre
+            float a[3][8];                                  // tile columns 4 tx + 2 .. 4 tx + 9 = virtual X-2 .. X+5
 #pragma unroll
-    for (int rr = 0; rr < 2; rr++) {
-        const int ly = tid / ET_W + rr * (ET_H / 2);
-        const int x = x0 + lx, y = y0 + ly;
-        if (x < cols && y < rows) {
-            double sxx = 0, sxy = 0, syy = 0;
-#pragma unroll
-            for (int dy = 0; dy < 3; dy++) {
-                double rxx = 0, rxy = 0, ryy = 0;
-#pragma unroll
-                for (int dx = 0; dx < 3; dx++) {
-                    const float gx = s_dx[ly + dy][lx + dx], gy = s_dy[ly + dy][lx + dx];
-                    rxx += (double)__fmul_rn(gx, gx);
-                    rxy += (double)__fmul_rn(gx, gy);
-                    ryy += (double)__fmul_rn(gy, gy);
-                }
-                sxx += rxx;
-                sxy += rxy;
-                syy += ryy;
+            for (int r = 0; r < 3; r++) {
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(&s_I[t - 1 + r][4 * (tid & 15)]);
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                a[r][0] = (float)((w0 >> 16) & 255u); a[r][1] = (float)(w0 >> 24);
+                a[r][2] = (float)(w1 & 255u); a[r][3] = (float)((w1 >> 8) & 255u); a[r][4] = (float)((w1 >> 16) & 255u); a[r][5] = (float)(w1 >> 24);
+                a[r][6] = (float)(w2 & 255u); a[r][7] = (float)((w2 >> 8) & 255u);
             }
-            const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
-            const float t = __fsub_rn(a, c);
-            const float lam = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
-            eig[(size_t)y * cols + x] = lam;
-            if (mask == nullptr || mask[(size_t)y * mask_pitch + x] != 0)
-                local_max = max(local_max, enc_ordered(__float_as_uint(lam)));
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                // dx: row filter [-1 0 1] (exact), column filter [s 2s s] as fma(S0+S2, s, S1*2s)
+                const float S0 = a[0][k + 2] - a[0][k], S1 = a[1][k + 2] - a[1][k], S2 = a[2][k + 2] - a[2][k];
+                gx[k] = __fmaf_rn(__fadd_rn(S0, S2), s, __fmul_rn(S1, s2));
+                // dy: row filter [s 2s s] as fma(C, s, fma(B, 2s, A*s)), column filter [-1 0 1]
+                const float R0 = __fmaf_rn(a[0][k + 2], s, __fmaf_rn(a[0][k + 1], s2, __fmul_rn(a[0][k], s)));
+                const float R2 = __fmaf_rn(a[2][k + 2], s, __fmaf_rn(a[2][k + 1], s2, __fmul_rn(a[2][k], s)));
+                gy[k] = __fsub_rn(R2, R0);
+            }
+            // virtual columns -1 and cols: the value at column 1 / cols - 2
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const int vx = X - 1 + k;
+                if (vx == -1 && k + 2 < 6) {
+                    gx[k] = gx[k + 2];
+                    gy[k] = gy[k + 2];
+                }
+            }
+#pragma unroll
+            for (int k = 2; k < 6; k++) {
+                const int vx = X - 1 + k;
+                if (vx == cols) {
+                    gx[k] = gx[k - 2];
+                    gy[k] = gy[k - 2];
+                }
+            }
+        };
+        // f64 horizontal 3-sums of the products of one derivative row, for the four output columns
+        auto hsums = [&](int vy, double (&hxx)[4], double (&hxy)[4], double (&hyy)[4]) {
+            float gx[6], gy[6];
+            deriv_row(vy, gx, gy);
+            double pxx[6], pxy[6], pyy[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                pxx[k] = (double)__fmul_rn(gx[k], gx[k]);
+                pxy[k] = (double)__fmul_rn(gx[k], gy[k]);
+                pyy[k] = (double)__fmul_rn(gy[k], gy[k]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                hxx[q] = (pxx[q] + pxx[q + 1]) + pxx[q + 2];
+                hxy[q] = (pxy[q] + pxy[q + 1]) + pxy[q + 2];
+                hyy[q] = (pyy[q] + pyy[q + 1]) + pyy[q + 2];
+            }
+        };
+        double hxx[3][4], hxy[3][4], hyy[3][4];  // derivative rows oy-1, oy, oy+1 (rolling)
+        hsums(Y0 - 1, hxx[0], hxy[0], hyy[0]);
+        hsums(Y0, hxx[1], hxy[1], hyy[1]);
+#pragma unroll
+        for (int rr = 0; rr < ET_R; rr++) {
+            const int y = Y0 + rr;
+            if (y >= rows) break;
+            hsums(y + 1, hxx[(rr + 2) % 3], hxy[(rr + 2) % 3], hyy[(rr + 2) % 3]);
+            const int r0 = rr % 3, r1 = (rr + 1) % 3, r2 = (rr + 2) % 3;
+            float lam[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double sxx = (hxx[r0][q] + hxx[r1][q]) + hxx[r2][q];
+                const double sxy = (hxy[r0][q] + hxy[r1][q]) + hxy[r2][q];
+                const double syy = (hyy[r0][q] + hyy[r1][q]) + hyy[r2][q];
+                const float a = __fmul_rn((float)sxx, 0.5f), b = (float)sxy, c = __fmul_rn((float)syy, 0.5f);
+                const float t = __fsub_rn(a, c);
+                lam[q] = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b))));
+            }
+            float *out = eig + (size_t)y * cols + X;
+            const bool full = X + 4 <= cols;
+            if (full && ((cols & 3) == 0) && ((reinterpret_cast<uintptr_t>(eig) & 15) == 0)) {
+                *reinterpret_cast<float4 *>(out) = make_float4(lam[0], lam[1], lam[2], lam[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (X + q < cols) out[q] = lam[q];
+            }
+            unsigned mbits = 0x01010101u;
+            if (mask != nullptr) {
+                if (full && ((mask_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 3) == 0)) {
+                    mbits = __ldg(reinterpret_cast<const unsigned *>(mask + (size_t)y * mask_pitch + X));
+                } else {
+                    mbits = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (X + q < cols && mask[(size_t)y * mask_pitch + X + q] != 0) mbits |= 1u << (8 * q);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (X + q < cols && ((mbits >> (8 * q)) & 255u) != 0) local_max = max(local_max, enc_ordered(__float_as_uint(lam[q])));
         }
     }
 #pragma unroll
@@ -145,40 +215,83 @@ __global__ void __launch_bounds__(256) candidates_kernel(const float *__restrict
         counters[3] = (int)tenc;
         counters[4] = shift;
     }
-    const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    const int y = blockIdx.y + 1;
-    bool is_cand = false;
-    float v = 0.f;
-    if (x < p.cols - 1 && y < p.rows - 1) {
-        const float *c = eig + (size_t)y * p.cols + x;
-        v = *c;
-        if (v > thr && v != 0.f && (mask == nullptr || mask[(size_t)y * p.mask_pitch + x] != 0)) {
-            is_cand = true;
-#pragma unroll
-            for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-                for (int dx = -1; dx <= 1; dx++) {
-                    const float nb = c[dy * p.cols + dx];
-                    const float tn = nb > thr ? nb : 0.f;
-                    if (tn > v) is_cand = false;
-                }
-        }
-    }
-    const unsigned ballot = __ballot_sync(0xffffffffu, is_cand);
-    if (ballot == 0) return;
+    // Grid-stride over chunks of four consecutive pixels of one row (one 128-bit load of the eigenvalue map and one 32-bit load
+    // of the mask per chunk when the rows are 16-byte aligned); a pixel that fails the threshold costs nothing more, the eight
+    // neighbours are read only for the few that pass.  One atomicAdd per warp and pass reserves the output slots.
     const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == __ffs(ballot) - 1) base = atomicAdd(&counters[0], __popc(ballot));
-    base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
-    if (is_cand) {
-        const int idx = base + __popc(ballot & ((1u << lane) - 1));
-        const uint32_t venc = enc_ordered(__float_as_uint(v));
-        if (idx < p.cap) {
-            cand[idx] = ((unsigned long long)venc << 32) | (uint32_t)(y * p.cols + x);
-            atomicAdd(&cell_count[(y / p.cell) * p.gw + (x / p.cell)], 1);
-            atomicAdd(&hist[min((venc - tenc) >> shift, (uint32_t)(kCandHistBins - 1))], 1u);
-        } else {
-            counters[1] = 1;  // overflow: reported as LFVIO_ERR_CAPACITY by the caller
+    const int chunks_per_row = (p.cols + 3) >> 2;
+    const long long total = (long long)chunks_per_row * (p.rows - 2);
+    const bool vec_ok = ((p.cols & 3) == 0) && ((reinterpret_cast<uintptr_t>(eig) & 15) == 0);
+    const bool mvec_ok = mask != nullptr && ((p.mask_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(mask) & 3) == 0);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long c0 = first - lane; c0 < total; c0 += stride) {  // (whole warps stay in the loop together: ballots below)
+        const long long c = c0 + lane;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        unsigned pass = 0;
+        int x0 = 0, y = 0;
+        if (c < total) {
+            y = (int)(c / chunks_per_row) + 1;
+            x0 = (int)(c % chunks_per_row) * 4;
+            const float *row = eig + (size_t)y * p.cols;
+            if (vec_ok) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(row + x0));
+                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (x0 + k < p.cols) v[k] = row[x0 + k];
+            }
+            unsigned mbits = 0xffffffffu;
+            if (mvec_ok && x0 + 4 <= p.cols) mbits = __ldg(reinterpret_cast<const unsigned *>(mask + (size_t)y * p.mask_pitch + x0));
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int x = x0 + k;
+                if (x < 1 || x >= p.cols - 1) continue;
+                if (!(v[k] > thr) || v[k] == 0.f) continue;
+                bool m_ok = true;
+                if (mask != nullptr) m_ok = (mvec_ok && x0 + 4 <= p.cols) ? (((mbits >> (8 * k)) & 255u) != 0) : (mask[(size_t)y * p.mask_pitch + x] != 0);
+                if (!m_ok) continue;
+                const float *cc = row + x;
+                bool is_max = true;
+#pragma unroll
+                for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; dx++) {
+                        const float nb = cc[dy * p.cols + dx];
+                        const float tn = nb > thr ? nb : 0.f;
+                        if (tn > v[k]) is_max = false;
+                    }
+                if (is_max) pass |= 1u << k;
+            }
+        }
+        if (!__any_sync(0xffffffffu, pass != 0)) continue;
+        // warp-aggregated append: exclusive scan of the per-lane counts
+        const int cnt = __popc(pass);
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const int warp_total = __shfl_sync(0xffffffffu, inc, 31);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&counters[0], warp_total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        int idx = base + inc - cnt;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!(pass & (1u << k))) continue;
+            const int x = x0 + k;
+            const uint32_t venc = enc_ordered(__float_as_uint(v[k]));
+            if (idx < p.cap) {
+                cand[idx] = ((unsigned long long)venc << 32) | (uint32_t)(y * p.cols + x);
+                atomicAdd(&cell_count[(y / p.cell) * p.gw + (x / p.cell)], 1);
+                atomicAdd(&hist[min((venc - tenc) >> shift, (uint32_t)(kCandHistBins - 1))], 1u);
+            } else {
+                counters[1] = 1;  // overflow: reported as LFVIO_ERR_CAPACITY by the caller
+            }
+            idx++;
         }
     }
 }
@@ -386,7 +499,8 @@ int launch_corner_candidates(const float *eig, const uint8_t *mask, int mask_pit
     p.cap = cs.cand_cap;
     p.gw = cs.gw;
     p.cell = cs.cell;
-    dim3 grid(cdiv(cols - 2, 256), rows - 2);
+    const long long chunks = (long long)((cols + 3) / 4) * (rows - 2);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((chunks + 255) / 256, 148 * 8));
     candidates_kernel<<<grid, 256, 0, s>>>(eig, mask, max_bits, p, cs.cand, cs.cell_count, cs.hist, cs.counters);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;

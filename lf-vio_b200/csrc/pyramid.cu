@@ -6,8 +6,11 @@
 // integer sum, (sum + 128) >> 8; level size (w+1)/2 x (h+1)/2; stop when a level would be <= winSize.
 // Scharr derivatives are NOT materialised: the LK kernel recomputes them from its shared-memory tile.
 //
-// Tile kernel: a CTA produces 32x8 output pixels from a 67x19 input tile staged in shared memory
-// (separable: horizontal pass into smem, vertical pass out).  Traffic: read 1 B/px, write 1/4 B/px.
+// Register kernel (round 2): a thread produces a 4 x 2 block of output pixels from a 12 x 7 input window held in registers
+// (seven rows of three aligned 32-bit loads; rows are shared between the two output rows, columns between the four outputs);
+// no shared memory, no barrier, one 32-bit store per output row.  The window of a block away from the image border needs no
+// reflection: only border blocks take the slow path.  Traffic: read 1 B/px (re-reads of the window overlap are L1 hits),
+// write 1/4 B/px.
 #include <cstring>
 
 #include "frontend.cuh"
@@ -16,41 +19,65 @@ namespace lfvio {
 
 namespace {
 
-constexpr int TW = 32, TH = 8;
-constexpr int IN_W = 2 * TW + 3, IN_H = 2 * TH + 3;
+constexpr int PD_THREADS = 128;
 
-__global__ void __launch_bounds__(TW *TH) pyr_down_kernel(ImgLevel src, ImgLevel dst) {
-    __shared__ uint8_t s_in[IN_H][IN_W + 1];
-    __shared__ uint16_t s_row[IN_H][TW];
-    const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * TH;
-    const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
-    const int tid = threadIdx.y * TW + threadIdx.x;
-    for (int k = tid; k < IN_W * IN_H; k += TW * TH) {
-        const int ty = k / IN_W, tx = k % IN_W;
-        const int y = reflect101(iy0 + ty, src.rows), x = reflect101(ix0 + tx, src.cols);
-        s_in[ty][tx] = src.data[(size_t)y * src.pitch + x];
+__device__ __forceinline__ uint32_t hsum5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) { return a + 4 * b + 6 * c + 4 * d + e; }
+
+__global__ void __launch_bounds__(PD_THREADS) pyr_down_kernel(ImgLevel src, ImgLevel dst) {
+    const int bx = blockIdx.x * PD_THREADS + threadIdx.x;  // block of 4 output columns
+    const int by = blockIdx.y;                             // block of 2 output rows
+    const int ox = 4 * bx, oy = 2 * by;
+    if (ox >= dst.cols || oy >= dst.rows) return;
+    const int ix = 2 * ox - 2, iy = 2 * oy - 2;  // window: input columns ix .. ix+10, rows iy .. iy+6
+    uint32_t h[7][4];                            // horizontally filtered rows
+    const bool interior = ix >= 2 && ix + 14 <= src.cols && iy >= 0 && iy + 7 <= src.rows && ((src.pitch & 3) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(src.data) & 3) == 0);
+    if (interior) {
+        // ix - 2 is a multiple of 4: three aligned words cover bytes ix-2 .. ix+9; byte ix+10 comes from the fourth
+        const uint8_t *base = src.data + (size_t)iy * src.pitch + (ix - 2);
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(base + (size_t)r * src.pitch);
+            const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+            uint32_t p[11];
+            p[0] = (w0 >> 16) & 255u; p[1] = w0 >> 24;
+            p[2] = w1 & 255u; p[3] = (w1 >> 8) & 255u; p[4] = (w1 >> 16) & 255u; p[5] = w1 >> 24;
+            p[6] = w2 & 255u; p[7] = (w2 >> 8) & 255u; p[8] = (w2 >> 16) & 255u; p[9] = w2 >> 24;
+            p[10] = w3 & 255u;
+#pragma unroll
+            for (int q = 0; q < 4; q++) h[r][q] = hsum5(p[2 * q], p[2 * q + 1], p[2 * q + 2], p[2 * q + 3], p[2 * q + 4]);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 7; r++) {
+            const uint8_t *row = src.data + (size_t)reflect101(iy + r, src.rows) * src.pitch;
+            uint32_t p[11];
+#pragma unroll
+            for (int c = 0; c < 11; c++) p[c] = row[reflect101(ix + c, src.cols)];
+#pragma unroll
+            for (int q = 0; q < 4; q++) h[r][q] = hsum5(p[2 * q], p[2 * q + 1], p[2 * q + 2], p[2 * q + 3], p[2 * q + 4]);
+        }
     }
-    __syncthreads();
-    for (int k = tid; k < IN_H * TW; k += TW * TH) {
-        const int ty = k / TW, ox = k % TW;
-        const uint8_t *p = &s_in[ty][2 * ox];
-        s_row[ty][ox] = (uint16_t)(p[0] + 4 * p[1] + 6 * p[2] + 4 * p[3] + p[4]);
-    }
-    __syncthreads();
-    const int ox = ox0 + threadIdx.x, oy = oy0 + threadIdx.y;
-    if (ox < dst.cols && oy < dst.rows) {
-        const int ty = 2 * threadIdx.y;
-        const int v = s_row[ty][threadIdx.x] + 4 * s_row[ty + 1][threadIdx.x] + 6 * s_row[ty + 2][threadIdx.x] +
-                      4 * s_row[ty + 3][threadIdx.x] + s_row[ty + 4][threadIdx.x];
-        dst.data[(size_t)oy * dst.pitch + ox] = (uint8_t)((v + 128) >> 8);
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        if (oy + rr >= dst.rows) break;
+        uint8_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) o[q] = (uint8_t)((hsum5(h[2 * rr][q], h[2 * rr + 1][q], h[2 * rr + 2][q], h[2 * rr + 3][q], h[2 * rr + 4][q]) + 128u) >> 8);
+        uint8_t *out = dst.data + (size_t)(oy + rr) * dst.pitch + ox;
+        if (ox + 4 <= dst.cols && ((dst.pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(dst.data) & 3) == 0)) {
+            *reinterpret_cast<uint32_t *>(out) = o[0] | (o[1] << 8) | (o[2] << 16) | ((uint32_t)o[3] << 24);
+        } else {
+            for (int q = 0; q < 4 && ox + q < dst.cols; q++) out[q] = o[q];
+        }
     }
 }
 
 }  // namespace
 
 int launch_pyr_down(const ImgLevel &src, const ImgLevel &dst, cudaStream_t s) {
-    dim3 grid(cdiv(dst.cols, TW), cdiv(dst.rows, TH));
-    pyr_down_kernel<<<grid, dim3(TW, TH), 0, s>>>(src, dst);
+    dim3 grid(cdiv(cdiv(dst.cols, 4), PD_THREADS), cdiv(dst.rows, 2));
+    pyr_down_kernel<<<grid, PD_THREADS, 0, s>>>(src, dst);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }
