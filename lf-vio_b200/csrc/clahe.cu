@@ -22,35 +22,48 @@ struct ClaheGeom {
 
 __global__ void __launch_bounds__(256) clahe_hist_kernel(const uint8_t *__restrict__ src, int pitch, ClaheGeom g,
                                                          uint32_t *__restrict__ hist) {
-    __shared__ uint32_t sh[256];
+    // one private histogram per warp (fewer atomics on one word), merged at the end; the slice of the tile is walked as ONE flat
+    // range of 4-pixel chunks so that all 256 threads work whatever the tile width (a 160-pixel tile row has 40 chunks)
+    __shared__ uint32_t sh[8][256];
     const int tile = blockIdx.x;
     const int ty = tile / kClaheTiles, tx = tile % kClaheTiles;
-    sh[threadIdx.x] = 0;
+    for (int k = threadIdx.x; k < 8 * 256; k += blockDim.x) (&sh[0][0])[k] = 0;
     __syncthreads();
+    uint32_t *my = sh[threadIdx.x >> 5];
     // this CTA's slice of tile rows
     const int r0 = (int)(((long long)g.tile_h * blockIdx.y) / g.splits);
     const int r1 = (int)(((long long)g.tile_h * (blockIdx.y + 1)) / g.splits);
     const int x_base = tx * g.tile_w;
     const bool interior_x = (x_base + g.tile_w <= g.cols);
-    for (int r = r0; r < r1; r++) {
-        const int y = reflect101(ty * g.tile_h + r, g.rows);
-        const uint8_t *row = src + (size_t)y * pitch;
-        if (interior_x && ((x_base & 3) == 0) && ((g.tile_w & 3) == 0) && ((pitch & 3) == 0)) {
-            const uchar4 *row4 = reinterpret_cast<const uchar4 *>(row + x_base);
-            for (int x = threadIdx.x; x < g.tile_w / 4; x += blockDim.x) {
-                uchar4 v = row4[x];
-                atomicAdd(&sh[v.x], 1u);
-                atomicAdd(&sh[v.y], 1u);
-                atomicAdd(&sh[v.z], 1u);
-                atomicAdd(&sh[v.w], 1u);
+    if (interior_x && ((x_base & 3) == 0) && ((g.tile_w & 3) == 0) && ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+        const int w4 = g.tile_w >> 2, n = (r1 - r0) * w4;
+        int r = r0 + (int)threadIdx.x / w4, x = (int)threadIdx.x % w4;
+        const int dr = 256 / w4, dx = 256 % w4;
+        for (int i = threadIdx.x; i < n; i += 256) {
+            const int y = reflect101(ty * g.tile_h + r, g.rows);
+            const uchar4 v = __ldg(reinterpret_cast<const uchar4 *>(src + (size_t)y * pitch + x_base) + x);
+            atomicAdd(&my[v.x], 1u);
+            atomicAdd(&my[v.y], 1u);
+            atomicAdd(&my[v.z], 1u);
+            atomicAdd(&my[v.w], 1u);
+            r += dr;
+            x += dx;
+            if (x >= w4) {
+                x -= w4;
+                r++;
             }
-        } else {
-            for (int x = threadIdx.x; x < g.tile_w; x += blockDim.x)
-                atomicAdd(&sh[row[reflect101(x_base + x, g.cols)]], 1u);
+        }
+    } else {
+        for (int r = r0; r < r1; r++) {
+            const int y = reflect101(ty * g.tile_h + r, g.rows);
+            const uint8_t *row = src + (size_t)y * pitch;
+            for (int x = threadIdx.x; x < g.tile_w; x += blockDim.x) atomicAdd(&my[row[reflect101(x_base + x, g.cols)]], 1u);
         }
     }
     __syncthreads();
-    uint32_t v = sh[threadIdx.x];
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v += sh[k][threadIdx.x];
     if (v) atomicAdd(&hist[tile * 256 + threadIdx.x], v);
 }
 
@@ -127,58 +140,65 @@ __global__ void __launch_bounds__(256) clahe_apply_kernel(const uint8_t *__restr
     const int ya0 = max(0, ((2 * band - 1) * g.tile_h + 1) >> 1), ya1 = min(g.rows, ((2 * band + 1) * g.tile_h + 1) >> 1);
     const int chunks_per_row = (g.cols + 3) / 4;
     const bool vec_ok = ((src_pitch & 3) == 0) && ((dst_pitch & 3) == 0) && ((g.cols & 3) == 0);
-    const long long total = (long long)chunks_per_row * max(ya1 - ya0, 0);
-    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (long long)gridDim.x * blockDim.x) {
-        const int y = ya0 + (int)(c / chunks_per_row);
-        const int x0 = (int)(c % chunks_per_row) * 4;
-        const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
-        const int ty1f = cv_floor(tyf);
-        const float ya = __fsub_rn(tyf, (float)ty1f);
-        const float yb = __fsub_rn(1.0f, ya);
-        // (the band limits above are the exact integer statement of ty1f == band - 1; the f32 product can land on the other side
-        // of a boundary for no y below 2^22 / tile_h — checked by the bit-exact tests at every supported size — but the table of the
-        // neighbouring band would be the wrong one, so such a row falls back to the byte LUTs)
-        const bool band_ok = (ty1f == band - 1);
-        uint8_t in[4], out[4];
+    // rows of the band over blockIdx.x, chunks of a row over the threads: no division per chunk, the row weights once per row
+    // a thread keeps its four columns (column weights and table rows once), the band's rows in turn
+    for (int ch = threadIdx.x; ch < chunks_per_row; ch += blockDim.x) {
+        const int x0 = 4 * ch;
         const int nvalid = min(4, g.cols - x0);
-        if (vec_ok) {
-            const uchar4 v = *reinterpret_cast<const uchar4 *>(src + (size_t)y * src_pitch + x0);
-            in[0] = v.x; in[1] = v.y; in[2] = v.z; in[3] = v.w;
-        } else {
-            for (int k = 0; k < nvalid; k++) in[k] = src[(size_t)y * src_pitch + x0 + k];
-        }
+        float xa[4], xa1[4];
+        int tx1f[4];
+        const uint32_t *tab[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (k >= nvalid) break;
-            const int x = x0 + k;
-            const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
-            const int tx1f = cv_floor(txf);
-            const float xa = __fsub_rn(txf, (float)tx1f);
-            const float xa1 = __fsub_rn(1.0f, xa);
-            const int sv = in[k];
-            float l11, l12, l21, l22;
-            if (band_ok) {
-                const uint32_t w = s_tab[min(max(tx1f + 1, 0), kClaheBands - 1)][sv];
-                l11 = (float)(w & 255u);
-                l12 = (float)((w >> 8) & 255u);
-                l21 = (float)((w >> 16) & 255u);
-                l22 = (float)(w >> 24);
-            } else {
-                const int a1 = max(ty1f, 0), a2 = min(ty1f + 1, kClaheTiles - 1), b1 = max(tx1f, 0), b2 = min(tx1f + 1, kClaheTiles - 1);
-                l11 = (float)lut[(a1 * kClaheTiles + b1) * 256 + sv];
-                l12 = (float)lut[(a1 * kClaheTiles + b2) * 256 + sv];
-                l21 = (float)lut[(a2 * kClaheTiles + b1) * 256 + sv];
-                l22 = (float)lut[(a2 * kClaheTiles + b2) * 256 + sv];
-            }
-            const float top = __fadd_rn(__fmul_rn(l11, xa1), __fmul_rn(l12, xa));
-            const float bot = __fadd_rn(__fmul_rn(l21, xa1), __fmul_rn(l22, xa));
-            const float res = __fadd_rn(__fmul_rn(top, yb), __fmul_rn(bot, ya));
-            out[k] = (uint8_t)min(max(cv_round(res), 0), 255);
+            const float txf = __fsub_rn(__fmul_rn((float)(x0 + k), inv_tw), 0.5f);
+            tx1f[k] = cv_floor(txf);
+            xa[k] = __fsub_rn(txf, (float)tx1f[k]);
+            xa1[k] = __fsub_rn(1.0f, xa[k]);
+            tab[k] = s_tab[min(max(tx1f[k] + 1, 0), kClaheBands - 1)];
         }
-        if (vec_ok) {
-            *reinterpret_cast<uchar4 *>(dst + (size_t)y * dst_pitch + x0) = make_uchar4(out[0], out[1], out[2], out[3]);
-        } else {
-            for (int k = 0; k < nvalid; k++) dst[(size_t)y * dst_pitch + x0 + k] = out[k];
+        for (int y = ya0 + blockIdx.x; y < ya1; y += gridDim.x) {
+            const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+            const int ty1f = cv_floor(tyf);
+            const float ya = __fsub_rn(tyf, (float)ty1f);
+            const float yb = __fsub_rn(1.0f, ya);
+            // (the band limits above are the exact integer statement of ty1f == band - 1; should the f32 product ever land on the
+            // other side of a boundary, the table of this band would be the wrong one, so such a row falls back to the byte LUTs)
+            const bool band_ok = (ty1f == band - 1);
+            uint8_t in[4], out[4];
+            if (vec_ok) {
+                const uchar4 v = *reinterpret_cast<const uchar4 *>(src + (size_t)y * src_pitch + x0);
+                in[0] = v.x; in[1] = v.y; in[2] = v.z; in[3] = v.w;
+            } else {
+                for (int k = 0; k < nvalid; k++) in[k] = src[(size_t)y * src_pitch + x0 + k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k >= nvalid) break;
+                const int sv = in[k];
+                float l11, l12, l21, l22;
+                if (band_ok) {
+                    const uint32_t w = tab[k][sv];
+                    l11 = (float)(w & 255u);
+                    l12 = (float)((w >> 8) & 255u);
+                    l21 = (float)((w >> 16) & 255u);
+                    l22 = (float)(w >> 24);
+                } else {
+                    const int a1 = max(ty1f, 0), a2 = min(ty1f + 1, kClaheTiles - 1), b1 = max(tx1f[k], 0), b2 = min(tx1f[k] + 1, kClaheTiles - 1);
+                    l11 = (float)lut[(a1 * kClaheTiles + b1) * 256 + sv];
+                    l12 = (float)lut[(a1 * kClaheTiles + b2) * 256 + sv];
+                    l21 = (float)lut[(a2 * kClaheTiles + b1) * 256 + sv];
+                    l22 = (float)lut[(a2 * kClaheTiles + b2) * 256 + sv];
+                }
+                const float top = __fadd_rn(__fmul_rn(l11, xa1[k]), __fmul_rn(l12, xa[k]));
+                const float bot = __fadd_rn(__fmul_rn(l21, xa1[k]), __fmul_rn(l22, xa[k]));
+                const float res = __fadd_rn(__fmul_rn(top, yb), __fmul_rn(bot, ya));
+                out[k] = (uint8_t)min(max(cv_round(res), 0), 255);
+            }
+            if (vec_ok) {
+                *reinterpret_cast<uchar4 *>(dst + (size_t)y * dst_pitch + x0) = make_uchar4(out[0], out[1], out[2], out[3]);
+            } else {
+                for (int k = 0; k < nvalid; k++) dst[(size_t)y * dst_pitch + x0 + k] = out[k];
+            }
         }
     }
     (void)chunks_per_band;
@@ -213,12 +233,9 @@ int launch_clahe(const uint8_t *src, int src_pitch, uint8_t *dst, int dst_pitch,
     LFVIO_LAUNCH_CHECK();
     clahe_lut_kernel<<<kClaheTiles * kClaheTiles, 256, 0, s>>>(hist, lut, clip, lut_scale);
     LFVIO_LAUNCH_CHECK();
-    // nine row bands x enough CTAs per band to fill the machine about twice
-    const long long chunks_band = (long long)((cols + 3) / 4) * (g.tile_h + 1);
-    long long want = (chunks_band + 255) / 256;
-    const long long per_band = std::max<long long>(1, (2LL * n_sm + kClaheTiles) / (kClaheTiles + 1));
-    const int gx = (int)(want < per_band ? want : per_band);
-    clahe_apply_kernel<<<dim3(gx, kClaheTiles + 1), 256, 0, s>>>(src, src_pitch, dst, dst_pitch, g, lut, (int)chunks_band);
+    // nine row bands x enough CTAs per band (each takes rows of the band in turn) to put about four CTAs on every SM
+    const int per_band = std::max(1, std::min(g.tile_h + 1, cdiv(4 * n_sm, kClaheTiles + 1)));
+    clahe_apply_kernel<<<dim3(per_band, kClaheTiles + 1), 256, 0, s>>>(src, src_pitch, dst, dst_pitch, g, lut, 0);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }
