@@ -295,16 +295,53 @@ __global__ void __launch_bounds__(TRI_WARPS * 32) triangulate_kernel(const doubl
     }
 }
 
-template <class T>
-struct DevArr {
-    T *p = nullptr;
-    ~DevArr() {
-        if (p) cudaFree(p);
+// Per-thread arena of the two stage-level entry points below (the host Estimator calls both once per image): one device
+// buffer, one page-locked mirror of it and one stream, grown on demand and kept.  A call packs its inputs into the mirror, sends
+// them in ONE asynchronous copy, launches on the arena's stream, brings the outputs back in one copy and synchronises that stream
+// only — no cudaMalloc / cudaFree and no default-stream synchronisation per call (round 1: 6-8 of each, which serialised the
+// estimator against the tracker and window streams).
+struct StepArena {
+    int device = -1;
+    cudaStream_t s = nullptr;
+    char *d = nullptr, *h = nullptr;
+    size_t cap = 0;
+    void release() {
+        if (device >= 0) cudaSetDevice(device);
+        if (d) cudaFree(d);
+        if (h) cudaFreeHost(h);
+        if (s) cudaStreamDestroy(s);
+        d = h = nullptr;
+        s = nullptr;
+        cap = 0;
+        device = -1;
     }
-    int put(const T *h, size_t n) {
-        LFVIO_CUDA_TRY(cudaMalloc(&p, sizeof(T) * (n ? n : 1)));
-        if (h && n) LFVIO_CUDA_TRY(cudaMemcpy(p, h, sizeof(T) * n, cudaMemcpyHostToDevice));
+    ~StepArena() { release(); }
+    int ensure(int dev, size_t bytes) {
+        if (dev != device) release();
+        if (!s) {
+            device = dev;
+            LFVIO_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        }
+        if (bytes > cap) {
+            if (d) cudaFree(d);
+            if (h) cudaFreeHost(h);
+            d = h = nullptr;
+            cap = 0;
+            const size_t want = std::max<size_t>(bytes + bytes / 2, 1 << 16);
+            LFVIO_CUDA_TRY(cudaMalloc(&d, want));
+            LFVIO_CUDA_TRY(cudaMallocHost(&h, want));
+            cap = want;
+        }
         return LFVIO_OK;
+    }
+};
+static thread_local StepArena t_arena;
+struct Packer {  // sub-buffers at 256-byte offsets, same offsets on both sides
+    size_t off = 0;
+    size_t take(size_t bytes) {
+        const size_t o = off;
+        off = (off + bytes + 255) & ~(size_t)255;
+        return o;
     }
 };
 
@@ -345,18 +382,27 @@ extern "C" int lfvio_preintegrate(const lfvio_imu_interval *intervals, int n_int
         LFVIO_REQUIRE(intervals[i].first >= 0 && intervals[i].count >= 0 && intervals[i].first + intervals[i].count <= n_samples,
                       "lfvio_preintegrate: interval outside the sample arrays");
     LFVIO_CUDA_TRY(cudaSetDevice(device));
-    DevArr<lfvio_imu_interval> d_iv;
-    DevArr<double> d_dt, d_acc, d_gyr, d_state;
-    DevArr<lfvio_imu_factor> d_out;
-    LFVIO_TRY(d_iv.put(intervals, n_intervals));
-    LFVIO_TRY(d_dt.put(dt, n_samples));
-    LFVIO_TRY(d_acc.put(acc, 3 * (size_t)n_samples));
-    LFVIO_TRY(d_gyr.put(gyr, 3 * (size_t)n_samples));
-    LFVIO_TRY(d_out.put(nullptr, n_intervals));
-    LFVIO_TRY(d_state.put(nullptr, 15 * (size_t)n_intervals));
-    LFVIO_TRY(launch_preintegrate(d_iv.p, n_intervals, d_dt.p, d_acc.p, d_gyr.p, *noise, g, d_out.p, d_state.p, 0));
-    LFVIO_CUDA_TRY(cudaMemcpy(out, d_out.p, sizeof(lfvio_imu_factor) * n_intervals, cudaMemcpyDeviceToHost));
-    if (state_out) LFVIO_CUDA_TRY(cudaMemcpy(state_out, d_state.p, sizeof(double) * 15 * n_intervals, cudaMemcpyDeviceToHost));
+    Packer pk;
+    const size_t o_iv = pk.take(sizeof(lfvio_imu_interval) * n_intervals), o_dt = pk.take(sizeof(double) * n_samples);
+    const size_t o_acc = pk.take(sizeof(double) * 3 * n_samples), o_gyr = pk.take(sizeof(double) * 3 * n_samples);
+    const size_t in_bytes = pk.off;
+    const size_t o_out = pk.take(sizeof(lfvio_imu_factor) * n_intervals), o_state = pk.take(sizeof(double) * 15 * n_intervals);
+    StepArena &A = t_arena;
+    LFVIO_TRY(A.ensure(device, pk.off));
+    memcpy(A.h + o_iv, intervals, sizeof(lfvio_imu_interval) * n_intervals);
+    if (n_samples) {
+        memcpy(A.h + o_dt, dt, sizeof(double) * n_samples);
+        memcpy(A.h + o_acc, acc, sizeof(double) * 3 * n_samples);
+        memcpy(A.h + o_gyr, gyr, sizeof(double) * 3 * n_samples);
+    }
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(A.d, A.h, in_bytes, cudaMemcpyHostToDevice, A.s));
+    LFVIO_TRY(launch_preintegrate(reinterpret_cast<lfvio_imu_interval *>(A.d + o_iv), n_intervals, reinterpret_cast<double *>(A.d + o_dt),
+                                  reinterpret_cast<double *>(A.d + o_acc), reinterpret_cast<double *>(A.d + o_gyr), *noise, g,
+                                  reinterpret_cast<lfvio_imu_factor *>(A.d + o_out), reinterpret_cast<double *>(A.d + o_state), A.s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(A.h + o_out, A.d + o_out, pk.off - o_out, cudaMemcpyDeviceToHost, A.s));
+    LFVIO_CUDA_TRY(cudaStreamSynchronize(A.s));
+    memcpy(out, A.h + o_out, sizeof(lfvio_imu_factor) * n_intervals);
+    if (state_out) memcpy(state_out, A.h + o_state, sizeof(double) * 15 * n_intervals);
     return LFVIO_OK;
 }
 
@@ -373,17 +419,27 @@ extern "C" int lfvio_triangulate(const double *Ps, const double *Rs, int n_frame
         LFVIO_REQUIRE(K >= 0 && start_frame[l] >= 0 && start_frame[l] + K <= n_frames, "lfvio_triangulate: track leaves the window");
     }
     LFVIO_CUDA_TRY(cudaSetDevice(device));
-    DevArr<double> d_P, d_R, d_t, d_r, d_pts, d_depth;
-    DevArr<int> d_sf, d_of;
-    LFVIO_TRY(d_P.put(Ps, 3 * (size_t)n_frames));
-    LFVIO_TRY(d_R.put(Rs, 9 * (size_t)n_frames));
-    LFVIO_TRY(d_t.put(tic, 3));
-    LFVIO_TRY(d_r.put(ric, 9));
-    LFVIO_TRY(d_pts.put(obs_pts, 3 * (size_t)n_obs));
-    LFVIO_TRY(d_depth.put(depth, n_features));
-    LFVIO_TRY(d_sf.put(start_frame, n_features));
-    LFVIO_TRY(d_of.put(obs_first, (size_t)n_features + 1));
-    LFVIO_TRY(launch_triangulate(d_P.p, d_R.p, d_t.p, d_r.p, d_sf.p, d_of.p, d_pts.p, n_features, n_frames, init_depth, d_depth.p, 0));
-    LFVIO_CUDA_TRY(cudaMemcpy(depth, d_depth.p, sizeof(double) * n_features, cudaMemcpyDeviceToHost));
+    Packer pk;
+    const size_t o_P = pk.take(sizeof(double) * 3 * n_frames), o_R = pk.take(sizeof(double) * 9 * n_frames);
+    const size_t o_t = pk.take(sizeof(double) * 3), o_r = pk.take(sizeof(double) * 9);
+    const size_t o_pts = pk.take(sizeof(double) * 3 * (size_t)n_obs), o_sf = pk.take(sizeof(int) * n_features);
+    const size_t o_of = pk.take(sizeof(int) * ((size_t)n_features + 1)), o_depth = pk.take(sizeof(double) * n_features);
+    StepArena &A = t_arena;
+    LFVIO_TRY(A.ensure(device, pk.off));
+    memcpy(A.h + o_P, Ps, sizeof(double) * 3 * n_frames);
+    memcpy(A.h + o_R, Rs, sizeof(double) * 9 * n_frames);
+    memcpy(A.h + o_t, tic, sizeof(double) * 3);
+    memcpy(A.h + o_r, ric, sizeof(double) * 9);
+    if (n_obs) memcpy(A.h + o_pts, obs_pts, sizeof(double) * 3 * (size_t)n_obs);
+    memcpy(A.h + o_sf, start_frame, sizeof(int) * n_features);
+    memcpy(A.h + o_of, obs_first, sizeof(int) * ((size_t)n_features + 1));
+    memcpy(A.h + o_depth, depth, sizeof(double) * n_features);
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(A.d, A.h, pk.off, cudaMemcpyHostToDevice, A.s));
+    LFVIO_TRY(launch_triangulate(reinterpret_cast<double *>(A.d + o_P), reinterpret_cast<double *>(A.d + o_R), reinterpret_cast<double *>(A.d + o_t),
+                                 reinterpret_cast<double *>(A.d + o_r), reinterpret_cast<int *>(A.d + o_sf), reinterpret_cast<int *>(A.d + o_of),
+                                 reinterpret_cast<double *>(A.d + o_pts), n_features, n_frames, init_depth, reinterpret_cast<double *>(A.d + o_depth), A.s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(A.h + o_depth, A.d + o_depth, sizeof(double) * n_features, cudaMemcpyDeviceToHost, A.s));
+    LFVIO_CUDA_TRY(cudaStreamSynchronize(A.s));
+    memcpy(depth, A.h + o_depth, sizeof(double) * n_features);
     return LFVIO_OK;
 }

@@ -3,6 +3,9 @@
 #include "estimator.h"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <cstring>
 
 namespace lfvio_host {
@@ -10,6 +13,37 @@ namespace lfvio_host {
 int ESTIMATE_TD = 1, ESTIMATE_EXTRINSIC = 1, NUM_ITERATIONS = 8, EST_ROW = 960;
 double TR = 0.0, TD = -0.008, FOCAL_LENGTH = 160.0, MIN_PARALLAX = 10.0 / 160.0;
 Vec3 G{0.0, 0.0, 9.81007};
+
+// LFVIO_DEBUG_HOST=1: where the host time of processImage() goes (printed when an Estimator is destroyed)
+namespace {
+struct HostTimers {
+    const bool on = getenv("LFVIO_DEBUG_HOST") != nullptr;
+    double acc[12] = {0};
+    long calls[12] = {0};
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+    }
+    void report() const {
+        if (!on) return;
+        static const char *nm[12] = {"addFeatureCheckParallax", "flushIMU (pre-integration)", "triangulate", "vector2double + buildFactors", "lfvio_window_optimize(_full)", "double2vector", "lfvio_window_marginalize", "slideWindow + removeFailures", "", "", "", ""};
+        for (int i = 0; i < 8; i++)
+            if (calls[i]) fprintf(stderr, "Estimator host %-30s %9.1f us x %ld\n", nm[i], acc[i] / calls[i], calls[i]);
+    }
+} g_ht;
+struct Lap {
+    int i;
+    double t0;
+    explicit Lap(int i_) : i(i_), t0(g_ht.on ? HostTimers::now() : 0.0) {}
+    ~Lap() {
+        if (g_ht.on) {
+            g_ht.acc[i] += HostTimers::now() - t0;
+            g_ht.calls[i]++;
+        }
+    }
+};
+}  // namespace
 
 namespace detail {
 
@@ -240,6 +274,7 @@ Estimator::Estimator(int window_size, int max_features, int device)
     last_status = lfvio_window_create(window_size, max_features, 16 * max_features, device, &m_window);
 }
 Estimator::~Estimator() {
+    g_ht.report();
     if (m_window) lfvio_window_destroy(m_window);
 }
 const char *Estimator::lastError() const { return lfvio_last_error(); }
@@ -307,7 +342,10 @@ int Estimator::integrate(int j, bool propagate) {
             gyr[3 * k + a] = angular_velocity_buf[j][k][a];
         }
     double state[15];
-    const int st = lfvio_preintegrate(&I, 1, dt_buf[j].data(), acc.data(), gyr.data(), n, &imu_noise, G.data(), &m_pre[j], state, m_device);
+    // One gravity source for every propagation (processIMU uses the member g, estimator.cpp:118-131; EstimatorNode::predict too):
+    // the aligned gravity once the estimator runs, the configured G before (and after a state injection / clearState, which set g = G).
+    const Vec3 &grav = (solver_flag == NON_LINEAR) ? g : G;
+    const int st = lfvio_preintegrate(&I, 1, dt_buf[j].data(), acc.data(), gyr.data(), n, &imu_noise, grav.data(), &m_pre[j], state, m_device);
     if (st != LFVIO_OK) return st;
     pre_integrations[j] = &m_pre[j];
     if (propagate) {
@@ -337,7 +375,10 @@ int Estimator::repropagate(int j, const Vec3 &ba, const Vec3 &bg) {
 }
 
 void Estimator::processImage(const ImageFeatures &image, double header_stamp) {
-    marginalization_flag = f_manager.addFeatureCheckParallax(frame_count, image, td) ? MARGIN_OLD : MARGIN_SECOND_NEW;
+    {
+        Lap lap(0);
+        marginalization_flag = f_manager.addFeatureCheckParallax(frame_count, image, td) ? MARGIN_OLD : MARGIN_SECOND_NEW;
+    }
     if ((int)Headers.size() <= WINDOW_SIZE) Headers.resize(WINDOW_SIZE + 1, 0.0);
     Headers[frame_count] = header_stamp;
     {  // estimator.cpp:136-140: the frame joins all_image_frame with the pre-integration since the previous image
@@ -413,8 +454,11 @@ void Estimator::processImage(const ImageFeatures &image, double header_stamp) {
         }  // otherwise (states injected by the caller) the reboot is the caller's: failure_occur stays set
         return;
     }
-    slideWindow();
-    f_manager.removeFailures();
+    {
+        Lap lap(7);
+        slideWindow();
+        f_manager.removeFailures();
+    }
     key_poses.assign(Ps.begin(), Ps.end());
     last_R = Rs[WINDOW_SIZE];
     last_P = Ps[WINDOW_SIZE];
@@ -457,13 +501,20 @@ void Estimator::clearState() {
     last_marginalization_info = MarginalizationInfo{};
     f_manager.clearState();
     failure_occur = false;
+    g = G;  // (the reference leaves g as it was; the IMU-rate prediction must not run gravity-free until the next alignment)
 }
 
 void Estimator::solveOdometry() {
     if (frame_count < WINDOW_SIZE) return;
     if (solver_flag == NON_LINEAR) {
-        if (flushIMU() != LFVIO_OK) return;  // Ps/Vs/Rs[WINDOW_SIZE] predicted before triangulating against them
-        last_status = f_manager.triangulate(Ps, Rs, tic, ric, m_device);
+        {
+            Lap lap(1);
+            if (flushIMU() != LFVIO_OK) return;  // Ps/Vs/Rs[WINDOW_SIZE] predicted before triangulating against them
+        }
+        {
+            Lap lap(2);
+            last_status = f_manager.triangulate(Ps, Rs, tic, ric, m_device);
+        }
         if (last_status != LFVIO_OK) return;
         optimization();
     }
@@ -652,8 +703,18 @@ void Estimator::buildFactors() {
 void Estimator::optimization() {
     if (!m_window) return;
     if (flushIMU() != LFVIO_OK) return;  // pre_integrations[] and the predicted newest state up to date
+    double t_lap = g_ht.on ? HostTimers::now() : 0.0;
+    auto lap = [&](int i) {
+        if (g_ht.on) {
+            const double t = HostTimers::now();
+            g_ht.acc[i] += t - t_lap;
+            g_ht.calls[i]++;
+            t_lap = t;
+        }
+    };
     vector2double();
     buildFactors();
+    lap(3);
     lfvio_solver_opts o;
     lfvio_solver_default_opts(&o);
     o.max_num_iterations = NUM_ITERATIONS;
@@ -687,31 +748,6 @@ void Estimator::optimization() {
     double ex0[7];
     memcpy(ex0, para_Ex_Pose[0], sizeof(ex0));
     const double td0 = para_Td[0][0];
-    last_status = lfvio_window_optimize(m_window, &st, &fl, &o, &summary);  // ceres::Solve (estimator.cpp:825)
-    if (last_status == LFVIO_ERR_NUMERIC || last_status == LFVIO_ERR_CAPACITY) {
-        solve_failures++;
-        last_solve_failure = last_status;
-        last_status = LFVIO_OK;
-        bool finite = true;
-        for (double v : para_Pose) finite = finite && std::isfinite(v);
-        for (double v : para_SpeedBias) finite = finite && std::isfinite(v);
-        if (!finite || last_solve_failure == LFVIO_ERR_CAPACITY) {  // nothing usable came back: the state the solve started from
-            para_Pose = pose0;
-            para_SpeedBias = sb0;
-            memcpy(para_Ex_Pose[0], ex0, sizeof(ex0));
-            para_Feature = feat0;
-            para_Td[0][0] = td0;
-        }
-        if (last_solve_failure == LFVIO_ERR_CAPACITY) {  // the marginalisation would hit the same limit: go on without a prior
-            double2vector();
-            last_marginalization_info = MarginalizationInfo{};
-            return;
-        }
-    }
-    if (last_status != LFVIO_OK) return;
-    double2vector();
-    // ---- next prior (estimator.cpp:833-1005): the dropped factors are evaluated at the re-anchored state ----
-    vector2double();
     const int nmax = 15 * (WINDOW_SIZE + 1) + 7, bmax = 2 * (WINDOW_SIZE + 1) + 2;
     MarginalizationInfo next;
     next.block_id.resize(bmax);
@@ -728,7 +764,47 @@ void Estimator::optimization() {
     out.r0 = next.r0.data();
     out.cap_n = nmax;
     out.cap_blocks = bmax;
-    last_status = lfvio_window_marginalize(m_window, &st, &fl, &o, marginalization_flag == MARGIN_OLD ? LFVIO_MARGIN_OLD : LFVIO_MARGIN_SECOND_NEW, &out);
+    const int mflag = marginalization_flag == MARGIN_OLD ? LFVIO_MARGIN_OLD : LFVIO_MARGIN_SECOND_NEW;
+    // One call does solve + gauge re-anchoring + next prior on the device (two graph launches, one synchronisation) whenever the
+    // re-anchoring is the ordinary one; after a detected failure double2vector() anchors at last_R0 / last_P0 instead
+    // (estimator.cpp:1059-1064), which the device does not know: then the solve and the marginalisation are two calls.
+    const bool one_call = !failure_occur;
+    if (one_call) {
+        last_status = lfvio_window_optimize_full(m_window, &st, &fl, &o, mflag, &summary, &out);  // ceres::Solve (estimator.cpp:825) + :833-1005
+    } else {
+        last_status = lfvio_window_optimize(m_window, &st, &fl, &o, &summary);  // ceres::Solve (estimator.cpp:825)
+    }
+    lap(4);
+    if (last_status == LFVIO_ERR_NUMERIC || last_status == LFVIO_ERR_CAPACITY) {
+        solve_failures++;
+        last_solve_failure = last_status;
+        last_status = LFVIO_OK;
+        bool finite = true;
+        for (double v : para_Pose) finite = finite && std::isfinite(v);
+        for (double v : para_SpeedBias) finite = finite && std::isfinite(v);
+        if (!finite || last_solve_failure == LFVIO_ERR_CAPACITY) {  // nothing usable came back: the state the solve started from
+            para_Pose = pose0;
+            para_SpeedBias = sb0;
+            memcpy(para_Ex_Pose[0], ex0, sizeof(ex0));
+            para_Feature = feat0;
+            para_Td[0][0] = td0;
+        }
+        if (last_solve_failure == LFVIO_ERR_CAPACITY || one_call) {
+            // capacity: the marginalisation would hit the same limit; one call: its prior was not produced.  Go on without a prior.
+            double2vector();
+            last_marginalization_info = MarginalizationInfo{};
+            return;
+        }
+    }
+    if (last_status != LFVIO_OK) return;
+    double2vector();  // (after the one-call path the state is already re-anchored: this is then the copy into Ps / Rs / ..)
+    if (!one_call) {
+        // ---- next prior (estimator.cpp:833-1005): the dropped factors are evaluated at the re-anchored state ----
+        vector2double();
+        lap(5);
+        last_status = lfvio_window_marginalize(m_window, &st, &fl, &o, mflag, &out);
+        lap(6);
+    }
     if (last_status == LFVIO_ERR_NUMERIC || last_status == LFVIO_ERR_CAPACITY) {  // no usable prior: drop it (its block ids would be stale after the slide)
         solve_failures++;
         last_solve_failure = last_status;
@@ -974,6 +1050,7 @@ extern "C" int lfvio_host_estimator_set_states(void *h, const double *P, const d
     e->last_P0 = e->Ps[0];
     e->last_R0 = e->Rs[0];
     if (nonlinear) e->solver_flag = Estimator::NON_LINEAR;
+    e->g = G;  // injected states live in the configured gravity frame
     return LFVIO_OK;
 }
 
