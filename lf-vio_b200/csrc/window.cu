@@ -692,6 +692,8 @@ extern "C" int lfvio_window_create(int window_size, int max_landmarks, int max_p
 extern "C" void lfvio_window_destroy(lfvio_window *w) {
     if (!w) return;
     cudaSetDevice(w->device);
+    if (getenv("LFVIO_DEBUG_HOST"))
+        fprintf(stderr, "lfvio_window: %d graph keys, %d captures, %d graph launches\n", (int)w->graphs.size(), (int)w->graph_captures, (int)w->graph_launches);
     if (w->stream) {
         cudaStreamSynchronize(w->stream);
         cudaStreamDestroy(w->stream);
