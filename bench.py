@@ -793,8 +793,10 @@ def main():
         "latency_bound": True,
         "fp64": {"kernel": "step_kernel", "flop_per_launch": step_flop,
                  "achieved_gflops": (step_flop / (stages["step_kernel"][1] * 1e-3) / 1e9) if "step_kernel" in stages else None,
-                 "note": "one CTA, a chain of 15 F + 7 dependent pivots (DFMA 23 cycles, rsqrt 61, shuffle 26 on sm_100, "
-                         "tools/probe/ubench.cu): the yardstick is the length of that chain, not HBM or the fp64 pipe"},
+                 "note": "one CTA, a chain of 15 F + 7 dependent pivots (per pivot one DFMA 9.4 + one shuffle 26 + one reciprocal 40 cycles on "
+                         "sm_100, 113 measured: tools/probe/prim_probe.cu) plus the block hand-overs: the yardstick is the length of that "
+                         "chain, not HBM or the fp64 pipe; the figure is an average over launches that factor (~85 us) and launches that "
+                         "re-use the factor after a rejected step (~5 us)"},
         "stage_ms_per_step": {k: round(v[0], 5) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])},
         "note": "configs 1-3 are launch/latency bound (a whole 1280x960 frame is ~3 us of HBM time, SURVEY.md §7); stage timers put "
                 "event records between the kernels, so graph replay is off in that pass and the stages add up to more than ms_per_step",

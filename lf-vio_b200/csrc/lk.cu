@@ -30,6 +30,9 @@ constexpr int DW = WIN + 1;       // 42: derivative positions ip .. ip+41
 constexpr int LK_THREADS = 128;
 constexpr int SEGS = 3, SEG_LEN = 14;  // 41 rows x 3 segments = 123 working threads
 constexpr int W_BITS = 14;
+constexpr int JM = 8;                        // margin of the staged search tile of the next image around the first guess
+constexpr int JT_H = WIN + 1 + 2 * JM;       // 58 rows
+constexpr int JT_W = 80;                     // bytes per row: 42 + 2 * 8 columns + up to 15 of 16-byte alignment slack
 
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(LK_THREADS) lk_kernel(Pyramid prev, const __gr
     __shared__ short s_dx[DW][DW + 2], s_dy[DW][DW + 2];
     __shared__ short s_Iw[WIN][WIN + 1], s_Ix[WIN][WIN + 1], s_Iy[WIN][WIN + 1];
     __shared__ long long s_red[2][4 * 3];
+    __shared__ __align__(16) uint8_t s_J[JT_H][JT_W];  // search tile of the next image (round 2): the iterations read shared memory
 
     const int tid = threadIdx.x;
     const bool worker = tid < WIN * SEGS;
@@ -163,6 +167,25 @@ __global__ void __launch_bounds__(LK_THREADS) lk_kernel(Pyramid prev, const __gr
                 s_I[ty][tx] = I.data[(size_t)y * I.pitch + x];
             }
             __syncthreads();
+        }
+        // ---- stage the search tile of J around this level's first guess: one L2 round trip per level instead of one per
+        //      iteration (the per-pixel byte loads of the window were the iteration's latency).  Only when the tile lies inside the
+        //      image and the rows are 16-byte aligned; an iteration whose window leaves the tile reads global memory as before. ----
+        int jtx0 = 0, jty0 = 0;
+        bool jt_ok = false;
+        {
+            const int gx = cv_floor(__fsub_rn(nextFull.x, halfWin)), gy = cv_floor(__fsub_rn(nextFull.y, halfWin));
+            jtx0 = (gx - JM) & ~15;
+            jty0 = gy - JM;
+            jt_ok = gx - JM >= 0 && jty0 >= 0 && jty0 + JT_H <= J.rows && jtx0 + JT_W <= J.cols && ((J.pitch & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(J.data) & 15) == 0);
+            if (jt_ok) {
+                for (int k = tid; k < JT_H * (JT_W / 16); k += LK_THREADS) {
+                    const int ty = k / (JT_W / 16), q = k % (JT_W / 16);
+                    *reinterpret_cast<uint4 *>(&s_J[ty][16 * q]) =
+                        __ldg(reinterpret_cast<const uint4 *>(J.data + (size_t)(jty0 + ty) * J.pitch + jtx0) + q);
+                }
+            }
         }
         // ---- Scharr gradients at ip .. ip+41 (zero outside the image) ----
         for (int k = tid; k < DW * DW; k += LK_THREADS) {
@@ -238,7 +261,21 @@ __global__ void __launch_bounds__(LK_THREADS) lk_kernel(Pyramid prev, const __gr
                 const int y = iny + wrow;
                 int b1 = 0, b2 = 0;
                 const bool interior = (inx >= 0) && (inx + WIN < J.cols) && (iny >= 0) && (iny + WIN < J.rows);
-                if (interior) {
+                const bool in_tile = jt_ok && interior && inx >= jtx0 && inx + WIN + 1 <= jtx0 + JT_W && iny >= jty0 && iny + WIN + 1 <= jty0 + JT_H;
+                if (in_tile) {
+                    const uint8_t *r0 = &s_J[y - jty0][inx - jtx0 + wx0];
+                    const uint8_t *r1 = r0 + JT_W;
+                    int p00 = r0[0], p10 = r1[0];
+                    for (int x = wx0; x < wx1; x++) {
+                        const int p01 = r0[(x - wx0) + 1], p11 = r1[(x - wx0) + 1];
+                        const int diff = descale(p00 * wj.w00 + p01 * wj.w01 + p10 * wj.w10 + p11 * wj.w11, W_BITS - 5) -
+                                         s_Iw[wrow][x];
+                        b1 += diff * s_Ix[wrow][x];
+                        b2 += diff * s_Iy[wrow][x];
+                        p00 = p01;
+                        p10 = p11;
+                    }
+                } else if (interior) {
                     const uint8_t *r0 = J.data + (size_t)y * J.pitch + inx + wx0;
                     const uint8_t *r1 = r0 + J.pitch;
                     int p00 = __ldg(r0), p10 = __ldg(r1);
