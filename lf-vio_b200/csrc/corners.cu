@@ -19,7 +19,10 @@
 //     one is accepted); only the top-valued prefix needed to produce K corners is activated (histogram
 //     cut), and the K best accepted keys are emitted in descending order == OpenCV's acceptance order.
 // Traffic: read 1 B/px + write 4 B/px (eig), then read 4 B/px + 1 B/px mask = 10 B/px.
+#include <cstring>
+
 #include "frontend.cuh"
+#include "tma.cuh"
 
 namespace lfvio {
 
@@ -40,35 +43,47 @@ __device__ __forceinline__ float dec_ordered(uint32_t e) {
 // OpenCV's boxFilter) and rolls them down the strip — 3 conversions + 12 f64 additions per pixel instead of 27 + 27, no shared
 // memory for floats, one barrier.  Rounding sequence unchanged (see the header of this file): bit-exact against cv2.
 constexpr int ET_W = 64;       // tile width; the tile is 16 strips of ET_R rows high
-constexpr int ET_TW = ET_W + 8;  // byte tile: virtual columns x0-4 .. x0+67, rows y0-2 .. y0+ET_H+1
+constexpr int ET_TW = ET_W + 32;  // byte tile: virtual columns x0-16 .. x0+79 (one TMA box: 16-byte aligned start), rows y0-2 .. y0+ET_H+1
+constexpr int ET_XO = 16;        // tile column of virtual column x0
 
 template <int ET_R>
 __global__ void __launch_bounds__(256) min_eig_kernel(const uint8_t *__restrict__ img, int pitch,
                                                       const uint8_t *__restrict__ mask, int mask_pitch,
                                                       float *__restrict__ eig, int rows, int cols,
-                                                      uint32_t *__restrict__ max_bits) {
+                                                      uint32_t *__restrict__ max_bits, const __grid_constant__ CUtensorMap tmap, int use_tma) {
     constexpr int ET_H = 16 * ET_R, ET_TH = ET_H + 4;
-    __shared__ __align__(16) uint8_t s_I[ET_TH][ET_TW];
+    __shared__ __align__(128) uint8_t s_I[ET_TH][ET_TW];
+    __shared__ uint64_t s_mbar;
     __shared__ uint32_t s_max[8];
     const int x0 = blockIdx.x * ET_W, y0 = blockIdx.y * ET_H;
     const int tid = threadIdx.x;
-    // ---- byte tile at virtual coordinates, REFLECT_101 ----
-    const bool interior = x0 >= 4 && x0 + ET_W + 4 <= cols && y0 >= 2 && y0 + ET_H + 2 <= rows && ((pitch & 3) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(img) & 3) == 0);
-    if (interior) {
-        const uint8_t *base = img + (size_t)(y0 - 2) * pitch + (x0 - 4);
+    // ---- byte tile at virtual coordinates: one TMA box load (cp.async.bulk.tensor.2d, completion on an mbarrier) for tiles away
+    //      from the image border, REFLECT_101 gathered with plain loads for the others ----
+    const bool interior = x0 >= ET_XO && x0 + ET_TW - ET_XO <= cols && y0 >= 2 && y0 + ET_H + 2 <= rows;
+    if (interior && use_tma) {
+        if (tid == 0) {
+            mbar_init(&s_mbar, 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s_mbar, ET_TH * ET_TW);
+            tma_load_tile(&s_I[0][0], &tmap, x0 - ET_XO, y0 - 2, &s_mbar);
+        }
+        __syncthreads();  // the barrier is initialised before anybody waits on it
+        mbar_wait(&s_mbar, 0);
+    } else if (interior && ((pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(img) & 3) == 0)) {
+        const uint8_t *base = img + (size_t)(y0 - 2) * pitch + (x0 - ET_XO);
         for (int k = tid; k < ET_TH * (ET_TW / 4); k += 256) {
             const int ty = k / (ET_TW / 4), w = k % (ET_TW / 4);
             *reinterpret_cast<uint32_t *>(&s_I[ty][4 * w]) = __ldg(reinterpret_cast<const uint32_t *>(base + (size_t)ty * pitch) + w);
         }
+        __syncthreads();
     } else {
         for (int k = tid; k < ET_TH * ET_TW; k += 256) {
             const int ty = k / ET_TW, tx = k % ET_TW;
-            const int y = reflect101(y0 - 2 + ty, rows), x = reflect101(x0 - 4 + tx, cols);
+            const int y = reflect101(y0 - 2 + ty, rows), x = reflect101(x0 - ET_XO + tx, cols);
             s_I[ty][tx] = img[(size_t)y * pitch + x];
         }
+        __syncthreads();
     }
-    __syncthreads();
     const float s = (float)(1.0 / (4 * 3 * 255.0));  // Sobel scale for u8, ksize 3, blockSize 3
     const float s2 = 2.0f * s;
     const int X = x0 + 4 * (tid & 15), Y0 = y0 + ET_R * (tid >> 4);  // first output of this strip
@@ -78,10 +93,10 @@ __global__ void __launch_bounds__(256) min_eig_kernel(const uint8_t *__restrict_
         // REFLECT_101 position (the box filter's border rule on the covariance images)
         auto deriv_row = [&](int vy, float (&gx)[6], float (&gy)[6]) {
             const int t = reflect101(vy, rows) - (y0 - 2);  // tile row of the centre
-            float a[3][8];                                  // tile columns 4 tx + 2 .. 4 tx + 9 = virtual X-2 .. X+5
+            float a[3][8];                                  // tile columns 4 tx + 14 .. 4 tx + 21 = virtual X-2 .. X+5
 #pragma unroll
             for (int r = 0; r < 3; r++) {
-                const uint32_t *w = reinterpret_cast<const uint32_t *>(&s_I[t - 1 + r][4 * (tid & 15)]);
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(&s_I[t - 1 + r][4 * (tid & 15) + ET_XO - 4]);
                 const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
                 a[r][0] = (float)((w0 >> 16) & 255u); a[r][1] = (float)(w0 >> 24);
                 a[r][2] = (float)(w1 & 255u); a[r][3] = (float)((w1 >> 8) & 255u); a[r][4] = (float)((w1 >> 16) & 255u); a[r][5] = (float)(w1 >> 24);
@@ -478,10 +493,15 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelParams p, unsign
 }  // namespace
 
 int launch_min_eig(const uint8_t *img, int pitch, const uint8_t *mask, int mask_pitch, float *eig, int rows,
-                   int cols, uint32_t *max_bits, cudaStream_t s) {
+                   int cols, uint32_t *max_bits, cudaStream_t s, const CUtensorMap *tile_map) {
     LFVIO_CUDA_TRY(cudaMemsetAsync(max_bits, 0, sizeof(uint32_t), s));
     // (strips of 8 rows — 1.25 derivative rows per output row instead of 1.5 — measured slower at 3840 x 2880: 120 against 112 us)
-    min_eig_kernel<4><<<dim3(cdiv(cols, ET_W), cdiv(rows, 64)), 256, 0, s>>>(img, pitch, mask, mask_pitch, eig, rows, cols, max_bits);
+    // tile_map: tensor map of `img` with a 96 x 68 box (encode_u8_tmap); null -> the tiles are staged with plain loads
+    CUtensorMap tm;
+    if (tile_map) tm = *tile_map;
+    else memset(&tm, 0, sizeof(tm));
+    min_eig_kernel<4><<<dim3(cdiv(cols, ET_W), cdiv(rows, 64)), 256, 0, s>>>(img, pitch, mask, mask_pitch, eig, rows, cols, max_bits, tm,
+                                                                              tile_map ? 1 : 0);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

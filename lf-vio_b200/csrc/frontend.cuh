@@ -60,7 +60,7 @@ int launch_lk(const Pyramid &prev, const PyrTmaps &prev_tm, const Pyramid &next,
 // ---- K4 Shi-Tomasi --------------------------------------------------------------------------
 // eig: rows x cols f32 (pitch in elements = cols).  max_bits: one u32, ordered-float encoding.
 int launch_min_eig(const uint8_t *img, int pitch, const uint8_t *mask, int mask_pitch, float *eig, int rows,
-                   int cols, uint32_t *max_bits, cudaStream_t s);
+                   int cols, uint32_t *max_bits, cudaStream_t s, const CUtensorMap *tile_map = nullptr);
 
 struct CornerScratch {
     unsigned long long *cand;       // capacity cand_cap: (value bits << 32) | linear index

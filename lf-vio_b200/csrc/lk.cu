@@ -17,6 +17,7 @@
 // bitwise.  The scalar f32 update math is written with un-fused intrinsics to follow OpenCV's rounding.
 // Algorithmic HBM bytes: 2 * 43^2 B per feature per level.
 #include "frontend.cuh"
+#include "tma.cuh"
 
 namespace lfvio {
 
@@ -64,37 +65,6 @@ __device__ __forceinline__ void block_sum(long long (&v)[K], long long *buf) {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < K; k++) v[k] = buf[0 * K + k] + buf[1 * K + k] + buf[2 * K + k] + buf[3 * K + k];
-}
-
-// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers -------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    }
-}
-// one 48 x 44 u8 box whose top-left pixel is (x, y); out-of-range bytes (x >= cols) are zero-filled by the TMA unit
-__device__ __forceinline__ void tma_load_tile(void *dst, const CUtensorMap *tmap, int x, int y, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar))
-        : "memory");
 }
 
 __global__ void __launch_bounds__(LK_THREADS) lk_kernel(Pyramid prev, const __grid_constant__ PyrTmaps prev_tm, Pyramid next,

@@ -14,6 +14,7 @@
 #include <cstring>
 
 #include "frontend.cuh"
+#include "tma.cuh"
 
 namespace lfvio {
 
@@ -87,29 +88,36 @@ int launch_build_pyramid(const Pyramid &p, cudaStream_t s) {
     return LFVIO_OK;
 }
 
-void make_pyramid_tmaps(const Pyramid &p, PyrTmaps *out) {
+bool encode_u8_tmap(CUtensorMap *out, const uint8_t *data, int rows, int cols, int pitch, int box_w, int box_h) {
     typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+            qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            fn = nullptr;
+        }
+        return reinterpret_cast<EncodeTiled>(fn);
+    }();
+    if (!encode) return false;
+    if ((reinterpret_cast<uintptr_t>(data) & 15) || (pitch & 15)) return false;  // TMA needs 16-byte aligned base and pitch
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estride[2] = {1, 1};
+    return encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(data), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+void make_pyramid_tmaps(const Pyramid &p, PyrTmaps *out) {
     memset(out, 0, sizeof(*out));
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
-        qres != cudaDriverEntryPointSuccess) {
-        cudaGetLastError();
-        return;
-    }
-    EncodeTiled encode = reinterpret_cast<EncodeTiled>(fn);
     for (int l = 0; l < p.levels && l < kTmaLevels; l++) {
         const ImgLevel &L = p.lvl[l];
-        if ((reinterpret_cast<uintptr_t>(L.data) & 15) || (L.pitch & 15)) return;  // TMA needs 16-byte aligned base and pitch
-        const cuuint64_t gdim[2] = {(cuuint64_t)L.cols, (cuuint64_t)L.rows};
-        const cuuint64_t gstride[1] = {(cuuint64_t)L.pitch};
-        const cuuint32_t box[2] = {64, 44};  // the 44 x 44 LK tile + 16-byte alignment slack of the row start
-        const cuuint32_t estride[2] = {1, 1};
-        if (encode(&out->m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, L.data, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return;
+        // box: the 44 x 44 LK tile + 16-byte alignment slack of the row start
+        if (!encode_u8_tmap(&out->m[l], L.data, L.rows, L.cols, L.pitch, 64, 44)) return;
     }
     out->valid = 1;
 }

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "frontend.cuh"
+#include "tma.cuh"
 
 namespace lfvio {
 
@@ -146,6 +147,8 @@ struct lfvio_tracker {
     std::vector<DevBuf<uint8_t>> pyr_store[2];
     Pyramid pyr[2];
     PyrTmaps pyr_tm[2];
+    CUtensorMap eig_tm[2];     // level 0 of either pyramid slot with the 96 x 68 box of min_eig_kernel
+    bool eig_tm_ok[2] = {false, false};
     int cur_slot = 0;
     long frames = 0;
     // CLAHE scratch
@@ -222,6 +225,7 @@ int tracker_init(lfvio_tracker *t, const lfvio_tracker_cfg *cfg, int device) {
     for (int k = 0; k < 2; k++) {
         LFVIO_TRY(alloc_pyramid(&t->pyr[k], &t->pyr_store[k], rows, cols, 3, 41));
         make_pyramid_tmaps(t->pyr[k], &t->pyr_tm[k]);
+        t->eig_tm_ok[k] = encode_u8_tmap(&t->eig_tm[k], t->pyr[k].lvl[0].data, t->pyr[k].lvl[0].rows, t->pyr[k].lvl[0].cols, t->pyr[k].lvl[0].pitch, 96, 68);
     }
     LFVIO_TRY(t->clahe_hist.alloc(kClaheTiles * kClaheTiles * 256));
     LFVIO_TRY(t->clahe_lut.alloc(kClaheTiles * kClaheTiles * 256));
@@ -337,7 +341,7 @@ int frame_body(lfvio_tracker *t, const uint8_t *src, int src_pitch, double cur_t
         // goodFeaturesToTrack(forw_img, n_pts, MAX_CNT - forw_pts.size(), 0.01, MIN_DIST, mask) + addPoints()
         t->prof.begin(TS_MIN_EIG, s);
         LFVIO_TRY(launch_min_eig(forw.lvl[0].data, forw.lvl[0].pitch, t->mask.p, t->pitch, t->corners.eig.p, c.rows, c.cols,
-                                 t->corners.max_bits.p, s));
+                                 t->corners.max_bits.p, s, t->eig_tm_ok[forw_slot] ? &t->eig_tm[forw_slot] : nullptr));
         t->prof.end(s);
         t->prof.begin(TS_CANDIDATES, s);
         LFVIO_TRY(launch_corner_candidates(t->corners.eig.p, t->mask.p, t->pitch, c.rows, c.cols, t->corners.max_bits.p,
@@ -767,7 +771,9 @@ extern "C" int lfvio_corner_min_eigen_val(const uint8_t *img, int rows, int cols
     DevBuf<uint32_t> mx;
     LFVIO_TRY(eig.alloc((size_t)rows * cols));
     LFVIO_TRY(mx.alloc(1));
-    LFVIO_TRY(launch_min_eig(src.buf.p, src.pitch, nullptr, 0, eig.p, rows, cols, mx.p, 0));
+    CUtensorMap tm;
+    const bool tm_ok = encode_u8_tmap(&tm, src.buf.p, rows, cols, src.pitch, 96, 68);
+    LFVIO_TRY(launch_min_eig(src.buf.p, src.pitch, nullptr, 0, eig.p, rows, cols, mx.p, 0, tm_ok ? &tm : nullptr));
     LFVIO_CUDA_TRY(cudaDeviceSynchronize());
     LFVIO_CUDA_TRY(cudaMemcpy(out, eig.p, sizeof(float) * (size_t)rows * cols, cudaMemcpyDeviceToHost));
     return LFVIO_OK;
@@ -789,7 +795,9 @@ extern "C" int lfvio_good_features_to_track(const uint8_t *img, int rows, int co
     LFVIO_TRY(cs.alloc(rows, cols, cell));
     DevBuf<float2> outp;
     LFVIO_TRY(outp.alloc(max_corners));
-    LFVIO_TRY(launch_min_eig(src.buf.p, src.pitch, mask ? msk.buf.p : nullptr, msk.pitch, cs.eig.p, rows, cols, cs.max_bits.p, 0));
+    CUtensorMap tm;
+    const bool tm_ok = encode_u8_tmap(&tm, src.buf.p, rows, cols, src.pitch, 96, 68);
+    LFVIO_TRY(launch_min_eig(src.buf.p, src.pitch, mask ? msk.buf.p : nullptr, msk.pitch, cs.eig.p, rows, cols, cs.max_bits.p, 0, tm_ok ? &tm : nullptr));
     LFVIO_TRY(launch_corner_candidates(cs.eig.p, mask ? msk.buf.p : nullptr, msk.pitch, rows, cols, cs.max_bits.p, quality, cs.cs, 0));
     LFVIO_TRY(launch_corner_select(cs.cs, cols, (float)min_distance, max_corners, nullptr, outp.p, nullptr, nullptr, nullptr,
                                    max_corners, 0));

@@ -191,7 +191,8 @@ def test_device_resident_solve_then_marginalize(lfvio_mod, win, problem):
 
 
 # ---- larger windows (BASELINE.json configs 3/4 shapes): global-memory Cholesky path, more landmarks ------------
-@pytest.mark.parametrize("n_frames,n_lm,feats", [(11, 900, 500), (21, 1500, 800)])
+# (21, 3600, 2000) is the shape bench.py runs at BASELINE config 4 (R ~ 31 k projection factors, D = 322, L > 1024: pre_kernel / gnlm_kernel)
+@pytest.mark.parametrize("n_frames,n_lm,feats", [(11, 900, 500), (21, 1500, 800), (21, 3600, 2000)])
 def test_large_window_matches_oracle(lfvio_mod, gpu, n_frames, n_lm, feats):
     opts = lfvio_mod.solver_default_opts()
     w = synthwin.make_window(seed=7, n_frames=n_frames, n_landmarks=n_lm, feats_per_frame=feats, opts=opts, perturb=0.3)
