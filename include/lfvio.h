@@ -295,6 +295,56 @@ int lfvio_window_optimize_dev(lfvio_window *w, int with_marginalize, int margin_
 int lfvio_window_download(lfvio_window *w, lfvio_window_state *state, lfvio_solve_summary *summary);
 
 /* ==========================================================================================
+ * FeatureManager on the device: the track list of the window as a structure of arrays in HBM
+ * (FeaturePerId / FeaturePerFrame, feature_manager.h:17-64), its bookkeeping as kernels, and the projection-factor list
+ * of Estimator::optimization() (estimator.cpp:725-772) built where it is consumed.  List order == the reference's
+ * std::list order (insertion order; ids ascend).  Every call is ordered on the handle's own stream; calls that return
+ * counts synchronise it.  A capacity error (LFVIO_ERR_CAPACITY) is sticky until lfvio_fm_clear().
+ * ========================================================================================== */
+typedef struct lfvio_fm lfvio_fm;
+/* FeatureManager(Rs) + setRic: window_size = WINDOW_SIZE, capacity = live features the store can hold,
+ * max_proj_factors = size of the handle's own factor buffer, min_parallax = MIN_PARALLAX, init_depth = INIT_DEPTH.     */
+int lfvio_fm_create(int window_size, int capacity, int max_proj_factors, double min_parallax, double init_depth,
+                    int device, lfvio_fm **out);
+void lfvio_fm_destroy(lfvio_fm *f);
+/* FeatureManager::clearState (feature_manager.cpp:31-34)                                                              */
+int lfvio_fm_clear(lfvio_fm *f);
+/* FeatureManager::addFeatureCheckParallax (feature_manager.cpp:45-95): ids ascending (the reference iterates a std::map),
+ * feat8 = n x [x y z u v vx vy vz] as in the feature message (estimator.cpp:118-124, camera 0).  Returns the key-frame
+ * decision (1 => MARGIN_OLD) and last_track_num.                                                                       */
+int lfvio_fm_add_frame(lfvio_fm *f, int frame_count, const int *ids, const double *feat8, int n, double td,
+                       int *is_keyframe, int *last_track_num);
+/* removeBack (feature_manager.cpp:312-327), removeBackShiftDepth (:271-310; matrices 3 x 3 row-major),
+ * removeFront (:329-351), removeFailures (:134-143)                                                                    */
+int lfvio_fm_remove_back(lfvio_fm *f);
+int lfvio_fm_remove_back_shift_depth(lfvio_fm *f, const double *marg_R, const double *marg_P, const double *new_R,
+                                     const double *new_P);
+int lfvio_fm_remove_front(lfvio_fm *f, int frame_count);
+int lfvio_fm_remove_failures(lfvio_fm *f);
+/* mode 0 setDepth (:145-163), 1 clearDepth (:165-174): x in (one value per selected feature, list order);
+ * mode 2 getDepthVector (:176-190): x out.  *n_out = getFeatureCount() (:36-43).                                       */
+int lfvio_fm_depth(lfvio_fm *f, int mode, double *x, int n_cap, int *n_out);
+/* FeatureManager::triangulate (feature_manager.cpp:199-253) over the store: Ps (F x 3) / Rs (F x 9 row-major) IMU poses,
+ * tic (3) / ric (9) extrinsics from the host; estimated_depth updated in place on the device.                         */
+int lfvio_fm_triangulate(lfvio_fm *f, const double *Ps, const double *Rs, const double *tic, const double *ric);
+/* The residual-block loop of estimator.cpp:725-772 + para_Feature (vector2double, :1044-1046) into the handle's own
+ * device buffers; lfvio_fm_download_factors copies the last build out (lm_first has n_landmarks + 1 entries).           */
+int lfvio_fm_build_factors(lfvio_fm *f, int *n_proj, int *n_landmarks);
+int lfvio_fm_download_factors(lfvio_fm *f, lfvio_proj_factor *proj, int proj_cap, int *lm_first, double *para_feature,
+                              int lm_cap);
+int lfvio_fm_factors_dev(lfvio_fm *f, const lfvio_proj_factor **proj, const int **lm_first, const double **para_feature,
+                         void **stream);
+/* The list as (feature_id, start_frame, n_observations) + estimated_depth in list order; returns its length.           */
+int lfvio_fm_snapshot(lfvio_fm *f, int *meta3, double *depth, int cap);
+/* lfvio_window_optimize_full with the projection factors, landmark ranges and para_Feature taken from the device
+ * manager (factors->proj is ignored; state->n_landmarks and state->para_Feature are outputs, the latter with room for the
+ * window's max_landmarks) and FeatureManager::setDepth of the result (double2vector, estimator.cpp:560-563) applied on
+ * the device.  The factor list never exists on the host.                                                               */
+int lfvio_window_optimize_full_fm(lfvio_window *w, lfvio_fm *fm, lfvio_window_state *state,
+                                  const lfvio_factor_list *factors, const lfvio_solver_opts *opts, int margin_flag,
+                                  lfvio_solve_summary *summary, lfvio_prior *prior_out);
+
+/* ==========================================================================================
  * The two steps right before optimization(): they produce the constants the
  * factors above consume.
  * ========================================================================================== */

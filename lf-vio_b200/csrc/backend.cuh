@@ -41,6 +41,27 @@ struct StateLayout {
     __host__ __device__ int block_lsize(int id) const { return id < 2 * F ? ((id & 1) ? 9 : 6) : (id == 2 * F ? 6 : 1); }
 };
 
+// Projection factors built on the device by the FeatureManager (fm.cu): what the host needs to know about a list it never sees.
+struct DevFactorSrc {
+    int n_proj, n_landmarks;
+    unsigned frame_j_mask;  // bit j: a landmark hosted in frame 0 is observed from frame j (marginalisation plan)
+    int n_marg_lm;          // landmarks hosted in frame 0; their indices are already in the MARGIN_OLD landmark list
+};
+struct FmBuildDst {
+    lfvio_proj_factor *proj;
+    int *lm_first;
+    double *para_feature;
+    int *marg_lm;
+    int proj_cap, lm_cap;
+};
+int fm_build_factors_into(lfvio_fm *f, const FmBuildDst &dst, DevFactorSrc *src);
+int fm_set_depth_from_dev(lfvio_fm *f, const double *x_dev);
+int fm_window_size(const lfvio_fm *f);
+int fm_device(const lfvio_fm *f);
+int launch_triangulate_slots(const double *Ps, const double *Rs, const double *tic, const double *ric, const int *start_frame,
+                             const int *n_obs, const double *obs, int rec, int n_slots, int n_frames, double init_depth, double *depth,
+                             cudaStream_t s);
+
 struct DevPrior {
     int n, n_blocks;
     int block_id[kMaxPriorBlocks];

@@ -190,12 +190,14 @@ constexpr int TRI_MAX_ROWS = 64;  // 2 K <= 64: up to 32 observations (kMaxFrame
 __global__ void __launch_bounds__(TRI_WARPS * 32) triangulate_kernel(const double *Ps, const double *Rs, const double *tic,
                                                                     const double *ric, const int *start_frame,
                                                                     const int *obs_first, const double *obs_pts, int n,
-                                                                    int n_frames, double init_depth, double *depth) {
+                                                                    int n_frames, double init_depth, double *depth,
+                                                                    const int *n_obs, int rec) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int l = blockIdx.x * TRI_WARPS + wid;
     if (l >= n) return;
     if (depth[l] > 0) return;  // feature_manager.cpp:207-208: already has a depth
-    const int o0 = obs_first[l], K = obs_first[l + 1] - o0;
+    // packed tracks (obs_first) or the device FeatureManager's slots (n_obs: n_frames records of `rec` doubles per slot)
+    const int o0 = n_obs ? l * n_frames : obs_first[l], K = n_obs ? n_obs[l] : obs_first[l + 1] - o0;
     if (K < 2 || 2 * K > TRI_MAX_ROWS) return;  // used_num >= 2 (:204); longer tracks cannot exist (K <= F)
     const int f0 = start_frame[l];
     if (!(f0 < (n_frames - 1) - 2)) return;     // start_frame < WINDOW_SIZE - 2 (:204)
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(TRI_WARPS * 32) triangulate_kernel(const doubl
             const DM3 R = transpose3(R0) * R1;
             const DM3 Rt = transpose3(R);       // P.leftCols<3>()
             const D3 pt = -(Rt * t);            // P.rightCols<1>()
-            const D3 f = unit3(d3(obs_pts[3 * (size_t)(o0 + k)], obs_pts[3 * (size_t)(o0 + k) + 1], obs_pts[3 * (size_t)(o0 + k) + 2]));
+            const D3 f = unit3(d3(obs_pts[rec * (size_t)(o0 + k)], obs_pts[rec * (size_t)(o0 + k) + 1], obs_pts[rec * (size_t)(o0 + k) + 2]));
             const int sel = row & 1;  // row 2k: f0 P2 - f2 P0 ; row 2k+1: f1 P2 - f2 P1   (:234-235)
             const double fa = sel ? f.y : f.x;
 #pragma unroll
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(TRI_WARPS * 32) triangulate_kernel(const doubl
         double X[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) X[i] = (bi == 0) ? V[i][0] : (bi == 1 ? V[i][1] : (bi == 2 ? V[i][2] : V[i][3]));
-        const double px = obs_pts[3 * (size_t)o0], py = obs_pts[3 * (size_t)o0 + 1], pz = obs_pts[3 * (size_t)o0 + 2];
+        const double px = obs_pts[rec * (size_t)o0], py = obs_pts[rec * (size_t)o0 + 1], pz = obs_pts[rec * (size_t)o0 + 2];
         double d = (X[0] / X[3]) * px + (X[1] / X[3]) * py + (X[2] / X[3]) * pz;  // :243-245 (range along the bearing)
         if (d < 0) d = init_depth;                                                 // :246-249
         depth[l] = d;
@@ -362,7 +364,17 @@ int launch_triangulate(const double *Ps, const double *Rs, const double *tic, co
                        cudaStream_t s) {
     if (n <= 0) return LFVIO_OK;
     triangulate_kernel<<<cdiv(n, TRI_WARPS), TRI_WARPS * 32, 0, s>>>(Ps, Rs, tic, ric, start_frame, obs_first, obs_pts, n, n_frames,
-                                                                    init_depth, depth);
+                                                                    init_depth, depth, nullptr, 3);
+    LFVIO_LAUNCH_CHECK();
+    return LFVIO_OK;
+}
+
+int launch_triangulate_slots(const double *Ps, const double *Rs, const double *tic, const double *ric, const int *start_frame,
+                             const int *n_obs, const double *obs, int rec, int n_slots, int n_frames, double init_depth, double *depth,
+                             cudaStream_t s) {
+    if (n_slots <= 0) return LFVIO_OK;
+    triangulate_kernel<<<cdiv(n_slots, TRI_WARPS), TRI_WARPS * 32, 0, s>>>(Ps, Rs, tic, ric, start_frame, nullptr, obs, n_slots, n_frames,
+                                                                          init_depth, depth, n_obs, rec);
     LFVIO_LAUNCH_CHECK();
     return LFVIO_OK;
 }

@@ -220,7 +220,8 @@ int publish_plan(lfvio_window *w, int flag) {
 
 // Which blocks are dropped / kept and in which column order (estimator.cpp:833-1005, marginalization_factor.cpp:174-205),
 // canonical order by block id instead of the reference's address-keyed unordered_map.
-int build_marg_plan(lfvio_window *w, int flag, const lfvio_factor_list *fl, const lfvio_solver_opts *o, int L) {
+int build_marg_plan(lfvio_window *w, int flag, const lfvio_factor_list *fl, const lfvio_solver_opts *o, int L,
+                    const DevFactorSrc *src = nullptr) {
     MargPlan &pl = w->plan[flag];
     memset(&pl, 0, sizeof(pl));
     w->plan_valid[flag] = false;
@@ -251,7 +252,16 @@ int build_marg_plan(lfvio_window *w, int flag, const lfvio_factor_list *fl, cons
                 touch(3, false);
             }
         int last_l = -1;
-        for (int k = 0; k < fl->n_proj; k++)
+        if (src) {  // the list was built on the device: which frames the landmarks hosted in frame 0 are seen from
+            for (int j = 1; j < F; j++)
+                if (src->frame_j_mask >> j & 1u) {
+                    touch(0, true);
+                    touch(2 * j, false);
+                    touch(2 * F, false);
+                    if (o->estimate_td) touch(2 * F + 1, false);
+                }
+        }
+        for (int k = 0; !src && k < fl->n_proj; k++)
             if (fl->proj[k].frame_i == 0) {
                 touch(0, true);
                 touch(2 * fl->proj[k].frame_j, false);
@@ -289,9 +299,9 @@ int build_marg_plan(lfvio_window *w, int flag, const lfvio_factor_list *fl, cons
         }
     pl.n = pos - pl.m_p;
     pl.dim = pos;
-    pl.n_lm = (int)lms.size();
+    pl.n_lm = (src && flag == LFVIO_MARGIN_OLD) ? src->n_marg_lm : (int)lms.size();
     pl.lm_list = w->lm_list[flag].p;
-    if (pl.n_lm) {  // staged through pinned memory: no synchronisation on the upload path
+    if (!lms.empty()) {  // staged through pinned memory: no synchronisation on the upload path
         memcpy(w->h_lm[flag], lms.data(), sizeof(int) * lms.size());
         LFVIO_CUDA_TRY(cudaMemcpyAsync(w->lm_list[flag].p, w->h_lm[flag], sizeof(int) * lms.size(), cudaMemcpyHostToDevice, w->stream));
     }
@@ -378,21 +388,23 @@ int enqueue_prepare(lfvio_window *w) {
 
 // defer_prepare: the caller enqueues enqueue_prepare() itself (as part of a replayed graph).
 int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_list *fl, const lfvio_solver_opts *o,
-           bool defer_plans = false, bool defer_prepare = false) {
+           bool defer_plans = false, bool defer_prepare = false, const DevFactorSrc *src = nullptr) {
     LFVIO_REQUIRE(st && fl && o, "window: null argument");
     LFVIO_REQUIRE(st->n_frames == w->F, "window: n_frames != window_size + 1 of the handle");
-    LFVIO_REQUIRE(st->n_landmarks >= 0 && st->n_landmarks <= w->Lmax, "window: too many landmarks for this handle");
-    LFVIO_REQUIRE(fl->n_proj >= 0 && fl->n_proj <= w->Rmax, "window: too many projection factors for this handle");
+    const int n_proj = src ? src->n_proj : fl->n_proj;
+    const int n_lm = src ? src->n_landmarks : st->n_landmarks;
+    LFVIO_REQUIRE(n_lm >= 0 && n_lm <= w->Lmax, "window: too many landmarks for this handle");
+    LFVIO_REQUIRE(n_proj >= 0 && n_proj <= w->Rmax, "window: too many projection factors for this handle");
     LFVIO_REQUIRE(fl->n_imu >= 0 && fl->n_imu <= w->F - 1, "window: too many IMU factors");
     LFVIO_REQUIRE(o->max_num_iterations >= 0 && o->max_num_iterations < LFVIO_MAX_ITER_LOG, "window: bad max_num_iterations");
-    const int F = w->F, L = st->n_landmarks;
+    const int F = w->F, L = n_lm;
     StateLayout lay{F, L};
     uint8_t *hb = w->h_blob;
-    if (fl->n_proj) memcpy(hb + w->off_proj, fl->proj, sizeof(lfvio_proj_factor) * (size_t)fl->n_proj);
+    if (!src && n_proj) memcpy(hb + w->off_proj, fl->proj, sizeof(lfvio_proj_factor) * (size_t)n_proj);
     if (fl->n_imu) memcpy(hb + w->off_imu, fl->imu, sizeof(lfvio_imu_factor) * (size_t)fl->n_imu);
     // landmark -> factor ranges (the reference inserts factors landmark by landmark, estimator.cpp:725-772)
     int *lm = reinterpret_cast<int *>(hb + w->off_lm);
-    {
+    if (!src) {  // (a list built by lfvio_fm_build_factors is grouped and in range by construction)
         int k = 0;
         for (int l = 0; l < L; l++) {
             lm[l] = k;
@@ -414,7 +426,7 @@ int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_lis
     memset(&P, 0, sizeof(P));
     P.lay = lay;
     P.o = *o;
-    P.n_proj = fl->n_proj;
+    P.n_proj = n_proj;
     P.n_imu = fl->n_imu;
     P.proj = reinterpret_cast<const lfvio_proj_factor *>(w->blob.p + w->off_proj);
     P.imu = reinterpret_cast<const lfvio_imu_factor *>(w->blob.p + w->off_imu);
@@ -447,7 +459,7 @@ int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_lis
     }
     // launch geometry: counts rounded up to coarse buckets so that consecutive frames of a stream share one graph
     P.self_dev = w->P_dev.p;
-    P.g_nbp = std::max(1, std::min(cdiv(w->Rmax, 128), (cdiv(fl->n_proj, 128) + 7) / 8 * 8));
+    P.g_nbp = std::max(1, std::min(cdiv(w->Rmax, 128), (cdiv(n_proj, 128) + 7) / 8 * 8));
     P.g_L = std::max(1, std::min(w->Lmax, (L + 127) / 128 * 128));
     P.g_imu = F - 1;
     P.cap_L = w->Lmax;
@@ -459,26 +471,31 @@ int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_lis
     memcpy(hx + lay.sb(0), st->para_SpeedBias, sizeof(double) * 9 * F);
     memcpy(hx + lay.ex(), st->para_Ex_Pose, sizeof(double) * 7);
     hx[lay.td()] = st->para_Td[0];
-    if (L) memcpy(hx + lay.feat(0), st->para_Feature, sizeof(double) * L);
+    if (L && !src) memcpy(hx + lay.feat(0), st->para_Feature, sizeof(double) * L);
     // one DMA: everything up to the end of the state (unused capacity in between is skipped in three pieces)
     cudaStream_t s = w->stream;
     auto copy = [&](size_t off, size_t bytes) -> int {
         if (bytes) LFVIO_CUDA_TRY(cudaMemcpyAsync(w->blob.p + off, hb + off, bytes, cudaMemcpyHostToDevice, s));
         return LFVIO_OK;
     };
-    LFVIO_TRY(copy(w->off_proj, sizeof(lfvio_proj_factor) * (size_t)fl->n_proj));
-    LFVIO_TRY(copy(w->off_imu, w->off_px0 - w->off_imu + (P.prior.n ? sizeof(double) * 9 * P.prior.n_blocks : 0)));
+    if (src) {  // factors, ranges and inverse depths are already in the blob (written there by the FeatureManager's kernel)
+        LFVIO_TRY(copy(w->off_imu, w->off_lm - w->off_imu));
+        if (P.prior.n) LFVIO_TRY(copy(w->off_px0, sizeof(double) * 9 * P.prior.n_blocks));
+    } else {
+        LFVIO_TRY(copy(w->off_proj, sizeof(lfvio_proj_factor) * (size_t)n_proj));
+        LFVIO_TRY(copy(w->off_imu, w->off_px0 - w->off_imu + (P.prior.n ? sizeof(double) * 9 * P.prior.n_blocks : 0)));
+    }
     if (P.prior.n) {
         LFVIO_TRY(copy(w->off_pJ0, sizeof(double) * (size_t)P.prior.n * P.prior.n));
         LFVIO_TRY(copy(w->off_pr0, sizeof(double) * P.prior.n));
     }
-    LFVIO_TRY(copy(w->off_x, sizeof(double) * lay.size()));
+    LFVIO_TRY(copy(w->off_x, sizeof(double) * (src ? lay.feat(0) : lay.size())));
     if (!defer_prepare) LFVIO_TRY(enqueue_prepare(w));
     if (defer_plans) {
         w->plan_valid[0] = w->plan_valid[1] = false;
     } else {
-        LFVIO_TRY(build_marg_plan(w, LFVIO_MARGIN_OLD, fl, o, L));
-        LFVIO_TRY(build_marg_plan(w, LFVIO_MARGIN_SECOND_NEW, fl, o, L));
+        LFVIO_TRY(build_marg_plan(w, LFVIO_MARGIN_OLD, fl, o, L, src));
+        LFVIO_TRY(build_marg_plan(w, LFVIO_MARGIN_SECOND_NEW, fl, o, L, src));
     }
     w->uploaded = true;
     return LFVIO_OK;
@@ -715,10 +732,8 @@ extern "C" int lfvio_window_optimize(lfvio_window *w, lfvio_window_state *state,
 }
 
 // Estimator::optimization() in one call: solve -> double2vector/vector2double gauge fix -> next prior, one upload, one sync.
-extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *state, const lfvio_factor_list *factors,
-                                          const lfvio_solver_opts *opts, int margin_flag, lfvio_solve_summary *summary,
-                                          lfvio_prior *prior_out) {
-    clear_error();
+static int optimize_full_impl(lfvio_window *w, lfvio_window_state *state, const lfvio_factor_list *factors, const lfvio_solver_opts *opts,
+                              int margin_flag, lfvio_solve_summary *summary, lfvio_prior *prior_out, const DevFactorSrc *src) {
     // LFVIO_DEBUG_HOST=1: where the host time of this call goes (averages printed every 200 calls)
     static const bool dbg_host = getenv("LFVIO_DEBUG_HOST") != nullptr;
     static double t_acc[6] = {0, 0, 0, 0, 0, 0};
@@ -729,7 +744,7 @@ extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *s
     LFVIO_REQUIRE(w && prior_out, "lfvio_window_optimize_full: null argument");
     LFVIO_REQUIRE(margin_flag == LFVIO_MARGIN_OLD || margin_flag == LFVIO_MARGIN_SECOND_NEW, "lfvio_window_optimize_full: bad margin_flag");
     LFVIO_CUDA_TRY(cudaSetDevice(w->device));
-    LFVIO_TRY(upload(w, state, factors, opts, /*defer_plans=*/true, /*defer_prepare=*/true));
+    LFVIO_TRY(upload(w, state, factors, opts, /*defer_plans=*/true, /*defer_prepare=*/true, src));
     lap(0);
     cudaStream_t s = w->stream;
     const DevProblem &P = w->P;
@@ -744,7 +759,7 @@ extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *s
         return LFVIO_OK;
     }));
     lap(1);
-    LFVIO_TRY(build_marg_plan(w, margin_flag, factors, opts, state->n_landmarks));  // host work under the running solve
+    LFVIO_TRY(build_marg_plan(w, margin_flag, factors, opts, w->P.lay.L, src));  // host work under the running solve
     lap(2);
     prior_out->n = 0;
     prior_out->n_blocks = 0;
@@ -799,6 +814,38 @@ extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *s
         for (int i = 0; i < 6; i++) fprintf(stderr, "optimize_full host %-44s %8.1f us\n", nm[i], t_acc[i] / t_calls);
     }
     return LFVIO_OK;
+}
+
+extern "C" int lfvio_window_optimize_full(lfvio_window *w, lfvio_window_state *state, const lfvio_factor_list *factors,
+                                          const lfvio_solver_opts *opts, int margin_flag, lfvio_solve_summary *summary,
+                                          lfvio_prior *prior_out) {
+    clear_error();
+    return optimize_full_impl(w, state, factors, opts, margin_flag, summary, prior_out, nullptr);
+}
+
+// The same with the projection factors, their landmark ranges and para_Feature taken from a device FeatureManager: its build
+// kernel writes them straight into this handle's problem block, the host sees three counts and a frame mask, and the optimised
+// inverse depths go back into the manager (FeatureManager::setDepth) without leaving the device.
+extern "C" int lfvio_window_optimize_full_fm(lfvio_window *w, lfvio_fm *fm, lfvio_window_state *state, const lfvio_factor_list *factors,
+                                             const lfvio_solver_opts *opts, int margin_flag, lfvio_solve_summary *summary,
+                                             lfvio_prior *prior_out) {
+    clear_error();
+    LFVIO_REQUIRE(w && fm && state && factors && opts, "lfvio_window_optimize_full_fm: null argument");
+    LFVIO_REQUIRE(fm_window_size(fm) == w->F - 1 && fm_device(fm) == w->device, "lfvio_window_optimize_full_fm: the manager and the window differ in size or device");
+    LFVIO_CUDA_TRY(cudaSetDevice(w->device));
+    FmBuildDst dst;
+    dst.proj = reinterpret_cast<lfvio_proj_factor *>(w->blob.p + w->off_proj);
+    dst.lm_first = reinterpret_cast<int *>(w->blob.p + w->off_lm);
+    dst.para_feature = reinterpret_cast<double *>(w->blob.p + w->off_x) + StateLayout{w->F, 0}.feat(0);
+    dst.marg_lm = w->lm_list[LFVIO_MARGIN_OLD].p;
+    dst.proj_cap = w->Rmax;
+    dst.lm_cap = w->Lmax;
+    DevFactorSrc src;
+    LFVIO_TRY(fm_build_factors_into(fm, dst, &src));  // synchronises the manager's stream: the block is complete
+    state->n_landmarks = src.n_landmarks;
+    LFVIO_TRY(optimize_full_impl(w, state, factors, opts, margin_flag, summary, prior_out, &src));
+    // double2vector(): f_manager.setDepth(getFeatureDepth) (estimator.cpp:560-563) from the re-anchored state on the device
+    return fm_set_depth_from_dev(fm, w->x_out.p + w->P.lay.feat(0));
 }
 
 extern "C" int lfvio_window_upload(lfvio_window *w, const lfvio_window_state *state, const lfvio_factor_list *factors,

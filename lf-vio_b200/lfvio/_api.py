@@ -337,6 +337,11 @@ def solver_default_opts() -> "backend.SolverOpts":
     return backend.default_opts(lib)
 
 
+def FeatureStore(window_size: int = 10, capacity: int = 2048, max_proj: int = 16384, min_parallax: float = 10.0 / 160.0,
+                 init_depth: float = 5.0, device: int = 0) -> "backend.FeatureStore":
+    return backend.FeatureStore(lib, check, window_size, capacity, max_proj, min_parallax, init_depth, device)
+
+
 def Window(window_size: int = 10, max_landmarks: int = 1000, max_proj: int = 16384, device: int = 0) -> "backend.Window":
     return backend.Window(lib, check, window_size, max_landmarks, max_proj, device)
 

@@ -151,6 +151,24 @@ def bind(lib):
     lib.lfvio_window_upload.argtypes = [C.c_void_p, C.POINTER(WindowState), C.POINTER(FactorList), C.POINTER(SolverOpts)]
     lib.lfvio_window_optimize_dev.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.lfvio_window_download.argtypes = [C.c_void_p, C.POINTER(WindowState), C.POINTER(SolveSummary)]
+    # FeatureManager on the device
+    lib.lfvio_fm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_void_p)]
+    lib.lfvio_fm_destroy.argtypes = [C.c_void_p]
+    lib.lfvio_fm_destroy.restype = None
+    lib.lfvio_fm_clear.argtypes = [C.c_void_p]
+    lib.lfvio_fm_add_frame.argtypes = [C.c_void_p, C.c_int, _ip, _dp, C.c_int, C.c_double, _ip, _ip]
+    lib.lfvio_fm_remove_back.argtypes = [C.c_void_p]
+    lib.lfvio_fm_remove_back_shift_depth.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+    lib.lfvio_fm_remove_front.argtypes = [C.c_void_p, C.c_int]
+    lib.lfvio_fm_remove_failures.argtypes = [C.c_void_p]
+    lib.lfvio_fm_depth.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, _ip]
+    lib.lfvio_fm_triangulate.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+    lib.lfvio_fm_build_factors.argtypes = [C.c_void_p, _ip, _ip]
+    lib.lfvio_fm_download_factors.argtypes = [C.c_void_p, C.POINTER(ProjFactor), C.c_int, _ip, _dp, C.c_int]
+    lib.lfvio_fm_factors_dev.argtypes = [C.c_void_p, C.POINTER(C.POINTER(ProjFactor)), C.POINTER(_ip), C.POINTER(_dp), C.POINTER(C.c_void_p)]
+    lib.lfvio_fm_snapshot.argtypes = [C.c_void_p, _ip, _dp, C.c_int]
+    lib.lfvio_window_optimize_full_fm.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(WindowState), C.POINTER(FactorList),
+                                                  C.POINTER(SolverOpts), C.c_int, C.POINTER(SolveSummary), C.POINTER(Prior)]
 
 
 def default_opts(lib) -> SolverOpts:
@@ -180,6 +198,88 @@ class EvalResult:
         self.jac_imu = self.jac_imu[: 450 * self.n_imu].reshape(-1, 15, 30)
         self.res_prior = self.res_prior[: self.n_prior]
         return self
+
+
+class FeatureStore:
+    """lfvio_fm handle: the reference's FeatureManager as a structure of arrays on the device."""
+
+    def __init__(self, lib, check, window_size: int = 10, capacity: int = 2048, max_proj: int = 16384, min_parallax: float = 10.0 / 160.0,
+                 init_depth: float = 5.0, device: int = 0):
+        self._lib, self._check = lib, check
+        self.W, self.capacity, self.max_proj = window_size, capacity, max_proj
+        self._h = C.c_void_p()
+        check(lib.lfvio_fm_create(window_size, capacity, max_proj, min_parallax, init_depth, device, C.byref(self._h)), "lfvio_fm_create")
+
+    def close(self):
+        if self._h:
+            self._lib.lfvio_fm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self):
+        self._check(self._lib.lfvio_fm_clear(self._h), "lfvio_fm_clear")
+
+    def add_frame(self, frame_count: int, ids, feat8, td: float = 0.0):
+        """addFeatureCheckParallax: ids ascending, feat8 n x [x y z u v vx vy vz]; returns (is_keyframe, last_track_num)."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        f8 = np.ascontiguousarray(feat8, np.float64).reshape(-1, 8)
+        key, trk = C.c_int(0), C.c_int(0)
+        self._check(self._lib.lfvio_fm_add_frame(self._h, frame_count, _p(ids, C.c_int), _p(f8), len(ids), td, C.byref(key), C.byref(trk)),
+                    "lfvio_fm_add_frame")
+        return bool(key.value), trk.value
+
+    def remove_back(self):
+        self._check(self._lib.lfvio_fm_remove_back(self._h), "lfvio_fm_remove_back")
+
+    def remove_back_shift_depth(self, marg_R, marg_P, new_R, new_P):
+        a = [np.ascontiguousarray(x, np.float64) for x in (marg_R, marg_P, new_R, new_P)]
+        self._check(self._lib.lfvio_fm_remove_back_shift_depth(self._h, *[_p(x) for x in a]), "lfvio_fm_remove_back_shift_depth")
+
+    def remove_front(self, frame_count: int):
+        self._check(self._lib.lfvio_fm_remove_front(self._h, frame_count), "lfvio_fm_remove_front")
+
+    def remove_failures(self):
+        self._check(self._lib.lfvio_fm_remove_failures(self._h), "lfvio_fm_remove_failures")
+
+    def set_depth(self, x, clear: bool = False):
+        x = np.ascontiguousarray(x, np.float64)
+        n = C.c_int(0)
+        self._check(self._lib.lfvio_fm_depth(self._h, 1 if clear else 0, _p(x), len(x), C.byref(n)), "lfvio_fm_depth")
+        return n.value
+
+    def depth_vector(self) -> np.ndarray:
+        x, n = np.zeros(self.capacity), C.c_int(0)
+        self._check(self._lib.lfvio_fm_depth(self._h, 2, _p(x), self.capacity, C.byref(n)), "lfvio_fm_depth")
+        return x[: n.value].copy()
+
+    def triangulate(self, Ps, Rs, tic, ric):
+        a = [np.ascontiguousarray(x, np.float64) for x in (Ps, Rs, tic, ric)]
+        assert a[0].size == 3 * (self.W + 1) and a[1].size == 9 * (self.W + 1)
+        self._check(self._lib.lfvio_fm_triangulate(self._h, *[_p(x) for x in a]), "lfvio_fm_triangulate")
+
+    def build_factors(self):
+        """Returns (proj records, lm_first, para_Feature) of the list built on the device (copied out for inspection)."""
+        R, L = C.c_int(0), C.c_int(0)
+        self._check(self._lib.lfvio_fm_build_factors(self._h, C.byref(R), C.byref(L)), "lfvio_fm_build_factors")
+        proj = (ProjFactor * max(R.value, 1))()
+        lm = np.zeros(L.value + 1, np.int32)
+        feat = np.zeros(max(L.value, 1))
+        self._check(self._lib.lfvio_fm_download_factors(self._h, proj, max(R.value, 1), _p(lm, C.c_int), _p(feat), L.value),
+                    "lfvio_fm_download_factors")
+        return list(proj)[: R.value], lm, feat[: L.value]
+
+    def snapshot(self):
+        """[(feature_id, start_frame, n_obs, estimated_depth)] in list order."""
+        meta, depth = np.zeros((self.capacity, 3), np.int32), np.zeros(self.capacity)
+        n = self._lib.lfvio_fm_snapshot(self._h, _p(meta, C.c_int), _p(depth), self.capacity)
+        if n < 0:
+            self._check(n, "lfvio_fm_snapshot")
+        return [(int(meta[i, 0]), int(meta[i, 1]), int(meta[i, 2]), float(depth[i])) for i in range(n)]
 
 
 class Window:
@@ -215,6 +315,22 @@ class Window:
         st, fl = w.state(), w.factors()
         self._check(self._lib.lfvio_window_optimize_full(self._h, C.byref(st), C.byref(fl), C.byref(w.opts), flag, C.byref(s),
                                                          C.byref(out.c)), "lfvio_window_optimize_full")
+        return s, out
+
+    def optimize_full_fm(self, fm: "FeatureStore", w: WindowProblem, flag: int = MARGIN_OLD, out: PriorData | None = None, max_landmarks: int = 4096):
+        """optimize_full with the projection factors and para_Feature taken from the device FeatureStore (w.proj / w.feat are
+        ignored on input; w.feat returns the optimised inverse depths); returns (summary, prior)."""
+        out = out or PriorData()
+        s = SolveSummary()
+        feat = np.zeros(max_landmarks)
+        st = WindowState(w.F, 0, _p(w.pose), _p(w.sb), _p(w.ex), _p(feat), _p(w.td))
+        pr = C.pointer(w.prior.c) if (w.prior is not None and w.prior.n > 0) else None
+        fl = FactorList(0, None, w.n_imu, w.imu, pr)
+        self._check(self._lib.lfvio_window_optimize_full_fm(self._h, fm._h, C.byref(st), C.byref(fl), C.byref(w.opts), flag, C.byref(s),
+                                                            C.byref(out.c)), "lfvio_window_optimize_full_fm")
+        w.feat = feat[: st.n_landmarks].copy()
+        w.L = st.n_landmarks
+        w._feat_buf = w.feat if w.L > 0 else np.zeros(1)
         return s, out
 
     def marginalize(self, w: WindowProblem, flag: int, out: PriorData | None = None) -> PriorData:

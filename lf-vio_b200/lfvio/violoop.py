@@ -287,6 +287,52 @@ class VioLoop:
         return self
 
 
+class VioLoopStore(VioLoop):
+    """The same loop with the FeatureManager on the device (lfvio.FeatureStore): observations go in once per frame, the
+    triangulation, the factor list, setDepth and removeBackShiftDepth run where the tracks live, and the solve consumes the
+    list without it ever existing on the host (lfvio_window_optimize_full_fm)."""
+
+    def __init__(self, world: World, window, store, opts, F=11, perturb=0.3, seed=0):
+        from . import _api  # (not importable in the library-free mode; this class needs the device)
+        self.window, self.store = window, store
+        store.clear()
+        ops = Ops("device-store", None, lambda iv, dt, acc, gyr, nz, g: _api.preintegrate(iv, dt, acc, gyr, nz, g), None)
+        super().__init__(world, ops, opts, F, perturb, seed)
+
+    def _add_frame_obs(self, k_world, slot):
+        obs = self.w.frames[k_world]
+        ids = np.array(sorted(obs), np.int32)
+        f8 = np.zeros((len(ids), 8))
+        for r, i in enumerate(ids):
+            b, vel, row = obs[int(i)]
+            f8[r] = [b[0], b[1], b[2], 0.0, row, vel[0], vel[1], vel[2]]
+        self.store.add_frame(slot, ids, f8, 0.0)
+
+    def _triangulate(self):
+        Rs = np.array([_quat_to_rot(self.pose[f, 3:]) for f in range(self.F)])
+        self.store.triangulate(self.pose[:, :3], Rs, self.ex[:3], _quat_to_rot(self.ex[3:]))
+
+    def _optimize(self):
+        self._triangulate()
+        imu = []
+        for i, f in enumerate(self.imu):
+            f.frame_i = i
+            imu.append(f)
+        prob = B.WindowProblem(self.F, self.pose, self.sb, self.ex, np.zeros(0), self.td, [], imu, self.prior, self.opts)
+        summ, prior = self.window.optimize_full_fm(self.store, prob, B.MARGIN_OLD)
+        self.pose[:], self.sb[:], self.ex[:], self.td = prob.pose, prob.sb, prob.ex, float(prob.td[0])
+        self.prior = prior
+        self.iterations.append(int(summ.iterations))
+
+    def _slide_window(self):
+        R0, P0 = _quat_to_rot(self.pose[0, 3:]), self.pose[0, :3].copy()
+        ric, tic = _quat_to_rot(self.ex[3:]), self.ex[:3]
+        self.pose[:-1], self.sb[:-1] = self.pose[1:].copy(), self.sb[1:].copy()
+        self.imu = self.imu[1:]
+        R1, P1 = _quat_to_rot(self.pose[0, 3:]), self.pose[0, :3]
+        self.store.remove_back_shift_depth(R0 @ ric, P0 + R0 @ tic, R1 @ ric, P1 + R1 @ tic)
+
+
 def ate_rmse(est_pos: np.ndarray, true_pos: np.ndarray) -> float:
     """Absolute trajectory error: RMSE after the least-squares SE(3) alignment (Umeyama without scale)."""
     mu_e, mu_t = est_pos.mean(0), true_pos.mean(0)

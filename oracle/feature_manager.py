@@ -19,6 +19,7 @@ import numpy as np
 class Feature:
     def __init__(self, fid, start):
         self.id, self.start, self.pts, self.depth = fid, start, [], -1.0
+        self.aux = []  # per observation: (velocity, uv, cur_td) or None — carried along, never read by the bookkeeping
 
     @property
     def end(self):
@@ -32,7 +33,8 @@ class FeatureManagerOracle:
         self.last_track_num = 0
 
     def add_feature_check_parallax(self, frame_count, image: dict) -> bool:
-        """image: {feature_id: bearing (3,)} iterated in ascending id order (std::map)."""
+        """image: {feature_id: bearing (3,)} or {feature_id: (bearing, (velocity, uv, cur_td))}, iterated in ascending id
+        order (std::map)."""
         self.last_track_num = 0
         for fid in sorted(image):
             f = next((x for x in self.feature if x.id == fid), None)
@@ -41,7 +43,10 @@ class FeatureManagerOracle:
                 self.feature.append(f)
             else:
                 self.last_track_num += 1
-            f.pts.append(np.asarray(image[fid], float))
+            val = image[fid]
+            b, aux = val if isinstance(val, tuple) else (val, None)
+            f.pts.append(np.asarray(b, float))
+            f.aux.append(aux)
         if frame_count < 2 or self.last_track_num < 20:
             return True
         s, n = 0.0, 0
@@ -67,6 +72,7 @@ class FeatureManagerOracle:
                 f.start -= 1
             else:
                 f.pts.pop(0)
+                f.aux.pop(0)
                 if not f.pts:
                     continue
             keep.append(f)
@@ -81,6 +87,7 @@ class FeatureManagerOracle:
                 j = self.W - 1 - f.start
                 if f.end >= frame_count - 1:
                     f.pts.pop(j)
+                    f.aux.pop(j)
                     if not f.pts:
                         continue
             keep.append(f)
@@ -93,6 +100,7 @@ class FeatureManagerOracle:
                 f.start -= 1
             else:
                 uv_i = f.pts.pop(0)
+                f.aux.pop(0)
                 if len(f.pts) < 2:
                     continue
                 w = marg_R @ (uv_i * f.depth) + marg_P
@@ -100,6 +108,30 @@ class FeatureManagerOracle:
                 f.depth = d if d > 0 else self.init_depth
             keep.append(f)
         self.feature = keep
+
+    def _selected(self):
+        return [f for f in self.feature if len(f.pts) >= 2 and f.start < self.W - 2]
+
+    def set_depth(self, x):
+        """setDepth / clearDepth (feature_manager.cpp:138-174): estimated_depth = 1 / x over the selected features."""
+        for f, v in zip(self._selected(), x):
+            f.depth = 1.0 / float(v)
+
+    def depth_vector(self):
+        """getDepthVector (feature_manager.cpp:176-190)."""
+        return np.array([1.0 / f.depth for f in self._selected()])
+
+    def factor_list(self):
+        """The residual-block loop of Estimator::optimization (estimator.cpp:725-772) and para_Feature (vector2double,
+        :1044-1046): [(imu_i, imu_j, feature_index, pts_i, pts_j, aux_i, aux_j)] in insertion order, landmark ranges,
+        inverse depths."""
+        out, first, lam = [], [0], []
+        for l, f in enumerate(self._selected()):
+            for j in range(1, len(f.pts)):
+                out.append((f.start, f.start + j, l, f.pts[0], f.pts[j], f.aux[0], f.aux[j]))
+            first.append(len(out))
+            lam.append(1.0 / f.depth)
+        return out, np.array(first, np.int32), np.array(lam)
 
     def snapshot(self):
         """[(id, start_frame, n_obs, depth)] in list order."""

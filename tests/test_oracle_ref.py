@@ -321,4 +321,13 @@ def test_feature_manager_stream(host, min_parallax):
         assert [tuple(m[:3]) for m in meta.tolist()] == [s[:3] for s in snap] == [tuple(r) for r in hm[:nh].tolist()], k
         assert np.abs(depth - np.array([s[3] for s in snap])).max() < 1e-12 and np.abs(depth - hd[:nh]).max() < 1e-12, k
         assert cnt == hc.value
+        if cnt:  # setDepth / getDepthVector over the selected features (the restatement's set_depth / depth_vector)
+            x = rng.uniform(0.1, 0.5, cnt)
+            rf.set_depth(x)
+            py.set_depth(x)
+            assert np.array_equal(rf.depth_vector(), py.depth_vector()), k
+            assert np.array_equal(rf.snapshot()[1], np.array([s[3] for s in py.snapshot()])), k
+            rf.snapshot(set_depth=depth)  # back to the depths of the stream
+            for f, dd in zip(py.feature, depth):
+                f.depth = float(dd)
     host.lfvio_host_fm_destroy(h)
