@@ -346,7 +346,7 @@ def initialisation_leg(lfvio, device):
             "note": "one-shot work at start-up / restart; the SfM entries reuse a per-process device scratch, the other stage-level entries allocate theirs per call"}
 
 
-def node_path_closed_loop(lfvio, world, device):
+def node_path_closed_loop(lfvio, world, device, device_store=True):
     """FeatureTrackerNode::img_callback -> PointCloud message -> EstimatorNode::process() (the C++ host mirrors of the reference's two
     nodes, lf-vio_b200/host/nodes.cpp) on the rendered stream, host images in, odometry out, cold start (initialStructure runs
     inside).  Wall time per frame from the frame at which the estimator is initialised; ATE of the TUM trajectory it writes."""
@@ -382,6 +382,8 @@ def node_path_closed_loop(lfvio, world, device):
     keep = [np.ascontiguousarray(x, np.float64) for x in (w.noise, w.G, w.tic, w.ric, np.zeros(3), np.zeros(3))]
     host.lfvio_host_estimator_set_params(est, vp(keep[0]), vp(keep[1]), vp(keep[2]), vp(keep[3]), 0.0, 0.0, 1, vp(keep[4]), vp(keep[5]))
     host.lfvio_host_estimator_enable_initialization(est, 9, 0)
+    host.lfvio_host_estimator_use_device_store.argtypes = [C.c_void_p, C.c_int]
+    host.lfvio_host_estimator_use_device_store(est, 1 if device_store else 0)  # FeatureManager on the device once initialised
     out = np.zeros((512, 9), np.float32)
     imgs = [np.ascontiguousarray(im) for im in w.images]
     host.lfvio_host_estimator_node_imu(enode, float(w.times[0]), vp(w.imu[1][0]), vp(w.imu[1][1]))
@@ -419,9 +421,11 @@ def node_path_closed_loop(lfvio, world, device):
         return None
     return {"frames_per_s": n_steady / t_steady if t_steady > 0 else None, "ms_per_frame": 1e3 * t_steady / max(n_steady, 1),
             "frames_timed": n_steady, "initialised_at_frame": k_init, "odometry_messages": int(len(tum)), "ate_rmse_m": ate,
+            "feature_manager": "device store (lfvio_fm_*)" if device_store else "host list",
             "path": "FeatureTrackerNode::img_callback -> PointCloud -> EstimatorNode::process() (C++ host mirrors over the C-ABI), one host "
-                    "thread, host images in, 200 Hz IMU messages in, odometry out; includes the host-side FeatureManager / slideWindow and "
-                    "the per-frame uploads; cold start (the frames up to and including the one in which initialStructure succeeds are not timed)"}
+                    "thread, host images in, 200 Hz IMU messages in, odometry out; FeatureManager / slideWindow included (on the device "
+                    "once initialStructure has succeeded: no projection-factor list is built or uploaded by the host); cold start (the "
+                    "frames up to and including the one in which initialStructure succeeds are not timed)"}
 
 
 def main():

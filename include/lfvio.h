@@ -309,6 +309,12 @@ int lfvio_fm_create(int window_size, int capacity, int max_proj_factors, double 
 void lfvio_fm_destroy(lfvio_fm *f);
 /* FeatureManager::clearState (feature_manager.cpp:31-34)                                                              */
 int lfvio_fm_clear(lfvio_fm *f);
+/* Replace the content of the store with a list held on the host (the state of the reference's std::list<FeaturePerId> at the
+ * moment the estimator leaves its initialisation): n features in list order, ids ascending; feature i has the
+ * observations obs9[obs_first[i] .. obs_first[i+1]) of 9 doubles each, [point 3 | velocity 3 | uv 2 | cur_td]
+ * (FeaturePerFrame, feature_manager.h:17-38), in consecutive frames from start_frame[i].  solve_flag may be NULL (0).   */
+int lfvio_fm_load(lfvio_fm *f, int n, const int *ids, const int *start_frame, const int *obs_first, const double *depth,
+                  const int *solve_flag, const double *obs9);
 /* FeatureManager::addFeatureCheckParallax (feature_manager.cpp:45-95): ids ascending (the reference iterates a std::map),
  * feat8 = n x [x y z u v vx vy vz] as in the feature message (estimator.cpp:118-124, camera 0).  Returns the key-frame
  * decision (1 => MARGIN_OLD) and last_track_num.                                                                       */

@@ -403,6 +403,85 @@ __device__ void solve_upper_back_inv(M S, int D, double *y, const double *s_PL) 
     }
 }
 
+// The same with the block chain taken off the barrier: warp 0 solves block b through U11^-1, publishes y_b and forms ITSELF the
+// correction of the 16 rows of block b - 1 (kept in registers and applied when that block's turn comes), while the other warps
+// subtract y_b from the rows of the blocks below b - 1 — one chain step behind.  Named barriers: 3/4 "y_b published" (workers
+// wait, warp 0 arrives), 5/6 "rows updated with y_b" (warp 0 waits, workers arrive), alternating by block parity.  Warp 0 waits
+// for the update with y_{b+2} before it touches block b, and a worker can only arrive for b - 2 after warp 0 has passed that
+// wait, so no barrier is ever entered for two blocks at once.  Warps 4, 8, 12 (warp 0's scheduler) sit it out as in the
+// factorisation.  11 blocks of the 10-frame window: 8.2 us -> see DESIGN.md.
+template <class M>
+__device__ void solve_upper_back_la(M S, int D, double *y, const double *s_PL) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const int nblk = (D + NB - 1) / NB;
+    const bool idle = wid >= 4 && (wid & 3) == 0;
+    const int n_idle = ((nt >> 5) - 1) / 4;
+    const int nworkers = nt - 32 - 32 * n_idle, wtid = (wid - 1 - wid / 4) * 32 + lane;
+    const int nbar = nt - 32 * n_idle;
+    const uint32_t ya = smem_u32(y), pla = smem_u32(s_PL);
+    __syncthreads();  // z complete
+    if (wid == 0) {
+        const int c = lane & 15, hh = lane >> 4;
+        double corr = 0;  // lane c: what y_{b+1} takes off row c of block b
+        for (int blk = nblk - 1; blk >= 0; blk--) {
+            const int j0 = blk * NB, nb = min(NB, D - j0);
+            if (blk + 2 < nblk) bar_sync(5 + ((blk + 2) & 1), nbar);  // rows of this block carry y_{b+2}, y_{b+3}, ..
+            if (blk + 1 < nblk) {
+                if (lane < NB) sts(ya + 8u * (j0 + lane), lds(ya + 8u * (j0 + lane)) - corr);
+                __syncwarp();
+            }
+            {
+                const int r0 = hh * 8;
+                const uint32_t pl = pla + 8u * (blk * NB * NB);
+                double e = 0, o = 0;
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    const int r = r0 + u;
+                    const double z0 = (r < nb) ? lds(ya + 8u * (j0 + r)) : 0.0, z1 = (r + 1 < nb) ? lds(ya + 8u * (j0 + r + 1)) : 0.0;
+                    e = fma(lds(pl + 8u * (r * NB + c)), z0, e);
+                    o = fma(lds(pl + 8u * ((r + 1) * NB + c)), z1, o);
+                }
+                double acc = e + o;
+                acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                __syncwarp();  // every lane has read its z before any lane overwrites one
+                if (lane < nb) sts(ya + 8u * (j0 + lane), acc);
+                __syncwarp();
+            }
+            if (blk >= 2) bar_arrive(3 + (blk & 1), nbar);  // y_b is out
+            if (blk >= 1) {  // look ahead: rows of block b - 1 (a full block), eight columns of block b per half warp
+                const typename M::hnd e = S.h(j0 - NB + c, j0 + hh * 8);
+                double s0 = 0, s1 = 0;
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    const int t = hh * 8 + u;
+                    if (t < nb) s0 = fma(M::ld(M::right(e, u)), lds(ya + 8u * (j0 + t)), s0);
+                    if (t + 1 < nb) s1 = fma(M::ld(M::right(e, u + 1)), lds(ya + 8u * (j0 + t + 1)), s1);
+                }
+                double sum = s0 + s1;
+                sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+                corr = sum;
+            }
+        }
+    } else if (!idle) {
+        for (int blk = nblk - 1; blk >= 2; blk--) {
+            const int j0 = blk * NB, nb = min(NB, D - j0);
+            bar_sync(3 + (blk & 1), nbar);
+            for (int i = wtid; i < j0 - NB; i += nworkers) {
+                const typename M::hnd e = S.h(i, j0);
+                double s0 = 0, s1 = 0;
+#pragma unroll 4
+                for (int t = 0; t < NB; t += 2) {
+                    if (t < nb) s0 = fma(M::ld(M::right(e, t)), lds(ya + 8u * (j0 + t)), s0);
+                    if (t + 1 < nb) s1 = fma(M::ld(M::right(e, t + 1)), lds(ya + 8u * (j0 + t + 1)), s1);
+                }
+                sts(ya + 8u * i, lds(ya + 8u * i) - (s0 + s1));
+            }
+            bar_arrive(5 + (blk & 1), nbar);
+        }
+    }
+    __syncthreads();
+}
+
 #endif  // __CUDACC__
 
 }  // namespace lfvio

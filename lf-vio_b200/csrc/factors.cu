@@ -81,11 +81,12 @@ __device__ void eval_projection(const lfvio_proj_factor &f, const double *x, con
     const DM3 Ri = qrot(Qi), Rj = qrot(Qj), ric = qrot(qic);
     const double n = norm3(pts_camera_j);
     const double x1 = pts_camera_j.x, x2 = pts_camera_j.y, x3 = pts_camera_j.z;
-    const double n3 = pow(n, 3.0);
+    // norm_jaco = I / n - x x^T / n^3 (pow(norm, 3) and nine divisions in the original): one reciprocal, the rest products
+    const double inv_n = 1.0 / n, inv_n3 = inv_n * inv_n * inv_n;
     DM3 nj;
-    nj.m[0][0] = 1.0 / n - x1 * x1 / n3; nj.m[0][1] = -x1 * x2 / n3;          nj.m[0][2] = -x1 * x3 / n3;
-    nj.m[1][0] = -x1 * x2 / n3;          nj.m[1][1] = 1.0 / n - x2 * x2 / n3; nj.m[1][2] = -x2 * x3 / n3;
-    nj.m[2][0] = -x1 * x3 / n3;          nj.m[2][1] = -x2 * x3 / n3;          nj.m[2][2] = 1.0 / n - x3 * x3 / n3;
+    nj.m[0][0] = inv_n - x1 * x1 * inv_n3; nj.m[0][1] = -x1 * x2 * inv_n3;        nj.m[0][2] = -x1 * x3 * inv_n3;
+    nj.m[1][0] = nj.m[0][1];               nj.m[1][1] = inv_n - x2 * x2 * inv_n3; nj.m[1][2] = -x2 * x3 * inv_n3;
+    nj.m[2][0] = nj.m[0][2];               nj.m[2][1] = nj.m[1][2];               nj.m[2][2] = inv_n - x3 * x3 * inv_n3;
     double red[2][3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {

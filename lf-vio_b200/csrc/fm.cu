@@ -19,6 +19,7 @@
 //                   feature writes its lfvio_proj_factor records, its range and 1 / depth — the arrays lfvio_window consumes.
 // Counts come back in one small pinned block (key-frame decision, list length, L, R, capacity error).
 #include <cstring>
+#include <vector>
 
 #include "backend.cuh"
 
@@ -514,6 +515,43 @@ extern "C" int lfvio_fm_clear(lfvio_fm *f) {  // FeatureManager::clearState (fea
     LFVIO_CUDA_TRY(cudaSetDevice(f->device));
     fm_clear_kernel<<<1, FM_THREADS, 0, f->stream>>>(f->d);
     LFVIO_LAUNCH_CHECK();
+    return LFVIO_OK;
+}
+
+// Replace the content of the store (the host-side list at the moment the estimator leaves its initialisation): feature i of the
+// list goes to slot i.
+extern "C" int lfvio_fm_load(lfvio_fm *f, int n, const int *ids, const int *start_frame, const int *obs_first, const double *depth,
+                             const int *solve_flag, const double *obs9) {
+    clear_error();
+    LFVIO_REQUIRE(f && n >= 0 && n <= f->C && (n == 0 || (ids && start_frame && obs_first && depth && obs9)), "lfvio_fm_load: bad arguments");
+    const int NF = f->W + 1;
+    std::vector<int> id(f->C, -1), st(f->C, 0), no(f->C, 0), fl(f->C, 0), ord(f->C, 0);
+    std::vector<double> dep(f->C, -1.0), obs((size_t)(n ? n : 1) * NF * OBS_W, 0.0);
+    for (int i = 0; i < n; i++) {
+        const int k = obs_first[i + 1] - obs_first[i];
+        LFVIO_REQUIRE(k >= 1 && k <= NF && start_frame[i] >= 0 && start_frame[i] + k <= NF, "lfvio_fm_load: a track leaves the window");
+        LFVIO_REQUIRE(i == 0 || ids[i] > ids[i - 1], "lfvio_fm_load: ids must ascend");
+        id[i] = ids[i];
+        st[i] = start_frame[i];
+        no[i] = k;
+        fl[i] = solve_flag ? solve_flag[i] : 0;
+        ord[i] = i;
+        dep[i] = depth[i];
+        memcpy(&obs[(size_t)i * NF * OBS_W], obs9 + (size_t)obs_first[i] * OBS_W, sizeof(double) * OBS_W * k);
+    }
+    int meta[M_COUNT] = {0};
+    meta[M_NLIST] = n;
+    LFVIO_CUDA_TRY(cudaSetDevice(f->device));
+    cudaStream_t s = f->stream;
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(f->d.id, id.data(), sizeof(int) * f->C, cudaMemcpyHostToDevice, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(f->d.start, st.data(), sizeof(int) * f->C, cudaMemcpyHostToDevice, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(f->d.nobs, no.data(), sizeof(int) * f->C, cudaMemcpyHostToDevice, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(f->d.flag, fl.data(), sizeof(int) * f->C, cudaMemcpyHostToDevice, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(f->d.order, ord.data(), sizeof(int) * f->C, cudaMemcpyHostToDevice, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(f->d.depth, dep.data(), sizeof(double) * f->C, cudaMemcpyHostToDevice, s));
+    if (n) LFVIO_CUDA_TRY(cudaMemcpyAsync(f->d.obs, obs.data(), sizeof(double) * (size_t)n * NF * OBS_W, cudaMemcpyHostToDevice, s));
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(f->d.meta, meta, sizeof(meta), cudaMemcpyHostToDevice, s));
+    LFVIO_CUDA_TRY(cudaStreamSynchronize(s));  // (the sources are stack / heap buffers of this call)
     return LFVIO_OK;
 }
 

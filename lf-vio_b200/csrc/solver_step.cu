@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(PRE_THREADS) pre_kernel(const DevProblem *__re
 // so   model_cost_change = -(J v)^T (r + J v / 2) = -v^T g - v^T H v / 2   (ceres TrustRegionMinimizer) needs only the
 // scalars the strategy already has; jj = |J_s a|^2 is the Cauchy-point denominator.
 __device__ void cand_tail(const DevProblem &P, const SolverScratch &w, double *x0, double *x1, SolverCtl *ctl, double gn2_in,
-                          double gdot_in, double *s_red) {
+                          double gdot_in, double *s_red, double *s_delta /* D + L, shared */) {
     const StateLayout lay = P.lay;
     const lfvio_solver_opts &o = P.o;
     const int D = lay.D(), L = lay.L;
@@ -195,10 +195,10 @@ __device__ void cand_tail(const DevProblem &P, const SolverScratch &w, double *x
         dsn = radius;
     } else {
         const double b_dot_a = -alpha * gdot;
-        const double a_sq = pow(alpha * gnorm, 2.0);
-        const double bma_sq = a_sq - 2 * b_dot_a + pow(gnn, 2.0);
+        const double a_sq = (alpha * gnorm) * (alpha * gnorm);  // (pow(x, 2.0) of the original: exact either way)
+        const double bma_sq = a_sq - 2 * b_dot_a + gnn * gnn;
         const double cc = b_dot_a - a_sq;
-        const double dd = sqrt(cc * cc + bma_sq * (pow(radius, 2.0) - a_sq));
+        const double dd = sqrt(cc * cc + bma_sq * (radius * radius - a_sq));
         const double beta = (cc <= 0) ? (dd - cc) / bma_sq : (radius * radius - a_sq) / (dd + cc);
         cg = -alpha * (1.0 - beta);
         cn = beta;
@@ -209,53 +209,75 @@ __device__ void cand_tail(const DevProblem &P, const SolverScratch &w, double *x
     const double vHv = cg * cg * jj - 2.0 * cg * cn * (gg + mu * gdot) + cn * cn * (-gdot - mu * gn2);
     const double model_cost_change = ok ? (-vg - 0.5 * vHv) : 0.0;
     double dx2 = 0;
+    // ---- candidate x_plus_delta = Plus(x, step * scale): the scaled step of every column first (all threads, one round trip to
+    // the four column arrays), then poses (warp 0, one frame per lane), speed / biases (the other warps, one element per
+    // thread), extrinsic + td (last thread) and landmarks side by side ----
+    // (s_delta == nullptr: gnlm_kernel's last CTA, windows too large for the staging buffer — columns straight from global)
+    auto delta_global = [&](int col) { return (cg * w.gradient[col] + cn * w.gn[col]) / w.diagonal[col] * w.scale[col]; };
+    if (ok && s_delta)
+        for (int col = tid; col < D + L; col += nt) s_delta[col] = delta_global(col);
+    __syncthreads();
+    auto delta = [&](int col) { return s_delta ? s_delta[col] : delta_global(col); };
     if (ok) {
-        // ---- candidate x_plus_delta = Plus(x, step * scale) ----
-        auto delta = [&](int col) { return (cg * w.gradient[col] + cn * w.gn[col]) / w.diagonal[col] * w.scale[col]; };
         for (int f = tid; f < lay.F; f += nt) {
             double d[6];
 #pragma unroll
             for (int a = 0; a < 6; a++) d[a] = delta(lay.col_pose(f) + a);
-            pose_plus(x + lay.pose(f), d, xc + lay.pose(f));
+            double xi[7], xo[7];  // (the candidate is formed in registers: reading it back from global costs a round trip)
+#pragma unroll
+            for (int a = 0; a < 7; a++) xi[a] = x[lay.pose(f) + a];
+            pose_plus(xi, d, xo);
+#pragma unroll
             for (int a = 0; a < 7; a++) {
-                const double df = x[lay.pose(f) + a] - xc[lay.pose(f) + a];
+                xc[lay.pose(f) + a] = xo[a];
+                const double df = xi[a] - xo[a];
                 dx2 += df * df;
             }
-            for (int a = 0; a < 9; a++) {
-                const double dv = delta(lay.col_sb(f) + a);
-                const double nv = x[lay.sb(f) + a] + dv;
-                xc[lay.sb(f) + a] = nv;
-                const double df = x[lay.sb(f) + a] - nv;
-                dx2 += df * df;
-            }
+        }
+        for (int q = tid - 32; q < 9 * lay.F; q += nt) {
+            if (q < 0) continue;
+            const int f = q / 9, a = q - 9 * f;
+            const double xv = x[lay.sb(f) + a];
+            const double nv = xv + delta(lay.col_sb(f) + a);
+            xc[lay.sb(f) + a] = nv;
+            const double df = xv - nv;
+            dx2 += df * df;
         }
         if (tid == nt - 1) {  // extrinsic + td
             if (o.estimate_extrinsic) {
                 double d[6];
 #pragma unroll
                 for (int a = 0; a < 6; a++) d[a] = delta(lay.col_ex() + a);
-                pose_plus(x + lay.ex(), d, xc + lay.ex());
+                double xi[7], xo[7];
+#pragma unroll
+                for (int a = 0; a < 7; a++) xi[a] = x[lay.ex() + a];
+                pose_plus(xi, d, xo);
+#pragma unroll
                 for (int a = 0; a < 7; a++) {
-                    const double df = x[lay.ex() + a] - xc[lay.ex() + a];
+                    xc[lay.ex() + a] = xo[a];
+                    const double df = xi[a] - xo[a];
                     dx2 += df * df;
                 }
             } else {
                 for (int a = 0; a < 7; a++) xc[lay.ex() + a] = x[lay.ex() + a];
             }
             if (o.estimate_td) {
-                const double nv = x[lay.td()] + delta(lay.col_td());
+                const double xv = x[lay.td()];
+                const double nv = xv + delta(lay.col_td());
                 xc[lay.td()] = nv;
-                dx2 += (x[lay.td()] - nv) * (x[lay.td()] - nv);
+                dx2 += (xv - nv) * (xv - nv);
             } else {
                 xc[lay.td()] = x[lay.td()];
             }
         }
         for (int l = tid; l < L; l += nt) {
-            const double nv = x[lay.feat(l)] + delta(D + l);
+            const double xv = x[lay.feat(l)];
+            const double nv = xv + delta(D + l);
             xc[lay.feat(l)] = nv;
-            dx2 += (x[lay.feat(l)] - nv) * (x[lay.feat(l)] - nv);
+            dx2 += (xv - nv) * (xv - nv);
         }
     }
+    if (tid == 0) ctl->phase_clk[15] = gtimer_ns();
     dx2 = block_sum(dx2, s_red);
     if (tid == 0) {
         const double step_norm = sqrt(dx2);
@@ -288,13 +310,69 @@ __device__ __forceinline__ double landmark_dot(const DevProblem &P, const Solver
     double s = ws[12] * v[col_td];
 #pragma unroll
     for (int a = 0; a < 6; a++) s = fma(ws[a], v[ci + a], fma(ws[6 + a], v[col_ex + a], s));
-    for (int k = k0; k < k1; k++) {
-        const int cj = w.proj_colj[k];
-        const double *wj = w.proj_wj + 6 * (size_t)k;
+    // four factors per pass, their index and weight loads issued together (one factor at a time serialises one L2 round trip each)
+    for (int k = k0; k < k1; k += 4) {
+        int cj[4];
+        double wv[4][6];
 #pragma unroll
-        for (int a = 0; a < 6; a++) s = fma(wj[a], v[cj + a], s);
+        for (int u = 0; u < 4; u++) {
+            const int kk = min(k + u, k1 - 1);
+            cj[u] = w.proj_colj[kk];
+#pragma unroll
+            for (int a = 0; a < 6; a++) wv[u][a] = w.proj_wj[6 * (size_t)kk + a];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (k + u >= k1) break;
+#pragma unroll
+            for (int a = 0; a < 6; a++) s = fma(wv[u][a], v[cj[u] + a], s);
+        }
     }
     return s;
+}
+
+// The same in two parallel passes (used when the factors fit the staging buffer): t_k = w_jk^T v[c_jk ..] of EVERY factor, one
+// thread each with coalesced index / weight loads, into shared memory; then one thread per landmark adds its range of t and the
+// 13 shared columns.  All global loads of a pass are independent of each other: one round trip instead of one per factor.
+__device__ __forceinline__ void factor_dots(const SolverScratch &w, const double *v, int n_proj, double *s_t) {
+    for (int k = threadIdx.x; k < n_proj; k += blockDim.x) {
+        const int cj = w.proj_colj[k];
+        const double *wj = w.proj_wj + 6 * (size_t)k;
+        double wv[6];
+#pragma unroll
+        for (int a = 0; a < 6; a++) wv[a] = wj[a];
+        double s = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++) s = fma(wv[a], v[cj + a], s);
+        s_t[k] = s;
+    }
+}
+struct LandmarkHead {  // everything one landmark needs from global memory, loaded together
+    int ci, k0, k1;
+    double ws[13], c, g;
+};
+__device__ __forceinline__ LandmarkHead load_landmark(const DevProblem &P, const SolverScratch &w, int l) {
+    LandmarkHead h;
+    h.ci = w.lm_coli[l];
+    h.k0 = P.lm_first[l];
+    h.k1 = P.lm_first[l + 1];
+#pragma unroll
+    for (int a = 0; a < 13; a++) h.ws[a] = w.lm_ws[13 * (size_t)l + a];
+    h.c = w.lm_c[l];
+    h.g = w.lm_g[l];
+    return h;
+}
+__device__ __forceinline__ double landmark_dot_staged(const LandmarkHead &h, const double *v, const double *s_t, int col_ex, int col_td) {
+    double s = h.ws[12] * v[col_td];
+#pragma unroll
+    for (int a = 0; a < 6; a++) s = fma(h.ws[a], v[h.ci + a], fma(h.ws[6 + a], v[col_ex + a], s));
+    double s1 = 0;
+    for (int k = h.k0; k + 1 < h.k1; k += 2) {
+        s += s_t[k];
+        s1 += s_t[k + 1];
+    }
+    if ((h.k1 - h.k0) & 1) s += s_t[h.k1 - 1];
+    return s + s1;
 }
 
 // y_l = (g_l - w_l^T y_p) / (c_l + clamp(c_l) mu) for the landmarks l = first, first + stride, ... (one thread each);
@@ -336,10 +414,6 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
     const lfvio_solver_opts &o = P.o;
     const int D = lay.D(), L = lay.L, N = D + L;
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nwarp = nt >> 5;
-    if (ctl->reuse != 0) {
-        if (fused) cand_tail(P, w, x0, x1, ctl, 0.0, 0.0, s_red);
-        return;
-    }
     const int nblk = (D + NB - 1) / NB;
     const int PW = chol_panel_pitch(D);
     double *s_panel = smem;                        // NB * PW (16-byte aligned rows)
@@ -347,8 +421,27 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
     double *s_invd = s_y + ((D + 1) & ~1);         // nblk * NB reciprocal pivots
     double *s_a = s_invd + (size_t)nblk * NB;      // D (padded to even): Cauchy direction, reduced columns
     double *s_PL = s_a + ((D + 1) & ~1);           // nblk x NB x NB: U11^-T of every diagonal block
-    double *s_S = s_PL + (size_t)nblk * NB * NB;   // packed upper triangle when use_smem
+    double *s_dd = s_PL + (size_t)nblk * NB * NB;  // D (padded to even): diagonal_^2, the weights of the LM term
+    double *s_delta = s_dd + ((D + 1) & ~1);       // D + kFuseMaxL: the scaled step of cand_tail
+    double *s_S = s_delta + ((D + kFuseMaxL + 1) & ~1);  // packed upper triangle when use_smem
+    if (ctl->reuse != 0) {
+        if (fused) cand_tail(P, w, x0, x1, ctl, 0.0, 0.0, s_red, s_delta);
+        return;
+    }
+    const MatPacked Sp{s_S, D};
+    if (use_smem) {
+        // the reduced system on its way into shared memory while the Cauchy point is being formed: one asynchronous 8-byte
+        // copy per element of the upper triangle (rows are contiguous both in global and in the packed layout), a row per warp
+        for (int r = wid; r < D; r += nwarp) {
+            const double *src = w.S + (size_t)r * D;
+            const uint32_t drow = smem_u32(Sp.row(r));
+            for (int c = r + lane; c < D; c += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(drow + 8u * (unsigned)c), "l"(src + c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     PHASE_MARK(0);
+    const bool staged = fused && P.n_proj <= NB * PW;  // per-factor dot products staged in the (then idle) panel buffer
     const double mu = ctl->mu;
     double gg, jj_part = 0, gmax;
     if (fused) {
@@ -365,26 +458,44 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
             gm = fmax(gm, fabs(g / w.scale[c]));  // un-scaled gradient J^T r
             if (c < D) {
                 s_a[c] = g / d2;
+                s_dd[c] = dg * dg;
                 if (use_smem) {  // consumed: clear for the next accumulation (see launch_accumulate)
                     w.diag2[c] = 0.0;
                     w.grad[c] = 0.0;
                 }
             }
         }
+        PHASE_MARK(7);
         gg = block_sum(gga, s_red);
         gmax = block_max(gm, s_red);
+        PHASE_MARK(8);
         // landmark part of |J_s a|^2 (one thread per landmark)
-        for (int l = tid; l < L; l += nt) {
-            if (w.lm_coli[l] < 0) continue;
-            const double t = landmark_dot(P, w, s_a, l, lay.col_ex(), lay.col_td());
-            const double c_l = w.lm_c[l], cl = clamp_diag(c_l);
-            const double a_l = w.lm_g[l] / cl;
-            jj_part += t * t / (c_l + cl * mu) + 2.0 * a_l * t + c_l * a_l * a_l;
+        if (staged) {
+            factor_dots(w, s_a, P.n_proj, s_panel);  // (the panel is not in use yet: it is cleared after this phase)
+            __syncthreads();
+            for (int l = tid; l < L; l += nt) {
+                const LandmarkHead h = load_landmark(P, w, l);
+                if (h.ci < 0) continue;
+                const double t = landmark_dot_staged(h, s_a, s_panel, lay.col_ex(), lay.col_td());
+                const double cl = clamp_diag(h.c);
+                const double a_l = h.g / cl;
+                jj_part += t * t / (h.c + cl * mu) + 2.0 * a_l * t + h.c * a_l * a_l;
+            }
+            __syncthreads();  // all reads of the staging buffer before the panel is cleared
+        } else {
+            for (int l = tid; l < L; l += nt) {
+                if (w.lm_coli[l] < 0) continue;
+                const double t = landmark_dot(P, w, s_a, l, lay.col_ex(), lay.col_td());
+                const double c_l = w.lm_c[l], cl = clamp_diag(c_l);
+                const double a_l = w.lm_g[l] / cl;
+                jj_part += t * t / (c_l + cl * mu) + 2.0 * a_l * t + c_l * a_l * a_l;
+            }
         }
     } else {
         gg = ctl->acc[0];
         gmax = __longlong_as_double((long long)*reinterpret_cast<unsigned long long *>(&ctl->acc[2]));
     }
+    PHASE_MARK(9);
     // ---- x_norm over the non-constant parameter blocks (global sizes) ----
     {
         const double *x = ctl->cur ? x1 : x0;
@@ -404,40 +515,58 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
     for (int c = tid; c < D; c += nt) {
         s_y[c] = w.rhs[c];
         if (clear_sys) w.rhs[c] = 0.0;
+        if (!fused) s_dd[c] = w.diagonal[c] * w.diagonal[c];  // (pre_kernel formed diagonal_)
     }
-    // copy (or regularise in place) and, when fused, a_p^T S a_p on the way: coalesced upper triangle, four rows per warp
-    // and pass with all their loads issued before the first use (a row at a time cost one L2 round trip per row: 11 per warp)
-    const MatPacked Sp{s_S, D};
-    constexpr int RG = 4;
-    for (int rb = wid * RG; rb < D; rb += nwarp * RG) {
-        for (int cb = lane; rb + cb < D; cb += 32 * 6) {
-            double v[RG][6];
-#pragma unroll
-            for (int rr = 0; rr < RG; rr++) {
-                const int r = rb + rr;
-#pragma unroll
-                for (int u = 0; u < 6; u++) v[rr][u] = (r < D && r + cb + 32 * u < D) ? w.S[(size_t)r * D + r + cb + 32 * u] : 0.0;
+    PHASE_MARK(10);
+    if (use_smem) {
+        // the copy has landed: a_p^T S a_p (when fused) and the LM term from shared memory; the global copy is cleared for the next
+        // accumulation (only now: an asynchronous copy is not ordered against a later store of the same thread)
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        for (int r = wid; r < D; r += nwarp) {
+            double *drow = Sp.row(r);
+            double *src = w.S + (size_t)r * D;
+            const double ar = fused ? s_a[r] : 0.0;
+            for (int c = r + lane; c < D; c += 32) {
+                const double v = drow[c];
+                if (fused) jj_part += ar * v * s_a[c] * (c == r ? 1.0 : 2.0);
+                if (c == r) drow[c] = v + s_dd[c] * mu;
+                if (clear_sys) src[c] = 0.0;
             }
+        }
+    } else {
+        // regularise in place and, when fused, a_p^T S a_p on the way: coalesced upper triangle, four rows per warp and pass
+        // with all their loads issued before the first use
+        constexpr int RG = 4;
+        for (int rb = wid * RG; rb < D; rb += nwarp * RG) {
+            for (int cb = lane; rb + cb < D; cb += 32 * 6) {
+                double v[RG][6];
 #pragma unroll
-            for (int rr = 0; rr < RG; rr++) {
-                const int r = rb + rr;
-                if (r >= D) break;
-                double *src = w.S + (size_t)r * D;
-                double *dst = use_smem ? &Sp.at(r, r) - r : src;
-                const double ar = fused ? s_a[r] : 0.0;
+                for (int rr = 0; rr < RG; rr++) {
+                    const int r = rb + rr;
 #pragma unroll
-                for (int u = 0; u < 6; u++) {
-                    const int c = r + cb + 32 * u;
-                    if (c >= D) continue;
-                    if (fused) jj_part += ar * v[rr][u] * s_a[c] * (c == r ? 1.0 : 2.0);
-                    if (use_smem) dst[c] = v[rr][u] + (r == c ? w.diagonal[c] * w.diagonal[c] * mu : 0.0);
-                    if (clear_sys) src[c] = 0.0;
-                    else if (r == c) dst[c] = v[rr][u] + w.diagonal[c] * w.diagonal[c] * mu;
+                    for (int u = 0; u < 6; u++) v[rr][u] = (r < D && r + cb + 32 * u < D) ? w.S[(size_t)r * D + r + cb + 32 * u] : 0.0;
+                }
+#pragma unroll
+                for (int rr = 0; rr < RG; rr++) {
+                    const int r = rb + rr;
+                    if (r >= D) break;
+                    double *src = w.S + (size_t)r * D;
+                    const double ar = fused ? s_a[r] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 6; u++) {
+                        const int c = r + cb + 32 * u;
+                        if (c >= D) continue;
+                        if (fused) jj_part += ar * v[rr][u] * s_a[c] * (c == r ? 1.0 : 2.0);
+                        if (r == c) src[c] = v[rr][u] + s_dd[c] * mu;
+                    }
                 }
             }
         }
     }
+    PHASE_MARK(11);
     const double jj = fused ? block_sum(jj_part, s_red) : ctl->acc[1];  // (block_sum synchronises the copy)
+    PHASE_MARK(12);
     if (tid == 0) {
         ctl->alpha = gg / jj;
         ctl->gnorm = sqrt(gg);
@@ -456,12 +585,12 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
     if (!pd) {
         if (tid == 0) ctl->pad = 0;
         __syncthreads();
-        if (fused) cand_tail(P, w, x0, x1, ctl, 0.0, 0.0, s_red);
+        if (fused) cand_tail(P, w, x0, x1, ctl, 0.0, 0.0, s_red, s_delta);
         return;
     }
     PHASE_MARK(3);
-    if (use_smem) solve_upper_back_inv(Sp, D, s_y, s_PL);
-    else solve_upper_back_inv(MatFull{w.S, D}, D, s_y, s_PL);
+    if (use_smem) solve_upper_back_la(Sp, D, s_y, s_PL);
+    else solve_upper_back_la(MatFull{w.S, D}, D, s_y, s_PL);
     PHASE_MARK(4);
     double gn2 = 0, gdot = 0;
     int bad = 0;
@@ -474,7 +603,25 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
         gn2 += g * g;
         gdot += g * w.gradient[c];
     }
-    if (fused) landmark_backsub(P, w, s_y, mu, tid, nt, gn2, gdot, bad);
+    PHASE_MARK(13);
+    if (staged) {
+        factor_dots(w, s_y, P.n_proj, s_panel);  // (the factorisation is done with the panel)
+        __syncthreads();
+        for (int l = tid; l < L; l += nt) {
+            const LandmarkHead h = load_landmark(P, w, l);
+            const double dl = w.diagonal[D + l], gl = w.gradient[D + l];
+            double yl = 0;
+            if (h.ci >= 0) yl = (h.g - landmark_dot_staged(h, s_y, s_panel, lay.col_ex(), lay.col_td())) / (h.c + clamp_diag(h.c) * mu);
+            if (!isfinite(yl)) bad = 1;
+            const double g = -dl * yl;
+            w.gn[D + l] = g;
+            gn2 += g * g;
+            gdot += g * gl;
+        }
+    } else if (fused) {
+        landmark_backsub(P, w, s_y, mu, tid, nt, gn2, gdot, bad);
+    }
+    PHASE_MARK(14);
     gn2 = block_sum(gn2, s_red);
     gdot = block_sum(gdot, s_red);
     bad = __syncthreads_or(bad);
@@ -485,7 +632,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(const DevProblem *__
     }
     __syncthreads();
     PHASE_MARK(5);
-    if (fused) cand_tail(P, w, x0, x1, ctl, gn2, gdot, s_red);
+    if (fused) cand_tail(P, w, x0, x1, ctl, gn2, gdot, s_red, s_delta);
     PHASE_MARK(6);
 }
 
@@ -498,7 +645,7 @@ __global__ void __launch_bounds__(GNLM_WARPS * 32) gnlm_kernel(const DevProblem 
     __shared__ double s_red[33];
     __shared__ int s_last;
     if (ctl->reuse != 0) {
-        if (blockIdx.x == 0) cand_tail(P, w, x0, x1, ctl, 0.0, 0.0, s_red);
+        if (blockIdx.x == 0) cand_tail(P, w, x0, x1, ctl, 0.0, 0.0, s_red, nullptr);
         return;
     }
     double gn2 = 0, gdot = 0;
@@ -520,7 +667,7 @@ __global__ void __launch_bounds__(GNLM_WARPS * 32) gnlm_kernel(const DevProblem 
     __threadfence();
     const double gn2_all = atomicAdd(&ctl->acc[3], 0.0), gdot_all = atomicAdd(&ctl->acc[4], 0.0);
     __syncthreads();
-    cand_tail(P, w, x0, x1, ctl, gn2_all, gdot_all, s_red);
+    cand_tail(P, w, x0, x1, ctl, gn2_all, gdot_all, s_red, nullptr);
     if (threadIdx.x == 0) {
         ctl->acc[3] = ctl->acc[4] = 0.0;
         ctl->ticket2 = 0;
@@ -536,7 +683,8 @@ void chol_profile_read(long long *out) { cudaMemcpyFromSymbol(out, g_sub, sizeof
 static size_t chol_base_bytes(int D) {
     const int F = (D - 7) / 15;
     (void)F;
-    return sizeof(double) * ((size_t)NB * chol_panel_pitch(D) + 2 * (size_t)((D + 1) & ~1) + (size_t)cdiv(D, NB) * (NB + NB * NB));
+    return sizeof(double) * ((size_t)NB * chol_panel_pitch(D) + 3 * (size_t)((D + 1) & ~1) + (size_t)cdiv(D, NB) * (NB + NB * NB) +
+                             (size_t)((D + kFuseMaxL + 1) & ~1));
 }
 static bool chol_in_smem(int D) { return chol_base_bytes(D) + sizeof(double) * ((size_t)D * (D + 1) / 2) <= 218 * 1024; }
 

@@ -640,6 +640,11 @@ int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum, 
     if (getenv("LFVIO_DEBUG_STEP")) {
         static const char *names[6] = {"cauchy+xnorm", "copy+quadform", "cholesky", "tri-solve", "gn+backsub", "cand_tail"};
         for (int i = 0; i < 6; i++) fprintf(stderr, "step phase %-16s %8.2f us\n", names[i], (c.phase_clk[i + 1] - c.phase_clk[i]) / 1000.0);
+        auto us = [&](int a, int b) { return (c.phase_clk[b] - c.phase_clk[a]) / 1000.0; };
+        fprintf(stderr, "  cauchy: diag/gradient loop %.2f | gg,gmax sums %.2f | landmark dots %.2f | x_norm %.2f\n", us(0, 7), us(7, 8), us(8, 9), us(9, 1));
+        fprintf(stderr, "  copy: panel zero + rhs %.2f | S rows %.2f | jj sum %.2f | ctl + done check %.2f\n", us(1, 10), us(10, 11), us(11, 12), us(12, 2));
+        fprintf(stderr, "  gn: reduced columns %.2f | landmark backsub %.2f | sums %.2f\n", us(4, 13), us(13, 14), us(14, 5));
+        fprintf(stderr, "  cand_tail: dogleg scalars + candidate %.2f | dx2 sum + publish %.2f\n", us(5, 15), us(15, 6));
     }
     if (sum) {
         memset(sum, 0, sizeof(*sum));

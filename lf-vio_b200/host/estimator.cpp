@@ -271,11 +271,63 @@ Estimator::Estimator(int window_size, int max_features, int device)
     tic[0] = Vec3{0, 0, 0};
     ric[0] = Mat3{1, 0, 0, 0, 1, 0, 0, 0, 1};
     f_manager.window_size = window_size;
+    m_max_features = max_features;
     last_status = lfvio_window_create(window_size, max_features, 16 * max_features, device, &m_window);
 }
 Estimator::~Estimator() {
     g_ht.report();
+    if (m_store) lfvio_fm_destroy(m_store);
     if (m_window) lfvio_window_destroy(m_window);
+}
+
+// ---- FeatureManager on the device ---------------------------------------------------------------------
+// The host-side list (what the initialisation worked on) becomes the content of the device store.
+int Estimator::storeLoad() {
+    if (!m_store) {
+        const int st = lfvio_fm_create(WINDOW_SIZE, 2 * m_max_features, 16 * m_max_features, MIN_PARALLAX, f_manager.init_depth, m_device, &m_store);
+        if (st != LFVIO_OK) return st;
+    }
+    std::vector<int> ids, start, first{0}, flag;
+    std::vector<double> depth, obs;
+    for (const auto &it : f_manager.feature) {
+        ids.push_back(it.feature_id);
+        start.push_back(it.start_frame);
+        flag.push_back(it.solve_flag);
+        depth.push_back(it.estimated_depth);
+        for (const auto &o : it.feature_per_frame) {
+            const double rec[9] = {o.point[0], o.point[1], o.point[2], o.velocity[0], o.velocity[1], o.velocity[2], o.uv[0], o.uv[1], o.cur_td};
+            obs.insert(obs.end(), rec, rec + 9);
+        }
+        first.push_back((int)(obs.size() / 9));
+    }
+    const int st = lfvio_fm_load(m_store, (int)ids.size(), ids.data(), start.data(), first.data(), depth.data(), flag.data(), obs.data());
+    if (st == LFVIO_OK) m_store_live = true;
+    return st;
+}
+int Estimator::storeTriangulate() {
+    std::vector<double> P, R;
+    for (const auto &p : Ps) P.insert(P.end(), p.begin(), p.end());
+    for (const auto &r : Rs) R.insert(R.end(), r.begin(), r.end());
+    return lfvio_fm_triangulate(m_store, P.data(), R.data(), tic[0].data(), ric[0].data());
+}
+// The two-call path (after a detected failure the gauge is anchored on the host) needs the list on the host after all.
+int Estimator::storeDownloadFactors() {
+    int R = 0, L = 0;
+    int st = lfvio_fm_build_factors(m_store, &R, &L);
+    if (st != LFVIO_OK) return st;
+    m_proj.resize(R > 0 ? R : 1);
+    std::vector<int> lm_first(L + 1);
+    if ((int)para_Feature.size() < L) para_Feature.resize(L);
+    st = lfvio_fm_download_factors(m_store, m_proj.data(), (int)m_proj.size(), lm_first.data(), para_Feature.data(), L);
+    m_proj.resize(R);
+    m_store_L = L;
+    return st;
+}
+int Estimator::storeSize() {
+    if (!m_store_live) return (int)f_manager.feature.size();
+    std::vector<int> meta(3 * 2 * (size_t)m_max_features);
+    std::vector<double> depth(2 * (size_t)m_max_features);
+    return lfvio_fm_snapshot(m_store, meta.data(), depth.data(), 2 * m_max_features);
 }
 const char *Estimator::lastError() const { return lfvio_last_error(); }
 
@@ -375,9 +427,24 @@ int Estimator::repropagate(int j, const Vec3 &ba, const Vec3 &bg) {
 }
 
 void Estimator::processImage(const ImageFeatures &image, double header_stamp) {
+    if (use_device_store && !m_store_live && solver_flag == NON_LINEAR && (last_status = storeLoad()) != LFVIO_OK) return;
     {
         Lap lap(0);
-        marginalization_flag = f_manager.addFeatureCheckParallax(frame_count, image, td) ? MARGIN_OLD : MARGIN_SECOND_NEW;
+        if (m_store_live) {
+            m_ids.clear();
+            m_feat8.clear();
+            for (const auto &id_pts : image) {  // std::map: ascending ids
+                m_ids.push_back(id_pts.first);
+                const std::array<double, 8> &p = id_pts.second[0].second;
+                m_feat8.insert(m_feat8.end(), p.begin(), p.end());
+            }
+            int key = 1;
+            last_status = lfvio_fm_add_frame(m_store, frame_count, m_ids.data(), m_feat8.data(), (int)m_ids.size(), td, &key, &f_manager.last_track_num);
+            if (last_status != LFVIO_OK) return;
+            marginalization_flag = key ? MARGIN_OLD : MARGIN_SECOND_NEW;
+        } else {
+            marginalization_flag = f_manager.addFeatureCheckParallax(frame_count, image, td) ? MARGIN_OLD : MARGIN_SECOND_NEW;
+        }
     }
     if ((int)Headers.size() <= WINDOW_SIZE) Headers.resize(WINDOW_SIZE + 1, 0.0);
     Headers[frame_count] = header_stamp;
@@ -457,7 +524,7 @@ void Estimator::processImage(const ImageFeatures &image, double header_stamp) {
     {
         Lap lap(7);
         slideWindow();
-        f_manager.removeFailures();
+        if (!m_store_live) f_manager.removeFailures();  // (a no-op in LF-VIO: nothing ever sets solve_flag = 2)
     }
     key_poses.assign(Ps.begin(), Ps.end());
     last_R = Rs[WINDOW_SIZE];
@@ -500,6 +567,7 @@ void Estimator::clearState() {
     m_tmp_valid = false;
     last_marginalization_info = MarginalizationInfo{};
     f_manager.clearState();
+    m_store_live = false;  // the next initialisation works on the host-side list again
     failure_occur = false;
     g = G;  // (the reference leaves g as it was; the IMU-rate prediction must not run gravity-free until the next alignment)
 }
@@ -513,7 +581,7 @@ void Estimator::solveOdometry() {
         }
         {
             Lap lap(2);
-            last_status = f_manager.triangulate(Ps, Rs, tic, ric, m_device);
+            last_status = m_store_live ? storeTriangulate() : f_manager.triangulate(Ps, Rs, tic, ric, m_device);
         }
         if (last_status != LFVIO_OK) return;
         optimization();
@@ -589,6 +657,11 @@ void Estimator::slideWindow() {
 
 void Estimator::slideWindowNew() {
     sum_of_front++;
+    if (m_store_live) {
+        const int st = lfvio_fm_remove_front(m_store, frame_count);
+        if (st != LFVIO_OK) last_status = st;
+        return;
+    }
     f_manager.removeFront(frame_count);
 }
 
@@ -598,6 +671,11 @@ void Estimator::slideWindowOld() {
         const Mat3 R0 = matmul(back_R0, ric[0]), R1 = matmul(Rs[0], ric[0]);
         const Vec3 a = matvec(back_R0, tic[0]), b = matvec(Rs[0], tic[0]);
         const Vec3 P0{back_P0[0] + a[0], back_P0[1] + a[1], back_P0[2] + a[2]}, P1{Ps[0][0] + b[0], Ps[0][1] + b[1], Ps[0][2] + b[2]};
+        if (m_store_live) {
+            const int st = lfvio_fm_remove_back_shift_depth(m_store, R0.data(), P0.data(), R1.data(), P1.data());
+            if (st != LFVIO_OK) last_status = st;
+            return;
+        }
         f_manager.removeBackShiftDepth(R0, P0, R1, P1);
     } else {
         f_manager.removeBack();
@@ -620,9 +698,11 @@ void Estimator::vector2double() {
     const auto q = rot_to_quat(ric[0]);
     for (int k = 0; k < 3; k++) para_Ex_Pose[0][k] = tic[0][k];
     para_Ex_Pose[0][3] = q[0]; para_Ex_Pose[0][4] = q[1]; para_Ex_Pose[0][5] = q[2]; para_Ex_Pose[0][6] = q[3];
-    const std::vector<double> dep = f_manager.getDepthVector();
-    if (para_Feature.size() < dep.size()) para_Feature.resize(dep.size());
-    for (size_t i = 0; i < dep.size(); i++) para_Feature[i] = dep[i];
+    if (!m_store_live) {  // (with the device store para_Feature is written on the device, straight into the solver's state)
+        const std::vector<double> dep = f_manager.getDepthVector();
+        if (para_Feature.size() < dep.size()) para_Feature.resize(dep.size());
+        for (size_t i = 0; i < dep.size(); i++) para_Feature[i] = dep[i];
+    }
     if (ESTIMATE_TD) para_Td[0][0] = td;
 }
 
@@ -652,9 +732,18 @@ void Estimator::double2vector() {
     }
     tic[0] = Vec3{para_Ex_Pose[0][0], para_Ex_Pose[0][1], para_Ex_Pose[0][2]};
     ric[0] = quat_to_rot(para_Ex_Pose[0][6], para_Ex_Pose[0][3], para_Ex_Pose[0][4], para_Ex_Pose[0][5], false);
-    std::vector<double> dep(f_manager.getFeatureCount());
-    for (size_t i = 0; i < dep.size(); i++) dep[i] = para_Feature[i];
-    f_manager.setDepth(dep);
+    if (m_store_live) {
+        if (!m_depth_on_device && m_store_L > 0) {  // (the one-call path has applied setDepth on the device already)
+            int n = 0;
+            const int st = lfvio_fm_depth(m_store, 0, para_Feature.data(), m_store_L, &n);
+            if (st != LFVIO_OK) last_status = st;
+        }
+        m_depth_on_device = true;
+    } else {
+        std::vector<double> dep(f_manager.getFeatureCount());
+        for (size_t i = 0; i < dep.size(); i++) dep[i] = para_Feature[i];
+        f_manager.setDepth(dep);
+    }
     if (ESTIMATE_TD) td = para_Td[0][0];
 }
 
@@ -669,6 +758,7 @@ void Estimator::buildFactors() {
         m_imu.push_back(f);  // the > 10 s rule (estimator.cpp:720-721) is applied on device
     }
     m_proj.clear();
+    if (m_store_live) return;  // the projection factors are built on the device (lfvio_fm_build_factors)
     int feature_index = -1;
     for (auto &it_per_id : f_manager.feature) {
         it_per_id.used_num = (int)it_per_id.feature_per_frame.size();
@@ -736,7 +826,12 @@ void Estimator::optimization() {
         prior.J0 = lm.J0.data();
         prior.r0 = lm.r0.data();
     }
-    const int L = f_manager.getFeatureCount();
+    const bool one_call = !failure_occur;
+    m_depth_on_device = false;
+    m_store_L = 0;
+    if (m_store_live && !one_call && (last_status = storeDownloadFactors()) != LFVIO_OK) return;  // the list on the host after all
+    if (m_store_live && (int)para_Feature.size() < m_max_features) para_Feature.resize(m_max_features);
+    const int L = m_store_live ? m_store_L : f_manager.getFeatureCount();
     lfvio_window_state st{WINDOW_SIZE + 1, L, para_Pose.data(), para_SpeedBias.data(), para_Ex_Pose[0], para_Feature.data(), para_Td[0]};
     lfvio_factor_list fl{(int)m_proj.size(), m_proj.data(), (int)m_imu.size(), m_imu.data(), lm.valid() ? &prior : nullptr};
     // A failed solve is not fatal in the reference: ceres::Solve (estimator.cpp:825) leaves the parameter blocks at the last
@@ -768,8 +863,11 @@ void Estimator::optimization() {
     // One call does solve + gauge re-anchoring + next prior on the device (two graph launches, one synchronisation) whenever the
     // re-anchoring is the ordinary one; after a detected failure double2vector() anchors at last_R0 / last_P0 instead
     // (estimator.cpp:1059-1064), which the device does not know: then the solve and the marginalisation are two calls.
-    const bool one_call = !failure_occur;
-    if (one_call) {
+    if (one_call && m_store_live) {
+        last_status = lfvio_window_optimize_full_fm(m_window, m_store, &st, &fl, &o, mflag, &summary, &out);
+        m_store_L = st.n_landmarks;
+        m_depth_on_device = last_status == LFVIO_OK;
+    } else if (one_call) {
         last_status = lfvio_window_optimize_full(m_window, &st, &fl, &o, mflag, &summary, &out);  // ceres::Solve (estimator.cpp:825) + :833-1005
     } else {
         last_status = lfvio_window_optimize(m_window, &st, &fl, &o, &summary);  // ceres::Solve (estimator.cpp:825)
@@ -779,6 +877,7 @@ void Estimator::optimization() {
         solve_failures++;
         last_solve_failure = last_status;
         last_status = LFVIO_OK;
+        if (m_store_live && one_call) m_depth_on_device = true;  // the store keeps the depths the failed solve started from
         bool finite = true;
         for (double v : para_Pose) finite = finite && std::isfinite(v);
         for (double v : para_SpeedBias) finite = finite && std::isfinite(v);
@@ -1054,6 +1153,12 @@ extern "C" int lfvio_host_estimator_set_states(void *h, const double *P, const d
     return LFVIO_OK;
 }
 
+extern "C" int lfvio_host_estimator_use_device_store(void *h, int on) {
+    auto *e = static_cast<lfvio_host::Estimator *>(h);
+    e->use_device_store = on != 0;
+    return e->storeLive() ? 1 : 0;
+}
+
 // switch the mirror to the reference's own start-up: processImage() runs initialStructure() once the window is full
 extern "C" int lfvio_host_estimator_enable_initialization(void *h, unsigned long long ransac_seed, int stop_after) {
     auto *e = static_cast<lfvio_host::Estimator *>(h);
@@ -1120,7 +1225,7 @@ extern "C" int lfvio_host_estimator_get(void *h, double *P, double *R, double *V
         for (int k = 0; k < 9; k++) R[9 * i + k] = e->Rs[i][k];
     *td = e->td;
     info[0] = (int)e->marginalization_flag;
-    info[1] = (int)e->f_manager.feature.size();
+    info[1] = e->storeSize();
     info[2] = e->summary.iterations;
     info[3] = e->frame_count;
     info[4] = e->failure_occur ? 1 : 0;

@@ -172,6 +172,13 @@ class Estimator {
     bool visualInitialAlign();
     bool relativePose(Mat3 &relative_R, Vec3 &relative_T, int &l);
     InitialEXRotation initial_ex_rotation;
+    // FeatureManager on the device (lfvio_fm_*).  When set, the track list moves to the device store the
+    // first time processImage() runs with solver_flag == NON_LINEAR (from the host-side list the initialisation worked on) and
+    // stays there until clearState(): addFeatureCheckParallax, triangulate, the factor list, setDepth and the slides then run
+    // where the tracks live, and optimization() never builds or uploads a projection-factor list.  f_manager is stale meanwhile.
+    bool use_device_store = false;
+    bool storeLive() const { return m_store_live; }
+    int storeSize();  // features in the device store (synchronises it)
     bool run_initial_structure = false;  // false: the pre-initialisation behaviour of this mirror (the caller sets the states)
     bool stop_after_initial_structure = false;  // test hook: return from processImage right after a successful initialStructure
     std::map<double, ImageFrame> all_image_frame;
@@ -226,6 +233,14 @@ class Estimator {
 
   private:
     lfvio_window *m_window = nullptr;
+    lfvio_fm *m_store = nullptr;
+    bool m_store_live = false, m_depth_on_device = false;
+    int m_store_L = 0, m_max_features = 0;
+    int storeLoad();
+    int storeTriangulate();
+    int storeDownloadFactors();
+    std::vector<int> m_ids;      // staging of one image for lfvio_fm_add_frame
+    std::vector<double> m_feat8;
     int m_device;
     std::vector<lfvio_proj_factor> m_proj;
     std::vector<lfvio_imu_factor> m_imu;

@@ -470,3 +470,79 @@ def test_estimator_class_survives_a_failed_solve(lfvio_mod, gpu, host):
     ate = violoop.ate_rmse(np.array(est_pos), np.array(true_pos))
     print(f"{failures[-1]} failed solves survived; ATE of the {len(est_pos)} frames afterwards = {ate:.4f} m")
     assert np.isfinite(P).all() and ate < 0.5, ate
+
+
+def _run_class_stream(lfvio_mod, gpu, host, world, min_parallax, device_store, cold_start, estimate_td=0):
+    """One pass of a synthetic stream through the C++ Estimator mirror; returns per solved frame (P, V, ba, bg, td, info)."""
+    F = 11
+    rng = np.random.default_rng(3)
+    vp = lambda a: np.ascontiguousarray(a, np.float64).ctypes.data_as(C.c_void_p)
+    _bind_estimator(host)
+    host.lfvio_host_estimator_set_states.argtypes = [C.c_void_p] + [C.c_void_p] * 3 + [C.c_int]
+    host.lfvio_host_estimator_use_device_store.argtypes = [C.c_void_p, C.c_int]
+    est = host.lfvio_host_estimator_create(10, 1000, gpu)
+    assert est, lfvio_mod.lib.lfvio_last_error()
+    b0 = (np.zeros(3), np.zeros(3)) if cold_start else (world.ba + 0.005, world.bg + 0.0005)
+    keep = [np.ascontiguousarray(x, np.float64) for x in (world.noise, world.G, world.tic, world.ric, *b0)]
+    assert host.lfvio_host_estimator_set_params(est, vp(keep[0]), vp(keep[1]), vp(keep[2]), vp(keep[3]), 0.0, min_parallax, estimate_td, vp(keep[4]), vp(keep[5])) == 0
+    if cold_start:
+        assert host.lfvio_host_estimator_enable_initialization(est, 9, 0) == 0
+    assert host.lfvio_host_estimator_use_device_store(est, 1 if device_store else 0) == 0
+    P, R, V = np.zeros((F, 3)), np.zeros((F, 9)), np.zeros((F, 3))
+    ba, bg, td, info = np.zeros((F, 3)), np.zeros((F, 3)), np.zeros(1), np.zeros(8, np.int32)
+    out = []
+    for k in range(world.n_frames):
+        if not cold_start and k == F - 1:
+            if k > 0:
+                a0, g0, dt, acc, gyr = world.imu[k]
+                arrs = [np.ascontiguousarray(x, np.float64) for x in (a0, g0, dt, acc, gyr)]
+                assert host.lfvio_host_estimator_process_imu(est, *[vp(a) for a in arrs], len(dt)) == 0
+            Pt = np.array([world.truth(f)[0] for f in range(F)]) + rng.normal(0, 0.005, (F, 3))
+            Rt = np.array([world.truth(f)[1].ravel() for f in range(F)])
+            Vt = np.array([world.truth(f)[2] for f in range(F)]) + rng.normal(0, 0.01, (F, 3))
+            assert host.lfvio_host_estimator_set_states(est, vp(Pt), vp(Rt), vp(Vt), 1) == 0
+            obs = world.frames[k]
+            ids = np.array(list(obs.keys()), np.int32)
+            feat = np.array([[*b, 0.0, row, *vel] for (b, vel, row) in obs.values()])
+            rc = host.lfvio_host_estimator_process_image(est, ids.ctypes.data_as(C.c_void_p), vp(feat), len(ids), float(world.times[k]))
+        else:
+            rc = _feed(host, est, world, k, vp)
+        assert rc == 0, lfvio_mod.lib.lfvio_last_error()
+        host.lfvio_host_estimator_get(est, vp(P), vp(R), vp(V), vp(ba), vp(bg), vp(td), info.ctypes.data_as(C.c_void_p))
+        if k >= F - 1:
+            out.append((P.copy(), V.copy(), ba.copy(), bg.copy(), float(td[0]), info.copy()))
+    live = host.lfvio_host_estimator_use_device_store(est, 1 if device_store else 0)
+    host.lfvio_host_estimator_destroy(est)
+    return out, live
+
+
+@pytest.mark.parametrize("min_parallax,cold_start", [(0.0, False), (0.45, False), (1e9, False), (0.0, True)])
+def test_estimator_class_with_device_feature_store(lfvio_mod, gpu, host, min_parallax, cold_start):
+    """The C++ Estimator with its FeatureManager on the device (use_device_store) against the same class with the host-side
+    list, frame by frame: same key-frame decisions, same list length, same iteration counts, states equal to within the solve's
+    run-to-run spread (tests/test_feature_store_gpu.py measures it).  Key frames only, a mixture, non-key frames only, and the
+    cold start where the list moves to the device right after initialStructure()."""
+    from lfvio import synthwin, violoop
+
+    if cold_start:
+        E = synthwin.ESTIMATOR
+        old_td = E["td"]
+        E["td"] = 0.0
+        try:
+            world = violoop.World(seed=2, n_frames=40, pixel_noise=0.1)
+        finally:
+            E["td"] = old_td
+    else:
+        world = violoop.World(seed=6, n_frames=34, max_feat=60)
+    a, live_a = _run_class_stream(lfvio_mod, gpu, host, world, min_parallax, False, cold_start)
+    b, live_b = _run_class_stream(lfvio_mod, gpu, host, world, min_parallax, True, cold_start)
+    assert live_a == 0 and live_b == 1 and len(a) == len(b)
+    flags = []
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert x[5][0] == y[5][0] and x[5][1] == y[5][1] and x[5][2] == y[5][2], (i, x[5], y[5])  # flag, list length, iterations
+        assert x[5][5] == y[5][5] and x[5][6] == y[5][6]                                           # sum_of_back / sum_of_front
+        for u, v in zip(x[:4], y[:4]):
+            assert np.abs(u - v).max() < 2e-5, (i, np.abs(u - v).max())
+        flags.append(int(x[5][0]))
+    if min_parallax == 0.45:
+        assert 0 in flags[1:] and 1 in flags[1:], flags

@@ -8,5 +8,6 @@ import bench
 import lfvio
 world = bench.pixel_world(int(sys.argv[1]) if len(sys.argv) > 1 else 36)
 for rep in range(2):
-    r = bench.node_path_closed_loop(lfvio, world, 0)
-    print({k: v for k, v in r.items() if k != "path"})
+    for store in (False, True):
+        r = bench.node_path_closed_loop(lfvio, world, 0, device_store=store)
+        print({k: v for k, v in r.items() if k != "path"})
