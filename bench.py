@@ -663,13 +663,17 @@ def main():
             tracker.update_ids()
         node_s["tracker"] = time.perf_counter() - t_node
 
+    # (the argument structs of the call are built once: they only hold pointers to `work`'s arrays, which are refilled per step)
+    full_call = window.prepared_optimize_full(work, B.MARGIN_OLD, prior_out) if with_marg else None
+    state_pairs = list(zip((work.pose, work.sb, work.ex, work.feat, work.td), init))
+
     def estimator_node(k0, n):
         t_node = time.perf_counter()
         for k in range(k0, k0 + n):
-            for dst, s_ in zip((work.pose, work.sb, work.ex, work.feat, work.td), init):
+            for dst, s_ in state_pairs:
                 np.copyto(dst, s_)
             if with_marg:  # Estimator::optimization() in one call: solve, double2vector gauge fix, next prior (all on device)
-                window.optimize_full(work, B.MARGIN_OLD, prior_out)
+                full_call()
             else:
                 window.optimize(work)
         node_s["estimator"] = time.perf_counter() - t_node

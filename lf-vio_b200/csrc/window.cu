@@ -29,6 +29,11 @@ namespace {
 template <class T>
 struct DBuf {
     T *p = nullptr;
+    bool own = true;
+    void view(void *q) {  // a range of another allocation (not freed here)
+        p = static_cast<T *>(q);
+        own = false;
+    }
     int alloc(size_t n) {
         if (n == 0) n = 1;
         LFVIO_CUDA_TRY(cudaMalloc(&p, sizeof(T) * n));
@@ -36,11 +41,12 @@ struct DBuf {
         return LFVIO_OK;
     }
     ~DBuf() {
-        if (p) cudaFree(p);
+        if (p && own) cudaFree(p);
     }
 };
 
 size_t align8(size_t v) { return (v + 7) & ~size_t(7); }
+size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
 
 }  // namespace
 
@@ -53,8 +59,10 @@ struct lfvio_window {
     StageProfiler prof;
     int device = 0, F = 0, Lmax = 0, Rmax = 0, nmax = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;  // second branch of the per-upload constants (prior_prepare next to imu_prepare)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // blob offsets (bytes)
-    size_t off_proj = 0, off_imu = 0, off_lm = 0, off_px0 = 0, off_pJ0 = 0, off_pr0 = 0, off_x = 0, blob_bytes = 0;
+    size_t off_proj = 0, off_P = 0, off_imu = 0, off_lm = 0, off_px0 = 0, off_pJ0 = 0, off_pr0 = 0, off_x = 0, blob_bytes = 0;
     DBuf<uint8_t> blob;
     uint8_t *h_blob = nullptr;  // pinned
     DBuf<double> x[2], x_out, imu_sqrt_info, H0;
@@ -62,13 +70,15 @@ struct lfvio_window {
     DBuf<double> scratch;
     SolverScratch w;
     DBuf<SolverCtl> ctl;
+    DBuf<uint8_t> out_blob;      // [status | ctl | x_out | marg_out]: what a call returns, one D2H copy
+    uint8_t *h_out = nullptr;    // its pinned mirror; the four pointers below look into it
+    size_t out_marg_off = 0;
     SolverCtl *h_ctl = nullptr;  // pinned
     double *h_x = nullptr;       // pinned
     int *h_status = nullptr;     // pinned (tail of h_x): imu_prepare status words
     DBuf<int> status;
     DevProblem P;            // host mirror (launch geometry, sizes of the copies)
-    DBuf<DevProblem> P_dev;  // what the kernels read
-    DevProblem *h_P = nullptr;  // pinned staging of P
+    DevProblem *P_dev = nullptr;  // what the kernels read: the header of the blob
     EvalBuf e[2];
     bool uploaded = false;
     // One executable graph per launch geometry (g_* buckets, step variant, marginalisation flag ...), captured the first
@@ -94,12 +104,9 @@ struct lfvio_window {
     ~lfvio_window() {
         for (auto &kv : graphs)
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-        if (h_P) cudaFreeHost(h_P);
         if (h_plan) cudaFreeHost(h_plan);
         if (h_blob) cudaFreeHost(h_blob);
-        if (h_ctl) cudaFreeHost(h_ctl);
-        if (h_x) cudaFreeHost(h_x);
-        if (h_marg) cudaFreeHost(h_marg);
+        if (h_out) cudaFreeHost(h_out);
         for (int k = 0; k < 2; k++)
             if (h_lm[k]) cudaFreeHost(h_lm[k]);
     }
@@ -115,6 +122,9 @@ int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_pro
         int lo = 0, hi = 0;
         LFVIO_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         LFVIO_CUDA_TRY(cudaStreamCreateWithPriority(&w->stream, cudaStreamNonBlocking, hi));
+        LFVIO_CUDA_TRY(cudaStreamCreateWithPriority(&w->side, cudaStreamNonBlocking, hi));
+        LFVIO_CUDA_TRY(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
+        LFVIO_CUDA_TRY(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
     }
     const int F = window_size + 1;
     w->F = F;
@@ -123,23 +133,51 @@ int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_pro
     w->nmax = 15 * F + 7;
     const int NI = F - 1;
     StateLayout lay{F, max_landmarks};
+    // One block, one DMA per upload.  The projection factors END where the fixed-size part begins (their start moves with their
+    // count), the prior's n x n Jacobian follows it (a prefix is used): whatever the sizes, what an upload sends is ONE contiguous
+    // range.  The problem header the kernels read (DevProblem) leads the fixed part.
     size_t o = 0;
-    w->off_proj = o;
-    o = align8(o + sizeof(lfvio_proj_factor) * (size_t)max_proj);
+    w->off_proj = o;  // start of the region (where a device FeatureManager writes its list); host lists end at off_P
+    o = align16(o + sizeof(lfvio_proj_factor) * (size_t)max_proj);
+    w->off_P = o;
+    o = align16(o + sizeof(DevProblem));
     w->off_imu = o;
-    o = align8(o + sizeof(lfvio_imu_factor) * (size_t)NI);
-    w->off_lm = o;
-    o = align8(o + sizeof(int) * (size_t)(max_landmarks + 1));
+    o = align16(o + sizeof(lfvio_imu_factor) * (size_t)NI);
     w->off_px0 = o;
-    o = align8(o + sizeof(double) * 9 * (size_t)kMaxPriorBlocks);
-    w->off_pJ0 = o;
-    o = align8(o + sizeof(double) * (size_t)w->nmax * w->nmax);
+    o = align16(o + sizeof(double) * 9 * (size_t)kMaxPriorBlocks);
     w->off_pr0 = o;
-    o = align8(o + sizeof(double) * (size_t)w->nmax);
+    o = align16(o + sizeof(double) * (size_t)w->nmax);
     w->off_x = o;
-    o = align8(o + sizeof(double) * (size_t)lay.size());
+    o = align16(o + sizeof(double) * (size_t)lay.size());
+    w->off_lm = o;
+    o = align16(o + sizeof(int) * (size_t)(max_landmarks + 1));
+    w->off_pJ0 = o;
+    o = align16(o + sizeof(double) * (size_t)w->nmax * w->nmax);
     w->blob_bytes = o;
     LFVIO_TRY(w->blob.alloc(o));
+    w->P_dev = reinterpret_cast<DevProblem *>(w->blob.p + w->off_P);
+    {   // everything a call returns, in one block (one DMA back): [status | control block | state | next prior (prefix used)]
+        size_t q = 0;
+        const size_t o_status = q;
+        q = align16(q + 4 * sizeof(int));
+        const size_t o_ctl = q;
+        q = align16(q + sizeof(SolverCtl));
+        const size_t o_x = q;
+        q = align16(q + sizeof(double) * (size_t)lay.size());
+        w->out_marg_off = q;
+        q = align16(q + sizeof(double) * ((size_t)w->nmax * w->nmax + w->nmax + 9 * (size_t)kMaxPriorBlocks));
+        LFVIO_TRY(w->out_blob.alloc(q));
+        LFVIO_CUDA_TRY(cudaMallocHost(&w->h_out, q));
+        memset(w->h_out, 0, q);
+        w->status.view(w->out_blob.p + o_status);
+        w->ctl.view(w->out_blob.p + o_ctl);
+        w->x_out.view(w->out_blob.p + o_x);
+        w->marg_out.view(w->out_blob.p + w->out_marg_off);
+        w->h_status = reinterpret_cast<int *>(w->h_out + o_status);
+        w->h_ctl = reinterpret_cast<SolverCtl *>(w->h_out + o_ctl);
+        w->h_x = reinterpret_cast<double *>(w->h_out + o_x);
+        w->h_marg = reinterpret_cast<double *>(w->h_out + w->out_marg_off);
+    }
     LFVIO_CUDA_TRY(cudaMallocHost(&w->h_blob, o));
     memset(w->h_blob, 0, o);
     for (int k = 0; k < 2; k++) {
@@ -151,7 +189,6 @@ int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_pro
         LFVIO_TRY(w->rm[k].alloc(w->nmax));
         w->e[k] = EvalBuf{w->rp[k].p, w->Jp[k].p, w->ri[k].p, w->Ji[k].p, w->rm[k].p};
     }
-    LFVIO_TRY(w->x_out.alloc(lay.size()));
     LFVIO_TRY(w->imu_sqrt_info.alloc(225 * (size_t)NI));
     LFVIO_TRY(w->H0.alloc((size_t)w->nmax * w->nmax));
     // scratch: [S D*D | rhs D | diag2 D | grad D | lm_c L | lm_g L] (zeroed per iteration) | lm_ws | proj_wj | scale | ...
@@ -177,19 +214,12 @@ int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_pro
     s.y = p;          p += D;
     s.lm_coli = reinterpret_cast<int *>(p);
     s.proj_colj = s.lm_coli + L;
-    LFVIO_TRY(w->ctl.alloc(1));
-    LFVIO_TRY(w->P_dev.alloc(1));
-    LFVIO_CUDA_TRY(cudaMallocHost(&w->h_P, sizeof(DevProblem)));
     LFVIO_CUDA_TRY(cudaMallocHost(&w->h_plan, 2 * sizeof(MargPlan)));
     for (int k = 0; k < 2; k++) LFVIO_TRY(w->plan_dev[k].alloc(1));
     {
         const char *e = getenv("LFVIO_NO_GRAPH"), *e2 = getenv("LFVIO_NO_GRAPH_WINDOW");
         w->use_graphs = !(e && e[0] == '1') && !(e2 && e2[0] == '1');
     }
-    LFVIO_CUDA_TRY(cudaMallocHost(&w->h_ctl, sizeof(SolverCtl)));
-    LFVIO_CUDA_TRY(cudaMallocHost(&w->h_x, sizeof(double) * (lay.size() + 2)));
-    w->h_status = reinterpret_cast<int *>(w->h_x + lay.size());
-    LFVIO_TRY(w->status.alloc(4));
     {
         const size_t dim = (size_t)w->nmax + 15;
         for (int k = 0; k < 2; k++) {
@@ -198,8 +228,6 @@ int window_init(lfvio_window *w, int window_size, int max_landmarks, int max_pro
         }
         LFVIO_TRY(w->margT.alloc(dim * dim + dim));
         LFVIO_TRY(w->marg_work.alloc(marg_finish_workspace_doubles(15, w->nmax)));
-        LFVIO_TRY(w->marg_out.alloc((size_t)w->nmax * w->nmax + w->nmax + 9 * (size_t)kMaxPriorBlocks));
-        LFVIO_CUDA_TRY(cudaMallocHost(&w->h_marg, sizeof(double) * ((size_t)w->nmax * w->nmax + w->nmax + 9 * kMaxPriorBlocks)));
     }
     return LFVIO_OK;
 }
@@ -380,9 +408,15 @@ unsigned long long geometry_key(const lfvio_window *w, int variant, int flag, bo
 // Per-upload constants of the solve: square-root information of the IMU factors, H0 = J0^T J0 of the prior.
 int enqueue_prepare(lfvio_window *w) {
     cudaStream_t s = w->stream;
+    // two independent chains of dependent arithmetic (15 x 15 inverses + Cholesky per IMU factor; H0 = J0^T J0): side by side —
+    // a fork / join through events, which a stream capture turns into two branches of the graph
+    LFVIO_CUDA_TRY(cudaEventRecord(w->ev_fork, s));
+    LFVIO_CUDA_TRY(cudaStreamWaitEvent(w->side, w->ev_fork, 0));
+    LFVIO_TRY(launch_prior_prepare(w->P, w->H0.p, w->side));
+    LFVIO_CUDA_TRY(cudaEventRecord(w->ev_join, w->side));
     LFVIO_CUDA_TRY(cudaMemsetAsync(w->status.p, 0, sizeof(int) * 4, s));
     LFVIO_TRY(launch_imu_prepare(w->P, w->imu_sqrt_info.p, w->status.p, s));
-    LFVIO_TRY(launch_prior_prepare(w->P, w->H0.p, s));
+    LFVIO_CUDA_TRY(cudaStreamWaitEvent(s, w->ev_join, 0));
     return LFVIO_OK;
 }
 
@@ -400,7 +434,9 @@ int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_lis
     const int F = w->F, L = n_lm;
     StateLayout lay{F, L};
     uint8_t *hb = w->h_blob;
-    if (!src && n_proj) memcpy(hb + w->off_proj, fl->proj, sizeof(lfvio_proj_factor) * (size_t)n_proj);
+    const size_t proj_bytes = sizeof(lfvio_proj_factor) * (size_t)n_proj;
+    const size_t proj_at = src ? w->off_proj : w->off_P - proj_bytes;  // a host list ends where the fixed part begins
+    if (!src && n_proj) memcpy(hb + proj_at, fl->proj, proj_bytes);
     if (fl->n_imu) memcpy(hb + w->off_imu, fl->imu, sizeof(lfvio_imu_factor) * (size_t)fl->n_imu);
     // landmark -> factor ranges (the reference inserts factors landmark by landmark, estimator.cpp:725-772)
     int *lm = reinterpret_cast<int *>(hb + w->off_lm);
@@ -428,7 +464,7 @@ int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_lis
     P.o = *o;
     P.n_proj = n_proj;
     P.n_imu = fl->n_imu;
-    P.proj = reinterpret_cast<const lfvio_proj_factor *>(w->blob.p + w->off_proj);
+    P.proj = reinterpret_cast<const lfvio_proj_factor *>(w->blob.p + proj_at);
     P.imu = reinterpret_cast<const lfvio_imu_factor *>(w->blob.p + w->off_imu);
     P.lm_first = reinterpret_cast<const int *>(w->blob.p + w->off_lm);
     P.imu_sqrt_info = w->imu_sqrt_info.p;
@@ -458,38 +494,35 @@ int upload(lfvio_window *w, const lfvio_window_state *st, const lfvio_factor_lis
         P.prior.H0 = w->H0.p;
     }
     // launch geometry: counts rounded up to coarse buckets so that consecutive frames of a stream share one graph
-    P.self_dev = w->P_dev.p;
+    P.self_dev = w->P_dev;
     P.g_nbp = std::max(1, std::min(cdiv(w->Rmax, 128), (cdiv(n_proj, 128) + 7) / 8 * 8));
     P.g_L = std::max(1, std::min(w->Lmax, (L + 127) / 128 * 128));
     P.g_imu = F - 1;
     P.cap_L = w->Lmax;
     P.cap_n = w->nmax;
-    *w->h_P = P;
-    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->P_dev.p, w->h_P, sizeof(DevProblem), cudaMemcpyHostToDevice, w->stream));
+    memcpy(hb + w->off_P, &P, sizeof(DevProblem));
     double *hx = reinterpret_cast<double *>(hb + w->off_x);
     memcpy(hx + lay.pose(0), st->para_Pose, sizeof(double) * 7 * F);
     memcpy(hx + lay.sb(0), st->para_SpeedBias, sizeof(double) * 9 * F);
     memcpy(hx + lay.ex(), st->para_Ex_Pose, sizeof(double) * 7);
     hx[lay.td()] = st->para_Td[0];
     if (L && !src) memcpy(hx + lay.feat(0), st->para_Feature, sizeof(double) * L);
-    // one DMA: everything up to the end of the state (unused capacity in between is skipped in three pieces)
+    // one DMA: [projection factors | header | IMU factors | prior x0, r0 | state | landmark ranges | prior J0 (n x n prefix)]
     cudaStream_t s = w->stream;
     auto copy = [&](size_t off, size_t bytes) -> int {
         if (bytes) LFVIO_CUDA_TRY(cudaMemcpyAsync(w->blob.p + off, hb + off, bytes, cudaMemcpyHostToDevice, s));
         return LFVIO_OK;
     };
-    if (src) {  // factors, ranges and inverse depths are already in the blob (written there by the FeatureManager's kernel)
-        LFVIO_TRY(copy(w->off_imu, w->off_lm - w->off_imu));
-        if (P.prior.n) LFVIO_TRY(copy(w->off_px0, sizeof(double) * 9 * P.prior.n_blocks));
+    const size_t j0_bytes = P.prior.n ? sizeof(double) * (size_t)P.prior.n * P.prior.n : 0;
+    if (src) {
+        // ranges, inverse depths and factors are already in the blob (written there by the FeatureManager's kernel): the header
+        // up to the fixed part of the state, then the prior's Jacobian
+        LFVIO_TRY(copy(w->off_P, w->off_x + sizeof(double) * lay.feat(0) - w->off_P));
+        LFVIO_TRY(copy(w->off_pJ0, j0_bytes));
     } else {
-        LFVIO_TRY(copy(w->off_proj, sizeof(lfvio_proj_factor) * (size_t)n_proj));
-        LFVIO_TRY(copy(w->off_imu, w->off_px0 - w->off_imu + (P.prior.n ? sizeof(double) * 9 * P.prior.n_blocks : 0)));
+        const size_t end = j0_bytes ? w->off_pJ0 + j0_bytes : w->off_lm + sizeof(int) * ((size_t)L + 1);
+        LFVIO_TRY(copy(proj_at, end - proj_at));
     }
-    if (P.prior.n) {
-        LFVIO_TRY(copy(w->off_pJ0, sizeof(double) * (size_t)P.prior.n * P.prior.n));
-        LFVIO_TRY(copy(w->off_pr0, sizeof(double) * P.prior.n));
-    }
-    LFVIO_TRY(copy(w->off_x, sizeof(double) * (src ? lay.feat(0) : lay.size())));
     if (!defer_prepare) LFVIO_TRY(enqueue_prepare(w));
     if (defer_plans) {
         w->plan_valid[0] = w->plan_valid[1] = false;
@@ -609,17 +642,18 @@ __global__ void gauge_fix_kernel(const DevProblem *__restrict__ Pd, const double
     for (int k = 3; k < 9; k++) so[k] = sb[k];
 }
 
-int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum, bool select_state = true) {
+int download(lfvio_window *w, lfvio_window_state *st, lfvio_solve_summary *sum, bool select_state = true, size_t marg_doubles = 0) {
     cudaStream_t s = w->stream;
     const StateLayout lay = w->P.lay;
     if (select_state) {
         select_state_kernel<<<cdiv(lay.size(), 256), 256, 0, s>>>(w->P.self_dev, w->x[0].p, w->x[1].p, w->ctl.p, w->x_out.p);
         LFVIO_LAUNCH_CHECK();
     }
-    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_x, w->x_out.p, sizeof(double) * lay.size(), cudaMemcpyDeviceToHost, s));
-    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_ctl, w->ctl.p, sizeof(SolverCtl), cudaMemcpyDeviceToHost, s));
-    int *status = w->h_status;  // pinned: a D2H copy into pageable memory would be staged synchronously
-    LFVIO_CUDA_TRY(cudaMemcpyAsync(status, w->status.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    // one DMA back: status, control block, state and (marg_doubles > 0) the next prior
+    const size_t out_bytes = marg_doubles ? w->out_marg_off + sizeof(double) * marg_doubles
+                                          : (size_t)(reinterpret_cast<uint8_t *>(w->h_x) - w->h_out) + sizeof(double) * lay.size();
+    LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_out, w->out_blob.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    int *status = w->h_status;
     LFVIO_CUDA_TRY(cudaStreamSynchronize(s));
     if (st) {
         memcpy(st->para_Pose, w->h_x + lay.pose(0), sizeof(double) * 7 * lay.F);
@@ -720,6 +754,12 @@ extern "C" void lfvio_window_destroy(lfvio_window *w) {
         cudaStreamSynchronize(w->stream);
         cudaStreamDestroy(w->stream);
     }
+    if (w->side) {
+        cudaStreamSynchronize(w->side);
+        cudaStreamDestroy(w->side);
+    }
+    if (w->ev_fork) cudaEventDestroy(w->ev_fork);
+    if (w->ev_join) cudaEventDestroy(w->ev_join);
     delete w;
 }
 
@@ -749,7 +789,14 @@ static int optimize_full_impl(lfvio_window *w, lfvio_window_state *state, const 
     LFVIO_REQUIRE(w && prior_out, "lfvio_window_optimize_full: null argument");
     LFVIO_REQUIRE(margin_flag == LFVIO_MARGIN_OLD || margin_flag == LFVIO_MARGIN_SECOND_NEW, "lfvio_window_optimize_full: bad margin_flag");
     LFVIO_CUDA_TRY(cudaSetDevice(w->device));
+    // (same switch) device-side timeline of the call: events between its parts, read after the call's own synchronisation
+    static cudaEvent_t dev_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    static double dev_acc[4] = {0, 0, 0, 0};
+    if (dbg_host && !dev_ev[0])
+        for (auto &e : dev_ev) cudaEventCreate(&e);
+    if (dbg_host) cudaEventRecord(dev_ev[0], w->stream);
     LFVIO_TRY(upload(w, state, factors, opts, /*defer_plans=*/true, /*defer_prepare=*/true, src));
+    if (dbg_host) cudaEventRecord(dev_ev[1], w->stream);
     lap(0);
     cudaStream_t s = w->stream;
     const DevProblem &P = w->P;
@@ -763,6 +810,7 @@ static int optimize_full_impl(lfvio_window *w, lfvio_window_state *state, const 
         LFVIO_LAUNCH_CHECK();
         return LFVIO_OK;
     }));
+    if (dbg_host) cudaEventRecord(dev_ev[2], s);
     lap(1);
     LFVIO_TRY(build_marg_plan(w, margin_flag, factors, opts, w->P.lay.L, src));  // host work under the running solve
     lap(2);
@@ -782,11 +830,20 @@ static int optimize_full_impl(lfvio_window *w, lfvio_window_state *state, const 
         w->last_marg_flag = margin_flag;
         nn = (size_t)pl.n * pl.n;
         for (int b = 0; b < pl.n_keep; b++) x0_len += P.lay.block_gsize(pl.keep_id[b]);
-        LFVIO_CUDA_TRY(cudaMemcpyAsync(w->h_marg, w->marg_out.p, sizeof(double) * (nn + pl.n + x0_len), cudaMemcpyDeviceToHost, s));
     }
+    if (dbg_host) cudaEventRecord(dev_ev[3], s);
     lap(3);
-    LFVIO_TRY(download(w, state, summary, false));
+    LFVIO_TRY(download(w, state, summary, false, do_marg ? nn + pl.n + x0_len : 0));
     lap(4);
+    if (dbg_host) {
+        cudaEventRecord(dev_ev[4], s);
+        cudaEventSynchronize(dev_ev[4]);
+        for (int i = 0; i < 4; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, dev_ev[i], dev_ev[i + 1]);
+            dev_acc[i] += 1e3 * ms;
+        }
+    }
     if (do_marg && getenv("LFVIO_DEBUG_STEP")) {
         long long mc[8];
         marg_profile_read(mc);
@@ -817,6 +874,8 @@ static int optimize_full_impl(lfvio_window *w, lfvio_window_state *state, const 
         static const char *nm[6] = {"upload (pack + enqueue H2D)", "enqueue graph 1 (solve)", "marginalisation plan (host)", "enqueue graph 2 + D2H",
                                     "download (wait for the stream + copy out)", "prior copy out"};
         for (int i = 0; i < 6; i++) fprintf(stderr, "optimize_full host %-44s %8.1f us\n", nm[i], t_acc[i] / t_calls);
+        static const char *dn[4] = {"H2D (from the call's first enqueue)", "graph 1: prepare + solve + gauge", "plan copy + graph 2: marginalisation", "D2H"};
+        for (int i = 0; i < 4; i++) fprintf(stderr, "optimize_full device %-42s %8.1f us\n", dn[i], dev_acc[i] / t_calls);
     }
     return LFVIO_OK;
 }

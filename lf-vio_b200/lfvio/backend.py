@@ -317,6 +317,21 @@ class Window:
                                                          C.byref(out.c)), "lfvio_window_optimize_full")
         return s, out
 
+    def prepared_optimize_full(self, w: WindowProblem, flag: int = MARGIN_OLD, out: PriorData | None = None):
+        """The same C-ABI call with its argument structs built once: returns call() -> status for loops that make the call many
+        times on the same numpy-owned buffers (the structs only hold pointers to them), e.g. bench.py's estimator node."""
+        out = out or PriorData()
+        keep = (w.state(), w.factors(), SolveSummary(), out, w)
+        fn, h, check = self._lib.lfvio_window_optimize_full, self._h, self._check
+        a = (C.byref(keep[0]), C.byref(keep[1]), C.byref(w.opts), flag, C.byref(keep[2]), C.byref(out.c))
+
+        def call():
+            check(fn(h, *a), "lfvio_window_optimize_full")
+            return keep[2]
+
+        call.keep = keep
+        return call
+
     def optimize_full_fm(self, fm: "FeatureStore", w: WindowProblem, flag: int = MARGIN_OLD, out: PriorData | None = None, max_landmarks: int = 4096):
         """optimize_full with the projection factors and para_Feature taken from the device FeatureStore (w.proj / w.feat are
         ignored on input; w.feat returns the optimised inverse depths); returns (summary, prior)."""
