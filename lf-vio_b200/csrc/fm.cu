@@ -443,6 +443,7 @@ static int fm_meta(lfvio_fm *f) {  // counts back to the host: one small copy + 
 extern "C" int lfvio_fm_create(int window_size, int capacity, int max_proj_factors, double min_parallax, double init_depth, int device,
                                lfvio_fm **out) {
     clear_error();
+    if (out) *out = nullptr;
     LFVIO_REQUIRE(out && window_size >= 2 && window_size + 1 <= 32 && capacity > 0 && max_proj_factors > 0, "lfvio_fm_create: bad arguments");
     LFVIO_CUDA_TRY(cudaSetDevice(device));
     lfvio_fm *f = new lfvio_fm();
@@ -496,8 +497,11 @@ extern "C" int lfvio_fm_create(int window_size, int capacity, int max_proj_facto
     d.freel = f->freel.p; d.depth = f->depth.p; d.obs = f->obs.p; d.meta = f->meta.p;
     f->proj_cap = max_proj_factors;
     fm_clear_kernel<<<1, FM_THREADS, 0, f->stream>>>(d);
-    LFVIO_LAUNCH_CHECK();
-    LFVIO_CUDA_TRY(cudaStreamSynchronize(f->stream));
+    count_launch();
+    if (cudaPeekAtLastError() != cudaSuccess || cudaStreamSynchronize(f->stream) != cudaSuccess) {
+        set_error("lfvio_fm_create: clearing the store failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail(LFVIO_ERR_CUDA);
+    }
     *out = f;
     return LFVIO_OK;
 }

@@ -332,6 +332,8 @@ struct StepArena {
             const size_t want = std::max<size_t>(bytes + bytes / 2, 1 << 16);
             LFVIO_CUDA_TRY(cudaMalloc(&d, want));
             LFVIO_CUDA_TRY(cudaMallocHost(&h, want));
+            LFVIO_CUDA_TRY(cudaMemset(d, 0, want));  // (the alignment gaps between the sub-buffers travel in the one D2H copy)
+            memset(h, 0, want);
             cap = want;
         }
         return LFVIO_OK;

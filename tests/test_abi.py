@@ -34,6 +34,23 @@ def test_bad_arguments_fail_loudly(lfvio_mod):
     assert b"bad arguments" in lfvio_mod.lib.lfvio_last_error()
 
 
+def test_feature_store_arguments_and_missing_device_fail_loudly(lfvio_mod):
+    """lfvio_fm_*: argument errors are reported before any device work, and without a CUDA device the handle is not created
+    (there is no host-side fallback store)."""
+    import ctypes as C
+
+    L = lfvio_mod.lib
+    h = C.c_void_p()
+    assert L.lfvio_fm_create(1, 16, 16, 0.1, 5.0, 0, C.byref(h)) == -2 and not h.value            # window_size < 2
+    assert L.lfvio_fm_create(40, 16, 16, 0.1, 5.0, 0, C.byref(h)) == -2 and not h.value           # more than 32 frames
+    assert L.lfvio_fm_create(10, 0, 16, 0.1, 5.0, 0, C.byref(h)) == -2 and b"bad arguments" in L.lfvio_last_error()
+    assert L.lfvio_fm_add_frame(None, 0, None, None, 0, 0.0, None, None) == -2
+    assert L.lfvio_fm_build_factors(None, None, None) == -2 and b"null handle" in L.lfvio_last_error()
+    assert L.lfvio_window_optimize_full_fm(None, None, None, None, None, 0, None, None) == -2
+    if L.lfvio_device_count() == 0:
+        assert L.lfvio_fm_create(10, 16, 16, 0.1, 5.0, 0, C.byref(h)) == -1 and not h.value       # LFVIO_ERR_CUDA, no handle
+
+
 def test_product_never_imports_oracle():
     """The product tree must not reference the oracle (no CPU fallback)."""
     bad = []

@@ -165,3 +165,17 @@ def test_closed_loop_with_device_store_tracks_truth(lfvio_mod, gpu):
     assert ks_h == ks_d == list(range(10, 60))
     assert ate_d < 0.12 and abs(ate_d - ate_h) < 1e-5, (ate_d, ate_h)
     assert abs(loop.td - host.td) < 1e-6
+
+
+def test_device_store_three_steps(lfvio_mod, gpu):
+    """Three frames of the loop over the device store (add-frame, triangulate, build, solve from the device-built list, setDepth on
+    the device, removeBackShiftDepth): the short case tools/sanitize.sh runs under compute-sanitizer."""
+    world = violoop.World(seed=4, n_frames=16, max_feat=80)
+    opts = lfvio_mod.solver_default_opts()
+    opts.row = 960
+    opts.estimate_td = 1
+    loop = violoop.VioLoopStore(world, lfvio_mod.Window(W, 512, 8192), lfvio_mod.FeatureStore(W, 1024, 8192), opts, F=W + 1)
+    for _ in range(3):
+        assert loop.step()
+    assert loop.iterations == [8, 8, 8] or all(0 < i <= 8 for i in loop.iterations)
+    assert np.isfinite(loop.pose).all() and len(loop.store.snapshot()) > 50
