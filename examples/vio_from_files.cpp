@@ -25,10 +25,11 @@
 using namespace lfvio_host;
 
 static void usage() {
-    std::puts("usage: vio_from_files imu.txt features.txt result_tum.txt [calib.txt] [td] [ransac_seed]\n"
+    std::puts("usage: vio_from_files imu.txt features.txt result_tum.txt [calib.txt] [td] [ransac_seed] [host_list]\n"
               "  imu.txt:      stamp ax ay az gx gy gz\n"
               "  features.txt: blocks \"F stamp n\" + n lines \"id x y z u v vx vy vz\"\n"
               "  calib.txt:    ric (9, row-major) tic (3) acc_n gyr_n acc_w gyr_w g_norm\n"
+              "  host_list:    1 keeps the FeatureManager on the host (default 0: on the device once the estimator is initialised)\n"
               "  writes \"stamp px py pz qx qy qz qw\" per optimised frame (TUM)");
 }
 
@@ -69,6 +70,7 @@ int main(int argc, char **argv) {
     node.estimator.setParameter();            // tic / ric / td from TIC0 / RIC0 / TD
     node.estimator.run_initial_structure = true;
     if (argc > 6) node.estimator.ransac_seed = std::strtoull(argv[6], nullptr, 10);
+    node.estimator.use_device_store = !(argc > 7 && std::atoi(argv[7]) == 1);  // track list on the device (lfvio_fm_*)
 
     // merge the two streams by time stamp, as the ROS callbacks would arrive
     ImuMsg im;
