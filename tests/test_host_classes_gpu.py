@@ -382,9 +382,11 @@ def test_estimator_class_closed_loop_from_cold_start(lfvio_mod, gpu, host):
     assert ate < 0.05, ate
 
 
-def test_estimator_class_failure_reboot_and_reinitialisation(lfvio_mod, gpu, host):
+@pytest.mark.parametrize("device_store", [0, 1])
+def test_estimator_class_failure_reboot_and_reinitialisation(lfvio_mod, gpu, host, device_store):
     """The restart path (estimator.cpp:196-204): failureDetection() trips (here: last_P moved by 10 m), the
-    estimator reboots (clearState + setParameter), the window refills and initialStructure() runs a second time."""
+    estimator reboots (clearState + setParameter), the window refills and initialStructure() runs a second time.  With the
+    FeatureManager on the device the reboot goes back to the host-side list for the initialisation and loads the store again."""
     from lfvio import synthwin, violoop
 
     E = synthwin.ESTIMATOR
@@ -403,6 +405,8 @@ def test_estimator_class_failure_reboot_and_reinitialisation(lfvio_mod, gpu, hos
     keep = [np.ascontiguousarray(x, np.float64) for x in (world.noise, world.G, world.tic, world.ric, np.zeros(3), np.zeros(3))]
     assert host.lfvio_host_estimator_set_params(est, vp(keep[0]), vp(keep[1]), vp(keep[2]), vp(keep[3]), 0.0, 0.0, 0, vp(keep[4]), vp(keep[5])) == 0
     assert host.lfvio_host_estimator_enable_initialization(est, 9, 0) == 0
+    host.lfvio_host_estimator_use_device_store.argtypes = [C.c_void_p, C.c_int]
+    host.lfvio_host_estimator_use_device_store(est, device_store)
     P, R, V = np.zeros((F, 3)), np.zeros((F, 9)), np.zeros((F, 3))
     ba, bg, td, info, ii, g = np.zeros((F, 3)), np.zeros((F, 3)), np.zeros(1), np.zeros(8, np.int32), np.zeros(8, np.int32), np.zeros(3)
     flags, est_pos, true_pos = [], [], []
@@ -417,6 +421,7 @@ def test_estimator_class_failure_reboot_and_reinitialisation(lfvio_mod, gpu, hos
         if k >= k_fail + F and ii[0] == 1:
             est_pos.append(P[F - 1].copy())
             true_pos.append(world.truth(k)[0])
+    assert host.lfvio_host_estimator_use_device_store(est, device_store) == device_store   # the store is live again after the reboot
     host.lfvio_host_estimator_destroy(est)
     assert all(f[0] == 1 and f[1] == 0 for f in flags[F - 1:k_fail])          # running, no reboot yet
     assert flags[k_fail] == (0, 1, 0)                                         # rebooted: INITIAL, frame_count 0
@@ -427,7 +432,8 @@ def test_estimator_class_failure_reboot_and_reinitialisation(lfvio_mod, gpu, hos
     assert len(est_pos) == world.n_frames - (k_fail + F) and ate < 0.05, ate
 
 
-def test_estimator_class_survives_a_failed_solve(lfvio_mod, gpu, host):
+@pytest.mark.parametrize("device_store", [0, 1])
+def test_estimator_class_survives_a_failed_solve(lfvio_mod, gpu, host, device_store):
     """A solve that fails numerically is not fatal (the reference's ceres::Solve leaves the state at the last accepted point
     and processImage goes on to failureDetection / slideWindow, estimator.cpp:183-215): a pre-integration with a singular
     covariance makes lfvio_window_optimize return LFVIO_ERR_NUMERIC for as long as it stays in the window; the window must keep
@@ -450,6 +456,8 @@ def test_estimator_class_survives_a_failed_solve(lfvio_mod, gpu, host):
     keep = [np.ascontiguousarray(x, np.float64) for x in (world.noise, world.G, world.tic, world.ric, np.zeros(3), np.zeros(3))]
     assert host.lfvio_host_estimator_set_params(est, vp(keep[0]), vp(keep[1]), vp(keep[2]), vp(keep[3]), 0.0, 0.0, 0, vp(keep[4]), vp(keep[5])) == 0
     assert host.lfvio_host_estimator_enable_initialization(est, 9, 0) == 0
+    host.lfvio_host_estimator_use_device_store.argtypes = [C.c_void_p, C.c_int]
+    host.lfvio_host_estimator_use_device_store(est, device_store)  # (a failed solve then leaves the store's depths as they were)
     P, R, V = np.zeros((F, 3)), np.zeros((F, 9)), np.zeros((F, 3))
     ba, bg, td, info = np.zeros((F, 3)), np.zeros((F, 3)), np.zeros(1), np.zeros(8, np.int32)
     k_poke, failures, est_pos, true_pos = 20, [], [], []
