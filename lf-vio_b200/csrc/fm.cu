@@ -325,30 +325,10 @@ __global__ void __launch_bounds__(FM_THREADS) fm_build_factors_kernel(FmDev f, F
             if (l < dst.lm_cap && k0 + nfac <= dst.proj_cap) {
                 dst.lm_first[l] = k0;
                 dst.para_feature[l] = 1.0 / f.depth[s];
+                f.order2[l] = s;  // landmark -> slot, for the factor pass below (order2 is scratch outside the slides)
                 if (host0) {
                     dst.marg_lm[m] = l;
                     atomicOr(&s_mask, ((2u << nfac) - 1u) & ~1u);  // frames 1 .. nfac
-                }
-                const double *o0 = obs_at(f, s, 0);
-                const int fi = f.start[s];
-                for (int j = 1; j <= nfac; j++) {
-                    const double *oj = obs_at(f, s, j);
-                    lfvio_proj_factor r;
-                    r.frame_i = fi;
-                    r.frame_j = fi + j;
-                    r.landmark = l;
-                    r.reserved = 0;
-                    for (int q = 0; q < 3; q++) {
-                        r.pts_i[q] = o0[q];
-                        r.pts_j[q] = oj[q];
-                        r.vel_i[q] = o0[3 + q];
-                        r.vel_j[q] = oj[3 + q];
-                    }
-                    r.td_i = o0[8];
-                    r.td_j = oj[8];
-                    r.row_i = o0[7];
-                    r.row_j = oj[7];
-                    dst.proj[k0 + j - 1] = r;
                 }
             } else {
                 f.meta[M_ERR] = 3;  // factor list larger than the handle's capacity
@@ -365,6 +345,36 @@ __global__ void __launch_bounds__(FM_THREADS) fm_build_factors_kernel(FmDev f, F
         f.meta[M_NPROJ] = k_base;
         f.meta[M_MASK] = (int)s_mask;
         f.meta[M_NMARG] = m_base;
+    }
+    __syncthreads();
+    if (f.meta[M_ERR] != 0) return;
+    // the records, one thread per FACTOR (consecutive threads write consecutive 144-byte records): its landmark is the last
+    // range that starts at or before it
+    for (int k = threadIdx.x; k < k_base; k += FM_THREADS) {
+        int lo = 0, hi = lm_base - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (dst.lm_first[mid] <= k) lo = mid;
+            else hi = mid - 1;
+        }
+        const int l = lo, s = f.order2[l], j = k - dst.lm_first[l] + 1, fi = f.start[s];
+        const double *o0 = obs_at(f, s, 0), *oj = obs_at(f, s, j);
+        lfvio_proj_factor r;
+        r.frame_i = fi;
+        r.frame_j = fi + j;
+        r.landmark = l;
+        r.reserved = 0;
+        for (int q = 0; q < 3; q++) {
+            r.pts_i[q] = o0[q];
+            r.pts_j[q] = oj[q];
+            r.vel_i[q] = o0[3 + q];
+            r.vel_j[q] = oj[3 + q];
+        }
+        r.td_i = o0[8];
+        r.td_j = oj[8];
+        r.row_i = o0[7];
+        r.row_j = oj[7];
+        dst.proj[k] = r;
     }
 }
 
